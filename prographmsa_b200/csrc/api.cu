@@ -1,0 +1,469 @@
+// api.cu -- C-ABI glue (include/pgm_b200.h): context, error reporting, timing, and the host-side
+// scheduling of HP-2 (pair descriptors, length-binned chunks sized to the scratch budget).
+#include "internal.h"
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+
+static thread_local char g_err[1024] = "";
+void pgm_set_error(const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int nw_pick_C(int max_L1);
+
+struct TimedSection { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; };
+
+struct pgm_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    uint64_t scratch_bytes = 6ull << 30;
+    bool timing_on = false;
+    pgm_timing timing{};
+    std::vector<TimedSection> sections;       // pending (resolved at sync)
+    std::vector<cudaEvent_t> event_pool;
+    // model cache
+    DevBuf d_model; std::vector<double> cachedQ; int cached_n = 0;
+    // HP-2 scratch
+    DevBuf d_codes, d_descs, d_tasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
+           d_counts, d_scores, d_misc, d_rows, d_seqlen;
+    HostPinned h_stage;
+};
+
+// ---- timing ----------------------------------------------------------------------------------------
+enum { K_NW_FWD = 0, K_NW_WALK, K_ML, K_EMIT, K_GFILL, K_GTRACE };
+
+static cudaEvent_t get_event(pgm_ctx* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+struct ScopedKernelTimer {
+    pgm_ctx* c; TimedSection s;
+    ScopedKernelTimer(pgm_ctx* ctx, int kind) : c(ctx) {
+        s.kind = kind;
+        if (c->timing_on) { s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
+    }
+    ~ScopedKernelTimer() {
+        if (c->timing_on) { cudaEventRecord(s.b, c->stream); c->sections.push_back(s); }
+    }
+};
+static void resolve_timing(pgm_ctx* c) {
+    for (auto& s : c->sections) {
+        float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b);
+        switch (s.kind) {
+            case K_NW_FWD: c->timing.nw_forward_ms += ms; c->timing.nw_forward_launches++; break;
+            case K_NW_WALK: c->timing.nw_walk_ms += ms; c->timing.nw_walk_launches++; break;
+            case K_ML: c->timing.ml_ms += ms; c->timing.ml_launches++; break;
+            case K_EMIT: c->timing.emission_ms += ms; c->timing.emission_launches++; break;
+            case K_GFILL: c->timing.graph_fill_ms += ms; c->timing.graph_fill_launches++; break;
+            case K_GTRACE: c->timing.graph_trace_ms += ms; c->timing.graph_trace_launches++; break;
+        }
+        c->event_pool.push_back(s.a); c->event_pool.push_back(s.b);
+    }
+    c->sections.clear();
+}
+
+extern "C" {
+
+const char* pgm_last_error(void) { return g_err; }
+int pgm_abi_version(void) { return 1; }
+
+int pgm_create(int device, pgm_ctx** out) {
+    if (!out) { pgm_set_error("pgm_create: out is NULL"); return PGM_ERR_ARG; }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        pgm_set_error("no CUDA device available (%s); libpgm_b200 has no CPU fallback", cudaGetErrorString(e));
+        cudaGetLastError();
+        return PGM_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) { pgm_set_error("device %d out of range (0..%d)", device, count - 1); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop; PGM_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        pgm_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+        return PGM_ERR_CUDA;
+    }
+    pgm_ctx* c = new pgm_ctx();
+    c->device = device;
+    PGM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    *out = c;
+    return 0;
+}
+
+void pgm_destroy(pgm_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    resolve_timing(c);
+    for (DevBuf* b : {&c->d_model, &c->d_codes, &c->d_descs, &c->d_tasks, &c->d_tab, &c->d_tb, &c->d_colbuf, &c->d_list,
+                      &c->d_list_len, &c->d_gaps, &c->d_dist, &c->d_var, &c->d_counts, &c->d_scores, &c->d_misc, &c->d_rows,
+                      &c->d_seqlen}) b->release();
+    c->h_stage.release();
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int pgm_sync(pgm_ctx* c) {
+    PGM_CUDA(cudaSetDevice(c->device));
+    PGM_CUDA(cudaStreamSynchronize(c->stream));
+    resolve_timing(c);
+    return 0;
+}
+
+int pgm_set_scratch_bytes(pgm_ctx* c, uint64_t bytes) {
+    if (bytes < (64ull << 20)) { pgm_set_error("scratch budget must be >= 64 MiB"); return PGM_ERR_ARG; }
+    c->scratch_bytes = bytes; return 0;
+}
+void* pgm_stream(pgm_ctx* c) { return (void*)c->stream; }
+int pgm_enable_timing(pgm_ctx* c, int on) { c->timing_on = on != 0; return 0; }
+int pgm_get_timing(pgm_ctx* c, pgm_timing* out) {
+    int rc = pgm_sync(c); if (rc) return rc;
+    *out = c->timing; return 0;
+}
+
+} // extern "C"
+
+static void reset_timing(pgm_ctx* c) { resolve_timing(c); memset(&c->timing, 0, sizeof(c->timing)); }
+
+// ---- model upload -----------------------------------------------------------------------------------
+static int prepare_model(pgm_ctx* c, const pgm_ml_params* prm, MlDev& ml) {
+    const int n = prm->n_states;
+    if (n < 2 || n > 63) { pgm_set_error("n_states %d out of range (2..63)", n); return PGM_ERR_ARG; }
+    const size_t nn = (size_t)n * n;
+    const bool need_basis = prm->mldist_flag || prm->mldist_gap_flag;
+    if (need_basis && (!prm->Q || !prm->pi)) { pgm_set_error("Q / pi are required for ML distances"); return PGM_ERR_ARG; }
+    int rc = c->d_model.reserve(sizeof(double) * (2 * nn + n));
+    if (rc) return rc;
+    if (need_basis && !(c->cached_n == n && c->cachedQ.size() == nn && memcmp(c->cachedQ.data(), prm->Q, nn * 8) == 0)) {
+        std::vector<double> buf(2 * nn + n);
+        rc = pgm_eigen_basis(prm->Q, n, buf.data(), buf.data() + 2 * nn, buf.data() + nn);
+        if (rc) return rc;
+        PGM_CUDA(cudaMemcpyAsync(c->d_model.p, buf.data(), buf.size() * 8, cudaMemcpyHostToDevice, c->stream));
+        PGM_CUDA(cudaStreamSynchronize(c->stream));
+        c->cachedQ.assign(prm->Q, prm->Q + nn); c->cached_n = n;
+    }
+    ml.n = n;
+    ml.V = c->d_model.as<double>(); ml.Vi = ml.V + nn; ml.sigma = ml.V + 2 * nn;
+    ml.mldist_flag = prm->mldist_flag; ml.mldist_gap_flag = prm->mldist_gap_flag;
+    ml.indel_rate = prm->indel_rate; ml.min_dist = prm->min_dist; ml.max_dist = prm->max_dist;
+    ml.cutoff_dist = prm->cutoff_dist; ml.DIST_MAX = prm->DIST_MAX; ml.VAR_MAX = prm->VAR_MAX; ml.VAR_MIN = prm->VAR_MIN;
+    return 0;
+}
+
+static inline void pair_from_index_host(int64_t p, int64_t N, int64_t& i, int64_t& j) {
+    const double b = 2.0 * N - 1.0;
+    int64_t ii = (int64_t)std::floor((b - std::sqrt(b * b - 8.0 * (double)p)) * 0.5);
+    if (ii < 0) ii = 0;
+    while (ii > 0 && ii * N - ii * (ii + 1) / 2 > p) --ii;
+    while ((ii + 1) * N - (ii + 1) * (ii + 2) / 2 <= p) ++ii;
+    i = ii; j = p - (ii * N - ii * (ii + 1) / 2) + ii + 1;
+}
+
+// ---- HP-2a: NW + ML over a pair range, device-resident buffers -------------------------------------------
+static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* d_codes, const uint32_t* offsets, int N,
+                           const int32_t* score_tab, int go, int ge, int64_t pb, int64_t pe,
+                           double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps_user, int32_t* d_scores) {
+    PGM_CUDA(cudaSetDevice(c->device));
+    const int64_t total_pairs = (int64_t)N * (N - 1) / 2;
+    if (N < 0 || pb < 0 || pe < pb || pe > total_pairs) { pgm_set_error("pair range [%lld,%lld) invalid for N=%d", (long long)pb, (long long)pe, N); return PGM_ERR_ARG; }
+    if (!prm || !offsets || !score_tab) { pgm_set_error("NULL argument"); return PGM_ERR_ARG; }
+    const int64_t np = pe - pb;
+    if (np == 0) return 0;
+    if (np > 0x7fffffffll) { pgm_set_error("pair range too large for one call (%lld); shard it", (long long)np); return PGM_ERR_ARG; }
+    MlDev ml; int rc = prepare_model(c, prm, ml); if (rc) return rc;
+    const int n = prm->n_states, n1 = n + 1;
+
+    // score table -> int8 (reference tables are within [-4, 11]; reject anything that does not fit)
+    std::vector<int8_t> tab8((size_t)n1 * n1);
+    for (size_t i = 0; i < tab8.size(); ++i) {
+        if (score_tab[i] < -128 || score_tab[i] > 127) { pgm_set_error("score table entry %d does not fit int8", score_tab[i]); return PGM_ERR_ARG; }
+        tab8[i] = (int8_t)score_tab[i];
+    }
+    rc = c->d_tab.reserve(tab8.size()); if (rc) return rc;
+    PGM_CUDA(cudaMemcpyAsync(c->d_tab.p, tab8.data(), tab8.size(), cudaMemcpyHostToDevice, c->stream));
+    PGM_CUDA(cudaStreamSynchronize(c->stream));    // tab8 is a stack-lifetime buffer
+
+    // per-call outputs that live across chunks
+    rc = c->d_list_len.reserve((size_t)np * 4); if (rc) return rc;
+    uint32_t* d_gaps = d_gaps_user;
+    if (!d_gaps) { rc = c->d_gaps.reserve((size_t)np * 4); if (rc) return rc; d_gaps = c->d_gaps.as<uint32_t>(); }
+    rc = c->d_misc.reserve(64); if (rc) return rc;
+    PGM_CUDA(cudaMemsetAsync(c->d_misc.p, 0, 64, c->stream));
+    int* d_err = c->d_misc.as<int>();
+    unsigned long long* d_evals = (unsigned long long*)(c->d_misc.as<char>() + 16);
+
+    int max_len = 0;
+    for (int k = 0; k < N; ++k) max_len = std::max<int>(max_len, (int)(offsets[k + 1] - offsets[k]));
+    if (max_len > 60000) { pgm_set_error("sequence length %d exceeds the supported 60000", max_len); return PGM_ERR_ARG; }
+
+    // walk the range row by row, cutting chunks by the traceback scratch budget
+    const uint64_t tb_budget_words = std::max<uint64_t>(c->scratch_bytes / 4, 1u << 20);
+    int64_t i, j; pair_from_index_host(pb, N, i, j);
+    int64_t p = pb;
+    std::vector<PairDesc> descs; std::vector<NwTask> tasks;
+    const int JC = 4 * 8;                          // pairs per CTA task (4 per warp)
+    while (p < pe) {
+        descs.clear(); tasks.clear();
+        uint64_t tb_words = 0, list_entries = 0, cells = 0;
+        int chunk_maxL1 = 0, chunk_maxL2 = 0;
+        // pass 1: decide chunk extent + C (C depends on the longest seq1 of the chunk)
+        int64_t ci = i, cj = j, cp = p;
+        while (cp < pe) {
+            const int L1 = (int)(offsets[ci + 1] - offsets[ci]);
+            const int L2 = (int)(offsets[cj + 1] - offsets[cj]);
+            const int newmax = std::max(chunk_maxL1, L1);
+            const int Cn = nw_pick_C(newmax);
+            const int nb = (L1 + 32 * Cn - 1) / (32 * Cn);
+            const uint64_t w = (uint64_t)nb * (L2 + 31) * 32;
+            // conservative: band count may shrink if C grows later, never grows
+            if (!descs.empty() && tb_words + w > tb_budget_words) break;
+            if (descs.size() >= (size_t)(48u << 20) / sizeof(PairDesc) * 8) break;   // <= 384 MiB of descriptors
+            PairDesc d; d.s1_off = offsets[ci]; d.s2_off = offsets[cj]; d.L1 = L1; d.L2 = L2;
+            d.tb_off = 0; d.list_off = 0; d.out_idx = (uint32_t)(cp - pb);
+            descs.push_back(d);
+            tb_words += w; chunk_maxL1 = newmax; chunk_maxL2 = std::max(chunk_maxL2, L2);
+            ++cp; ++cj;
+            if (cj >= N) { ++ci; cj = ci + 1; }
+        }
+        const int C = nw_pick_C(chunk_maxL1);
+        const int max_bands = std::max(1, (chunk_maxL1 + 32 * C - 1) / (32 * C));
+        // pass 2: offsets + tasks (consecutive descs share seq1 while s1_off is unchanged)
+        tb_words = 0;
+        for (size_t k = 0; k < descs.size(); ++k) {
+            PairDesc& d = descs[k];
+            const int nb = ((int)d.L1 + 32 * C - 1) / (32 * C);
+            d.tb_off = tb_words; tb_words += (uint64_t)nb * (d.L2 + 31) * 32;
+            d.list_off = (uint32_t)list_entries; list_entries += std::min(d.L1, d.L2);
+            cells += (uint64_t)(d.L1 + 1) * (d.L2 + 1);
+            if (tasks.empty() || descs[tasks.back().desc_begin].s1_off != d.s1_off || descs[tasks.back().desc_begin].L1 != d.L1 ||
+                k - tasks.back().desc_begin >= (size_t)JC) {
+                NwTask t; t.desc_begin = (uint32_t)k; t.desc_end = (uint32_t)k + 1; tasks.push_back(t);
+            } else tasks.back().desc_end = (uint32_t)k + 1;
+        }
+        if (list_entries > 0xffffffffull) { pgm_set_error("chunk too large"); return PGM_ERR_ARG; }
+        const int npairs = (int)descs.size(), ntasks = (int)tasks.size();
+        const uint32_t colstride = (uint32_t)((chunk_maxL2 + 2 + 31) & ~31);
+
+        if ((rc = c->d_descs.reserve(descs.size() * sizeof(PairDesc)))) return rc;
+        if ((rc = c->d_tasks.reserve(tasks.size() * sizeof(NwTask)))) return rc;
+        if ((rc = c->d_tb.reserve(std::max<uint64_t>(tb_words, 1) * 4))) return rc;
+        if ((rc = c->d_list.reserve(std::max<uint64_t>(list_entries, 1) * 2))) return rc;
+        if ((rc = c->d_colbuf.reserve((size_t)ntasks * 8 * 2 * colstride * 4))) return rc;
+        // stage descriptors through pinned memory so the copy is truly async
+        const size_t stage_bytes = descs.size() * sizeof(PairDesc) + tasks.size() * sizeof(NwTask);
+        PGM_CUDA(cudaStreamSynchronize(c->stream));            // previous chunk may still read the staging area
+        if ((rc = c->h_stage.reserve(stage_bytes))) return rc;
+        memcpy(c->h_stage.p, descs.data(), descs.size() * sizeof(PairDesc));
+        memcpy(c->h_stage.as<char>() + descs.size() * sizeof(PairDesc), tasks.data(), tasks.size() * sizeof(NwTask));
+        PGM_CUDA(cudaMemcpyAsync(c->d_descs.p, c->h_stage.p, descs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, c->stream));
+        PGM_CUDA(cudaMemcpyAsync(c->d_tasks.p, c->h_stage.as<char>() + descs.size() * sizeof(PairDesc), tasks.size() * sizeof(NwTask),
+                                 cudaMemcpyHostToDevice, c->stream));
+        {
+            ScopedKernelTimer t(c, K_NW_FWD);
+            rc = launch_nw_forward(c->stream, C, ntasks, n, max_bands, d_codes, c->d_descs.as<PairDesc>(), c->d_tasks.as<NwTask>(),
+                                   c->d_tab.as<int8_t>(), go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores);
+            if (rc) return rc;
+        }
+        {
+            ScopedKernelTimer t(c, K_NW_WALK);
+            rc = launch_nw_walk(c->stream, C, npairs, n, d_codes, c->d_descs.as<PairDesc>(), c->d_tb.as<uint32_t>(),
+                                c->d_list.as<uint16_t>(), c->d_list_len.as<uint32_t>(), d_gaps, d_err);
+            if (rc) return rc;
+        }
+        {
+            ScopedKernelTimer t(c, K_ML);
+            rc = launch_ml_from_lists(c->stream, ml, npairs, c->d_descs.as<PairDesc>(), c->d_list.as<uint16_t>(),
+                                      c->d_list_len.as<uint32_t>(), d_gaps, d_dist, d_var, d_counts, d_evals);
+            if (rc) return rc;
+        }
+        c->timing.nw_cells += cells;
+        c->timing.tb_bytes += tb_words * 4;
+        p = cp; i = ci; j = cj;
+    }
+    // error flag + evaluation counter come back with the sync of whoever consumes the results
+    struct { int err; int pad[3]; unsigned long long evals; } h;
+    PGM_CUDA(cudaMemcpyAsync(&h, c->d_misc.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    PGM_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.ml_evaluations += h.evals;
+    if (h.err) { pgm_set_error("error while backtracking"); return PGM_ERR_BACKTRACK; }
+    return 0;
+}
+
+static void scatter_pairs(const double* dp, const double* vp, int N, double* dist, double* var) {
+    for (size_t k = 0; k < (size_t)N * N; ++k) dist[k] = var[k] = 0;
+    size_t p = 0;
+    for (int i = 0; i < N; ++i)
+        for (int j = i + 1; j < N; ++j, ++p) {
+            dist[(size_t)i * N + j] = dist[(size_t)j * N + i] = dp[p];
+            var[(size_t)i * N + j] = var[(size_t)j * N + i] = vp[p];
+        }
+}
+
+extern "C" {
+
+int pgm_nw_ml_pair_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* d_codes, const uint32_t* offsets, int N,
+                             const int32_t* score_tab, int go, int ge, int64_t pb, int64_t pe,
+                             double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps, int32_t* d_scores) {
+    if (!c) { pgm_set_error("ctx is NULL"); return PGM_ERR_ARG; }
+    reset_timing(c);
+    return nw_ml_range_dev(c, prm, d_codes, offsets, N, score_tab, go, ge, pb, pe, d_dist, d_var, d_counts, d_gaps, d_scores);
+}
+
+int pgm_nw_ml_pair_range(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* codes, const uint32_t* offsets, int N,
+                         const int32_t* score_tab, int go, int ge, int64_t pb, int64_t pe,
+                         double* dist, double* var, int32_t* counts, uint32_t* gaps, int32_t* scores) {
+    if (!c || !prm) { pgm_set_error("ctx/prm is NULL"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(c->device));
+    reset_timing(c);
+    if (N < 0 || !offsets) { pgm_set_error("bad sequence set"); return PGM_ERR_ARG; }
+    const int64_t np = pe - pb;
+    if (np < 0) { pgm_set_error("pair range invalid"); return PGM_ERR_ARG; }
+    if (np == 0) return 0;
+    const size_t total = offsets[N], nn = (size_t)prm->n_states * prm->n_states;
+    int rc;
+    if ((rc = c->d_codes.reserve(std::max<size_t>(total, 1)))) return rc;
+    if ((rc = c->d_dist.reserve(np * 8))) return rc;
+    if ((rc = c->d_var.reserve(np * 8))) return rc;
+    if (counts && (rc = c->d_counts.reserve(np * nn * 4))) return rc;
+    if (gaps && (rc = c->d_gaps.reserve(np * 4))) return rc;
+    if (scores && (rc = c->d_scores.reserve(np * 4))) return rc;
+    PGM_CUDA(cudaMemcpyAsync(c->d_codes.p, codes, total, cudaMemcpyHostToDevice, c->stream));
+    rc = nw_ml_range_dev(c, prm, c->d_codes.as<uint8_t>(), offsets, N, score_tab, go, ge, pb, pe, c->d_dist.as<double>(),
+                         c->d_var.as<double>(), counts ? c->d_counts.as<int32_t>() : nullptr,
+                         gaps ? c->d_gaps.as<uint32_t>() : nullptr, scores ? c->d_scores.as<int32_t>() : nullptr);
+    if (rc) return rc;
+    PGM_CUDA(cudaMemcpyAsync(dist, c->d_dist.p, np * 8, cudaMemcpyDeviceToHost, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(var, c->d_var.p, np * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (counts) PGM_CUDA(cudaMemcpyAsync(counts, c->d_counts.p, np * nn * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (gaps) PGM_CUDA(cudaMemcpyAsync(gaps, c->d_gaps.p, np * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (scores) PGM_CUDA(cudaMemcpyAsync(scores, c->d_scores.p, np * 4, cudaMemcpyDeviceToHost, c->stream));
+    return pgm_sync(c);
+}
+
+int pgm_nw_ml_all_pairs(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* codes, const uint32_t* offsets, int N,
+                        const int32_t* score_tab, int go, int ge, double* dist, double* var) {
+    if (N < 0) { pgm_set_error("N < 0"); return PGM_ERR_ARG; }
+    const int64_t np = (int64_t)N * (N - 1) / 2;
+    std::vector<double> dp(std::max<int64_t>(np, 1)), vp(std::max<int64_t>(np, 1));
+    int rc = pgm_nw_ml_pair_range(c, prm, codes, offsets, N, score_tab, go, ge, 0, np, dp.data(), vp.data(), nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    scatter_pairs(dp.data(), vp.data(), N, dist, var);
+    return 0;
+}
+
+// ---- HP-2b: prealigned ------------------------------------------------------------------------------------
+static int prealigned_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* d_rows, int N, int L, int64_t pb, int64_t pe,
+                                double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps) {
+    PGM_CUDA(cudaSetDevice(c->device));
+    const int64_t total_pairs = (int64_t)N * (N - 1) / 2;
+    if (N < 0 || L < 0 || pb < 0 || pe < pb || pe > total_pairs) { pgm_set_error("pair range invalid"); return PGM_ERR_ARG; }
+    if (pe == pb) return 0;
+    MlDev ml; int rc = prepare_model(c, prm, ml); if (rc) return rc;
+    if ((rc = c->d_misc.reserve(64))) return rc;
+    PGM_CUDA(cudaMemsetAsync(c->d_misc.p, 0, 64, c->stream));
+    unsigned long long* d_evals = (unsigned long long*)(c->d_misc.as<char>() + 16);
+    {
+        ScopedKernelTimer t(c, K_ML);
+        rc = launch_ml_from_rows(c->stream, ml, N, L, pb, pe - pb, d_rows, d_dist, d_var, d_counts, d_gaps, d_evals);
+        if (rc) return rc;
+    }
+    unsigned long long ev = 0;
+    PGM_CUDA(cudaMemcpyAsync(&ev, d_evals, 8, cudaMemcpyDeviceToHost, c->stream));
+    PGM_CUDA(cudaStreamSynchronize(c->stream));
+    c->timing.ml_evaluations += ev;
+    return 0;
+}
+
+int pgm_prealigned_ml_pair_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* d_rows, int N, int L, int64_t pb, int64_t pe,
+                                     double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps) {
+    if (!c || !prm) { pgm_set_error("ctx/prm is NULL"); return PGM_ERR_ARG; }
+    reset_timing(c);
+    return prealigned_range_dev(c, prm, d_rows, N, L, pb, pe, d_dist, d_var, d_counts, d_gaps);
+}
+
+int pgm_prealigned_ml_pair_range(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* rows, int N, int L, int64_t pb, int64_t pe,
+                                 double* dist, double* var, int32_t* counts, uint32_t* gaps) {
+    if (!c || !prm) { pgm_set_error("ctx/prm is NULL"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(c->device));
+    reset_timing(c);
+    const int64_t np = pe - pb;
+    if (np < 0 || N < 0 || L < 0) { pgm_set_error("bad arguments"); return PGM_ERR_ARG; }
+    if (np == 0) return 0;
+    const size_t nn = (size_t)prm->n_states * prm->n_states;
+    int rc;
+    if ((rc = c->d_rows.reserve(std::max<size_t>((size_t)N * L, 1)))) return rc;
+    if ((rc = c->d_dist.reserve(np * 8))) return rc;
+    if ((rc = c->d_var.reserve(np * 8))) return rc;
+    if (counts && (rc = c->d_counts.reserve(np * nn * 4))) return rc;
+    if (gaps && (rc = c->d_gaps.reserve(np * 4))) return rc;
+    PGM_CUDA(cudaMemcpyAsync(c->d_rows.p, rows, (size_t)N * L, cudaMemcpyHostToDevice, c->stream));
+    rc = prealigned_range_dev(c, prm, c->d_rows.as<uint8_t>(), N, L, pb, pe, c->d_dist.as<double>(), c->d_var.as<double>(),
+                              counts ? c->d_counts.as<int32_t>() : nullptr, gaps ? c->d_gaps.as<uint32_t>() : nullptr);
+    if (rc) return rc;
+    PGM_CUDA(cudaMemcpyAsync(dist, c->d_dist.p, np * 8, cudaMemcpyDeviceToHost, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(var, c->d_var.p, np * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (counts) PGM_CUDA(cudaMemcpyAsync(counts, c->d_counts.p, np * nn * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (gaps) PGM_CUDA(cudaMemcpyAsync(gaps, c->d_gaps.p, np * 4, cudaMemcpyDeviceToHost, c->stream));
+    return pgm_sync(c);
+}
+
+int pgm_prealigned_ml_all_pairs(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* rows, int N, int L, double* dist, double* var) {
+    if (N < 0) { pgm_set_error("N < 0"); return PGM_ERR_ARG; }
+    const int64_t np = (int64_t)N * (N - 1) / 2;
+    std::vector<double> dp(std::max<int64_t>(np, 1)), vp(std::max<int64_t>(np, 1));
+    int rc = pgm_prealigned_ml_pair_range(c, prm, rows, N, L, 0, np, dp.data(), vp.data(), nullptr, nullptr);
+    if (rc) return rc;
+    scatter_pairs(dp.data(), vp.data(), N, dist, var);
+    return 0;
+}
+
+int pgm_ml_distances(pgm_ctx* c, const pgm_ml_params* prm, int64_t np, const int32_t* counts, const uint32_t* gaps,
+                     const double* seqlen, double* dist, double* var) {
+    if (!c || !prm) { pgm_set_error("ctx/prm is NULL"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(c->device));
+    reset_timing(c);
+    if (np < 0) { pgm_set_error("n_pairs < 0"); return PGM_ERR_ARG; }
+    if (np == 0) return 0;
+    MlDev ml; int rc = prepare_model(c, prm, ml); if (rc) return rc;
+    const size_t nn = (size_t)prm->n_states * prm->n_states;
+    if ((rc = c->d_counts.reserve(np * nn * 4))) return rc;
+    if ((rc = c->d_gaps.reserve(np * 4))) return rc;
+    if ((rc = c->d_seqlen.reserve(np * 8))) return rc;
+    if ((rc = c->d_dist.reserve(np * 8))) return rc;
+    if ((rc = c->d_var.reserve(np * 8))) return rc;
+    if ((rc = c->d_misc.reserve(64))) return rc;
+    PGM_CUDA(cudaMemsetAsync(c->d_misc.p, 0, 64, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(c->d_counts.p, counts, np * nn * 4, cudaMemcpyHostToDevice, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(c->d_gaps.p, gaps, np * 4, cudaMemcpyHostToDevice, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(c->d_seqlen.p, seqlen, np * 8, cudaMemcpyHostToDevice, c->stream));
+    {
+        ScopedKernelTimer t(c, K_ML);
+        rc = launch_ml_from_counts(c->stream, ml, np, c->d_counts.as<int32_t>(), c->d_gaps.as<uint32_t>(), c->d_seqlen.as<double>(),
+                                   c->d_dist.as<double>(), c->d_var.as<double>(), (unsigned long long*)(c->d_misc.as<char>() + 16));
+        if (rc) return rc;
+    }
+    PGM_CUDA(cudaMemcpyAsync(dist, c->d_dist.p, np * 8, cudaMemcpyDeviceToHost, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(var, c->d_var.p, np * 8, cudaMemcpyDeviceToHost, c->stream));
+    unsigned long long ev = 0;
+    PGM_CUDA(cudaMemcpyAsync(&ev, c->d_misc.as<char>() + 16, 8, cudaMemcpyDeviceToHost, c->stream));
+    rc = pgm_sync(c);
+    c->timing.ml_evaluations += ev;
+    return rc;
+}
+
+} // extern "C"
+
+// ---- accessors for the HP-1 host code (hp1_host.cu) -----------------------------------------------------
+cudaStream_t pgm_ctx_stream(pgm_ctx* c) { return c->stream; }
+int pgm_ctx_device(pgm_ctx* c) { return c->device; }
+uint64_t pgm_ctx_scratch(pgm_ctx* c) { return c->scratch_bytes; }
+pgm_timing* pgm_ctx_timing(pgm_ctx* c) { return &c->timing; }
+void pgm_ctx_reset_timing(pgm_ctx* c) { reset_timing(c); }
+void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok) { *tok = new ScopedKernelTimer(c, kind); }
+void pgm_ctx_time_end(pgm_ctx* c, void* tok) { (void)c; delete (ScopedKernelTimer*)tok; }

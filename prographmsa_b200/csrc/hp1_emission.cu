@@ -1,0 +1,114 @@
+// hp1_emission.cu -- K4 (exact flavour): emission-score matrix on fp32 CUDA cores.
+//
+// Replaces precomputeScores (reference GraphAlign.h:145-163) + ls_log_add (ls_log.h:22-59):
+//   T = M^T g2 (n x N2),  u = g1^T pi,  v = pi^T g2,
+//   S(y,x) = [sum_a g1(a,y) T(a,x)] / (u(y) v(x)),  then  S <- ls_log2(S) + match_init
+// all in fp32 with sequential-k accumulation and NO fused multiply-add (the reference is SSE2
+// mul/add; this file is compiled with --fmad=false and uses explicit _rn intrinsics), so this
+// flavour is bit-identical to the oracle and is what the traceback-identity tests run on.
+//
+// S is written in the DP's skewed layout: cell (y,x) on anti-diagonal d=y+x lives at
+// d*pitch + (y - max(0, d-(N2-1))), so the wavefront kernel reads whole diagonals coalesced.
+// Tiles are 32 diagonals x 32 rows in (d, y) coordinates so that the stores are coalesced too.
+#include "internal.h"
+
+__device__ __forceinline__ float ls_log2_add(float x, float add) {
+    // ls_log.h:30-56 (vector body): r = (b/(d-c) + add) + (float(e) + a)
+    const float a = 2.44247459618085927548717403238913328776812604856113966238617812902399112761292613763080658235564f;
+    const float b = -4.2040783745848554315883301529007786406310628696382695994938550046831869207082846248658671f;
+    const float c = -0.72123729809042963774358701619456664388406302428056983119308906451199556380646306f;
+    const uint32_t bits = __float_as_uint(x);
+    const float e = (float)((int)(bits >> 23) - 126);
+    const float d = __uint_as_float(((bits << 9) >> 9) ^ 0x3f000000u);
+    float vd = __fdiv_rn(b, __fsub_rn(d, c));
+    const float ve = __fadd_rn(e, a);
+    vd = __fadd_rn(vd, add);
+    return __fadd_rn(vd, ve);
+}
+
+// T = M^T g2, u, v.  grid = (ceil(maxN/128), n_jobs)
+__global__ void __launch_bounds__(128)
+emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs) {
+    const GraphJobDev& J = jobs[blockIdx.y];
+    extern __shared__ float sm[];            // Mf (n*n) + pif (n)
+    float* sM = sm; float* sPi = sm + n * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) sM[i] = J.Mf[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sPi[i] = J.pif[i];
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < J.N2) {
+        const float* g = J.sites2 + (size_t)n * k;
+        for (int a = 0; a < n; ++a) {                       // T(a,x) = sum_b M(b,a) g2(b,x)
+            float s = 0.f;
+            for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sM[b * n + a], g[b]));
+            J.Tbuf[a + (size_t)n * k] = s;
+        }
+        float s = 0.f;
+        for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sPi[b], g[b]));
+        J.v[k] = s;
+    }
+    if (k < J.N1) {
+        const float* g = J.sites1 + (size_t)n * k;
+        float s = 0.f;
+        for (int a = 0; a < n; ++a) s = __fadd_rn(s, __fmul_rn(g[a], sPi[a]));
+        J.u[k] = s;
+    }
+}
+
+// grid = (tiles_d, tiles_y, n_jobs), block = (32, 8)
+__global__ void __launch_bounds__(256)
+emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs) {
+    const GraphJobDev& J = jobs[blockIdx.z];
+    const int N1 = J.N1, N2 = J.N2;
+    const int d0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (d0 > N1 + N2 - 2 || y0 >= N1) return;
+    // x range touched: d - y for d in [d0, d0+31], y in [y0, y0+31]
+    const int xlo = d0 - (y0 + 31), nx = 63;
+    if (xlo + nx - 1 < 0 || xlo >= N2) return;
+    extern __shared__ float sm[];
+    float* g1t = sm;                       // [n][32]
+    float* Tt = sm + n * 32;               // [n][64]
+    const int tid = threadIdx.y * 32 + threadIdx.x;
+    for (int i = tid; i < n * 32; i += 256) {
+        const int a = i >> 5, yy = y0 + (i & 31);
+        g1t[i] = (yy < N1) ? J.sites1[a + (size_t)n * yy] : 0.f;
+    }
+    for (int i = tid; i < n * 64; i += 256) {
+        const int a = i >> 6, xx = xlo + (i & 63);
+        Tt[i] = (xx >= 0 && xx < N2 && (i & 63) < nx) ? J.Tbuf[a + (size_t)n * xx] : 0.f;
+    }
+    __syncthreads();
+    const int y = y0 + threadIdx.x;
+    if (y >= N1) return;
+    const float uy = J.u[y];
+    const float add = J.sc[2];             // match_init
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int d = d0 + threadIdx.y + 8 * r;
+        const int x = d - y;
+        if (x < 0 || x >= N2) continue;
+        const int xi = x - xlo;
+        float s = 0.f;
+        for (int a = 0; a < n; ++a) s = __fadd_rn(s, __fmul_rn(g1t[a * 32 + threadIdx.x], Tt[a * 64 + xi]));
+        const float q = __fdiv_rn(s, __fmul_rn(uy, J.v[x]));
+        const int ylo = max(0, d - (N2 - 1));
+        J.S[(size_t)d * J.pitch + (y - ylo)] = ls_log2_add(q, add);
+    }
+}
+
+int launch_emission_exact(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int max_N1, int max_N2) {
+    if (n_jobs == 0) return 0;
+    {
+        const int maxN = max_N1 > max_N2 ? max_N1 : max_N2;
+        dim3 grid((maxN + 127) / 128, n_jobs);
+        emission_prep_kernel<<<grid, 128, sizeof(float) * (n * n + n), st>>>(n, d_jobs);
+        PGM_CUDA(cudaGetLastError());
+    }
+    {
+        dim3 grid((max_N1 + max_N2 - 1 + 31) / 32, (max_N1 + 31) / 32, n_jobs);
+        const size_t smem = sizeof(float) * n * 96;
+        emission_exact_kernel<<<grid, dim3(32, 8), smem, st>>>(n, d_jobs);
+        PGM_CUDA(cudaGetLastError());
+    }
+    return 0;
+}

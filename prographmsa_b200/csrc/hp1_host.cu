@@ -1,0 +1,348 @@
+// hp1_host.cu -- host side of HP-1 behind pgm_align_graphs_batch / pgm_graph_batch_*:
+// DynProgScores (reference GraphAlign.h:98-143, incl. averageAlignmentLength :56-96) in double on the
+// host, predecessor lists in PredIterator order with their edge values (Graph.h:172-248), one packed
+// host->device arena per batch, sub-batching by the scratch budget, result fetch.
+#include "internal.h"
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+struct pgm_ctx;
+cudaStream_t pgm_ctx_stream(pgm_ctx* c);
+int pgm_ctx_device(pgm_ctx* c);
+uint64_t pgm_ctx_scratch(pgm_ctx* c);
+void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok);
+void pgm_ctx_time_end(pgm_ctx* c, void* tok);
+pgm_timing* pgm_ctx_timing(pgm_ctx* c);
+void pgm_ctx_reset_timing(pgm_ctx* c);
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int threads);
+
+namespace {
+
+constexpr float FINF = std::numeric_limits<float>::infinity();
+inline double LOG2(double x) { return std::log(x) / std::log(2); }     // GraphAlign.h:46-47 with USE_LS_LOG
+
+double average_alignment_length(const pgm_graph& g) {                   // GraphAlign.h:56-96, bottom-up
+    if (g.N == 0) return 0;
+    std::vector<double> cache(g.N, -2.0);
+    cache[0] = 0;
+    for (int cur = 1; cur < g.N; ++cur) {
+        double sum = 0; unsigned paths = 0;
+        for (int k = g.e_rowptr[cur]; k < g.e_rowptr[cur + 1]; ++k) {
+            const float c = g.e_val[k];
+            const float v = c == 0 ? FINF : c + 10000.0f;
+            if (v == 0.0f) {
+                const double res = cache[g.e_col[k]];
+                if (res >= 0.0) { sum += res + 1.0; ++paths; }
+            }
+        }
+        cache[cur] = paths > 0 ? sum / paths : -2.0;
+    }
+    return cache[g.N - 1];
+}
+
+void dynprog_scores(const pgm_graph& g1, const pgm_graph& g2, const pgm_dp_model& m, const pgm_dp_opts& o, float* s) {
+    const double l1 = average_alignment_length(g1), l2 = average_alignment_length(g2);
+    const double eps = m.epsilon, delta = m.delta, E = o.end_indel_prob;
+    const double exp_length = std::max(l1, l2) * std::exp(m.distance * o.indel_rate * (eps / (1.0 - eps) + 1.0));
+    const double nu = 2.0 / (2.0 + l1 + l2);
+    double tau = 1.0 / (1.0 + exp_length);
+    if (eps + tau >= 1.0) tau = (1.0 - eps) / 2.0;
+    s[0] = (float)LOG2(delta * (1.0 - eps - tau) / (1.0 - nu));                       // gap_init
+    s[1] = (float)LOG2(eps / (1.0 - nu));                                             // gap_extend
+    s[2] = (float)LOG2((1.0 - 2.0 * delta) * (1.0 - tau) / (1.0 - nu) / (1.0 - nu));  // match_init
+    s[5] = (float)LOG2(tau);                                                          // end_skip
+    if (E >= 0 && E <= 1) {
+        s[3] = (float)LOG2(tau * (1.0 - E) / (1.0 - 2.0 * delta) / (1.0 - tau));      // end_match
+        s[4] = (float)LOG2(tau * E / 2.0 / (1.0 - eps - tau) / delta);                // end_gap
+        s[6] = (float)LOG2(E / 2.0 * (1.0 - eps - tau) / (1.0 - E) / (1.0 - nu));     // start_gap
+        s[7] = (float)LOG2((1.0 - tau) * (1.0 - E));                                  // start_init
+    } else {
+        s[3] = (float)LOG2(tau / (1.0 - tau));
+        s[4] = (float)LOG2(tau / (1.0 - eps - tau));
+        s[6] = (float)LOG2(delta * (1.0 - eps - tau) / (1.0 - nu));
+        s[7] = (float)LOG2(1.0 - tau);
+    }
+    const double repeat_prob = 1.0 - std::exp(-m.distance * o.repeat_rate);
+    s[8] = (float)-LOG2(std::min<double>(1, repeat_prob / (1 - repeat_prob) * (1 - o.repeatext_prob)));   // repeat_init
+    s[9] = (float)-LOG2(std::min<double>(1, std::max<double>(0, o.repeatext_prob)));                      // repeat_ext
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+struct JobLayout {                // byte offsets into the upload arena / scratch arena / output arena
+    size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt;
+    size_t S, MXYW, Tbuf, u, v, alt_score, alt_prev;     // scratch
+    size_t map1, map2, result;                           // output
+    int np1, np2, cap, pitch;
+};
+
+} // namespace
+
+struct pgm_graph_batch {
+    int n_states = 0, n_jobs = 0, emission_mode = 0;
+    std::vector<GraphJobDev> jobs;          // host copy with DEVICE pointers
+    std::vector<JobLayout> lay;
+    std::vector<uint64_t> cell_updates;
+    DevBuf d_in, d_scratch, d_out, d_jobs;
+    HostPinned h_in, h_out;
+    size_t out_bytes = 0;
+    std::vector<std::pair<int, int>> sub;   // [begin, end) job ranges that fit the scratch budget
+    size_t scratch_bytes_used = 0;
+    int max_N1 = 0, max_N2 = 0;
+    uint64_t total_updates = 0, total_cells = 0;
+};
+
+extern "C" {
+
+int pgm_dynprog_scores(int n_states, const pgm_graph* g1, const pgm_graph* g2, const pgm_dp_model* model,
+                       const pgm_dp_opts* opts, float out[10]) {
+    (void)n_states;
+    if (!g1 || !g2 || !model || !opts || !out) { pgm_set_error("NULL argument"); return PGM_ERR_ARG; }
+    dynprog_scores(*g1, *g2, *model, *opts, out);
+    return 0;
+}
+
+int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, const pgm_graph* g2,
+                           const pgm_dp_model* models, const pgm_dp_opts* opts, pgm_graph_batch** out) {
+    if (!c || !out || n_jobs < 0 || (n_jobs > 0 && (!g1 || !g2 || !models || !opts))) { pgm_set_error("bad arguments"); return PGM_ERR_ARG; }
+    if (n < 2 || n > 64) { pgm_set_error("n_states %d out of range", n); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(pgm_ctx_device(c)));
+    cudaStream_t st = pgm_ctx_stream(c);
+    pgm_graph_batch* b = new pgm_graph_batch();
+    b->n_states = n; b->n_jobs = n_jobs; b->emission_mode = opts->emission_mode;
+    b->lay.resize(n_jobs); b->jobs.resize(n_jobs); b->cell_updates.resize(n_jobs);
+    size_t in_off = 0, out_off = 0;
+    std::vector<size_t> scratch_need(n_jobs);
+    for (int k = 0; k < n_jobs; ++k) {
+        const pgm_graph &a = g1[k], &bb = g2[k];
+        if (a.N < 2 || bb.N < 2) { delete b; pgm_set_error("job %d: graphs need at least start and end nodes", k); return PGM_ERR_ARG; }
+        JobLayout& L = b->lay[k];
+        L.np1 = a.e_rowptr[a.N] + (a.r_rowptr ? a.r_rowptr[a.N] : 0);
+        L.np2 = bb.e_rowptr[bb.N] + (bb.r_rowptr ? bb.r_rowptr[bb.N] : 0);
+        L.cap = 2 * (a.N + bb.N) + 8;
+        L.pitch = (int)align_up((size_t)std::min(a.N, bb.N), 32);
+        auto take = [&](size_t& off, size_t bytes) { size_t r = off; off = align_up(off + bytes, 128); return r; };
+        L.sites1 = take(in_off, sizeof(float) * n * a.N);
+        L.sites2 = take(in_off, sizeof(float) * n * bb.N);
+        L.Mf = take(in_off, sizeof(float) * n * n);
+        L.pif = take(in_off, sizeof(float) * n);
+        L.p1_ptr = take(in_off, 4 * (a.N + 1)); L.p1_idx = take(in_off, 4 * L.np1); L.p1_val = take(in_off, 4 * L.np1);
+        L.p1_alt = take(in_off, 4 * L.np1); L.p1_rep = take(in_off, L.np1);
+        L.p2_ptr = take(in_off, 4 * (bb.N + 1)); L.p2_idx = take(in_off, 4 * L.np2); L.p2_val = take(in_off, 4 * L.np2);
+        L.p2_alt = take(in_off, 4 * L.np2); L.p2_rep = take(in_off, L.np2);
+        L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 16);
+        const size_t diags = (size_t)a.N + bb.N - 1;
+        size_t so = 0;
+        L.S = take(so, diags * L.pitch * 4); L.MXYW = take(so, diags * L.pitch * 16);
+        L.Tbuf = take(so, sizeof(float) * n * bb.N); L.u = take(so, 4 * a.N); L.v = take(so, 4 * bb.N);
+        L.alt_score = take(so, 4 * std::max(a.N, bb.N)); L.alt_prev = take(so, 4 * std::max(a.N, bb.N));
+        scratch_need[k] = so;
+        b->max_N1 = std::max(b->max_N1, a.N); b->max_N2 = std::max(b->max_N2, bb.N);
+    }
+    // sub-batches by scratch budget (each job's scratch offsets are relative to its sub-batch)
+    const uint64_t budget = pgm_ctx_scratch(c);
+    std::vector<size_t> scratch_base(n_jobs);
+    {
+        int begin = 0; size_t used = 0;
+        for (int k = 0; k < n_jobs; ++k) {
+            if (k > begin && used + scratch_need[k] > budget) { b->sub.push_back({begin, k}); begin = k; used = 0; }
+            scratch_base[k] = used; used += scratch_need[k];
+            b->scratch_bytes_used = std::max(b->scratch_bytes_used, used);
+        }
+        if (n_jobs > begin) b->sub.push_back({begin, n_jobs});
+    }
+    int rc;
+    if ((rc = b->h_in.reserve(std::max<size_t>(in_off, 1))) || (rc = b->d_in.reserve(std::max<size_t>(in_off, 1))) ||
+        (rc = b->d_out.reserve(std::max<size_t>(out_off, 1))) || (rc = b->h_out.reserve(std::max<size_t>(out_off, 1))) ||
+        (rc = b->d_scratch.reserve(std::max<size_t>(b->scratch_bytes_used, 1))) ||
+        (rc = b->d_jobs.reserve(std::max<size_t>(sizeof(GraphJobDev) * n_jobs, 1)))) { pgm_graph_batch_destroy(c, b); return rc; }
+    b->out_bytes = out_off;
+    char* hin = b->h_in.as<char>();
+    char* din = b->d_in.as<char>(); char* dsc = b->d_scratch.as<char>(); char* dout = b->d_out.as<char>();
+    for (int k = 0; k < n_jobs; ++k) {
+        const pgm_graph* gs[2] = {&g1[k], &g2[k]};
+        const JobLayout& L = b->lay[k];
+        GraphJobDev& J = b->jobs[k];
+        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.cap = L.cap;
+        dynprog_scores(g1[k], g2[k], models[k], *opts, J.sc);
+        const float rinit = J.sc[8], rext = J.sc[9];
+        float* s1 = (float*)(hin + L.sites1); float* s2 = (float*)(hin + L.sites2);
+        for (size_t i = 0; i < (size_t)n * g1[k].N; ++i) s1[i] = (float)g1[k].sites[i];
+        for (size_t i = 0; i < (size_t)n * g2[k].N; ++i) s2[i] = (float)g2[k].sites[i];
+        float* Mf = (float*)(hin + L.Mf); float* pif = (float*)(hin + L.pif);
+        for (int i = 0; i < n * n; ++i) Mf[i] = (float)models[k].M[i];
+        for (int i = 0; i < n; ++i) pif[i] = (float)models[k].pi[i];
+        const size_t ptr_off[2] = {L.p1_ptr, L.p2_ptr}, idx_off[2] = {L.p1_idx, L.p2_idx}, val_off[2] = {L.p1_val, L.p2_val},
+                     alt_off[2] = {L.p1_alt, L.p2_alt}, rep_off[2] = {L.p1_rep, L.p2_rep};
+        uint64_t deg_sum[2] = {0, 0};
+        for (int w = 0; w < 2; ++w) {
+            const pgm_graph& g = *gs[w];
+            int* ptr = (int*)(hin + ptr_off[w]); int* idx = (int*)(hin + idx_off[w]);
+            float* val = (float*)(hin + val_off[w]); float* alt = (float*)(hin + alt_off[w]);
+            uint8_t* rep = (uint8_t*)(hin + rep_off[w]);
+            int q = 0;
+            for (int node = 0; node < g.N; ++node) {
+                ptr[node] = q;
+                for (int e = g.e_rowptr[node]; e < g.e_rowptr[node + 1]; ++e) {       // Graph.h:223-231
+                    const float cst = g.e_val[e];
+                    const float v = cst == 0 ? FINF : cst + 10000.0f;
+                    idx[q] = g.e_col[e]; val[q] = v; alt[q] = v; rep[q] = 0; ++q;
+                }
+                if (g.r_rowptr)
+                    for (int e = g.r_rowptr[node]; e < g.r_rowptr[node + 1]; ++e) {   // Graph.h:232-238
+                        const uint32_t u = g.r_units[e];
+                        float v, va;
+                        if (u == 0) { v = FINF; va = FINF; }
+                        else {
+                            const float um1 = (float)(u - 1);
+                            const float mm = rext * um1; v = rinit + mm;
+                            const float ma = FINF * um1; va = FINF + ma;      // markAlternativePath: (inf, inf)
+                        }
+                        idx[q] = g.r_col[e]; val[q] = v; alt[q] = va; rep[q] = 1; ++q;
+                    }
+                if (node >= 1 && node <= g.N - 2) deg_sum[w] += (uint64_t)(q - ptr[node]);
+            }
+            ptr[g.N] = q;
+        }
+        b->cell_updates[k] = deg_sum[0] * deg_sum[1];
+        b->total_updates += b->cell_updates[k];
+        b->total_cells += (uint64_t)J.N1 * J.N2;
+        char* sb = dsc + scratch_base[k];
+        J.sites1 = (const float*)(din + L.sites1); J.sites2 = (const float*)(din + L.sites2);
+        J.Mf = (const float*)(din + L.Mf); J.pif = (const float*)(din + L.pif);
+        J.p1_ptr = (const int*)(din + L.p1_ptr); J.p1_idx = (const int*)(din + L.p1_idx); J.p1_val = (const float*)(din + L.p1_val);
+        J.p1_rep = (const uint8_t*)(din + L.p1_rep); J.p1_alt = (const float*)(din + L.p1_alt);
+        J.p2_ptr = (const int*)(din + L.p2_ptr); J.p2_idx = (const int*)(din + L.p2_idx); J.p2_val = (const float*)(din + L.p2_val);
+        J.p2_rep = (const uint8_t*)(din + L.p2_rep); J.p2_alt = (const float*)(din + L.p2_alt);
+        J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.Tbuf = (float*)(sb + L.Tbuf);
+        J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
+        J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev);
+        J.map1 = (int*)(dout + L.map1); J.map2 = (int*)(dout + L.map2); J.result = (int*)(dout + L.result);
+    }
+    if (n_jobs) {
+        PGM_CUDA(cudaMemcpyAsync(b->d_in.p, b->h_in.p, in_off, cudaMemcpyHostToDevice, st));
+        PGM_CUDA(cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(GraphJobDev) * n_jobs, cudaMemcpyHostToDevice, st));
+        PGM_CUDA(cudaStreamSynchronize(st));
+    }
+    *out = b;
+    return 0;
+}
+
+int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
+    if (!c || !b) { pgm_set_error("NULL argument"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(pgm_ctx_device(c)));
+    cudaStream_t st = pgm_ctx_stream(c);
+    pgm_ctx_reset_timing(c);
+    const GraphJobDev* dj = b->d_jobs.as<GraphJobDev>();
+    for (auto& sb : b->sub) {
+        const int nj = sb.second - sb.first;
+        int mx1 = 0, mx2 = 0, mxd = 0;
+        for (int k = sb.first; k < sb.second; ++k) {
+            mx1 = std::max(mx1, b->jobs[k].N1); mx2 = std::max(mx2, b->jobs[k].N2);
+            mxd = std::max(mxd, std::min(b->jobs[k].N1, b->jobs[k].N2));
+        }
+        int rc; void* tok;
+        pgm_ctx_time_begin(c, 3, &tok);
+        if (b->emission_mode == PGM_EMISSION_TENSOR) rc = launch_emission_tensor(st, b->n_states, nj, dj + sb.first, b->jobs.data() + sb.first);
+        else rc = launch_emission_exact(st, b->n_states, nj, dj + sb.first, mx1, mx2);
+        pgm_ctx_time_end(c, tok);
+        if (rc) return rc;
+        const int threads = mxd <= 128 ? 128 : (mxd <= 256 ? 256 : (mxd <= 512 ? 512 : 1024));
+        pgm_ctx_time_begin(c, 4, &tok);
+        rc = launch_graph_fill(st, nj, dj + sb.first, threads);
+        pgm_ctx_time_end(c, tok);
+        if (rc) return rc;
+        pgm_ctx_time_begin(c, 5, &tok);
+        rc = launch_graph_trace(st, nj, dj + sb.first);
+        pgm_ctx_time_end(c, tok);
+        if (rc) return rc;
+    }
+    pgm_timing* t = pgm_ctx_timing(c);
+    t->graph_cell_updates += b->total_updates;
+    t->graph_cells += b->total_cells;
+    return 0;
+}
+
+int pgm_graph_batch_fetch(pgm_ctx* c, pgm_graph_batch* b, pgm_alignment* out) {
+    if (!c || !b || (b->n_jobs && !out)) { pgm_set_error("NULL argument"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(pgm_ctx_device(c)));
+    cudaStream_t st = pgm_ctx_stream(c);
+    if (b->n_jobs == 0) return 0;
+    PGM_CUDA(cudaMemcpyAsync(b->h_out.p, b->d_out.p, b->out_bytes, cudaMemcpyDeviceToHost, st));
+    PGM_CUDA(cudaStreamSynchronize(st));
+    const char* ho = b->h_out.as<char>();
+    int worst = 0;
+    for (int k = 0; k < b->n_jobs; ++k) {
+        const JobLayout& L = b->lay[k];
+        const int* res = (const int*)(ho + L.result);
+        pgm_alignment& A = out[k];
+        A.status = res[0]; A.length = res[1]; A.n_tr_indels = (uint32_t)res[2]; A.score = ((const float*)res)[3];
+        A.cell_updates = b->cell_updates[k];
+        if (A.status == 0 && A.length > A.capacity) A.status = PGM_ERR_CAPACITY;
+        if (A.status == 0) {
+            const int* m1 = (const int*)(ho + L.map1); const int* m2 = (const int*)(ho + L.map2);
+            for (int i = 0; i < A.length; ++i) {                 // device wrote end -> start (std::reverse, GraphAlign.h:512-513)
+                A.mapping1[i] = m1[A.length - 1 - i];
+                A.mapping2[i] = m2[A.length - 1 - i];
+            }
+        } else if (worst == 0) {
+            worst = A.status;
+            pgm_set_error(A.status == PGM_ERR_BACKTRACK ? "job %d: backtracking failed" : "job %d: mapping capacity too small", k);
+        }
+    }
+    return worst;
+}
+
+void pgm_graph_batch_destroy(pgm_ctx* c, pgm_graph_batch* b) {
+    if (!b) return;
+    if (c) { cudaSetDevice(pgm_ctx_device(c)); cudaStreamSynchronize(pgm_ctx_stream(c)); }
+    b->d_in.release(); b->d_scratch.release(); b->d_out.release(); b->d_jobs.release();
+    b->h_in.release(); b->h_out.release();
+    delete b;
+}
+
+int pgm_align_graphs_batch(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, const pgm_graph* g2,
+                           const pgm_dp_model* models, const pgm_dp_opts* opts, pgm_alignment* out) {
+    pgm_graph_batch* b = nullptr;
+    int rc = pgm_graph_batch_create(c, n, n_jobs, g1, g2, models, opts, &b);
+    if (rc) return rc;
+    rc = pgm_graph_batch_run(c, b);
+    if (!rc) rc = pgm_graph_batch_fetch(c, b, out);
+    pgm_graph_batch_destroy(c, b);
+    return rc;
+}
+
+int pgm_emission_scores(pgm_ctx* c, int n, const pgm_graph* g1, const pgm_graph* g2, const pgm_dp_model* model,
+                        float match_init, int emission_mode, float* S) {
+    if (!c || !g1 || !g2 || !model || !S) { pgm_set_error("NULL argument"); return PGM_ERR_ARG; }
+    pgm_dp_opts o{}; o.indel_rate = 0.0093359375; o.end_indel_prob = 0.12; o.repeat_rate = 0.1; o.repeatext_prob = 0.3;
+    o.emission_mode = emission_mode;
+    pgm_graph_batch* b = nullptr;
+    int rc = pgm_graph_batch_create(c, n, 1, g1, g2, model, &o, &b);
+    if (rc) return rc;
+    cudaStream_t st = pgm_ctx_stream(c);
+    b->jobs[0].sc[2] = match_init;
+    cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(GraphJobDev), cudaMemcpyHostToDevice, st);
+    if (emission_mode == PGM_EMISSION_TENSOR) rc = launch_emission_tensor(st, n, 1, b->d_jobs.as<GraphJobDev>(), b->jobs.data());
+    else rc = launch_emission_exact(st, n, 1, b->d_jobs.as<GraphJobDev>(), g1->N, g2->N);
+    if (!rc) {
+        const GraphJobDev& J = b->jobs[0];
+        const size_t diags = (size_t)J.N1 + J.N2 - 1;
+        std::vector<float> sk(diags * J.pitch);
+        cudaError_t e = cudaMemcpyAsync(sk.data(), J.S, sk.size() * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { pgm_set_error("CUDA error: %s", cudaGetErrorString(e)); rc = PGM_ERR_CUDA; }
+        else
+            for (int x = 0; x < J.N2; ++x)
+                for (int y = 0; y < J.N1; ++y) {
+                    const int d = y + x, ylo = std::max(0, d - (J.N2 - 1));
+                    S[y + (size_t)J.N1 * x] = sk[(size_t)d * J.pitch + (y - ylo)];
+                }
+    }
+    pgm_graph_batch_destroy(c, b);
+    return rc;
+}
+
+} // extern "C"

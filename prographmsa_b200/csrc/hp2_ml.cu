@@ -1,0 +1,263 @@
+// hp2_ml.cu -- K3 (+K2 fused): batched ML distance estimation, one warp per sequence pair.
+//
+// Replaces DistanceFactoryML<A>::computeDistance / computeMLDist (reference DistanceFactoryML.h:66-190)
+// with ModelFactory<A>::getModel(t) inlined (ModelFactory.h:48-67,103-127), and -- for the ROWS
+// front-end -- the column scan of DistanceFactoryPrealigned<A>::computePwDistances
+// (DistanceFactoryPrealigned.h:57-84).
+//
+//   P(t) = V diag(exp(sigma t_c)) Vi at the CLAMPED t_c = clamp(max(0,t), min_dist, max_dist),
+//   P' = Q P = V diag(sigma e) Vi,  P'' = Q P' = V diag(sigma^2 e) Vi
+//   f = sum c_ij P'_ij / P_ij,  ff = sum c_ij (P''_ij P_ij - P'_ij^2) / P_ij^2   (+ the -M gap terms)
+// Newton with the reference's bracket / midpoint / iteration-cap rules, iterating on the UNclamped t.
+//
+// Design: the n x n count matrix is a histogram in the warp's shared memory (built from the NW
+// walk's matched-state list, from two MSA rows, or copied from caller counts); it is compacted in
+// place to its non-zero entries, so every Newton evaluation costs nnz * 3n FP64 FMAs spread over
+// the 32 lanes instead of the reference's three dense n^3 products.  All lanes carry the scalar
+// Newton state redundantly (xor-shuffle reductions give every lane identical bits), so the loop has
+// no divergence.  FP64 on CUDA cores; agreement with the reference is ~1e-13 relative on P(t).
+#include "internal.h"
+
+#define ML_WARPS 4
+#define ML_THREADS (ML_WARPS * 32)
+
+enum { FRONT_LIST = 0, FRONT_ROWS = 1, FRONT_COUNTS = 2 };
+
+struct MlFront {
+    // LIST
+    const PairDesc* descs; const uint16_t* list; const uint32_t* list_len; const uint32_t* gaps_in;
+    // ROWS
+    const uint8_t* rows; int N; int L; long long pair_begin;
+    // COUNTS
+    const int32_t* counts_in; const double* seqlen_in;
+    uint32_t* gaps_out; int32_t* counts_out;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void pair_from_index(long long p, int N, int& i, int& j) {
+    // p = i*N - i(i+1)/2 + (j-i-1);  solve for the largest i with start(i) <= p
+    const double b = 2.0 * N - 1.0;
+    long long ii = (long long)floor((b - sqrt(b * b - 8.0 * (double)p)) * 0.5);
+    if (ii < 0) ii = 0;
+    while (ii > 0 && ii * N - ii * (ii + 1) / 2 > p) --ii;
+    while ((ii + 1) * N - (ii + 1) * (ii + 2) / 2 <= p) ++ii;
+    i = (int)ii;
+    j = (int)(p - (ii * N - ii * (ii + 1) / 2) + ii + 1);
+}
+
+template <int FRONT>
+__global__ void __launch_bounds__(ML_THREADS)
+ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out, double* __restrict__ var_out,
+          unsigned long long* __restrict__ evals_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int n = ml.n, nn = n * n;
+    double* sV = (double*)smem_raw;            // n*n
+    double* sVi = sV + nn;                     // n*n
+    double* sSig = sVi + nn;                   // n
+    double* sW = sSig + n;                     // ML_WARPS * 3 * n
+    uint32_t* sHist = (uint32_t*)(sW + ML_WARPS * 3 * n);   // ML_WARPS * nn
+
+    for (int i = threadIdx.x; i < nn; i += ML_THREADS) { sV[i] = ml.V[i]; sVi[i] = ml.Vi[i]; }
+    for (int i = threadIdx.x; i < n; i += ML_THREADS) sSig[i] = ml.sigma[i];
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* w0 = sW + warp * 3 * n; double* w1 = w0 + n; double* w2 = w1 + n;
+    uint32_t* hist = sHist + warp * nn;
+    unsigned long long my_evals = 0;
+
+    for (long long p = (long long)blockIdx.x * ML_WARPS + warp; p < n_pairs; p += (long long)gridDim.x * ML_WARPS) {
+        for (int i = lane; i < nn; i += 32) hist[i] = 0;
+        __syncwarp();
+        uint32_t gaps = 0;
+        double seqlen = 0;
+        long long out_idx = p;
+
+        if (FRONT == FRONT_LIST) {
+            const PairDesc d = fr.descs[p];
+            out_idx = d.out_idx;
+            const uint32_t len = fr.list_len[out_idx];
+            const uint16_t* lp = fr.list + d.list_off;
+            for (uint32_t k = lane; k < len; k += 32) atomicAdd(&hist[lp[k]], 1u);
+            gaps = fr.gaps_in[out_idx];
+            seqlen = ((double)d.L1 + (double)d.L2) / 2.0;
+        } else if (FRONT == FRONT_ROWS) {
+            int i, j;
+            pair_from_index(fr.pair_begin + p, fr.N, i, j);
+            const uint8_t* __restrict__ r1 = fr.rows + (size_t)i * fr.L;
+            const uint8_t* __restrict__ r2 = fr.rows + (size_t)j * fr.L;
+            const int lim = n < 20 ? n : 20;               // hard-coded 20, DistanceFactoryPrealigned.h:65
+            int carry = 0;                                   // 0 = none/match, 1 = run in seq1 (A), 2 = run in seq2 (B)
+            for (int base = 0; base < fr.L; base += 32) {
+                const int k = base + lane;
+                int type = 3;                                // 3 = skip (both gaps / out of range)
+                if (k < fr.L) {
+                    const int c1 = r1[k], c2 = r2[k];
+                    const bool g1 = (c1 == 254), g2 = (c2 == 254);
+                    if (!g1 && !g2) { type = 0; if (c1 < lim && c2 < lim) atomicAdd(&hist[c1 * n + c2], 1u); }
+                    else if (g1 && g2) type = 3;
+                    else if (!g1) type = 1;
+                    else type = 2;
+                }
+                const uint32_t mA = __ballot_sync(0xffffffffu, type == 1);
+                const uint32_t mB = __ballot_sync(0xffffffffu, type == 2);
+                const uint32_t mM = __ballot_sync(0xffffffffu, type == 0);
+                const uint32_t ns = mA | mB | mM;
+                const uint32_t below = ns & ((1u << lane) - 1u);
+                int prev = carry;
+                if (below) { const int q = 31 - __clz(below); prev = ((mA >> q) & 1u) ? 1 : (((mB >> q) & 1u) ? 2 : 0); }
+                const bool ev = (type == 1 && prev != 1) || (type == 2 && prev != 2);
+                gaps += __popc(__ballot_sync(0xffffffffu, ev));
+                if (ns) { const int q = 31 - __clz(ns); carry = ((mA >> q) & 1u) ? 1 : (((mB >> q) & 1u) ? 2 : 0); }
+            }
+            seqlen = ((double)fr.L + (double)fr.L) / 2.0;
+        } else {
+            const int32_t* cp = fr.counts_in + (size_t)p * nn;
+            for (int i = lane; i < nn; i += 32) hist[i] = (uint32_t)cp[i];
+            gaps = fr.gaps_in[p];
+            seqlen = fr.seqlen_in[p];
+        }
+        __syncwarp();
+        if (fr.counts_out) {
+            int32_t* co = fr.counts_out + (size_t)out_idx * nn;
+            for (int i = lane; i < nn; i += 32) co[i] = (int32_t)hist[i];
+        }
+        if (fr.gaps_out && lane == 0) fr.gaps_out[out_idx] = gaps;
+
+        // ident / total, then in-place compaction to (idx << 20 | count)
+        double ident = 0, total = 0;
+        uint32_t nnz = 0;
+        for (int base = 0; base < nn; base += 32) {
+            const int idx = base + lane;
+            const uint32_t c = (idx < nn) ? hist[idx] : 0u;
+            if (c) { total += c; if (idx / n == idx % n) ident += c; }
+            const uint32_t m = __ballot_sync(0xffffffffu, c != 0);
+            __syncwarp();
+            if (c) hist[nnz + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)idx << 20) | c;
+            nnz += __popc(m);
+            __syncwarp();
+        }
+        ident = warp_sum(ident); total = warp_sum(total);
+
+        // computeDistance (DistanceFactoryML.h:138-190)
+        double dist0 = 1.0 - ident / total;
+        double dist, var;
+        if (ml.mldist_flag || ml.mldist_gap_flag) {
+            if (total == 0 || dist0 > 0.85) { dist = dist0 = ml.DIST_MAX; var = ml.VAR_MAX; }
+            else { dist = dist0 = -log(1.0 - dist0 - 0.2 * dist0 * dist0); var = dist / total; }
+            if (total > 0 && ident != total) {
+                // computeMLDist (DistanceFactoryML.h:66-136)
+                const double var0 = var;
+                double dist_min = 0, dist_max = INFINITY, delta = 1;
+                unsigned iteration = 0;
+                while (fabs(delta) > 1e-5) {
+                    if (iteration > 20) {
+                        if (dist_max == INFINITY) { dist = ml.DIST_MAX; var = ml.VAR_MAX; }
+                        else { dist = dist0; var = var0; }
+                        break;
+                    }
+                    double tc = (0.0 < dist) ? dist : 0.0;                 // parseDistance (ModelFactory.h:104,125)
+                    tc = fmax(fmin(tc, ml.max_dist), ml.min_dist);
+                    __syncwarp();
+                    for (int k = lane; k < n; k += 32) {
+                        const double s = sSig[k], e = exp(s * tc);
+                        w0[k] = e; w1[k] = s * e; w2[k] = s * s * e;
+                    }
+                    __syncwarp();
+                    double f = 0, ff = 0;
+                    for (uint32_t q = lane; q < nnz; q += 32) {
+                        const uint32_t h = hist[q];
+                        const int idx = (int)(h >> 20);
+                        const double c = (double)(h & 0xfffffu);
+                        const int i = idx / n, j = idx - i * n;
+                        double pp0 = 0, pp1 = 0, pp2 = 0;
+                        for (int k = 0; k < n; ++k) {
+                            const double a = sV[i * n + k] * sVi[k * n + j];
+                            pp0 = fma(a, w0[k], pp0); pp1 = fma(a, w1[k], pp1); pp2 = fma(a, w2[k], pp2);
+                        }
+                        f += c * pp1 / pp0;
+                        ff += (c * (pp2 * pp0 - pp1 * pp1)) / (pp0 * pp0);
+                    }
+                    f = warp_sum(f); ff = warp_sum(ff);
+                    ++my_evals;
+                    if (ml.mldist_gap_flag) {
+                        const double grate = ml.indel_rate * seqlen * dist;
+                        f += (-grate + (double)gaps) / dist;
+                        // sic: the reference negates an unsigned (DistanceFactoryML.h:102)
+                        ff += (double)(uint32_t)(0u - gaps) / (dist * dist);
+                    }
+                    var = -1.0 / ff;
+                    if (f > 0) dist_min = fmax(dist_min, dist); else dist_max = fmin(dist_max, dist);
+                    double nd = dist - f / ff;
+                    if (!(nd < dist_max && nd > dist_min)) {
+                        const double upper = (dist_max == INFINITY) ? dist * 3 : dist_max;
+                        nd = (upper + dist_min) / 2.0;
+                    }
+                    delta = 1.0 - nd / dist;
+                    dist = nd;
+                    ++iteration;
+                }
+            }
+        } else {
+            if (total == 0) { dist = dist0 = 1.0; var = ml.VAR_MAX; }
+            else { dist = dist0; var = dist0 / total; }
+        }
+        if (!(dist < ml.DIST_MAX)) { dist = ml.DIST_MAX; var = ml.VAR_MAX; }
+        if (dist > ml.cutoff_dist) dist = ml.cutoff_dist;
+        if (var < ml.VAR_MIN) var = ml.VAR_MIN;
+        if (!(var < ml.VAR_MAX)) var = ml.VAR_MAX;
+        if (lane == 0) { dist_out[out_idx] = dist; var_out[out_idx] = var; }
+        __syncwarp();
+    }
+    if (evals_out && lane == 0 && my_evals) atomicAdd(evals_out, my_evals);
+}
+
+static size_t ml_smem(int n) { return sizeof(double) * (2 * n * n + n + ML_WARPS * 3 * n) + sizeof(uint32_t) * ML_WARPS * n * n; }
+
+template <int FRONT>
+static int launch_ml(cudaStream_t st, const MlDev& ml, const MlFront& fr, long long n_pairs, double* d_dist, double* d_var,
+                     unsigned long long* d_evals) {
+    if (n_pairs <= 0) return 0;
+    const size_t smem = ml_smem(ml.n);
+    if (ml.n * ml.n >= 4096) { pgm_set_error("ML kernel supports n_states <= 63"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaFuncSetAttribute(ml_kernel<FRONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ml_kernel<FRONT>, ML_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long want = (n_pairs + ML_WARPS - 1) / ML_WARPS;
+    long long grid = (long long)sms * per_sm;
+    if (grid > want) grid = want;
+    ml_kernel<FRONT><<<(unsigned)grid, ML_THREADS, smem, st>>>(ml, fr, n_pairs, d_dist, d_var, d_evals);
+    PGM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_pairs, const PairDesc* d_descs, const uint16_t* d_list,
+                         const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist, double* d_var,
+                         int32_t* d_counts, unsigned long long* d_evals) {
+    MlFront fr{};
+    fr.descs = d_descs; fr.list = d_list; fr.list_len = d_list_len; fr.gaps_in = d_gaps; fr.counts_out = d_counts;
+    return launch_ml<FRONT_LIST>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
+}
+
+int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,
+                        const uint8_t* d_rows, double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps,
+                        unsigned long long* d_evals) {
+    MlFront fr{};
+    fr.rows = d_rows; fr.N = N; fr.L = L; fr.pair_begin = pair_begin; fr.counts_out = d_counts; fr.gaps_out = d_gaps;
+    return launch_ml<FRONT_ROWS>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
+}
+
+int launch_ml_from_counts(cudaStream_t st, const MlDev& ml, int64_t n_pairs, const int32_t* d_counts, const uint32_t* d_gaps,
+                          const double* d_seqlen, double* d_dist, double* d_var, unsigned long long* d_evals) {
+    MlFront fr{};
+    fr.counts_in = d_counts; fr.gaps_in = d_gaps; fr.seqlen_in = d_seqlen;
+    return launch_ml<FRONT_COUNTS>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
+}

@@ -1,0 +1,226 @@
+// hp2_nw.cu -- K1: batched global (Gotoh) alignment + packed traceback, and the traceback walk.
+//
+// Replaces DistanceFactoryAlign<A>::alignPair (reference DistanceFactoryAlign.h:58-127):
+//   W(0,0)=0; W(0,x)=X(0,x)=go+(x-1)ge; Y(0,x)=-10000; W(y,0)=Y(y,0)=go+(y-1)ge; X(y,0)=-10000
+//   Wd=W(y-1,x-1)+T(s2(y),s1(x)); X=max(X(y,x-1)+ge, W(y,x-1)+go); Y=max(Y(y-1,x)+ge, W(y-1,x)+go)
+//   W=max(max(X,Y),Wd)
+// and its traceback, which looks only at the cell (not at a state): W==Wd -> diagonal (count the
+// residue pair), else W==X -> left, else W==Y -> up; a gap is counted when a left-run or up-run opens.
+// So the direction is a pure function of the cell: 2 bits per cell, computed in the forward pass.
+//
+// Design (B200): one warp per sequence pair, lanes own C consecutive columns in registers, the
+// wavefront is skewed across lanes (lane l works on row t-l at step t) and the three values that
+// cross a lane boundary (W, X of the lane's last column and the row's residue) move by warp
+// shuffle.  A CTA handles pairs that share seq1 and builds its int8 query profile
+// prof[band][residue][lane][16] once in shared memory: one conflict-free LDS.128 per lane per row
+// yields all C substitution scores.  Direction bits: 2*C <= 32 bits per lane per step, one coalesced
+// 128-byte store per warp-step into HBM scratch.  Sequences longer than 32*C columns are processed
+// in column bands; the band's right boundary column (W, X per row) goes through a per-warp global
+// buffer (L2-resident).  The walk is a separate kernel with one THREAD per pair: it is a dependent
+// chain of ~L1+L2 loads, so it needs tens of thousands of chains in flight, not a warp each.
+//
+// Integer arithmetic only: bit-exact against the oracle.
+#include "internal.h"
+
+#define NW_WARPS 8
+#define NW_THREADS (NW_WARPS * 32)
+#define NW_MINFTY (-10000)
+
+template <int C>
+__global__ void __launch_bounds__(NW_THREADS)
+nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict__ descs,
+                  const NwTask* __restrict__ tasks, const int8_t* __restrict__ tab, int n1, int go, int ge,
+                  uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int8_t* s_tab = (int8_t*)smem;                           // n1*n1, padded to 16
+    const int tab_bytes = (n1 * n1 + 15) & ~15;
+    int8_t* prof = (int8_t*)(smem + tab_bytes);              // [band][r][lane][16]
+
+    const NwTask task = tasks[blockIdx.x];
+    const PairDesc d0 = descs[task.desc_begin];
+    const int L1 = (int)d0.L1;
+    const uint8_t* __restrict__ s1 = codes + d0.s1_off;
+    const int nbands = (L1 + 32 * C - 1) / (32 * C);
+
+    for (int i = threadIdx.x; i < n1 * n1; i += NW_THREADS) s_tab[i] = tab[i];
+    __syncthreads();
+    // profile: prof[b][r][lane][k] = T(r, s1(x)), x = b*32C + lane*C + k (0-based); 0 beyond L1
+    const int per_band = n1 * 512;
+    for (int idx = threadIdx.x; idx < nbands * per_band; idx += NW_THREADS) {
+        const int b = idx / per_band, rem = idx - b * per_band;
+        const int r = rem >> 9, lk = rem & 511, lane = lk >> 4, k = lk & 15;
+        const int x = b * 32 * C + lane * C + k;
+        int8_t v = 0;
+        if (k < C && x < L1) v = s_tab[r + n1 * (int)s1[x]];     // scoring_matrix(s2, s1), column-major
+        prof[idx] = v;
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int32_t* colW = colbuf + (size_t)(blockIdx.x * NW_WARPS + warp) * 2 * colbuf_stride;
+    int32_t* colX = colW + colbuf_stride;
+
+    for (uint32_t di = task.desc_begin + warp; di < task.desc_end; di += NW_WARPS) {
+        const PairDesc d = descs[di];
+        const int L2 = (int)d.L2;
+        const uint8_t* __restrict__ s2 = codes + d.s2_off;
+        const int steps = L2 + 31;
+        uint32_t* __restrict__ tbp = tb + d.tb_off;
+
+        for (int b = 0; b < nbands; ++b) {
+            const int x0 = b * 32 * C + lane * C;            // columns x0+1 .. x0+C (1-based)
+            int Wup[C], Yup[C];
+#pragma unroll
+            for (int k = 0; k < C; ++k) { Wup[k] = go + (x0 + k) * ge; Yup[k] = NW_MINFTY; }
+            int Wdiag = (x0 == 0) ? 0 : go + (x0 - 1) * ge;  // W(y-1, x0) for y-1 = 0
+            int Wlast = 0, Xlast = 0, rcur = 0;
+            // lane 0 prefetch of its left-boundary inputs for row 1
+            int nxtW = 0, nxtX = NW_MINFTY, nxtR = 0;
+            if (lane == 0 && L2 > 0) {
+                nxtR = s2[0];
+                if (b == 0) { nxtW = go; } else { nxtW = __ldcg(colW + 1); nxtX = __ldcg(colX + 1); }
+            }
+            const int8_t* pb = prof + (size_t)b * per_band + lane * 16;
+            const bool has_next_band = (b + 1 < nbands);
+            for (int t = 0; t < steps; ++t) {
+                int Wl = __shfl_up_sync(0xffffffffu, Wlast, 1);
+                int Xl = __shfl_up_sync(0xffffffffu, Xlast, 1);
+                int r = __shfl_up_sync(0xffffffffu, rcur, 1);
+                const int y = t - lane + 1;
+                if (lane == 0) {
+                    Wl = nxtW; Xl = nxtX; r = nxtR;
+                    const int yn = y + 1;
+                    if (yn <= L2) {                            // prefetch next row's inputs
+                        nxtR = s2[yn - 1];
+                        if (b == 0) { nxtW = go + (yn - 1) * ge; nxtX = NW_MINFTY; }
+                        else { nxtW = __ldcg(colW + yn); nxtX = __ldcg(colX + yn); }
+                    }
+                }
+                if (y >= 1 && y <= L2) {
+                    const uint4 pw = *reinterpret_cast<const uint4*>(pb + r * 512);
+                    const uint32_t pws[4] = {pw.x, pw.y, pw.z, pw.w};
+                    int Wleft = Wl, Xleft = Xl, dg = Wdiag;
+                    uint32_t bits = 0;
+#pragma unroll
+                    for (int k = 0; k < C; ++k) {
+                        const int s = (int)(int8_t)((pws[k >> 2] >> (8 * (k & 3))) & 0xff);
+                        const int wd = dg + s;
+                        const int xv = max(Xleft + ge, Wleft + go);
+                        const int yv = max(Yup[k] + ge, Wup[k] + go);
+                        const int wn = max(max(xv, yv), wd);
+                        const uint32_t dir = (wn == wd) ? 0u : ((wn == xv) ? 1u : 2u);
+                        bits |= dir << (2 * k);
+                        dg = Wup[k];
+                        Wup[k] = wn; Yup[k] = yv;
+                        Wleft = wn; Xleft = xv;
+                    }
+                    Wdiag = Wl;
+                    Wlast = Wleft; Xlast = Xleft; rcur = r;
+                    tbp[((size_t)b * steps + t) * 32 + lane] = bits;
+                    if (lane == 31 && has_next_band) { colW[y] = Wlast; colX[y] = Xlast; }
+                    if (scores_out != nullptr && y == L2) {
+                        const int kk = L1 - 1 - x0;            // column L1 in this lane?
+                        if (kk >= 0 && kk < C) {
+                            int v = 0;
+#pragma unroll
+                            for (int k = 0; k < C; ++k) if (k == kk) v = Wup[k];
+                            scores_out[d.out_idx] = v;
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        if (scores_out != nullptr && lane == 0 && (L1 == 0 || L2 == 0)) {
+            // degenerate: W(L2,L1) is a boundary cell
+            scores_out[d.out_idx] = (L1 == 0 && L2 == 0) ? 0 : go + (max(L1, L2) - 1) * ge;
+        }
+    }
+}
+
+// One thread per pair: follow the 2-bit directions from (L2,L1) until x==0 or y==0
+// (DistanceFactoryAlign.h:99-123).  Emits the matched state pairs (s1*n+s2, both < n) and the
+// number of gap openings.
+__global__ void __launch_bounds__(128)
+nw_walk_kernel(int C, int n_pairs, int n, const uint8_t* __restrict__ codes, const PairDesc* __restrict__ descs,
+               const uint32_t* __restrict__ tb, uint16_t* __restrict__ list, uint32_t* __restrict__ list_len,
+               uint32_t* __restrict__ gaps_out, int* __restrict__ err) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pairs) return;
+    const PairDesc d = descs[p];
+    const uint8_t* __restrict__ s1 = codes + d.s1_off;
+    const uint8_t* __restrict__ s2 = codes + d.s2_off;
+    const uint32_t* __restrict__ tbp = tb + d.tb_off;
+    uint16_t* __restrict__ lp = list + d.list_off;
+    const int steps = (int)d.L2 + 31;
+    const int bandw = 32 * C;
+    int x = (int)d.L1, y = (int)d.L2;
+    uint32_t gaps = 0, nl = 0;
+    bool o1 = false, o2 = false;
+    while (x != 0 && y != 0) {
+        const int xz = x - 1;
+        const int b = xz / bandw, rem = xz - b * bandw;
+        const int lane = rem / C, k = rem - lane * C;
+        const int t = y - 1 + lane;
+        const uint32_t w = __ldg(tbp + ((size_t)b * steps + t) * 32 + lane);
+        const uint32_t dir = (w >> (2 * k)) & 3u;
+        if (dir == 0u) {
+            const int c1 = s1[xz], c2 = s2[y - 1];
+            if (c1 < n && c2 < n) lp[nl++] = (uint16_t)(c1 * n + c2);
+            o1 = o2 = false; --x; --y;
+        } else if (dir == 1u) {
+            if (!o1) ++gaps;
+            o1 = true; o2 = false; --x;
+        } else if (dir == 2u) {
+            if (!o2) ++gaps;
+            o1 = false; o2 = true; --y;
+        } else {
+            *err = 1;                                          // reference: error("error while backtracking")
+            break;
+        }
+    }
+    list_len[d.out_idx] = nl;
+    gaps_out[d.out_idx] = gaps;
+}
+
+template <int C>
+static int launch_fwd_t(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
+                        const PairDesc* d_descs, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
+                        uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
+    const int n1 = n_states + 1;
+    const size_t smem = ((n1 * n1 + 15) & ~15) + (size_t)max_bands * n1 * 512;
+    if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nw_forward_kernel<C><<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_descs, d_tasks, d_tab, n1, go, ge, d_tb,
+                                                           d_colbuf, colbuf_stride, d_scores);
+    PGM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int launch_nw_forward(cudaStream_t st, int C, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
+                      const PairDesc* d_descs, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
+                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
+    if (n_tasks == 0) return 0;
+#define CASE(c) case c: return launch_fwd_t<c>(st, n_tasks, n_states, max_bands, d_codes, d_descs, d_tasks, d_tab, go, ge, d_tb, d_colbuf, colbuf_stride, d_scores);
+    switch (C) {
+        CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
+    }
+#undef CASE
+    pgm_set_error("unsupported NW column count per lane C=%d", C);
+    return PGM_ERR_ARG;
+}
+
+int launch_nw_walk(cudaStream_t st, int C, int n_pairs, int n_states, const uint8_t* d_codes, const PairDesc* d_descs,
+                   const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps, int* d_err) {
+    if (n_pairs == 0) return 0;
+    nw_walk_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(C, n_pairs, n_states, d_codes, d_descs, d_tb, d_list,
+                                                          d_list_len, d_gaps, d_err);
+    PGM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int nw_pick_C(int max_L1) {
+    static const int cs[] = {4, 6, 8, 10, 12, 13, 14, 16};
+    for (int c : cs) if (32 * c >= max_L1) return c;
+    return 16;
+}

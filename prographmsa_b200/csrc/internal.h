@@ -1,0 +1,123 @@
+// internal.h -- shared between the C-ABI glue (api.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/pgm_b200.h"
+
+void pgm_set_error(const char* fmt, ...);
+
+#define PGM_CUDA(call)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (call);                                                                \
+        if (e_ != cudaSuccess) {                                                                \
+            pgm_set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(e_), __FILE__, __LINE__, \
+                          cudaGetErrorString(e_));                                              \
+            return PGM_ERR_CUDA;                                                                \
+        }                                                                                       \
+    } while (0)
+
+// ---- eigen_host.cpp ---------------------------------------------------------------------------
+// Q (n*n row-major) -> V, sigma, Vi with Q = V diag(sigma) Vi (rho-symmetrised Jacobi). 0 or PGM_ERR_MODEL.
+int pgm_eigen_basis(const double* Q, int n, double* V, double* sigma, double* Vi);
+
+// ---- growable device buffer ---------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            pgm_set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            cudaGetLastError();
+            return PGM_ERR_NOMEM;
+        }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+struct HostPinned {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes) {
+        if (bytes <= cap) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); pgm_set_error("cudaMallocHost(%zu) failed", want); return PGM_ERR_NOMEM; }
+        cap = want;
+        return 0;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+// ---- HP-2 device structs ------------------------------------------------------------------------
+struct PairDesc {           // 32 B, one per sequence pair of a chunk
+    uint32_t s1_off, s2_off;    // offsets of seq1 (columns) / seq2 (rows) into codes
+    uint32_t L1, L2;
+    uint64_t tb_off;            // word offset of this pair's packed traceback
+    uint32_t list_off;          // offset of this pair's matched-state list (uint16 entries)
+    uint32_t out_idx;           // index into the packed outputs
+};
+struct NwTask { uint32_t desc_begin, desc_end; };   // descs sharing seq1: one CTA builds its profile once
+
+struct MlDev {              // ML constants + eigen-basis in device memory
+    int n;
+    const double *V, *Vi, *sigma;   // n*n row-major, n*n row-major, n
+    int mldist_flag, mldist_gap_flag;
+    double indel_rate, min_dist, max_dist, cutoff_dist, DIST_MAX, VAR_MAX, VAR_MIN;
+};
+
+// kernels (hp2_nw.cu / hp2_ml.cu); all launch on `st`
+int launch_nw_forward(cudaStream_t st, int C, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
+                      const PairDesc* d_descs, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
+                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores);
+int launch_nw_walk(cudaStream_t st, int C, int n_pairs, int n_states, const uint8_t* d_codes, const PairDesc* d_descs,
+                   const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps, int* d_err);
+// front-end LIST: histogram from matched-state lists; ROWS: scan two MSA rows
+int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_pairs, const PairDesc* d_descs, const uint16_t* d_list,
+                         const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist, double* d_var,
+                         int32_t* d_counts, unsigned long long* d_evals);
+int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,
+                        const uint8_t* d_rows, double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps,
+                        unsigned long long* d_evals);
+int launch_ml_from_counts(cudaStream_t st, const MlDev& ml, int64_t n_pairs, const int32_t* d_counts, const uint32_t* d_gaps,
+                          const double* d_seqlen, double* d_dist, double* d_var, unsigned long long* d_evals);
+
+// ---- HP-1 (hp1_*.cu) ------------------------------------------------------------------------------
+struct GraphJobDev {        // one alignGraphs job, all pointers into the batch's device arena
+    int N1, N2;
+    int pitch;                  // skewed-layout pitch (>= N1): cell (y,x) lives at (y+x)*pitch + y
+    const float* sites1;        // n * N1 (float cast of Graph::sites), column-major
+    const float* sites2;        // n * N2
+    const float* Mf;            // n*n row-major float cast of Model::M
+    const float* pif;           // n
+    // unified predecessor lists (regular edges ascending, then repeat edges ascending; Graph.h:196,241-247)
+    const int* p1_ptr; const int* p1_idx; const float* p1_val; const uint8_t* p1_rep;
+    const int* p2_ptr; const int* p2_idx; const float* p2_val; const uint8_t* p2_rep;
+    // alternative-path preds (values with repeat_init = repeat_ext = +inf; GraphAlign.h:165-198)
+    const float* p1_alt; const float* p2_alt;
+    float sc[10];               // DynProgScores
+    float* S;                   // skewed
+    float4* MXYW;               // skewed {M,X,Y,W}
+    float* Tbuf;                // n * N2 scratch: T = M^T g2
+    float* u; float* v;         // g1^T pi (N1), pi^T g2 (N2)
+    int* map1; int* map2;       // output mappings (capacity cap), written reversed then flipped
+    int cap;
+    float* alt_score; int* alt_prev;   // markAlternativePath scratch, max(N1,N2) each
+    int* result;                // [0]=status [1]=length [2]=n_tr_indels ; score at ((float*)result)[3]
+};
+
+int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, int max_N1, int max_N2);
+int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const GraphJobDev* h_jobs);
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs);
+int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs);

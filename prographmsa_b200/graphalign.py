@@ -1,0 +1,121 @@
+"""Host-side mirror of alignGraphs<A> (GraphAlign.h:6-23,201) over the C ABI.
+
+  alignGraphs(g1, g2, model, opts) -> AlignmentResult{score, n_tr_indels, mapping1, mapping2}
+  alignGraphsBatch(jobs, opts): all ready guide-tree nodes of one level in one call.
+Raises RuntimeError("backtracking failed") where the reference calls error() (GraphAlign.h:410,449,482).
+"""
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+EMISSION_EXACT = 0
+EMISSION_TENSOR = 1
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def c_graph(g, keep):
+    keep.append(g)
+    has_rep = g.r_col.size > 0
+    return _lib.Graph(g.N, _p(g.sites), _p(g.e_rowptr), _p(g.e_col), _p(g.e_val),
+                      _p(g.r_rowptr), _p(g.r_col) if has_rep else None, _p(g.r_units) if has_rep else None)
+
+
+def c_model(model, keep):
+    M = np.ascontiguousarray(model.M, dtype=np.float64)
+    pi = np.ascontiguousarray(model.pi, dtype=np.float64)
+    keep += [M, pi]
+    return _lib.DPModel(_p(M), _p(pi), model.distance, model.epsilon, model.delta)
+
+
+def c_opts(opts, emission_mode=EMISSION_EXACT):
+    return _lib.DPOpts(opts.indel_rate, opts.end_indel_prob, opts.repeat_rate, opts.repeatext_prob, int(emission_mode))
+
+
+class GraphBatch:
+    """A batch of alignGraphs jobs staged on the device (pgm_graph_batch_*): create once, run many
+    times without host<->device traffic, fetch results."""
+
+    def __init__(self, jobs, opts, emission_mode=EMISSION_EXACT, ctx=None):
+        self.ctx = ctx or _lib.default_context()
+        self.n_jobs = len(jobs)
+        keep = []
+        n = jobs[0][0].n if jobs else 20
+        G1 = (_lib.Graph * max(1, self.n_jobs))(); G2 = (_lib.Graph * max(1, self.n_jobs))()
+        MM = (_lib.DPModel * max(1, self.n_jobs))()
+        for k, (g1, g2, model) in enumerate(jobs):
+            G1[k] = c_graph(g1, keep); G2[k] = c_graph(g2, keep); MM[k] = c_model(model, keep)
+        o = c_opts(opts, emission_mode)
+        self._h = C.c_void_p()
+        _lib.check(_lib.lib().pgm_graph_batch_create(self.ctx.handle, n, self.n_jobs, G1, G2, MM, C.byref(o), C.byref(self._h)))
+        self.caps = [2 * (g1.N + g2.N) + 8 for g1, g2, _ in jobs]
+
+    def run(self):
+        _lib.check(_lib.lib().pgm_graph_batch_run(self.ctx.handle, self._h))
+
+    def fetch(self):
+        out = (_lib.Alignment * max(1, self.n_jobs))()
+        bufs = []
+        for k in range(self.n_jobs):
+            m1 = np.zeros(self.caps[k], dtype=np.int32); m2 = np.zeros(self.caps[k], dtype=np.int32)
+            bufs.append((m1, m2))
+            out[k].mapping1 = _p(m1); out[k].mapping2 = _p(m2); out[k].capacity = self.caps[k]
+        rc = _lib.lib().pgm_graph_batch_fetch(self.ctx.handle, self._h, out)
+        if rc == -4:
+            raise RuntimeError("backtracking failed")
+        _lib.check(rc)
+        res = []
+        for k in range(self.n_jobs):
+            ln = out[k].length
+            res.append(dict(score=float(out[k].score), n_tr_indels=int(out[k].n_tr_indels),
+                            mapping1=bufs[k][0][:ln].astype(np.int64), mapping2=bufs[k][1][:ln].astype(np.int64),
+                            cell_updates=int(out[k].cell_updates)))
+        return res
+
+    def close(self):
+        if self._h:
+            _lib.lib().pgm_graph_batch_destroy(self.ctx.handle, self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def alignGraphsBatch(jobs, opts, emission_mode=EMISSION_EXACT, ctx=None):
+    """jobs: list of (g1, g2, model)."""
+    if not jobs:
+        return []
+    b = GraphBatch(jobs, opts, emission_mode, ctx)
+    try:
+        b.run()
+        return b.fetch()
+    finally:
+        b.close()
+
+
+def alignGraphs(g1, g2, model, opts, emission_mode=EMISSION_EXACT, ctx=None):
+    return alignGraphsBatch([(g1, g2, model)], opts, emission_mode, ctx)[0]
+
+
+def dynprog_scores(g1, g2, model, opts):
+    keep = []
+    a, b, m, o = c_graph(g1, keep), c_graph(g2, keep), c_model(model, keep), c_opts(opts)
+    out = np.zeros(10, dtype=np.float32)
+    _lib.check(_lib.lib().pgm_dynprog_scores(g1.n, C.byref(a), C.byref(b), C.byref(m), C.byref(o), _p(out)))
+    return out
+
+
+def emission_scores(g1, g2, model, match_init, emission_mode=EMISSION_EXACT, ctx=None):
+    ctx = ctx or _lib.default_context()
+    keep = []
+    a, b, m = c_graph(g1, keep), c_graph(g2, keep), c_model(model, keep)
+    S = np.zeros((g2.N, g1.N), dtype=np.float32)
+    _lib.check(_lib.lib().pgm_emission_scores(ctx.handle, g1.n, C.byref(a), C.byref(b), C.byref(m), C.c_float(match_init),
+                                              int(emission_mode), _p(S)))
+    return S.T

@@ -1,0 +1,136 @@
+"""GPU parity, HP-1: emission scores, DP score, traceback mappings and whole progressive alignments
+from the CUDA path (through the C ABI) against the CPU oracle and the reference binary's goldens.
+PGM_EMISSION_EXACT is bit-identical to the oracle, so every comparison here is exact."""
+import numpy as np
+import pytest
+
+from prographmsa_b200 import alphabet, model, synth, progressive
+from prographmsa_b200.graph import sequence_graph, CleanedGraph
+from prographmsa_b200.options import Options
+from common import golden, aa_codes
+
+pytestmark = pytest.mark.gpu
+AA = alphabet.AA
+
+
+@pytest.fixture(scope="module")
+def ga():
+    from prographmsa_b200 import graphalign
+    return graphalign
+
+
+@pytest.fixture(scope="module")
+def po():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def _interior(S):
+    return S[1:-1, 1:-1]
+
+
+def _same_alignment(a, b):
+    assert a["score"] == b["score"], (a["score"], b["score"])
+    assert a["n_tr_indels"] == b["n_tr_indels"]
+    assert np.array_equal(a["mapping1"], b["mapping1"]) and np.array_equal(a["mapping2"], b["mapping2"])
+
+
+def test_emission_exact_bitwise(ga, po):
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    a, b = synth.random_pair(97, 0.4, mf, seed=4)
+    g1, g2 = sequence_graph(a, 20), sequence_graph(b, 20)
+    m = mf.getModel(0.5, 0.5)
+    S_ref = po.precompute_scores(g1, g2, m, -0.25)
+    S = ga.emission_scores(g1, g2, m, -0.25)
+    assert np.array_equal(_interior(S).view(np.uint32), _interior(S_ref).view(np.uint32))
+
+
+def test_dynprog_scores_host(ga, po):
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    a, b = synth.random_pair(60, 0.4, mf, seed=5)
+    g1, g2 = sequence_graph(a, 20), sequence_graph(b, 20)
+    for o in (opts, Options(mldist_flag=True, end_indel_prob=-1.0), Options(mldist_flag=True, repeat_rate=0.0)):
+        m = mf.getModel(0.7, 0.9)
+        assert np.array_equal(ga.dynprog_scores(g1, g2, m, o).view(np.uint32), po.dynprog_scores(g1, g2, m, o).view(np.uint32))
+
+
+@pytest.mark.parametrize("L,t,seed", [(1, 0.3, 1), (2, 0.3, 2), (40, 0.1, 3), (150, 0.8, 4), (300, 1.5, 5), (700, 0.4, 6)])
+def test_leaf_pair_alignment_identical(ga, po, L, t, seed):
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    a, b = synth.random_pair(L, t, mf, seed=seed)
+    g1, g2 = sequence_graph(a, 20), sequence_graph(b, 20)
+    m = mf.getModel(t, t)
+    _same_alignment(ga.alignGraphs(g1, g2, m, opts), po.align_graphs(g1, g2, m, opts))
+
+
+def test_empty_sequences(ga, po):
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    e = sequence_graph(np.zeros(0, np.uint8), 20)
+    s = sequence_graph(np.array([3, 4, 5], np.uint8), 20)
+    m = mf.getModel(0.3, 0.3)
+    for g1, g2 in ((e, e), (e, s), (s, e)):
+        _same_alignment(ga.alignGraphs(g1, g2, m, opts), po.align_graphs(g1, g2, m, opts))
+
+
+@pytest.mark.parametrize("idx", range(10))
+def test_progressive_alignment_matches_reference_binary(ga, idx):
+    """whole families: every internal node's alignGraphs runs on the GPU; the final text equals the
+    reference binary's output"""
+    from test_oracle_golden import _opts_from_extra
+    fam = golden("alignments.json")["families"][idx]
+    opts = _opts_from_extra(fam["extra"])
+    mf = model.getDefault(opts)
+    seqs = {k: aa_codes(v) for k, v in fam["seqs"].items()}
+    tree = progressive.parse_newick(fam["newick"])
+    res = progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=lambda jobs, o: ga.alignGraphsBatch(jobs, o))
+    assert {k: AA.decode(v) for k, v in res.aligned.items()} == fam["aligned"]
+
+
+def test_merged_graph_jobs_identical_to_oracle(ga, po):
+    """every job of a 40-sequence progressive pass (skip edges, multi-predecessor nodes): score and
+    mappings identical to the oracle, job by job"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(40, 120, mf, seed=33, indel_rate=0.05)
+    tree = progressive.from_synth(root)
+    seen = []
+
+    def batch(jobs, o):
+        out = ga.alignGraphsBatch(jobs, o)
+        for (g1, g2, m), r in zip(jobs, out):
+            ref = po.align_graphs(g1, g2, m, o)
+            _same_alignment(r, ref)
+            assert r["cell_updates"] == ref["cell_updates"]
+            seen.append(g1.N * g2.N)
+        return out
+    progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
+    assert len(seen) == 39
+
+
+def test_repeat_edges_identical_to_oracle(ga, po):
+    """tandem-repeat edges: repeat predecessors, n_tr_indels and markAlternativePath"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    rng = np.random.default_rng(12)
+    unit = rng.integers(0, 20, 7).astype(np.uint8)
+    flank1, flank2 = rng.integers(0, 20, 15).astype(np.uint8), rng.integers(0, 20, 12).astype(np.uint8)
+    a = np.concatenate([flank1, np.tile(unit, 5), flank2])
+    b = np.concatenate([flank1, np.tile(unit, 3), flank2])
+    reps = {}
+    for name, s, nu in (("a", a, 5), ("b", b, 3)):
+        reps[name] = [dict(start=len(flank1), tr_hom=list(range(7)) * nu)]
+    results = {}
+    for name, s in (("a", a), ("b", b)):
+        results[name] = progressive._leaf(name, {name: s}, reps, 20)
+    ga_, gb_ = results["a"].graph, results["b"].graph
+    assert ga_.r_col.size > 0
+    m = mf.getModel(0.2, 0.2)
+    cg1, cg2 = CleanedGraph(ga_, opts.repeatext_prob), CleanedGraph(gb_, opts.repeatext_prob)
+    ref = po.align_graphs(cg1, cg2, m, opts)
+    got = ga.alignGraphs(cg1, cg2, m, opts)
+    _same_alignment(got, ref)
+    assert ref["n_tr_indels"] > 0
