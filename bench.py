@@ -1,0 +1,436 @@
+#!/usr/bin/env python3
+"""bench.py -- the driver's measurement contract for the two ProGraphMSA hot paths on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: launched under torch.distributed.run, one rank per GPU)
+
+Workload (BASELINE.json configs[1]): the all-pairs NW + ML distance matrix of a synthetic
+500-sequence x 400-aa WAG family (124,750 pairs, 2.0e10 DP cells).  One step = one full matrix.
+  value   NW cell updates per second (GCUPS), all stages included (forward DP with packed traceback,
+          traceback walk, ML Newton), sequences already resident in HBM, results left in HBM
+  e2e     the same through the C-ABI call with HOST buffers (H2D of the sequences and D2H of the
+          distance/variance entries inside the timed region)
+N > 1 shards the pair range over the ranks (no data-path collective while computing) and gathers the
+(distance, variance) entries with one NCCL all-gather -- strong scaling of a fixed matrix.
+At N = 1 the line also carries `graph_dp`: the graph-DP GCUPS half of BASELINE.json's metric.
+
+--impl reference times the reference's own CPU binary (oracle/_ref/ProGraphMSA_64, single-threaded by
+design; one independent instance per host core) on bounded samples of the same family.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+N_SEQ, SEQ_LEN, SEED = 500, 400, 1
+GRAPH_N_SEQ = 128
+WORKLOAD = "all-pairs NW+ML distance matrix, %d synthetic protein seqs x %d aa, WAG, -a -m" % (N_SEQ, SEQ_LEN)
+METRIC = "all-pairs NW+ML distance-matrix throughput (graph-DP GCUPS in graph_dp)"
+UNIT = "GCUPS"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), sm_max_mhz=float(d.get("sm_max_mhz", 1965.0)), source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
+
+
+def make_family():
+    from prographmsa_b200 import model, synth
+    from prographmsa_b200.options import Options
+    opts = Options(mldist_flag=True, nwdist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(N_SEQ, SEQ_LEN, mf, seed=SEED)
+    names = sorted(seqs)
+    return opts, mf, seqs, names, root
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        return dict(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own binary on the host cores
+# ------------------------------------------------------------------------------------------------------
+def _fasta(seqs, names):
+    from prographmsa_b200.alphabet import AA_LETTERS
+    return "".join(">%s\n%s\n" % (k, "".join(AA_LETTERS[c] for c in seqs[k])) for k in names)
+
+
+def _run_ref_instances(seqs, names, groups):
+    """run one binary instance per group (each group = list of sequence names), in parallel; -> (wall s, cells, pairs)"""
+    from oracle import pyoracle as po
+    binary = po.ref_binary()
+    cells = pairs = 0
+    with tempfile.TemporaryDirectory() as d:
+        procs = []
+        for gi, g in enumerate(groups):
+            path = os.path.join(d, "g%d.fa" % gi)
+            with open(path, "w") as f:
+                f.write(_fasta(seqs, g))
+            L = [len(seqs[k]) for k in g]
+            for a in range(len(g)):
+                for b in range(a + 1, len(g)):
+                    cells += (L[a] + 1) * (L[b] + 1); pairs += 1
+        t0 = time.perf_counter()
+        for gi in range(len(groups)):
+            procs.append(subprocess.Popen([binary, "-a", "-m", "-i", "0", "-T", "g%d.fa" % gi], cwd=d,
+                                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL))
+        for p in procs:
+            if p.wait() != 0:
+                raise RuntimeError("reference binary failed")
+        wall = time.perf_counter() - t0
+    return wall, cells, pairs
+
+
+def _port_sample(opts, mf, seqs, names, k):
+    """fallback when the binary is absent: the oracle port, 1 thread"""
+    from oracle import pyoracle as po
+    from prographmsa_b200 import alphabet, distance
+    tab, go, ge = distance.nw_table(alphabet.AA)
+    sub = [alphabet.AA.nw_codes(seqs[x]) for x in names[:k]]
+    t0 = time.perf_counter()
+    po.nw_ml_all_pairs(sub, 20, tab, go, ge, mf.Q, mf.freqs, opts)
+    wall = time.perf_counter() - t0
+    L = [len(s) for s in sub]
+    cells = sum((L[a] + 1) * (L[b] + 1) for a in range(k) for b in range(a + 1, k))
+    return wall, cells, k * (k - 1) // 2
+
+
+def cpu_baseline(opts, mf, seqs, names):
+    from oracle import pyoracle as po
+    if po.ref_binary():
+        k = 72                                       # 2,556 pairs ~ 4.1e8 cells: ~10 s on one core
+        wall, cells, pairs = _run_ref_instances(seqs, names, [names[:k]])
+        return dict(value=cells / wall / 1e9, unit=UNIT, cores=1, kind="reference",
+                    sample="oracle/_ref/ProGraphMSA_64 -a -m -i 0 -T on the first %d of the %d sequences (%d pairs, %.3g cells, %.1f s wall, "
+                           "incl. its BioNJ of %d taxa)" % (k, N_SEQ, pairs, cells, wall, k))
+    k = 24
+    wall, cells, pairs = _port_sample(opts, mf, seqs, names, k)
+    return dict(value=cells / wall / 1e9, unit=UNIT, cores=1, kind="port",
+                sample="oracle port on the first %d sequences (%d pairs, %.1f s)" % (k, pairs, wall))
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import pyoracle as po
+    opts, mf, seqs, names, _ = make_family()
+    cores = os.cpu_count() or 1
+    inst = max(1, min(cores, 64))
+    per = 24                                         # 276 pairs ~ 4.4e7 cells ~ 1 s per instance per step
+    per = min(per, max(2, N_SEQ // inst))
+    rng = np.random.default_rng(0)
+
+    def groups():
+        perm = rng.permutation(N_SEQ)
+        return [[names[i] for i in perm[g * per:(g + 1) * per]] for g in range(inst)]
+
+    if not po.ref_binary():
+        wall, cells, pairs = _port_sample(opts, mf, seqs, names, 24)
+        val = cells / wall / 1e9
+        line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=wall * 1e3,
+                    higher_is_better=True, scaling="strong", vs_baseline=None, dtype="int32+f64", data="synthetic",
+                    config=dict(workload=WORKLOAD), impl="reference",
+                    cpu_baseline=dict(value=val, unit=UNIT, cores=1, kind="port", sample="oracle port, first 24 sequences"),
+                    e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line)); return
+    for _ in range(args.warmup):
+        _run_ref_instances(seqs, names, groups())
+    tot_wall = tot_cells = 0.0
+    tot_pairs = 0
+    for _ in range(args.steps):
+        wall, cells, pairs = _run_ref_instances(seqs, names, groups())
+        tot_wall += wall; tot_cells += cells; tot_pairs += pairs
+    val = tot_cells / tot_wall / 1e9
+    sample = ("%d parallel single-threaded instances of oracle/_ref/ProGraphMSA_64 (-a -m -i 0 -T), each on a random %d-sequence "
+              "subsample of the family (%d pairs per step in total)" % (inst, per, tot_pairs // max(1, args.steps)))
+    line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=tot_wall / args.steps * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
+                dtype="int32+f64", data="synthetic", config=dict(workload=WORKLOAD, sample=sample), impl="reference",
+                cpu_baseline=dict(value=val, unit=UNIT, cores=inst, kind="reference", sample=sample),
+                e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def graph_dp_bench(ctx, torch, steps, warmup, pk):
+    """graph-DP GCUPS on 1 GPU: every internal-node alignGraphs job of a progressive pass over a
+    GRAPH_N_SEQ x 400 aa family (leaf x leaf up to profile x profile graphs), staged once and run as
+    one batch (value), and through alignGraphsBatch with host graphs (e2e)."""
+    from prographmsa_b200 import model, synth, progressive, graphalign
+    from prographmsa_b200.options import Options
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(GRAPH_N_SEQ, SEQ_LEN, mf, seed=SEED + 1)
+    tree = progressive.from_synth(root)
+    jobs = []
+
+    def batch(js, o):
+        jobs.extend(js)
+        return graphalign.alignGraphsBatch(js, o, ctx=ctx)
+    progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
+    out = {}
+    for mode_name, mode in (("exact", graphalign.EMISSION_EXACT), ("tensor", graphalign.EMISSION_TENSOR)):
+        try:
+            gb = graphalign.GraphBatch(jobs, opts, mode, ctx)
+            gb.run(); ctx.sync()
+        except Exception as e:      # tensor flavour may be unavailable in an early round
+            out[mode_name] = dict(unavailable=str(e)); continue
+        try:
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            ctx.enable_timing(True)
+            for _ in range(warmup):
+                gb.run(); ctx.sync()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            tm = dict(emission_ms=0.0, graph_fill_ms=0.0, graph_trace_ms=0.0, launches=0)
+            upd = cells = 0
+            for a, b in ev:
+                flush.fill_(1); torch.cuda.synchronize()
+                a.record(); gb.run(); ctx.sync(); b.record(); torch.cuda.synchronize()
+                t = ctx.timing()
+                for k in ("emission_ms", "graph_fill_ms", "graph_trace_ms"):
+                    tm[k] += t[k]
+                tm["launches"] += t["emission_launches"] + t["graph_fill_launches"] + t["graph_trace_launches"]
+                upd, cells = t["graph_cell_updates"], t["graph_cells"]
+            ms = sum(a.elapsed_time(b) for a, b in ev) / steps
+            res = gb.fetch()
+            # e2e: host graphs in, mappings out, per step
+            t0 = time.perf_counter()
+            for _ in range(max(1, steps // 2)):
+                graphalign.alignGraphsBatch(jobs, opts, mode, ctx)
+            e2e_ms = (time.perf_counter() - t0) / max(1, steps // 2) * 1e3
+            fill_ms = tm["graph_fill_ms"] / steps
+            # algorithmic HBM bytes of the fill kernel: 4 B S read + 16 B {M,X,Y,W} write per cell
+            alg_bytes = 20.0 * cells
+            out[mode_name] = dict(
+                value=upd / ms / 1e6, unit="GCUPS", ms_per_step=ms, jobs=len(jobs), cell_updates=upd, cells=cells,
+                e2e=dict(value=upd / e2e_ms / 1e6, unit="GCUPS", ms_per_step=e2e_ms),
+                kernels_ms=dict(emission=tm["emission_ms"] / steps, fill=fill_ms, trace=tm["graph_trace_ms"] / steps),
+                gpu_launches=tm["launches"],
+                roofline=dict(bound="hbm", kernel="graph_fill_kernel", achieved=alg_bytes / fill_ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
+                              frac=alg_bytes / fill_ms / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                              note="algorithmic bytes = 20 B/cell (4 B S read + 16 B MXYW write); the wavefront is dependency-latency bound"),
+                score_checksum=float(sum(r["score"] for r in res)))
+        finally:
+            gb.close()
+    out["workload"] = "all %d alignGraphs jobs of a progressive pass over %d synthetic seqs x %d aa (WAG), one batch" % (
+        len(jobs), GRAPH_N_SEQ, SEQ_LEN)
+    return out
+
+
+def run_ours(args):
+    import torch
+    from prographmsa_b200 import _lib, alphabet, distance
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pk = peaks()
+    opts, mf, seqs, names, _ = make_family()
+    AA = alphabet.AA
+    code_list = [AA.nw_codes(seqs[k]) for k in names]
+    codes, offsets = distance.pack_sequences(code_list)
+    tab, go, ge = distance.nw_table(AA)
+    keep = []
+    prm = distance.make_ml_params(mf, opts, keep)
+    P = N_SEQ * (N_SEQ - 1) // 2
+    per = (P + world - 1) // world                         # equal-sized shards (the last one is padded)
+    pb, pe = min(P, rank * per), min(P, (rank + 1) * per)
+    cells_total = 0
+    L = np.diff(offsets.astype(np.int64))
+    for i in range(N_SEQ):
+        cells_total += int(((L[i] + 1) * (L[i + 1:] + 1)).sum())
+
+    ctx = _lib.Context(local)
+    ctx.enable_timing(True)
+    lib = _lib.lib()
+    h_codes = torch.from_numpy(codes).pin_memory()
+    d_codes = h_codes.cuda()
+    d_out = torch.zeros(2, per, dtype=torch.float64, device="cuda")          # [dist; var] of my shard
+    d_all = torch.zeros(world, 2, per, dtype=torch.float64, device="cuda") if world > 1 else None
+    h_out = torch.zeros(world, 2, per, dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def vp(t):
+        return C.c_void_p(t.data_ptr())
+
+    def step_resident():
+        _lib.check(lib.pgm_nw_ml_pair_range_dev(ctx.handle, C.byref(prm), vp(d_codes), offsets.ctypes.data_as(C.c_void_p), N_SEQ,
+                                                tab.ctypes.data_as(C.c_void_p), go, ge, C.c_int64(pb), C.c_int64(pe),
+                                                vp(d_out[0]), vp(d_out[1]), None, None, None))
+        if world > 1:
+            dist.all_gather_into_tensor(d_all.view(-1), d_out.view(-1))
+
+    def step_e2e():
+        d_codes.copy_(h_codes, non_blocking=True)                            # H2D of this step's input
+        torch.cuda.current_stream().synchronize()
+        step_resident()
+        src = d_all if world > 1 else d_out.unsqueeze(0)
+        if rank == 0:
+            h_out.copy_(src, non_blocking=True)                               # D2H of the step's result
+        torch.cuda.current_stream().synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, acc=None):
+        tot = 0.0
+        for _ in range(steps):
+            flush.fill_(1)
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([a.elapsed_time(b)], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tot += float(t.item())
+            if acc is not None:
+                tm = ctx.timing()
+                for k in acc:
+                    acc[k] += tm[k]
+        return tot
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    acc = dict(nw_forward_ms=0.0, nw_walk_ms=0.0, ml_ms=0.0, nw_forward_launches=0, nw_walk_launches=0, ml_launches=0,
+               tb_bytes=0, ml_evaluations=0, nw_cells=0)
+    total_ms = timed(step_resident, args.steps, acc)
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_e2e()
+    e2e_ms = timed(step_e2e, args.steps)
+    # C-ABI host-buffer call (what the reference-side shim calls), rank-local range, for the record
+    dd = np.zeros(max(1, pe - pb)); vv = np.zeros(max(1, pe - pb))
+    t0 = time.perf_counter()
+    _lib.check(lib.pgm_nw_ml_pair_range(ctx.handle, C.byref(prm), codes.ctypes.data_as(C.c_void_p), offsets.ctypes.data_as(C.c_void_p), N_SEQ,
+                                        tab.ctypes.data_as(C.c_void_p), go, ge, C.c_int64(pb), C.c_int64(pe),
+                                        dd.ctypes.data_as(C.c_void_p), vv.ctypes.data_as(C.c_void_p), None, None, None))
+    cabi_host_ms = (time.perf_counter() - t0) * 1e3
+
+    if rank == 0:
+        ms = total_ms / args.steps
+        e2e = e2e_ms / args.steps
+        fwd_launches = max(1, acc["nw_forward_launches"])
+        fwd_ms = acc["nw_forward_ms"] / fwd_launches                          # average launch duration (this rank)
+        cells_rank = acc["nw_cells"] / args.steps
+        tb_rank = acc["tb_bytes"] / args.steps
+        launches_per_step = (acc["nw_forward_launches"] + acc["nw_walk_launches"] + acc["ml_launches"]) / args.steps
+        # algorithmic HBM bytes of the forward kernel per launch: the packed traceback it must write
+        # (2 bits/cell rounded up to the lane layout) + both sequences of every pair read once
+        seq_bytes = float(sum(int(L[i]) * (N_SEQ - 1 - i) + int(L[i + 1:].sum()) for i in range(N_SEQ))) / world
+        alg_bytes_launch = (tb_rank + seq_bytes) / (fwd_launches / args.steps)
+        cells_launch = cells_rank / (fwd_launches / args.steps)
+        lane_ops = 148 * 128 * pk["sm_max_mhz"] * 1e6                        # int32 lane-ops/s at max clock
+        line = dict(
+            metric=METRIC, value=cells_total / ms / 1e6, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+            ms_per_step=ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="int32+f64", data="synthetic",
+            config=dict(workload=WORKLOAD, pairs=P, nw_cells=cells_total, sharding="pair range / rank, NCCL all-gather of (dist,var)" if world > 1 else "single GPU",
+                        l2="256 MiB flush write between timed steps; per-step working set (%.1f GB packed traceback) >> 126 MB L2" % (tb_rank * world / 1e9)),
+            seconds_per_matrix=ms / 1e3,
+            e2e=dict(value=cells_total / e2e / 1e6, unit=UNIT, ms_per_step=e2e, h2d_bytes_per_step=int(codes.nbytes),
+                     d2h_bytes_per_step=int(world * 2 * per * 8), cabi_host_call_ms_rank0=cabi_host_ms),
+            gpu_launches=int(launches_per_step * args.steps),
+            kernels_ms_per_step=dict(nw_forward=acc["nw_forward_ms"] / args.steps, nw_walk=acc["nw_walk_ms"] / args.steps, ml=acc["ml_ms"] / args.steps),
+            ml_evaluations_per_step=acc["ml_evaluations"] / args.steps,
+            clocks=clocks,
+            roofline=dict(bound="hbm", kernel="nw_forward_kernel", achieved=alg_bytes_launch / fwd_ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
+                          frac=alg_bytes_launch / fwd_ms / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                          launch_ms=fwd_ms, algorithmic_bytes_per_launch=alg_bytes_launch),
+            roofline_issue=dict(bound="sm integer issue", kernel="nw_forward_kernel", achieved=9.0 * cells_launch / fwd_ms / 1e9,
+                                peak=lane_ops / 1e12, unit="Tlane-op/s", frac=9.0 * cells_launch / fwd_ms / 1e9 / (lane_ops / 1e12),
+                                note="algorithmic work = 9 int ops/cell (SURVEY.md §8d); peak = 148 SM x 128 lanes x sm_max_mhz",
+                                gcups_kernel=cells_launch / fwd_ms / 1e6),
+        )
+        if world == 1:
+            line["cpu_baseline"] = cpu_baseline(opts, mf, seqs, names)
+            try:
+                line["graph_dp"] = graph_dp_bench(ctx, torch, max(3, args.steps // 2), 3, pk)
+            except Exception as e:                                            # never lose the headline line
+                line["graph_dp"] = dict(error=repr(e))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

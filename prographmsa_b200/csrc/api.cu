@@ -21,7 +21,7 @@ struct TimedSection { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; };
 struct pgm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    uint64_t scratch_bytes = 6ull << 30;
+    uint64_t scratch_bytes = 8ull << 30;
     bool timing_on = false;
     pgm_timing timing{};
     std::vector<TimedSection> sections;       // pending (resolved at sync)
@@ -29,7 +29,8 @@ struct pgm_ctx {
     // model cache
     DevBuf d_model; std::vector<double> cachedQ; int cached_n = 0;
     // HP-2 scratch
-    DevBuf d_codes, d_descs, d_tasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
+    std::vector<NwTask> h_tasks; std::vector<int8_t> h_tab8;
+    DevBuf d_off, d_codes, d_descs, d_tasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
            d_counts, d_scores, d_misc, d_rows, d_seqlen;
     HostPinned h_stage;
 };
@@ -100,7 +101,7 @@ void pgm_destroy(pgm_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     resolve_timing(c);
-    for (DevBuf* b : {&c->d_model, &c->d_codes, &c->d_descs, &c->d_tasks, &c->d_tab, &c->d_tb, &c->d_colbuf, &c->d_list,
+    for (DevBuf* b : {&c->d_model, &c->d_off, &c->d_codes, &c->d_descs, &c->d_tasks, &c->d_tab, &c->d_tb, &c->d_colbuf, &c->d_list,
                       &c->d_list_len, &c->d_gaps, &c->d_dist, &c->d_var, &c->d_counts, &c->d_scores, &c->d_misc, &c->d_rows,
                       &c->d_seqlen}) b->release();
     c->h_stage.release();
@@ -179,15 +180,14 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     MlDev ml; int rc = prepare_model(c, prm, ml); if (rc) return rc;
     const int n = prm->n_states, n1 = n + 1;
 
-    // score table -> int8 (reference tables are within [-4, 11]; reject anything that does not fit)
-    std::vector<int8_t> tab8((size_t)n1 * n1);
+    // score table -> int8 (reference tables are within [-4, 11])
+    std::vector<int8_t>& tab8 = c->h_tab8; tab8.assign((size_t)n1 * n1, 0);
     for (size_t i = 0; i < tab8.size(); ++i) {
-        if (score_tab[i] < -128 || score_tab[i] > 127) { pgm_set_error("score table entry %d does not fit int8", score_tab[i]); return PGM_ERR_ARG; }
+        if (score_tab[i] < -32 || score_tab[i] > 31) { pgm_set_error("score table entry %d outside [-32, 31] (the profile stores 4*score+3 as int8)", score_tab[i]); return PGM_ERR_ARG; }
         tab8[i] = (int8_t)score_tab[i];
     }
     rc = c->d_tab.reserve(tab8.size()); if (rc) return rc;
     PGM_CUDA(cudaMemcpyAsync(c->d_tab.p, tab8.data(), tab8.size(), cudaMemcpyHostToDevice, c->stream));
-    PGM_CUDA(cudaStreamSynchronize(c->stream));    // tab8 is a stack-lifetime buffer
 
     // per-call outputs that live across chunks
     rc = c->d_list_len.reserve((size_t)np * 4); if (rc) return rc;
@@ -201,90 +201,84 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     int max_len = 0;
     for (int k = 0; k < N; ++k) max_len = std::max<int>(max_len, (int)(offsets[k + 1] - offsets[k]));
     if (max_len > 60000) { pgm_set_error("sequence length %d exceeds the supported 60000", max_len); return PGM_ERR_ARG; }
+    const int C = nw_pick_C(max_len);
+    const int max_bands = std::max(1, (max_len + 32 * C - 1) / (32 * C));
+    const uint32_t colstride = (uint32_t)((max_len + 2 + 31) & ~31);
 
-    // walk the range row by row, cutting chunks by the traceback scratch budget
+    // offsets on the device: pairs are derived from them inside the kernels (no per-pair descriptors)
+    rc = c->d_off.reserve((size_t)(N + 1) * 4); if (rc) return rc;
+    PGM_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+
+    // tasks = up to 32 consecutive pairs of one row; chunks = runs of tasks that fit the traceback budget
     const uint64_t tb_budget_words = std::max<uint64_t>(c->scratch_bytes / 4, 1u << 20);
-    int64_t i, j; pair_from_index_host(pb, N, i, j);
-    int64_t p = pb;
-    std::vector<PairDesc> descs; std::vector<NwTask> tasks;
-    const int JC = 4 * 8;                          // pairs per CTA task (4 per warp)
-    while (p < pe) {
-        descs.clear(); tasks.clear();
+    std::vector<NwTask>& tasks = c->h_tasks;
+    std::vector<size_t> chunk_end;                      // task index where each chunk ends
+    std::vector<uint64_t> chunk_tb, chunk_list, chunk_cells;
+    tasks.clear();
+    {
+        int64_t i, j; pair_from_index_host(pb, N, i, j);
+        int64_t p = pb;
         uint64_t tb_words = 0, list_entries = 0, cells = 0;
-        int chunk_maxL1 = 0, chunk_maxL2 = 0;
-        // pass 1: decide chunk extent + C (C depends on the longest seq1 of the chunk)
-        int64_t ci = i, cj = j, cp = p;
-        while (cp < pe) {
-            const int L1 = (int)(offsets[ci + 1] - offsets[ci]);
-            const int L2 = (int)(offsets[cj + 1] - offsets[cj]);
-            const int newmax = std::max(chunk_maxL1, L1);
-            const int Cn = nw_pick_C(newmax);
-            const int nb = (L1 + 32 * Cn - 1) / (32 * Cn);
-            const uint64_t w = (uint64_t)nb * (L2 + 31) * 32;
-            // conservative: band count may shrink if C grows later, never grows
-            if (!descs.empty() && tb_words + w > tb_budget_words) break;
-            if (descs.size() >= (size_t)(48u << 20) / sizeof(PairDesc) * 8) break;   // <= 384 MiB of descriptors
-            PairDesc d; d.s1_off = offsets[ci]; d.s2_off = offsets[cj]; d.L1 = L1; d.L2 = L2;
-            d.tb_off = 0; d.list_off = 0; d.out_idx = (uint32_t)(cp - pb);
-            descs.push_back(d);
-            tb_words += w; chunk_maxL1 = newmax; chunk_maxL2 = std::max(chunk_maxL2, L2);
-            ++cp; ++cj;
-            if (cj >= N) { ++ci; cj = ci + 1; }
+        while (p < pe) {
+            const int64_t row_end = std::min<int64_t>(N, j + (pe - p));          // exclusive j bound within this row
+            const uint32_t L1 = offsets[i + 1] - offsets[i];
+            const uint32_t nb = (L1 + 32u * C - 1u) / (32u * C);
+            for (int64_t j0 = j; j0 < row_end; j0 += NW_TASK_PAIRS) {
+                const int64_t j1 = std::min<int64_t>(row_end, j0 + NW_TASK_PAIRS);
+                const uint64_t span = offsets[j1] - offsets[j0];
+                const uint64_t w = (uint64_t)nb * 32u * (span + 31u * (uint64_t)(j1 - j0));
+                if (tb_words > 0 && (tb_words + w > tb_budget_words || list_entries + span > 0xf0000000ull)) {
+                    chunk_end.push_back(tasks.size()); chunk_tb.push_back(tb_words); chunk_list.push_back(list_entries);
+                    chunk_cells.push_back(cells);
+                    tb_words = 0; list_entries = 0; cells = 0;
+                }
+                NwTask t; t.i = (uint32_t)i; t.j0 = (uint32_t)j0; t.j1 = (uint32_t)j1; t.out_base = (uint32_t)(p - pb);
+                t.tb_base = tb_words; t.list_base = (uint32_t)list_entries; t.pad = 0;
+                tasks.push_back(t);
+                tb_words += w; list_entries += span;
+                cells += (uint64_t)(L1 + 1) * (span + (uint64_t)(j1 - j0));      // sum (L1+1)(L2+1)
+                p += j1 - j0;
+            }
+            ++i; j = i + 1;
         }
-        const int C = nw_pick_C(chunk_maxL1);
-        const int max_bands = std::max(1, (chunk_maxL1 + 32 * C - 1) / (32 * C));
-        // pass 2: offsets + tasks (consecutive descs share seq1 while s1_off is unchanged)
-        tb_words = 0;
-        for (size_t k = 0; k < descs.size(); ++k) {
-            PairDesc& d = descs[k];
-            const int nb = ((int)d.L1 + 32 * C - 1) / (32 * C);
-            d.tb_off = tb_words; tb_words += (uint64_t)nb * (d.L2 + 31) * 32;
-            d.list_off = (uint32_t)list_entries; list_entries += std::min(d.L1, d.L2);
-            cells += (uint64_t)(d.L1 + 1) * (d.L2 + 1);
-            if (tasks.empty() || descs[tasks.back().desc_begin].s1_off != d.s1_off || descs[tasks.back().desc_begin].L1 != d.L1 ||
-                k - tasks.back().desc_begin >= (size_t)JC) {
-                NwTask t; t.desc_begin = (uint32_t)k; t.desc_end = (uint32_t)k + 1; tasks.push_back(t);
-            } else tasks.back().desc_end = (uint32_t)k + 1;
-        }
-        if (list_entries > 0xffffffffull) { pgm_set_error("chunk too large"); return PGM_ERR_ARG; }
-        const int npairs = (int)descs.size(), ntasks = (int)tasks.size();
-        const uint32_t colstride = (uint32_t)((chunk_maxL2 + 2 + 31) & ~31);
-
-        if ((rc = c->d_descs.reserve(descs.size() * sizeof(PairDesc)))) return rc;
-        if ((rc = c->d_tasks.reserve(tasks.size() * sizeof(NwTask)))) return rc;
-        if ((rc = c->d_tb.reserve(std::max<uint64_t>(tb_words, 1) * 4))) return rc;
-        if ((rc = c->d_list.reserve(std::max<uint64_t>(list_entries, 1) * 2))) return rc;
-        if ((rc = c->d_colbuf.reserve((size_t)ntasks * 8 * 2 * colstride * 4))) return rc;
-        // stage descriptors through pinned memory so the copy is truly async
-        const size_t stage_bytes = descs.size() * sizeof(PairDesc) + tasks.size() * sizeof(NwTask);
-        PGM_CUDA(cudaStreamSynchronize(c->stream));            // previous chunk may still read the staging area
-        if ((rc = c->h_stage.reserve(stage_bytes))) return rc;
-        memcpy(c->h_stage.p, descs.data(), descs.size() * sizeof(PairDesc));
-        memcpy(c->h_stage.as<char>() + descs.size() * sizeof(PairDesc), tasks.data(), tasks.size() * sizeof(NwTask));
-        PGM_CUDA(cudaMemcpyAsync(c->d_descs.p, c->h_stage.p, descs.size() * sizeof(PairDesc), cudaMemcpyHostToDevice, c->stream));
-        PGM_CUDA(cudaMemcpyAsync(c->d_tasks.p, c->h_stage.as<char>() + descs.size() * sizeof(PairDesc), tasks.size() * sizeof(NwTask),
-                                 cudaMemcpyHostToDevice, c->stream));
+        chunk_end.push_back(tasks.size()); chunk_tb.push_back(tb_words); chunk_list.push_back(list_entries);
+        chunk_cells.push_back(cells);
+    }
+    uint64_t max_tb = 1, max_list = 1; size_t max_tasks = 1, prev = 0;
+    for (size_t k = 0; k < chunk_end.size(); ++k) {
+        max_tb = std::max(max_tb, chunk_tb[k]); max_list = std::max(max_list, chunk_list[k]);
+        max_tasks = std::max(max_tasks, chunk_end[k] - prev); prev = chunk_end[k];
+    }
+    if ((rc = c->d_tasks.reserve(tasks.size() * sizeof(NwTask)))) return rc;
+    if ((rc = c->d_tb.reserve(max_tb * 4))) return rc;
+    if ((rc = c->d_list.reserve(max_list * 2))) return rc;
+    if ((rc = c->d_colbuf.reserve(max_bands > 1 ? max_tasks * 8 * 2 * colstride * 4 : 256))) return rc;
+    PGM_CUDA(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), tasks.size() * sizeof(NwTask), cudaMemcpyHostToDevice, c->stream));
+    size_t t0 = 0;
+    for (size_t k = 0; k < chunk_end.size(); ++k) {
+        const int ntasks = (int)(chunk_end[k] - t0);
+        const NwTask* dt = c->d_tasks.as<NwTask>() + t0;
         {
             ScopedKernelTimer t(c, K_NW_FWD);
-            rc = launch_nw_forward(c->stream, C, ntasks, n, max_bands, d_codes, c->d_descs.as<PairDesc>(), c->d_tasks.as<NwTask>(),
-                                   c->d_tab.as<int8_t>(), go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores);
+            rc = launch_nw_forward(c->stream, C, ntasks, n, max_bands, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tab.as<int8_t>(),
+                                   go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores);
             if (rc) return rc;
         }
         {
             ScopedKernelTimer t(c, K_NW_WALK);
-            rc = launch_nw_walk(c->stream, C, npairs, n, d_codes, c->d_descs.as<PairDesc>(), c->d_tb.as<uint32_t>(),
+            rc = launch_nw_walk(c->stream, C, ntasks, n, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tb.as<uint32_t>(),
                                 c->d_list.as<uint16_t>(), c->d_list_len.as<uint32_t>(), d_gaps, d_err);
             if (rc) return rc;
         }
         {
             ScopedKernelTimer t(c, K_ML);
-            rc = launch_ml_from_lists(c->stream, ml, npairs, c->d_descs.as<PairDesc>(), c->d_list.as<uint16_t>(),
+            rc = launch_ml_from_lists(c->stream, ml, C, ntasks, c->d_off.as<uint32_t>(), dt, c->d_list.as<uint16_t>(),
                                       c->d_list_len.as<uint32_t>(), d_gaps, d_dist, d_var, d_counts, d_evals);
             if (rc) return rc;
         }
-        c->timing.nw_cells += cells;
-        c->timing.tb_bytes += tb_words * 4;
-        p = cp; i = ci; j = cj;
+        c->timing.nw_cells += chunk_cells[k];
+        c->timing.tb_bytes += chunk_tb[k] * 4;
+        t0 = chunk_end[k];
     }
     // error flag + evaluation counter come back with the sync of whoever consumes the results
     struct { int err; int pad[3]; unsigned long long evals; } h;

@@ -18,14 +18,11 @@
 // no divergence.  FP64 on CUDA cores; agreement with the reference is ~1e-13 relative on P(t).
 #include "internal.h"
 
-#define ML_WARPS 4
-#define ML_THREADS (ML_WARPS * 32)
-
 enum { FRONT_LIST = 0, FRONT_ROWS = 1, FRONT_COUNTS = 2 };
 
 struct MlFront {
     // LIST
-    const PairDesc* descs; const uint16_t* list; const uint32_t* list_len; const uint32_t* gaps_in;
+    const NwTask* tasks; const uint32_t* off; int C; const uint16_t* list; const uint32_t* list_len; const uint32_t* gaps_in;
     // ROWS
     const uint8_t* rows; int N; int L; long long pair_begin;
     // COUNTS
@@ -50,28 +47,40 @@ __device__ __forceinline__ void pair_from_index(long long p, int N, int& i, int&
     j = (int)(p - (ii * N - ii * (ii + 1) / 2) + ii + 1);
 }
 
-template <int FRONT>
-__global__ void __launch_bounds__(ML_THREADS)
+// ATAB (n <= 20): the products A[(i,j)][k] = V(i,k) Vi(k,j) live in shared memory (stride n+1 doubles,
+// conflict-free for LDS.64), so one likelihood evaluation costs one load + three FMAs per (entry, k).
+// Each lane register-blocks EB entries so the broadcast loads of the per-k weights are shared.
+#define ML_EB 4
+
+template <int FRONT, bool ATAB, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
 ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out, double* __restrict__ var_out,
           unsigned long long* __restrict__ evals_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int n = ml.n, nn = n * n;
-    double* sV = (double*)smem_raw;            // n*n
-    double* sVi = sV + nn;                     // n*n
-    double* sSig = sVi + nn;                   // n
-    double* sW = sSig + n;                     // ML_WARPS * 3 * n
-    uint32_t* sHist = (uint32_t*)(sW + ML_WARPS * 3 * n);   // ML_WARPS * nn
+    const int n = ml.n, nn = n * n, astride = n + 1;
+    double* sA = (double*)smem_raw;                                   // ATAB: nn*(n+1); else V (nn) then Vi (nn)
+    double* sV = sA; double* sVi = sA + nn;
+    double* sSig = sA + (ATAB ? nn * astride : 2 * nn);              // n
+    double* sW = sSig + ((n + 1) & ~1);                               // WARPS * n * 4   {w0,w1,w2,pad}
+    uint32_t* sHist = (uint32_t*)(sW + WARPS * n * 4);                // WARPS * nn
 
-    for (int i = threadIdx.x; i < nn; i += ML_THREADS) { sV[i] = ml.V[i]; sVi[i] = ml.Vi[i]; }
-    for (int i = threadIdx.x; i < n; i += ML_THREADS) sSig[i] = ml.sigma[i];
+    if (ATAB) {
+        for (int i = threadIdx.x; i < nn * n; i += WARPS * 32) {
+            const int e = i / n, k = i - e * n, r = e / n, c = e - r * n;
+            sA[e * astride + k] = ml.V[r * n + k] * ml.Vi[k * n + c];
+        }
+    } else {
+        for (int i = threadIdx.x; i < nn; i += WARPS * 32) { sV[i] = ml.V[i]; sVi[i] = ml.Vi[i]; }
+    }
+    for (int i = threadIdx.x; i < n; i += WARPS * 32) sSig[i] = ml.sigma[i];
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* w0 = sW + warp * 3 * n; double* w1 = w0 + n; double* w2 = w1 + n;
+    double* wb = sW + warp * n * 4;
     uint32_t* hist = sHist + warp * nn;
     unsigned long long my_evals = 0;
 
-    for (long long p = (long long)blockIdx.x * ML_WARPS + warp; p < n_pairs; p += (long long)gridDim.x * ML_WARPS) {
+    for (long long p = (long long)blockIdx.x * WARPS + warp; p < n_pairs; p += (long long)gridDim.x * WARPS) {
         for (int i = lane; i < nn; i += 32) hist[i] = 0;
         __syncwarp();
         uint32_t gaps = 0;
@@ -79,7 +88,11 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
         long long out_idx = p;
 
         if (FRONT == FRONT_LIST) {
-            const PairDesc d = fr.descs[p];
+            // p enumerates (task, slot); slots past the task's last pair are empty
+            const NwTask task = fr.tasks[p >> 5];
+            const uint32_t j = task.j0 + (uint32_t)(p & 31);
+            if (j >= task.j1) continue;
+            const NwPair d = nw_pair(task, j, fr.off, fr.C);
             out_idx = d.out_idx;
             const uint32_t len = fr.list_len[out_idx];
             const uint16_t* lp = fr.list + d.list_off;
@@ -154,6 +167,7 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
                 // computeMLDist (DistanceFactoryML.h:66-136)
                 const double var0 = var;
                 double dist_min = 0, dist_max = INFINITY, delta = 1;
+                double last_tc = -1.0, last_f = 0, last_ff = 0;
                 unsigned iteration = 0;
                 while (fabs(delta) > 1e-5) {
                     if (iteration > 20) {
@@ -163,28 +177,51 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
                     }
                     double tc = (0.0 < dist) ? dist : 0.0;                 // parseDistance (ModelFactory.h:104,125)
                     tc = fmax(fmin(tc, ml.max_dist), ml.min_dist);
-                    __syncwarp();
-                    for (int k = lane; k < n; k += 32) {
-                        const double s = sSig[k], e = exp(s * tc);
-                        w0[k] = e; w1[k] = s * e; w2[k] = s * s * e;
-                    }
-                    __syncwarp();
-                    double f = 0, ff = 0;
-                    for (uint32_t q = lane; q < nnz; q += 32) {
-                        const uint32_t h = hist[q];
-                        const int idx = (int)(h >> 20);
-                        const double c = (double)(h & 0xfffffu);
-                        const int i = idx / n, j = idx - i * n;
-                        double pp0 = 0, pp1 = 0, pp2 = 0;
-                        for (int k = 0; k < n; ++k) {
-                            const double a = sV[i * n + k] * sVi[k * n + j];
-                            pp0 = fma(a, w0[k], pp0); pp1 = fma(a, w1[k], pp1); pp2 = fma(a, w2[k], pp2);
+                    double f, ff;
+                    if (tc == last_tc) {
+                        // the likelihood is evaluated at the CLAMPED distance: outside [min_dist, max_dist] the
+                        // reference recomputes the same P, P', P'' every iteration -- reuse the identical sums
+                        f = last_f; ff = last_ff;
+                    } else {
+                        __syncwarp();
+                        for (int k = lane; k < n; k += 32) {
+                            const double s = sSig[k], e = exp(s * tc);
+                            wb[4 * k] = e; wb[4 * k + 1] = s * e; wb[4 * k + 2] = s * s * e;
                         }
-                        f += c * pp1 / pp0;
-                        ff += (c * (pp2 * pp0 - pp1 * pp1)) / (pp0 * pp0);
+                        __syncwarp();
+                        f = 0; ff = 0;
+                        for (uint32_t q0 = 0; q0 < nnz; q0 += 32 * ML_EB) {
+                            int ia[ML_EB], ib[ML_EB]; double cnt[ML_EB], a0[ML_EB], a1[ML_EB], a2[ML_EB];
+#pragma unroll
+                            for (int r = 0; r < ML_EB; ++r) {
+                                const uint32_t q = q0 + lane + 32 * r;
+                                const uint32_t h = (q < nnz) ? hist[q] : 0u;
+                                const int idx = (int)(h >> 20);
+                                cnt[r] = (double)(h & 0xfffffu);
+                                if (ATAB) { ia[r] = idx * astride; ib[r] = 0; }
+                                else { const int i = idx / n; ia[r] = i * n; ib[r] = idx - i * n; }
+                                a0[r] = a1[r] = a2[r] = 0;
+                            }
+                            for (int k = 0; k < n; ++k) {
+                                const double2 w01 = *reinterpret_cast<const double2*>(wb + 4 * k);
+                                const double w2 = wb[4 * k + 2];
+#pragma unroll
+                                for (int r = 0; r < ML_EB; ++r) {
+                                    const double a = ATAB ? sA[ia[r] + k] : sV[ia[r] + k] * sVi[k * n + ib[r]];
+                                    a0[r] = fma(a, w01.x, a0[r]); a1[r] = fma(a, w01.y, a1[r]); a2[r] = fma(a, w2, a2[r]);
+                                }
+                            }
+#pragma unroll
+                            for (int r = 0; r < ML_EB; ++r)
+                                if (cnt[r] != 0) {
+                                    f += cnt[r] * a1[r] / a0[r];
+                                    ff += (cnt[r] * (a2[r] * a0[r] - a1[r] * a1[r])) / (a0[r] * a0[r]);
+                                }
+                        }
+                        f = warp_sum(f); ff = warp_sum(ff);
+                        ++my_evals;
+                        last_tc = tc; last_f = f; last_ff = ff;
                     }
-                    f = warp_sum(f); ff = warp_sum(ff);
-                    ++my_evals;
                     if (ml.mldist_gap_flag) {
                         const double grate = ml.indel_rate * seqlen * dist;
                         f += (-grate + (double)gaps) / dist;
@@ -217,34 +254,42 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
     if (evals_out && lane == 0 && my_evals) atomicAdd(evals_out, my_evals);
 }
 
-static size_t ml_smem(int n) { return sizeof(double) * (2 * n * n + n + ML_WARPS * 3 * n) + sizeof(uint32_t) * ML_WARPS * n * n; }
+template <int FRONT, bool ATAB, int WARPS>
+static int launch_ml_t(cudaStream_t st, const MlDev& ml, const MlFront& fr, long long n_pairs, double* d_dist, double* d_var,
+                       unsigned long long* d_evals) {
+    const int n = ml.n, nn = n * n;
+    const size_t smem = sizeof(double) * ((ATAB ? (size_t)nn * (n + 1) : 2 * (size_t)nn) + ((n + 1) & ~1) + (size_t)WARPS * n * 4) +
+                        sizeof(uint32_t) * (size_t)WARPS * nn;
+    PGM_CUDA(cudaFuncSetAttribute(ml_kernel<FRONT, ATAB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ml_kernel<FRONT, ATAB, WARPS>, WARPS * 32, smem);
+    if (per_sm < 1) per_sm = 1;
+    long long want = (n_pairs + WARPS - 1) / WARPS;
+    long long grid = (long long)sms * per_sm;
+    if (grid > want) grid = want;
+    ml_kernel<FRONT, ATAB, WARPS><<<(unsigned)grid, WARPS * 32, smem, st>>>(ml, fr, n_pairs, d_dist, d_var, d_evals);
+    PGM_CUDA(cudaGetLastError());
+    return 0;
+}
 
 template <int FRONT>
 static int launch_ml(cudaStream_t st, const MlDev& ml, const MlFront& fr, long long n_pairs, double* d_dist, double* d_var,
                      unsigned long long* d_evals) {
     if (n_pairs <= 0) return 0;
-    const size_t smem = ml_smem(ml.n);
     if (ml.n * ml.n >= 4096) { pgm_set_error("ML kernel supports n_states <= 63"); return PGM_ERR_ARG; }
-    PGM_CUDA(cudaFuncSetAttribute(ml_kernel<FRONT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ml_kernel<FRONT>, ML_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
-    long long want = (n_pairs + ML_WARPS - 1) / ML_WARPS;
-    long long grid = (long long)sms * per_sm;
-    if (grid > want) grid = want;
-    ml_kernel<FRONT><<<(unsigned)grid, ML_THREADS, smem, st>>>(ml, fr, n_pairs, d_dist, d_var, d_evals);
-    PGM_CUDA(cudaGetLastError());
-    return 0;
+    if (ml.n <= 20) return launch_ml_t<FRONT, true, 8>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
+    return launch_ml_t<FRONT, false, 4>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
 }
 
-int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_pairs, const PairDesc* d_descs, const uint16_t* d_list,
-                         const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist, double* d_var,
-                         int32_t* d_counts, unsigned long long* d_evals) {
+int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int C, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
+                         const uint16_t* d_list, const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist,
+                         double* d_var, int32_t* d_counts, unsigned long long* d_evals) {
     MlFront fr{};
-    fr.descs = d_descs; fr.list = d_list; fr.list_len = d_list_len; fr.gaps_in = d_gaps; fr.counts_out = d_counts;
-    return launch_ml<FRONT_LIST>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
+    fr.tasks = d_tasks; fr.off = d_off; fr.C = C; fr.list = d_list; fr.list_len = d_list_len; fr.gaps_in = d_gaps;
+    fr.counts_out = d_counts;
+    return launch_ml<FRONT_LIST>(st, ml, fr, (long long)n_tasks * NW_TASK_PAIRS, d_dist, d_var, d_evals);
 }
 
 int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,

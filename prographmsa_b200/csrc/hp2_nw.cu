@@ -19,6 +19,12 @@
 // buffer (L2-resident).  The walk is a separate kernel with one THREAD per pair: it is a dependent
 // chain of ~L1+L2 loads, so it needs tens of thousands of chains in flight, not a warp each.
 //
+// Direction without compares: all DP values are carried scaled by 4 with a 2-bit priority tag in the
+// low bits -- diagonal candidate 4v+3, X = 4v+2, Y = 4v+1, W = 4v -- so one 3-input max both selects
+// the winner and, on ties, the reference's order (diagonal, then X, then Y); the tag of the maximum
+// IS the traceback direction.  The int8 profile stores 4*T+3 directly.  Per cell this is two fused
+// add-max (VIADDMNMX), one 3-input max, one mask and the adds -- no ISETP/SEL chain.
+//
 // Integer arithmetic only: bit-exact against the oracle.
 #include "internal.h"
 
@@ -28,18 +34,22 @@
 
 template <int C>
 __global__ void __launch_bounds__(NW_THREADS)
-nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict__ descs,
+nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
                   const NwTask* __restrict__ tasks, const int8_t* __restrict__ tab, int n1, int go, int ge,
-                  uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out) {
+                  uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out,
+                  int k_one, int k_four) {
+    // k_one == 1, k_four == 4 at run time: opaque multipliers that make the plain adds below integer
+    // multiply-adds, i.e. FMA-pipe instructions, so the ALU pipe (which carries the max/logic ops and
+    // is the kernel's limiter) and the FMA pipe are both busy
     extern __shared__ __align__(16) unsigned char smem[];
     int8_t* s_tab = (int8_t*)smem;                           // n1*n1, padded to 16
     const int tab_bytes = (n1 * n1 + 15) & ~15;
     int8_t* prof = (int8_t*)(smem + tab_bytes);              // [band][r][lane][16]
 
     const NwTask task = tasks[blockIdx.x];
-    const PairDesc d0 = descs[task.desc_begin];
-    const int L1 = (int)d0.L1;
-    const uint8_t* __restrict__ s1 = codes + d0.s1_off;
+    const uint32_t s1_off = off[task.i];
+    const int L1 = (int)(off[task.i + 1] - s1_off);
+    const uint8_t* __restrict__ s1 = codes + s1_off;
     const int nbands = (L1 + 32 * C - 1) / (32 * C);
 
     for (int i = threadIdx.x; i < n1 * n1; i += NW_THREADS) s_tab[i] = tab[i];
@@ -51,7 +61,7 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict_
         const int r = rem >> 9, lk = rem & 511, lane = lk >> 4, k = lk & 15;
         const int x = b * 32 * C + lane * C + k;
         int8_t v = 0;
-        if (k < C && x < L1) v = s_tab[r + n1 * (int)s1[x]];     // scoring_matrix(s2, s1), column-major
+        if (k < C && x < L1) v = (int8_t)(4 * (int)s_tab[r + n1 * (int)s1[x]] + 3);   // 4*scoring_matrix(s2,s1)+3 (diag tag)
         prof[idx] = v;
     }
     __syncthreads();
@@ -60,25 +70,29 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict_
     int32_t* colW = colbuf + (size_t)(blockIdx.x * NW_WARPS + warp) * 2 * colbuf_stride;
     int32_t* colX = colW + colbuf_stride;
 
-    for (uint32_t di = task.desc_begin + warp; di < task.desc_end; di += NW_WARPS) {
-        const PairDesc d = descs[di];
+    for (uint32_t j = task.j0 + warp; j < task.j1; j += NW_WARPS) {
+        const NwPair d = nw_pair(task, j, off, C);
         const int L2 = (int)d.L2;
         const uint8_t* __restrict__ s2 = codes + d.s2_off;
         const int steps = L2 + 31;
         uint32_t* __restrict__ tbp = tb + d.tb_off;
 
+        const int go4 = 4 * go, ge4 = 4 * ge;
+        const int gox = go4 + 2, goy = go4 + 1;               // gap-open into X (tag 2) / into Y (tag 1)
+        const int XINF = 4 * NW_MINFTY + 2, YINF = 4 * NW_MINFTY + 1;
+        const int k_mone = -k_one;
         for (int b = 0; b < nbands; ++b) {
             const int x0 = b * 32 * C + lane * C;            // columns x0+1 .. x0+C (1-based)
-            int Wup[C], Yup[C];
+            int Wup[C], Yup[C];                              // 4*W(y-1,x), 4*Y(y-1,x)+1
 #pragma unroll
-            for (int k = 0; k < C; ++k) { Wup[k] = go + (x0 + k) * ge; Yup[k] = NW_MINFTY; }
-            int Wdiag = (x0 == 0) ? 0 : go + (x0 - 1) * ge;  // W(y-1, x0) for y-1 = 0
+            for (int k = 0; k < C; ++k) { Wup[k] = go4 + (x0 + k) * ge4; Yup[k] = YINF; }
+            int Wdiag = (x0 == 0) ? 0 : go4 + (x0 - 1) * ge4;  // 4*W(y-1, x0) for y-1 = 0
             int Wlast = 0, Xlast = 0, rcur = 0;
             // lane 0 prefetch of its left-boundary inputs for row 1
-            int nxtW = 0, nxtX = NW_MINFTY, nxtR = 0;
+            int nxtW = 0, nxtX = XINF, nxtR = 0;
             if (lane == 0 && L2 > 0) {
                 nxtR = s2[0];
-                if (b == 0) { nxtW = go; } else { nxtW = __ldcg(colW + 1); nxtX = __ldcg(colX + 1); }
+                if (b == 0) { nxtW = go4; } else { nxtW = __ldcg(colW + 1); nxtX = __ldcg(colX + 1); }
             }
             const int8_t* pb = prof + (size_t)b * per_band + lane * 16;
             const bool has_next_band = (b + 1 < nbands);
@@ -92,7 +106,7 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict_
                     const int yn = y + 1;
                     if (yn <= L2) {                            // prefetch next row's inputs
                         nxtR = s2[yn - 1];
-                        if (b == 0) { nxtW = go + (yn - 1) * ge; nxtX = NW_MINFTY; }
+                        if (b == 0) { nxtW = go4 + (yn - 1) * ge4; nxtX = XINF; }
                         else { nxtW = __ldcg(colW + yn); nxtX = __ldcg(colX + yn); }
                     }
                 }
@@ -103,13 +117,13 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict_
                     uint32_t bits = 0;
 #pragma unroll
                     for (int k = 0; k < C; ++k) {
-                        const int s = (int)(int8_t)((pws[k >> 2] >> (8 * (k & 3))) & 0xff);
+                        const int s = (int)(int8_t)((pws[k >> 2] >> (8 * (k & 3))) & 0xff);   // 4*T+3
                         const int wd = dg + s;
-                        const int xv = max(Xleft + ge, Wleft + go);
-                        const int yv = max(Yup[k] + ge, Wup[k] + go);
-                        const int wn = max(max(xv, yv), wd);
-                        const uint32_t dir = (wn == wd) ? 0u : ((wn == xv) ? 1u : 2u);
-                        bits |= dir << (2 * k);
+                        const int xv = __viaddmax_s32(Xleft, ge4, Wleft * k_one + gox);
+                        const int yv = __viaddmax_s32(Yup[k], ge4, Wup[k] * k_one + goy);
+                        const int wt = __vimax3_s32(xv, yv, wd);                              // tagged maximum
+                        const int wn = wt & ~3;
+                        bits = bits * (uint32_t)k_four + (uint32_t)(wn * k_mone + wt);        // tag: 3 diag, 2 left, 1 up
                         dg = Wup[k];
                         Wup[k] = wn; Yup[k] = yv;
                         Wleft = wn; Xleft = xv;
@@ -124,7 +138,7 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict_
                             int v = 0;
 #pragma unroll
                             for (int k = 0; k < C; ++k) if (k == kk) v = Wup[k];
-                            scores_out[d.out_idx] = v;
+                            scores_out[d.out_idx] = v >> 2;
                         }
                     }
                 }
@@ -138,16 +152,19 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const PairDesc* __restrict_
     }
 }
 
-// One thread per pair: follow the 2-bit directions from (L2,L1) until x==0 or y==0
+// One thread per pair (one warp per task): follow the 2-bit tags from (L2,L1) until x==0 or y==0
 // (DistanceFactoryAlign.h:99-123).  Emits the matched state pairs (s1*n+s2, both < n) and the
 // number of gap openings.
 __global__ void __launch_bounds__(128)
-nw_walk_kernel(int C, int n_pairs, int n, const uint8_t* __restrict__ codes, const PairDesc* __restrict__ descs,
-               const uint32_t* __restrict__ tb, uint16_t* __restrict__ list, uint32_t* __restrict__ list_len,
-               uint32_t* __restrict__ gaps_out, int* __restrict__ err) {
-    const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n_pairs) return;
-    const PairDesc d = descs[p];
+nw_walk_kernel(int C, int n_tasks, int n, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
+               const NwTask* __restrict__ tasks, const uint32_t* __restrict__ tb, uint16_t* __restrict__ list,
+               uint32_t* __restrict__ list_len, uint32_t* __restrict__ gaps_out, int* __restrict__ err) {
+    const int ti = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (ti >= n_tasks) return;
+    const NwTask task = tasks[ti];
+    const uint32_t j = task.j0 + (threadIdx.x & 31);
+    if (j >= task.j1) return;
+    const NwPair d = nw_pair(task, j, off, C);
     const uint8_t* __restrict__ s1 = codes + d.s1_off;
     const uint8_t* __restrict__ s2 = codes + d.s2_off;
     const uint32_t* __restrict__ tbp = tb + d.tb_off;
@@ -163,15 +180,15 @@ nw_walk_kernel(int C, int n_pairs, int n, const uint8_t* __restrict__ codes, con
         const int lane = rem / C, k = rem - lane * C;
         const int t = y - 1 + lane;
         const uint32_t w = __ldg(tbp + ((size_t)b * steps + t) * 32 + lane);
-        const uint32_t dir = (w >> (2 * k)) & 3u;
-        if (dir == 0u) {
+        const uint32_t tag = (w >> (2 * (C - 1 - k))) & 3u;       // 3 diagonal, 2 left (X), 1 up (Y)
+        if (tag == 3u) {
             const int c1 = s1[xz], c2 = s2[y - 1];
             if (c1 < n && c2 < n) lp[nl++] = (uint16_t)(c1 * n + c2);
             o1 = o2 = false; --x; --y;
-        } else if (dir == 1u) {
+        } else if (tag == 2u) {
             if (!o1) ++gaps;
             o1 = true; o2 = false; --x;
-        } else if (dir == 2u) {
+        } else if (tag == 1u) {
             if (!o2) ++gaps;
             o1 = false; o2 = true; --y;
         } else {
@@ -185,23 +202,23 @@ nw_walk_kernel(int C, int n_pairs, int n, const uint8_t* __restrict__ codes, con
 
 template <int C>
 static int launch_fwd_t(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
-                        const PairDesc* d_descs, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
+                        const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
                         uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
     const int n1 = n_states + 1;
     const size_t smem = ((n1 * n1 + 15) & ~15) + (size_t)max_bands * n1 * 512;
     if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
     PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nw_forward_kernel<C><<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_descs, d_tasks, d_tab, n1, go, ge, d_tb,
-                                                           d_colbuf, colbuf_stride, d_scores);
+    nw_forward_kernel<C><<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_off, d_tasks, d_tab, n1, go, ge, d_tb,
+                                                           d_colbuf, colbuf_stride, d_scores, 1, 4);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
 
 int launch_nw_forward(cudaStream_t st, int C, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
-                      const PairDesc* d_descs, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
+                      const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
                       uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
     if (n_tasks == 0) return 0;
-#define CASE(c) case c: return launch_fwd_t<c>(st, n_tasks, n_states, max_bands, d_codes, d_descs, d_tasks, d_tab, go, ge, d_tb, d_colbuf, colbuf_stride, d_scores);
+#define CASE(c) case c: return launch_fwd_t<c>(st, n_tasks, n_states, max_bands, d_codes, d_off, d_tasks, d_tab, go, ge, d_tb, d_colbuf, colbuf_stride, d_scores);
     switch (C) {
         CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
     }
@@ -210,11 +227,12 @@ int launch_nw_forward(cudaStream_t st, int C, int n_tasks, int n_states, int max
     return PGM_ERR_ARG;
 }
 
-int launch_nw_walk(cudaStream_t st, int C, int n_pairs, int n_states, const uint8_t* d_codes, const PairDesc* d_descs,
-                   const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps, int* d_err) {
-    if (n_pairs == 0) return 0;
-    nw_walk_kernel<<<(n_pairs + 127) / 128, 128, 0, st>>>(C, n_pairs, n_states, d_codes, d_descs, d_tb, d_list,
-                                                          d_list_len, d_gaps, d_err);
+int launch_nw_walk(cudaStream_t st, int C, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
+                   const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
+                   int* d_err) {
+    if (n_tasks == 0) return 0;
+    nw_walk_kernel<<<(n_tasks + 3) / 4, 128, 0, st>>>(C, n_tasks, n_states, d_codes, d_off, d_tasks, d_tb, d_list,
+                                                      d_list_len, d_gaps, d_err);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -61,14 +61,31 @@ struct HostPinned {
 };
 
 // ---- HP-2 device structs ------------------------------------------------------------------------
-struct PairDesc {           // 32 B, one per sequence pair of a chunk
-    uint32_t s1_off, s2_off;    // offsets of seq1 (columns) / seq2 (rows) into codes
-    uint32_t L1, L2;
-    uint64_t tb_off;            // word offset of this pair's packed traceback
-    uint32_t list_off;          // offset of this pair's matched-state list (uint16 entries)
-    uint32_t out_idx;           // index into the packed outputs
+struct NwTask {             // 32 B: the pairs (i, j0 .. j1-1); one CTA builds seq i's profile once
+    uint32_t i, j0, j1;
+    uint32_t out_base;          // packed-output index of pair (i, j0)
+    uint64_t tb_base;           // word offset of pair (i, j0)'s packed traceback in the chunk scratch
+    uint32_t list_base;         // offset of pair (i, j0)'s matched-state list (uint16 entries)
+    uint32_t pad;
 };
-struct NwTask { uint32_t desc_begin, desc_end; };   // descs sharing seq1: one CTA builds its profile once
+#define NW_TASK_PAIRS 32        // pairs per task (4 per warp of the forward kernel, 1 per lane of the walk)
+
+// Everything else about a pair is derived on the device from the offsets array (a prefix sum of the
+// lengths), so no per-pair descriptor is ever built or copied:
+//   tb_off(i,j)   = tb_base   + nb(L1) * 32 * ((off[j] - off[j0]) + 31 * (j - j0))
+//   list_off(i,j) = list_base + (off[j] - off[j0])            (capacity L2 >= matched pairs)
+struct NwPair { uint32_t s1_off, s2_off, L1, L2, out_idx, list_off; uint64_t tb_off; };
+__device__ __forceinline__ NwPair nw_pair(const NwTask& t, uint32_t j, const uint32_t* __restrict__ off, int C) {
+    NwPair p;
+    p.s1_off = off[t.i]; p.L1 = off[t.i + 1] - p.s1_off;
+    p.s2_off = off[j]; p.L2 = off[j + 1] - p.s2_off;
+    const uint32_t nb = (p.L1 + 32u * C - 1u) / (32u * C);
+    const uint32_t span = (p.s2_off - off[t.j0]);
+    p.tb_off = t.tb_base + (uint64_t)nb * 32u * ((uint64_t)span + 31u * (j - t.j0));
+    p.list_off = t.list_base + span;
+    p.out_idx = t.out_base + (j - t.j0);
+    return p;
+}
 
 struct MlDev {              // ML constants + eigen-basis in device memory
     int n;
@@ -79,14 +96,15 @@ struct MlDev {              // ML constants + eigen-basis in device memory
 
 // kernels (hp2_nw.cu / hp2_ml.cu); all launch on `st`
 int launch_nw_forward(cudaStream_t st, int C, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
-                      const PairDesc* d_descs, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
+                      const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
                       uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores);
-int launch_nw_walk(cudaStream_t st, int C, int n_pairs, int n_states, const uint8_t* d_codes, const PairDesc* d_descs,
-                   const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps, int* d_err);
+int launch_nw_walk(cudaStream_t st, int C, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
+                   const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
+                   int* d_err);
 // front-end LIST: histogram from matched-state lists; ROWS: scan two MSA rows
-int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_pairs, const PairDesc* d_descs, const uint16_t* d_list,
-                         const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist, double* d_var,
-                         int32_t* d_counts, unsigned long long* d_evals);
+int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int C, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
+                         const uint16_t* d_list, const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist,
+                         double* d_var, int32_t* d_counts, unsigned long long* d_evals);
 int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,
                         const uint8_t* d_rows, double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps,
                         unsigned long long* d_evals);
