@@ -29,8 +29,8 @@ struct pgm_ctx {
     // model cache
     DevBuf d_model; std::vector<double> cachedQ; int cached_n = 0;
     // HP-2 scratch
-    std::vector<NwTask> h_tasks; std::vector<int8_t> h_tab8;
-    DevBuf d_off, d_codes, d_descs, d_tasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
+    std::vector<NwTask> h_tasks, h_ftasks; std::vector<int8_t> h_tab8;
+    DevBuf d_off, d_codes, d_descs, d_tasks, d_ftasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
            d_counts, d_scores, d_misc, d_rows, d_seqlen;
     HostPinned h_stage;
 };
@@ -101,7 +101,7 @@ void pgm_destroy(pgm_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     resolve_timing(c);
-    for (DevBuf* b : {&c->d_model, &c->d_off, &c->d_codes, &c->d_descs, &c->d_tasks, &c->d_tab, &c->d_tb, &c->d_colbuf, &c->d_list,
+    for (DevBuf* b : {&c->d_model, &c->d_off, &c->d_ftasks, &c->d_codes, &c->d_descs, &c->d_tasks, &c->d_tab, &c->d_tb, &c->d_colbuf, &c->d_list,
                       &c->d_list_len, &c->d_gaps, &c->d_dist, &c->d_var, &c->d_counts, &c->d_scores, &c->d_misc, &c->d_rows,
                       &c->d_seqlen}) b->release();
     c->h_stage.release();
@@ -201,8 +201,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     int max_len = 0;
     for (int k = 0; k < N; ++k) max_len = std::max<int>(max_len, (int)(offsets[k + 1] - offsets[k]));
     if (max_len > 60000) { pgm_set_error("sequence length %d exceeds the supported 60000", max_len); return PGM_ERR_ARG; }
-    const int C = nw_pick_C(max_len);
-    const int max_bands = std::max(1, (max_len + 32 * C - 1) / (32 * C));
+    const int max_bands = std::max(1, (max_len + 32 * 16 - 1) / (32 * 16));   // only C = 16 is ever multi-band
     const uint32_t colstride = (uint32_t)((max_len + 2 + 31) & ~31);
 
     // offsets on the device: pairs are derived from them inside the kernels (no per-pair descriptors)
@@ -222,6 +221,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
         while (p < pe) {
             const int64_t row_end = std::min<int64_t>(N, j + (pe - p));          // exclusive j bound within this row
             const uint32_t L1 = offsets[i + 1] - offsets[i];
+            const uint32_t C = (uint32_t)nw_pick_C((int)L1);                     // per row: keeps all 32 lanes busy
             const uint32_t nb = (L1 + 32u * C - 1u) / (32u * C);
             for (int64_t j0 = j; j0 < row_end; j0 += NW_TASK_PAIRS) {
                 const int64_t j1 = std::min<int64_t>(row_end, j0 + NW_TASK_PAIRS);
@@ -233,7 +233,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
                     tb_words = 0; list_entries = 0; cells = 0;
                 }
                 NwTask t; t.i = (uint32_t)i; t.j0 = (uint32_t)j0; t.j1 = (uint32_t)j1; t.out_base = (uint32_t)(p - pb);
-                t.tb_base = tb_words; t.list_base = (uint32_t)list_entries; t.pad = 0;
+                t.tb_base = tb_words; t.list_base = (uint32_t)list_entries; t.C = C;
                 tasks.push_back(t);
                 tb_words += w; list_entries += span;
                 cells += (uint64_t)(L1 + 1) * (span + (uint64_t)(j1 - j0));      // sum (L1+1)(L2+1)
@@ -250,6 +250,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
         max_tasks = std::max(max_tasks, chunk_end[k] - prev); prev = chunk_end[k];
     }
     if ((rc = c->d_tasks.reserve(tasks.size() * sizeof(NwTask)))) return rc;
+
     if ((rc = c->d_tb.reserve(max_tb * 4))) return rc;
     if ((rc = c->d_list.reserve(max_list * 2))) return rc;
     if ((rc = c->d_colbuf.reserve(max_bands > 1 ? max_tasks * 8 * 2 * colstride * 4 : 256))) return rc;
@@ -260,19 +261,19 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
         const NwTask* dt = c->d_tasks.as<NwTask>() + t0;
         {
             ScopedKernelTimer t(c, K_NW_FWD);
-            rc = launch_nw_forward(c->stream, C, ntasks, n, max_bands, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tab.as<int8_t>(),
+            rc = launch_nw_forward(c->stream, ntasks, n, max_bands, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tab.as<int8_t>(),
                                    go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores);
             if (rc) return rc;
         }
         {
             ScopedKernelTimer t(c, K_NW_WALK);
-            rc = launch_nw_walk(c->stream, C, ntasks, n, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tb.as<uint32_t>(),
+            rc = launch_nw_walk(c->stream, ntasks, n, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tb.as<uint32_t>(),
                                 c->d_list.as<uint16_t>(), c->d_list_len.as<uint32_t>(), d_gaps, d_err);
             if (rc) return rc;
         }
         {
             ScopedKernelTimer t(c, K_ML);
-            rc = launch_ml_from_lists(c->stream, ml, C, ntasks, c->d_off.as<uint32_t>(), dt, c->d_list.as<uint16_t>(),
+            rc = launch_ml_from_lists(c->stream, ml, ntasks, c->d_off.as<uint32_t>(), dt, c->d_list.as<uint16_t>(),
                                       c->d_list_len.as<uint32_t>(), d_gaps, d_dist, d_var, d_counts, d_evals);
             if (rc) return rc;
         }

@@ -22,7 +22,7 @@ enum { FRONT_LIST = 0, FRONT_ROWS = 1, FRONT_COUNTS = 2 };
 
 struct MlFront {
     // LIST
-    const NwTask* tasks; const uint32_t* off; int C; const uint16_t* list; const uint32_t* list_len; const uint32_t* gaps_in;
+    const NwTask* tasks; const uint32_t* off; const uint16_t* list; const uint32_t* list_len; const uint32_t* gaps_in;
     // ROWS
     const uint8_t* rows; int N; int L; long long pair_begin;
     // COUNTS
@@ -92,7 +92,7 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
             const NwTask task = fr.tasks[p >> 5];
             const uint32_t j = task.j0 + (uint32_t)(p & 31);
             if (j >= task.j1) continue;
-            const NwPair d = nw_pair(task, j, fr.off, fr.C);
+            const NwPair d = nw_pair(task, j, fr.off);
             out_idx = d.out_idx;
             const uint32_t len = fr.list_len[out_idx];
             const uint16_t* lp = fr.list + d.list_off;
@@ -283,11 +283,11 @@ static int launch_ml(cudaStream_t st, const MlDev& ml, const MlFront& fr, long l
     return launch_ml_t<FRONT, false, 4>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
 }
 
-int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int C, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
+int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
                          const uint16_t* d_list, const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist,
                          double* d_var, int32_t* d_counts, unsigned long long* d_evals) {
     MlFront fr{};
-    fr.tasks = d_tasks; fr.off = d_off; fr.C = C; fr.list = d_list; fr.list_len = d_list_len; fr.gaps_in = d_gaps;
+    fr.tasks = d_tasks; fr.off = d_off; fr.list = d_list; fr.list_len = d_list_len; fr.gaps_in = d_gaps;
     fr.counts_out = d_counts;
     return launch_ml<FRONT_LIST>(st, ml, fr, (long long)n_tasks * NW_TASK_PAIRS, d_dist, d_var, d_evals);
 }

@@ -33,11 +33,11 @@
 #define NW_MINFTY (-10000)
 
 template <int C>
-__global__ void __launch_bounds__(NW_THREADS)
-nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
-                  const NwTask* __restrict__ tasks, const int8_t* __restrict__ tab, int n1, int go, int ge,
-                  uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out,
-                  int k_one, int k_four) {
+__device__ __forceinline__ void
+nw_forward_body(const NwTask& task, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
+                const int8_t* __restrict__ tab, int n1, int go, int ge,
+                uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out,
+                int k_one, int k_four) {
     // k_one == 1, k_four == 4 at run time: opaque multipliers that make the plain adds below integer
     // multiply-adds, i.e. FMA-pipe instructions, so the ALU pipe (which carries the max/logic ops and
     // is the kernel's limiter) and the FMA pipe are both busy
@@ -46,7 +46,6 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
     const int tab_bytes = (n1 * n1 + 15) & ~15;
     int8_t* prof = (int8_t*)(smem + tab_bytes);              // [band][r][lane][16]
 
-    const NwTask task = tasks[blockIdx.x];
     const uint32_t s1_off = off[task.i];
     const int L1 = (int)(off[task.i + 1] - s1_off);
     const uint8_t* __restrict__ s1 = codes + s1_off;
@@ -69,48 +68,45 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int32_t* colW = colbuf + (size_t)(blockIdx.x * NW_WARPS + warp) * 2 * colbuf_stride;
     int32_t* colX = colW + colbuf_stride;
+    const int go4 = 4 * go, ge4 = 4 * ge;
+    const int gox = go4 + 2, goy = go4 + 1;                   // gap-open into X (tag 2) / into Y (tag 1)
+    const int XINF = 4 * NW_MINFTY + 2, YINF = 4 * NW_MINFTY + 1;
+    const int k_mone = -k_one;
 
     for (uint32_t j = task.j0 + warp; j < task.j1; j += NW_WARPS) {
-        const NwPair d = nw_pair(task, j, off, C);
+        const NwPair d = nw_pair(task, j, off);
         const int L2 = (int)d.L2;
         const uint8_t* __restrict__ s2 = codes + d.s2_off;
-        const int steps = L2 + 31;
-        uint32_t* __restrict__ tbp = tb + d.tb_off;
-
-        const int go4 = 4 * go, ge4 = 4 * ge;
-        const int gox = go4 + 2, goy = go4 + 1;               // gap-open into X (tag 2) / into Y (tag 1)
-        const int XINF = 4 * NW_MINFTY + 2, YINF = 4 * NW_MINFTY + 1;
-        const int k_mone = -k_one;
+        const int steps = L2 + 31;                            // traceback layout: [band][step][lane]
+        if (L2 > 0)
         for (int b = 0; b < nbands; ++b) {
             const int x0 = b * 32 * C + lane * C;            // columns x0+1 .. x0+C (1-based)
+            const int cols_b = min(L1 - b * 32 * C, 32 * C);
+            const int nsteps = L2 + (cols_b + C - 1) / C - 1; // lanes past the last column never start
             int Wup[C], Yup[C];                              // 4*W(y-1,x), 4*Y(y-1,x)+1
 #pragma unroll
             for (int k = 0; k < C; ++k) { Wup[k] = go4 + (x0 + k) * ge4; Yup[k] = YINF; }
             int Wdiag = (x0 == 0) ? 0 : go4 + (x0 - 1) * ge4;  // 4*W(y-1, x0) for y-1 = 0
             int Wlast = 0, Xlast = 0, rcur = 0;
-            // lane 0 prefetch of its left-boundary inputs for row 1
-            int nxtW = 0, nxtX = XINF, nxtR = 0;
-            if (lane == 0 && L2 > 0) {
-                nxtR = s2[0];
-                if (b == 0) { nxtW = go4; } else { nxtW = __ldcg(colW + 1); nxtX = __ldcg(colX + 1); }
-            }
+            // left-boundary inputs of lane 0 for the row it starts next (all lanes compute them: no branch)
+            const bool first = (b == 0);
+            int inW = first ? go4 : __ldcg(colW + 1);
+            int inX = first ? XINF : __ldcg(colX + 1);
+            int inR = s2[0];
             const int8_t* pb = prof + (size_t)b * per_band + lane * 16;
+            uint32_t* __restrict__ tbl = tb + d.tb_off + (size_t)b * steps * 32 + lane;
             const bool has_next_band = (b + 1 < nbands);
-            for (int t = 0; t < steps; ++t) {
+            for (int t = 0; t < nsteps; ++t) {
                 int Wl = __shfl_up_sync(0xffffffffu, Wlast, 1);
                 int Xl = __shfl_up_sync(0xffffffffu, Xlast, 1);
                 int r = __shfl_up_sync(0xffffffffu, rcur, 1);
-                const int y = t - lane + 1;
-                if (lane == 0) {
-                    Wl = nxtW; Xl = nxtX; r = nxtR;
-                    const int yn = y + 1;
-                    if (yn <= L2) {                            // prefetch next row's inputs
-                        nxtR = s2[yn - 1];
-                        if (b == 0) { nxtW = go4 + (yn - 1) * ge4; nxtX = XINF; }
-                        else { nxtW = __ldcg(colW + yn); nxtX = __ldcg(colX + yn); }
-                    }
+                if (lane == 0) { Wl = inW; Xl = inX; r = inR; }
+                {   // prefetch lane 0's inputs for row t+2 (clamped: rows past L2 are never used)
+                    const int yn = min(t + 2, L2);
+                    inR = s2[yn - 1];
+                    if (first) { inW += ge4; } else { inW = __ldcg(colW + yn); inX = __ldcg(colX + yn); }
                 }
-                if (y >= 1 && y <= L2) {
+                if ((unsigned)(t - lane) < (unsigned)L2) {      // row y = t - lane + 1 in [1, L2]
                     const uint4 pw = *reinterpret_cast<const uint4*>(pb + r * 512);
                     const uint32_t pws[4] = {pw.x, pw.y, pw.z, pw.w};
                     int Wleft = Wl, Xleft = Xl, dg = Wdiag;
@@ -130,17 +126,18 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
                     }
                     Wdiag = Wl;
                     Wlast = Wleft; Xlast = Xleft; rcur = r;
-                    tbp[((size_t)b * steps + t) * 32 + lane] = bits;
-                    if (lane == 31 && has_next_band) { colW[y] = Wlast; colX[y] = Xlast; }
-                    if (scores_out != nullptr && y == L2) {
-                        const int kk = L1 - 1 - x0;            // column L1 in this lane?
-                        if (kk >= 0 && kk < C) {
-                            int v = 0;
+                    *tbl = bits;
+                    if (has_next_band && lane == 31) { const int y = t - 30; colW[y] = Wlast; colX[y] = Xlast; }
+                }
+                tbl += 32;
+            }
+            if (scores_out != nullptr) {
+                const int kk = L1 - 1 - x0;                    // does this lane own column L1?
+                if (kk >= 0 && kk < C) {
+                    int v = 0;
 #pragma unroll
-                            for (int k = 0; k < C; ++k) if (k == kk) v = Wup[k];
-                            scores_out[d.out_idx] = v >> 2;
-                        }
-                    }
+                    for (int k = 0; k < C; ++k) if (k == kk) v = Wup[k];
+                    scores_out[d.out_idx] = v >> 2;
                 }
             }
             __syncwarp();
@@ -156,7 +153,7 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
 // (DistanceFactoryAlign.h:99-123).  Emits the matched state pairs (s1*n+s2, both < n) and the
 // number of gap openings.
 __global__ void __launch_bounds__(128)
-nw_walk_kernel(int C, int n_tasks, int n, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
+nw_walk_kernel(int n_tasks, int n, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
                const NwTask* __restrict__ tasks, const uint32_t* __restrict__ tb, uint16_t* __restrict__ list,
                uint32_t* __restrict__ list_len, uint32_t* __restrict__ gaps_out, int* __restrict__ err) {
     const int ti = blockIdx.x * 4 + (threadIdx.x >> 5);
@@ -164,7 +161,8 @@ nw_walk_kernel(int C, int n_tasks, int n, const uint8_t* __restrict__ codes, con
     const NwTask task = tasks[ti];
     const uint32_t j = task.j0 + (threadIdx.x & 31);
     if (j >= task.j1) return;
-    const NwPair d = nw_pair(task, j, off, C);
+    const int C = (int)task.C;
+    const NwPair d = nw_pair(task, j, off);
     const uint8_t* __restrict__ s1 = codes + d.s1_off;
     const uint8_t* __restrict__ s2 = codes + d.s2_off;
     const uint32_t* __restrict__ tbp = tb + d.tb_off;
@@ -200,38 +198,40 @@ nw_walk_kernel(int C, int n_tasks, int n, const uint8_t* __restrict__ codes, con
     gaps_out[d.out_idx] = gaps;
 }
 
-template <int C>
-static int launch_fwd_t(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
-                        const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
-                        uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
+// One launch for every task: the CTA dispatches on its task's C (columns per lane), so rows of
+// different lengths all keep their 32 lanes busy without paying one launch tail per length class.
+__global__ void __launch_bounds__(NW_THREADS)
+nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
+                  const NwTask* __restrict__ tasks, const int8_t* __restrict__ tab, int n1, int go, int ge,
+                  uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out,
+                  int k_one, int k_four) {
+    const NwTask task = tasks[blockIdx.x];
+#define CASE(c) case c: nw_forward_body<c>(task, codes, off, tab, n1, go, ge, tb, colbuf, colbuf_stride, scores_out, k_one, k_four); break;
+    switch (task.C) {
+        CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
+    }
+#undef CASE
+}
+
+int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
+                      const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
+                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
+    if (n_tasks == 0) return 0;
     const int n1 = n_states + 1;
     const size_t smem = ((n1 * n1 + 15) & ~15) + (size_t)max_bands * n1 * 512;
     if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
-    PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    nw_forward_kernel<C><<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_off, d_tasks, d_tab, n1, go, ge, d_tb,
-                                                           d_colbuf, colbuf_stride, d_scores, 1, 4);
+    PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    nw_forward_kernel<<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_off, d_tasks, d_tab, n1, go, ge, d_tb,
+                                                        d_colbuf, colbuf_stride, d_scores, 1, 4);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_nw_forward(cudaStream_t st, int C, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
-                      const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
-                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
-    if (n_tasks == 0) return 0;
-#define CASE(c) case c: return launch_fwd_t<c>(st, n_tasks, n_states, max_bands, d_codes, d_off, d_tasks, d_tab, go, ge, d_tb, d_colbuf, colbuf_stride, d_scores);
-    switch (C) {
-        CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
-    }
-#undef CASE
-    pgm_set_error("unsupported NW column count per lane C=%d", C);
-    return PGM_ERR_ARG;
-}
-
-int launch_nw_walk(cudaStream_t st, int C, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
+int launch_nw_walk(cudaStream_t st, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
                    const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
                    int* d_err) {
     if (n_tasks == 0) return 0;
-    nw_walk_kernel<<<(n_tasks + 3) / 4, 128, 0, st>>>(C, n_tasks, n_states, d_codes, d_off, d_tasks, d_tb, d_list,
+    nw_walk_kernel<<<(n_tasks + 3) / 4, 128, 0, st>>>(n_tasks, n_states, d_codes, d_off, d_tasks, d_tb, d_list,
                                                       d_list_len, d_gaps, d_err);
     PGM_CUDA(cudaGetLastError());
     return 0;

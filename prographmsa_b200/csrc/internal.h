@@ -66,7 +66,7 @@ struct NwTask {             // 32 B: the pairs (i, j0 .. j1-1); one CTA builds s
     uint32_t out_base;          // packed-output index of pair (i, j0)
     uint64_t tb_base;           // word offset of pair (i, j0)'s packed traceback in the chunk scratch
     uint32_t list_base;         // offset of pair (i, j0)'s matched-state list (uint16 entries)
-    uint32_t pad;
+    uint32_t C;                 // columns per lane of the forward kernel that wrote this task's traceback
 };
 #define NW_TASK_PAIRS 32        // pairs per task (4 per warp of the forward kernel, 1 per lane of the walk)
 
@@ -75,7 +75,8 @@ struct NwTask {             // 32 B: the pairs (i, j0 .. j1-1); one CTA builds s
 //   tb_off(i,j)   = tb_base   + nb(L1) * 32 * ((off[j] - off[j0]) + 31 * (j - j0))
 //   list_off(i,j) = list_base + (off[j] - off[j0])            (capacity L2 >= matched pairs)
 struct NwPair { uint32_t s1_off, s2_off, L1, L2, out_idx, list_off; uint64_t tb_off; };
-__device__ __forceinline__ NwPair nw_pair(const NwTask& t, uint32_t j, const uint32_t* __restrict__ off, int C) {
+__device__ __forceinline__ NwPair nw_pair(const NwTask& t, uint32_t j, const uint32_t* __restrict__ off) {
+    const uint32_t C = t.C;
     NwPair p;
     p.s1_off = off[t.i]; p.L1 = off[t.i + 1] - p.s1_off;
     p.s2_off = off[j]; p.L2 = off[j + 1] - p.s2_off;
@@ -95,14 +96,14 @@ struct MlDev {              // ML constants + eigen-basis in device memory
 };
 
 // kernels (hp2_nw.cu / hp2_ml.cu); all launch on `st`
-int launch_nw_forward(cudaStream_t st, int C, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
+int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
                       const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
                       uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores);
-int launch_nw_walk(cudaStream_t st, int C, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
+int launch_nw_walk(cudaStream_t st, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
                    const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
                    int* d_err);
 // front-end LIST: histogram from matched-state lists; ROWS: scan two MSA rows
-int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int C, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
+int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
                          const uint16_t* d_list, const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist,
                          double* d_var, int32_t* d_counts, unsigned long long* d_evals);
 int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,
