@@ -96,13 +96,18 @@ emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs) {
     }
 }
 
+int launch_emission_prep(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int maxN) {
+    dim3 grid((maxN + 127) / 128, n_jobs);
+    emission_prep_kernel<<<grid, 128, sizeof(float) * (n * n + n), st>>>(n, d_jobs);
+    PGM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int launch_emission_exact(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int max_N1, int max_N2) {
     if (n_jobs == 0) return 0;
     {
-        const int maxN = max_N1 > max_N2 ? max_N1 : max_N2;
-        dim3 grid((maxN + 127) / 128, n_jobs);
-        emission_prep_kernel<<<grid, 128, sizeof(float) * (n * n + n), st>>>(n, d_jobs);
-        PGM_CUDA(cudaGetLastError());
+        int rc = launch_emission_prep(st, n, n_jobs, d_jobs, max_N1 > max_N2 ? max_N1 : max_N2);
+        if (rc) return rc;
     }
     {
         dim3 grid((max_N1 + max_N2 - 1 + 31) / 32, (max_N1 + 31) / 32, n_jobs);

@@ -134,3 +134,50 @@ def test_repeat_edges_identical_to_oracle(ga, po):
     got = ga.alignGraphs(cg1, cg2, m, opts)
     _same_alignment(got, ref)
     assert ref["n_tr_indels"] > 0
+
+
+# ---- tensor-core emission (tcgen05, split-TF32): tolerance-based ------------------------------------
+S_TOL_BITS = 2e-5          # |S_tensor - S_exact| in log2 units (per cell); dropped lo*lo term + fp32 accumulate order
+SCORE_RTOL = 1e-5          # north_star: DP scores within 1e-5 relative
+
+
+@pytest.mark.parametrize("n,L", [(20, 97), (20, 300), (4, 333), (61, 150)])
+def test_emission_tensor_close_to_exact(ga, n, L):
+    opts = Options(mldist_flag=True)
+    if n == 61:
+        opts = opts.for_codon(); mf = model.getDefault(opts, alphabet.Codon)
+    elif n == 4:
+        mf = model.getDefault(opts, alphabet.DNA, custom_text="1 2 1 1 2 1 0.3 0.2 0.2 0.3")
+    else:
+        mf = model.getDefault(opts)
+    a, b = synth.random_pair(L, 0.5, mf, seed=n + L)
+    g1, g2 = sequence_graph(a, n), sequence_graph(b, n)
+    m = mf.getModel(0.6, 0.6)
+    # profile (non one-hot) columns too: push one graph through P
+    g2.sites[1:-1] = g2.sites[1:-1] @ m.P.T
+    S0 = ga.emission_scores(g1, g2, m, -0.3, ga.EMISSION_EXACT)
+    S1 = ga.emission_scores(g1, g2, m, -0.3, ga.EMISSION_TENSOR)
+    err = np.abs(_interior(S1) - _interior(S0)).max()
+    assert err <= S_TOL_BITS, err
+
+
+def test_tensor_alignments_within_tolerance(ga, po):
+    """every job of a progressive pass in tensor mode: score within 1e-5 relative of the oracle; the
+    traceback is identical unless the oracle's own score margin is inside the tolerance (ties reported)"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(32, 150, mf, seed=44, indel_rate=0.04)
+    tree = progressive.from_synth(root)
+    stats = dict(jobs=0, identical=0)
+
+    def batch(jobs, o):
+        out = ga.alignGraphsBatch(jobs, o, emission_mode=ga.EMISSION_TENSOR)
+        ref = [po.align_graphs(g1, g2, m, o) for g1, g2, m in jobs]
+        for r, e in zip(out, ref):
+            assert abs(r["score"] - e["score"]) <= SCORE_RTOL * abs(e["score"])
+            stats["jobs"] += 1
+            stats["identical"] += int(np.array_equal(r["mapping1"], e["mapping1"]) and np.array_equal(r["mapping2"], e["mapping2"]))
+        return ref                      # continue the pass on the reference path so every job sees reference inputs
+    progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
+    print("tensor-mode tracebacks identical: %d / %d jobs" % (stats["identical"], stats["jobs"]))
+    assert stats["identical"] >= stats["jobs"] - 2          # near-tie flips are reported, not hidden
