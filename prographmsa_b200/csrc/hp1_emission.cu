@@ -7,9 +7,10 @@
 // mul/add; this file is compiled with --fmad=false and uses explicit _rn intrinsics), so this
 // flavour is bit-identical to the oracle and is what the traceback-identity tests run on.
 //
-// S is written in the DP's skewed layout: cell (y,x) on anti-diagonal d=y+x lives at
-// d*pitch + (y - max(0, d-(N2-1))), so the wavefront kernel reads whole diagonals coalesced.
-// Tiles are 32 diagonals x 32 rows in (d, y) coordinates so that the stores are coalesced too.
+// S is written row-major by graph-1 node (S(y,x) at y*ldS + x): the wavefront kernel maps one thread
+// to one row y, which then streams its own row of S 16 bytes at a time.  Tiles are 32 rows x 32 columns;
+// a thread computes 4 consecutive rows of one column, so per k it needs one conflict-free load of T and
+// one broadcast 16-byte load of g1: 2 shared-memory loads per 8 flops.
 #include "internal.h"
 
 __device__ __forceinline__ float ls_log2_add(float x, float add) {
@@ -55,44 +56,42 @@ emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs) {
     }
 }
 
-// grid = (tiles_d, tiles_y, n_jobs), block = (32, 8)
+// grid = (tiles_x, tiles_y, n_jobs), block = (32, 8)
 __global__ void __launch_bounds__(256)
 emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs) {
     const GraphJobDev& J = jobs[blockIdx.z];
     const int N1 = J.N1, N2 = J.N2;
-    const int d0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
-    if (d0 > N1 + N2 - 2 || y0 >= N1) return;
-    // x range touched: d - y for d in [d0, d0+31], y in [y0, y0+31]
-    const int xlo = d0 - (y0 + 31), nx = 63;
-    if (xlo + nx - 1 < 0 || xlo >= N2) return;
-    extern __shared__ float sm[];
-    float* g1t = sm;                       // [n][32]
-    float* Tt = sm + n * 32;               // [n][64]
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    if (x0 >= N2 || y0 >= N1) return;
+    extern __shared__ __align__(16) float sm[];
+    float* g1t = sm;                       // [n][32 rows]
+    float* Tt = sm + n * 32;               // [n][32 cols]
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < n * 32; i += 256) {
-        const int a = i >> 5, yy = y0 + (i & 31);
-        g1t[i] = (yy < N1) ? J.sites1[a + (size_t)n * yy] : 0.f;
+    for (int i = tid; i < n * 32; i += 256) {           // sites are n contiguous floats per node: coalesced
+        const int yy = i / n, a = i - yy * n;
+        g1t[a * 32 + yy] = (y0 + yy < N1) ? J.sites1[(size_t)n * (y0 + yy) + a] : 0.f;
     }
-    for (int i = tid; i < n * 64; i += 256) {
-        const int a = i >> 6, xx = xlo + (i & 63);
-        Tt[i] = (xx >= 0 && xx < N2 && (i & 63) < nx) ? J.Tbuf[a + (size_t)n * xx] : 0.f;
+    for (int i = tid; i < n * 32; i += 256) {
+        const int xx = i / n, a = i - xx * n;
+        Tt[a * 32 + xx] = (x0 + xx < N2) ? J.Tbuf[(size_t)n * (x0 + xx) + a] : 0.f;
     }
     __syncthreads();
-    const int y = y0 + threadIdx.x;
-    if (y >= N1) return;
-    const float uy = J.u[y];
-    const float add = J.sc[2];             // match_init
+    const int x = x0 + threadIdx.x;
+    const int yl = threadIdx.y * 4;                      // 4 consecutive rows
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    for (int a = 0; a < n; ++a) {                        // sequential-k, mul then add (no FMA)
+        const float t = Tt[a * 32 + threadIdx.x];
+        const float4 g = *reinterpret_cast<const float4*>(g1t + a * 32 + yl);
+        s0 = __fadd_rn(s0, __fmul_rn(g.x, t)); s1 = __fadd_rn(s1, __fmul_rn(g.y, t));
+        s2 = __fadd_rn(s2, __fmul_rn(g.z, t)); s3 = __fadd_rn(s3, __fmul_rn(g.w, t));
+    }
+    if (x >= N2) return;
+    const float vx = J.v[x], add = J.sc[2];              // match_init
+    const float ss[4] = {s0, s1, s2, s3};
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-        const int d = d0 + threadIdx.y + 8 * r;
-        const int x = d - y;
-        if (x < 0 || x >= N2) continue;
-        const int xi = x - xlo;
-        float s = 0.f;
-        for (int a = 0; a < n; ++a) s = __fadd_rn(s, __fmul_rn(g1t[a * 32 + threadIdx.x], Tt[a * 64 + xi]));
-        const float q = __fdiv_rn(s, __fmul_rn(uy, J.v[x]));
-        const int ylo = max(0, d - (N2 - 1));
-        J.S[(size_t)d * J.pitch + (y - ylo)] = ls_log2_add(q, add);
+        const int y = y0 + yl + r;
+        if (y < N1) J.S[(size_t)y * J.ldS + x] = ls_log2_add(__fdiv_rn(ss[r], __fmul_rn(J.u[y], vx)), add);
     }
 }
 
@@ -110,8 +109,8 @@ int launch_emission_exact(cudaStream_t st, int n, int n_jobs, const GraphJobDev*
         if (rc) return rc;
     }
     {
-        dim3 grid((max_N1 + max_N2 - 1 + 31) / 32, (max_N1 + 31) / 32, n_jobs);
-        const size_t smem = sizeof(float) * n * 96;
+        dim3 grid((max_N2 + 31) / 32, (max_N1 + 31) / 32, n_jobs);
+        const size_t smem = sizeof(float) * n * 64;
         emission_exact_kernel<<<grid, dim3(32, 8), smem, st>>>(n, d_jobs);
         PGM_CUDA(cudaGetLastError());
     }

@@ -22,6 +22,7 @@
 // alternative-path marking for repeat edges.  With identical S it is bit-identical to the oracle.
 #include "internal.h"
 #include <math_constants.h>
+#include <algorithm>
 
 __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
     const int d = y + x;
@@ -29,64 +30,146 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
     return (size_t)d * pitch + (y - ylo);
 }
 
+#define GF_RING 4            // anti-diagonals of {M,X,Y,W} kept in shared memory (must be a power of two)
+// S is row-major by y; each (thread,row) streams its own row 16 bytes (4 columns) at a time with cp.async,
+// 8 columns (= 8 anti-diagonals) ahead, into a private ring of four float4 slots
+
+// Thread <-> ROW mapping: thread t owns rows y = t + r*blockDim (r < RPT).  Along the sweep the same
+// thread meets (y,0), (y,1), ... on consecutive anti-diagonals, so the LEFT neighbour (y, x-1) and the
+// row's own predecessor info stay in registers; the UP / DIAGONAL neighbours (y-1, .) come from the
+// previous two ring rows at index y-1 (no skew arithmetic).  STAGE: graph 2's node infos in shared memory.
+template <bool STAGE, int RPT>
 __global__ void __launch_bounds__(1024)
-graph_fill_kernel(const GraphJobDev* __restrict__ jobs) {
+graph_fill_kernel(const GraphJobDev* __restrict__ jobs, int ring_pitch) {
     const GraphJobDev& J = jobs[blockIdx.x];
     const int N1 = J.N1, N2 = J.N2, pitch = J.pitch;
     const float gap_init = J.sc[0], gap_extend = J.sc[1], start_gap = J.sc[6], start_init = J.sc[7];
     const float NINF = -CUDART_INF_F;
     float4* __restrict__ C = J.MXYW;
     const float* __restrict__ S = J.S;
+    const int T = (int)blockDim.x, tid = (int)threadIdx.x;
 
+    extern __shared__ __align__(16) unsigned char gsm[];
+    float4* ring = (float4*)gsm;                                                    // [GF_RING][ring_pitch], indexed by y
+    float4* sring = (float4*)(gsm + (size_t)GF_RING * ring_pitch * sizeof(float4)); // [4][RPT*T], private slots per (thread,row)
+    NodeInfo* s2 = (NodeInfo*)(sring + 4 * RPT * T);
+    if (STAGE) {
+        for (int i = tid; i < N2; i += T) s2[i] = J.ni2[i];
+        __syncthreads();
+    }
+    const NodeInfo* __restrict__ I2 = STAGE ? s2 : J.ni2;
+
+    auto cell = [&](int yy, int xx, int d) -> float4 {          // any earlier cell: ring when recent, else HBM/L2
+        const int dd = yy + xx;
+        if (d - dd < GF_RING) return ring[(dd & (GF_RING - 1)) * ring_pitch + yy];
+        return C[(size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)))];
+    };
+
+    NodeInfo ny[RPT]; bool ysimple[RPT]; float4 left[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int y = tid + r * T;
+        ny[r] = (y <= N1 - 2) ? J.ni1[y] : NodeInfo{0, 0, 0, 0.f};
+        ysimple[r] = (ny[r].cnt == 1 && ny[r].idx0 == y - 1);
+        left[r] = make_float4(NINF, NINF, NINF, NINF);
+    }
     const int dmax = (N1 - 2) + (N2 - 2);
+    const int ldS = J.ldS;
+    auto fetch_s4 = [&](int r, int y, int xq) {                  // S(y, xq..xq+3) -> sring[(xq/4)&3][r*T+tid], asynchronously
+        const float* src = S + (size_t)y * ldS + xq;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sring + ((xq >> 2) & 3) * (RPT * T) + r * T + tid);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+    };
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int y = tid + r * T;
+        if (y >= 1 && y <= N1 - 2) { fetch_s4(r, y, 0); if (4 < ldS) fetch_s4(r, y, 4); }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");      // the first rows need these within < 8 diagonals
+
     for (int d = 0; d <= dmax; ++d) {
-        const int ya = max(0, d - (N2 - 2)), yb = min(N1 - 2, d);
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int y = tid + r * T, x = d - y;
+            if (y >= 1 && y <= N1 - 2 && x >= 0 && (x & 3) == 0 && x + 8 < ldS) fetch_s4(r, y, x + 8);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 7;\n" ::: "memory");             // everything issued >= 8 diagonals ago has landed
         const int ylo = max(0, d - (N2 - 1));
-        for (int y = ya + (int)threadIdx.x; y <= yb; y += (int)blockDim.x) {
-            const int x = d - y;
+        float4* rcur = ring + (d & (GF_RING - 1)) * ring_pitch;
+        const float4* row1 = ring + ((d - 1) & (GF_RING - 1)) * ring_pitch;
+        const float4* row2 = ring + ((d - 2) & (GF_RING - 1)) * ring_pitch;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int y = tid + r * T, x = d - y;
+            if (y > N1 - 2 || x < 0 || x > N2 - 2) continue;
             float m = NINF, xs = NINF, ys = NINF, w = NINF;
-            if (y == 0 && x == 0) {
-                w = start_init;
-            } else if (x == 0) {
-                for (int ky = J.p1_ptr[y]; ky < J.p1_ptr[y + 1]; ++ky) {
-                    const int yp = J.p1_idx[ky];
-                    const float4 c = C[skew(yp, 0, N2, pitch)];
-                    ys = fmaxf(ys, __fsub_rn(fmaxf(__fadd_rn(c.z, gap_extend), __fadd_rn(c.w, start_gap)), J.p1_val[ky]));
+            if (x == 0) {
+                if (y == 0) w = start_init;
+                else {
+                    const int cnt = ny[r].cnt & 0x7fffffff;
+                    for (int ky = 0; ky < cnt; ++ky) {
+                        const int yp = ky ? J.p1_idx[ny[r].ptr + ky] : ny[r].idx0;
+                        const float ey = ky ? J.p1_val[ny[r].ptr + ky] : ny[r].val0;
+                        const float4 c = cell(yp, 0, d);
+                        ys = fmaxf(ys, __fsub_rn(fmaxf(__fadd_rn(c.z, gap_extend), __fadd_rn(c.w, start_gap)), ey));
+                    }
+                    w = ys;
                 }
-                w = ys;
-            } else if (y == 0) {
-                for (int kx = J.p2_ptr[x]; kx < J.p2_ptr[x + 1]; ++kx) {
-                    const int xp = J.p2_idx[kx];
-                    const float4 c = C[skew(0, xp, N2, pitch)];
-                    xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(c.y, gap_extend), __fadd_rn(c.w, start_gap)), J.p2_val[kx]));
-                }
-                w = xs;
             } else {
-                const float s = S[(size_t)d * pitch + (y - ylo)];
-                const int kx0 = J.p2_ptr[x], kx1 = J.p2_ptr[x + 1];
-                for (int ky = J.p1_ptr[y]; ky < J.p1_ptr[y + 1]; ++ky) {
-                    const int yp = J.p1_idx[ky];
-                    const float ey = J.p1_val[ky];
-                    const float4 cu = C[skew(yp, x, N2, pitch)];                 // (yp, x): Y, W
-                    const float Sy = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
-                    for (int kx = kx0; kx < kx1; ++kx) {
-                        const int xp = J.p2_idx[kx];
-                        const float ex = J.p2_val[kx];
-                        const float4 cd = C[skew(yp, xp, N2, pitch)];            // (yp, xp): W
-                        const float4 cl = C[skew(y, xp, N2, pitch)];             // (y, xp): X, W
-                        const float Sm = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
-                        const float Sx = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
-                        const float Sw = fmaxf(Sm, fmaxf(Sx, Sy));
-                        m = fmaxf(m, Sm); xs = fmaxf(xs, Sx); ys = fmaxf(ys, Sy); w = fmaxf(w, Sw);
+                const NodeInfo nx = I2[x];
+                if (y == 0) {
+                    const int cnt = nx.cnt & 0x7fffffff;
+                    for (int kx = 0; kx < cnt; ++kx) {
+                        const int xp = kx ? J.p2_idx[nx.ptr + kx] : nx.idx0;
+                        const float ex = kx ? J.p2_val[nx.ptr + kx] : nx.val0;
+                        const float4 c = cell(0, xp, d);
+                        xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(c.y, gap_extend), __fadd_rn(c.w, start_gap)), ex));
+                    }
+                    w = xs;
+                } else {
+                    const float s = reinterpret_cast<const float*>(sring + ((x >> 2) & 3) * (RPT * T) + r * T + tid)[x & 3];
+                    if (ysimple[r] && nx.cnt == 1 && nx.idx0 == x - 1) {
+                        // fast path (chain nodes, the overwhelming majority): one adjacent regular predecessor each
+                        const float ey = ny[r].val0, ex = nx.val0;
+                        const float4 cu = row1[y - 1];                               // (y-1, x)
+                        const float4 cd = row2[y - 1];                               // (y-1, x-1)
+                        const float4 cl = left[r];                                   // (y, x-1): this thread, last diagonal
+                        ys = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
+                        m = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
+                        xs = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
+                        w = fmaxf(m, fmaxf(xs, ys));
+                    } else {
+                        const int c1 = ny[r].cnt & 0x7fffffff, c2 = nx.cnt & 0x7fffffff;
+                        for (int ky = 0; ky < c1; ++ky) {
+                            const int yp = ky ? J.p1_idx[ny[r].ptr + ky] : ny[r].idx0;
+                            const float ey = ky ? J.p1_val[ny[r].ptr + ky] : ny[r].val0;
+                            const float4 cu = cell(yp, x, d);                        // (yp, x): Y, W
+                            const float Sy = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
+                            for (int kx = 0; kx < c2; ++kx) {
+                                const int xp = kx ? J.p2_idx[nx.ptr + kx] : nx.idx0;
+                                const float ex = kx ? J.p2_val[nx.ptr + kx] : nx.val0;
+                                const float4 cd = cell(yp, xp, d);                   // (yp, xp): W
+                                const float4 cl = cell(y, xp, d);                    // (y, xp): X, W
+                                const float Sm = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
+                                const float Sx = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
+                                const float Sw = fmaxf(Sm, fmaxf(Sx, Sy));
+                                m = fmaxf(m, Sm); xs = fmaxf(xs, Sx); ys = fmaxf(ys, Sy); w = fmaxf(w, Sw);
+                            }
+                        }
                     }
                 }
             }
-            C[(size_t)d * pitch + (y - ylo)] = make_float4(m, xs, ys, w);
+            const float4 out = make_float4(m, xs, ys, w);
+            left[r] = out;
+            rcur[y] = out;
+            C[(size_t)d * pitch + (y - ylo)] = out;
         }
         __syncthreads();
     }
     // end-node match (GraphAlign.h:262-280)
-    if (threadIdx.x == 0) {
+    if (tid == 0) {
         const float end_match = J.sc[3], end_gap = J.sc[4], end_skip = J.sc[5];
         float Wend = NINF;
         for (int ky = J.p1_ptr[N1 - 1]; ky < J.p1_ptr[N1]; ++ky)
@@ -190,13 +273,35 @@ graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
     float nscore = FINF; int nstate = 0, nx = -1, ny = -1;
     long guard = 0;
     const long guard_max = 4L * (N1 + N2) + 16;
+    // predecessor k of a node: the first one is inline in its NodeInfo (one 16-byte load)
+    auto pred1 = [&](const NodeInfo& ni, int k, int& idx, float& val, bool& rep) {
+        if (k == 0) { idx = ni.idx0; val = ni.val0; rep = ni.cnt < 0; }
+        else { idx = J.p1_idx[ni.ptr + k]; val = J.p1_val[ni.ptr + k]; rep = J.p1_rep[ni.ptr + k] != 0; }
+    };
+    auto pred2 = [&](const NodeInfo& ni, int k, int& idx, float& val, bool& rep) {
+        if (k == 0) { idx = ni.idx0; val = ni.val0; rep = ni.cnt < 0; }
+        else { idx = J.p2_idx[ni.ptr + k]; val = J.p2_val[ni.ptr + k]; rep = J.p2_rep[ni.ptr + k] != 0; }
+    };
+    const int PF = 8;                                   // prefetch distance (steps) along the diagonal
     while (x != 0 || y != 0) {
         if (++guard > guard_max) { status = PGM_ERR_BACKTRACK; break; }
+        {   // the path is mostly diagonal: pull the lines it will touch PF steps from now into L2
+            const int py = y - PF, px = x - PF;
+            if (py > 0 && px > 0) {
+                const size_t o = skew(py, px, N2, pitch);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(C + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(J.S + (size_t)py * J.ldS + px));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(J.ni1 + py));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(J.ni2 + px));
+            }
+        }
         best = FINF;
         bool landed_w = false;
         if (state == 2) {
-            for (int ky = J.p1_ptr[y]; ky < J.p1_ptr[y + 1]; ++ky) {
-                const int yp = J.p1_idx[ky]; const float ey = J.p1_val[ky]; const bool ry = J.p1_rep[ky] != 0;
+            const NodeInfo ni = J.ni1[y];
+            const int cnt = ni.cnt & 0x7fffffff;
+            for (int ky = 0; ky < cnt; ++ky) {
+                int yp; float ey; bool ry; pred1(ni, ky, yp, ey, ry);
                 const float4 c = C[skew(yp, x, N2, pitch)];
                 float q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.z, gap_extend), ey)));
                 if (best > q) { best = q; trx = false; try_ = ry; nx = x; ny = yp; nscore = c.z; nstate = 2; landed_w = false; }
@@ -204,8 +309,10 @@ graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
                 if (best > q) { best = q; trx = false; try_ = ry; nx = x; ny = yp; landed_w = true; }
             }
         } else if (state == 1) {
-            for (int kx = J.p2_ptr[x]; kx < J.p2_ptr[x + 1]; ++kx) {
-                const int xp = J.p2_idx[kx]; const float ex = J.p2_val[kx]; const bool rx = J.p2_rep[kx] != 0;
+            const NodeInfo ni = J.ni2[x];
+            const int cnt = ni.cnt & 0x7fffffff;
+            for (int kx = 0; kx < cnt; ++kx) {
+                int xp; float ex; bool rx; pred2(ni, kx, xp, ex, rx);
                 const float4 c = C[skew(y, xp, N2, pitch)];
                 float q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.y, gap_extend), ex)));
                 if (best > q) { best = q; trx = rx; try_ = false; nx = xp; ny = y; nscore = c.y; nstate = 1; landed_w = false; }
@@ -213,11 +320,13 @@ graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
                 if (best > q) { best = q; trx = rx; try_ = false; nx = xp; ny = y; landed_w = true; }
             }
         } else {
-            const float s = J.S[skew(y, x, N2, pitch)];
-            for (int ky = J.p1_ptr[y]; ky < J.p1_ptr[y + 1]; ++ky) {
-                const int yp = J.p1_idx[ky]; const float ey = J.p1_val[ky]; const bool ry = J.p1_rep[ky] != 0;
-                for (int kx = J.p2_ptr[x]; kx < J.p2_ptr[x + 1]; ++kx) {
-                    const int xp = J.p2_idx[kx]; const float ex = J.p2_val[kx]; const bool rx = J.p2_rep[kx] != 0;
+            const NodeInfo n1 = J.ni1[y], n2 = J.ni2[x];
+            const float s = J.S[(size_t)y * J.ldS + x];
+            const int c1 = n1.cnt & 0x7fffffff, c2 = n2.cnt & 0x7fffffff;
+            for (int ky = 0; ky < c1; ++ky) {
+                int yp; float ey; bool ry; pred1(n1, ky, yp, ey, ry);
+                for (int kx = 0; kx < c2; ++kx) {
+                    int xp; float ex; bool rx; pred2(n2, kx, xp, ex, rx);
                     const float4 c = C[skew(yp, xp, N2, pitch)];
                     const float q = fabsf(__fsub_rn(cur, __fsub_rn(__fsub_rn(__fadd_rn(c.w, s), ey), ex)));
                     if (best > q) { best = q; trx = rx; try_ = ry; ny = yp; nx = xp; landed_w = true; }
@@ -249,14 +358,32 @@ graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
     J.result[0] = status; J.result[1] = T.len; J.result[2] = (int)n_tr;
 }
 
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int threads);
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int threads) {
-    if (n_jobs == 0) return 0;
-    graph_fill_kernel<<<n_jobs, threads, 0, st>>>(d_jobs);
+template <bool STAGE, int RPT>
+static int launch_fill_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int threads, int ring_pitch, size_t smem) {
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<STAGE, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_fill_kernel<STAGE, RPT><<<n_jobs, threads, smem, st>>>(d_jobs, ring_pitch);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs) { return launch_graph_fill(st, n_jobs, d_jobs, 256); }
+
+// max_n1 / max_n2: largest graph-1 / graph-2 node counts in this launch
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2) {
+    if (n_jobs == 0) return 0;
+    const int rows = max_n1 > 1 ? max_n1 - 1 : 1;                   // rows 0 .. N1-2
+    const int rpt = rows <= 1024 ? 1 : (rows <= 2048 ? 2 : 4);
+    if (rows > 4096) { pgm_set_error("graph 1 has %d nodes; the wavefront kernel supports up to 4097", max_n1); return PGM_ERR_ARG; }
+    const int threads = std::min(1024, std::max(64, ((rows + rpt - 1) / rpt + 31) & ~31));
+    const int ring_pitch = (max_n1 + 3) & ~3;
+    const size_t ring = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * rpt * threads * sizeof(float4);
+    const size_t info = (size_t)max_n2 * sizeof(NodeInfo);
+    if (ring > 227 * 1024) { pgm_set_error("graph too large for the shared-memory diagonal ring (N1 = %d)", max_n1); return PGM_ERR_ARG; }
+    const bool stage = ring + info <= 200 * 1024;
+    const size_t smem = ring + (stage ? info : 0);
+#define GO(S_, R_) return launch_fill_t<S_, R_>(st, n_jobs, d_jobs, threads, ring_pitch, smem)
+    if (stage) { if (rpt == 1) GO(true, 1); if (rpt == 2) GO(true, 2); GO(true, 4); }
+    if (rpt == 1) GO(false, 1); if (rpt == 2) GO(false, 2); GO(false, 4);
+#undef GO
+}
 
 int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs) {
     if (n_jobs == 0) return 0;

@@ -16,7 +16,7 @@ void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok);
 void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int threads);
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2);
 
 namespace {
 
@@ -72,7 +72,7 @@ void dynprog_scores(const pgm_graph& g1, const pgm_graph& g2, const pgm_dp_model
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct JobLayout {                // byte offsets into the upload arena / scratch arena / output arena
-    size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt;
+    size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2;
     size_t S, MXYW, Tbuf, u, v, alt_score, alt_prev;     // scratch
     size_t map1, map2, result;                           // output
     int np1, np2, cap, pitch;
@@ -132,10 +132,11 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.p1_alt = take(in_off, 4 * L.np1); L.p1_rep = take(in_off, L.np1);
         L.p2_ptr = take(in_off, 4 * (bb.N + 1)); L.p2_idx = take(in_off, 4 * L.np2); L.p2_val = take(in_off, 4 * L.np2);
         L.p2_alt = take(in_off, 4 * L.np2); L.p2_rep = take(in_off, L.np2);
+        L.ni1 = take(in_off, sizeof(NodeInfo) * a.N); L.ni2 = take(in_off, sizeof(NodeInfo) * bb.N);
         L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 16);
         const size_t diags = (size_t)a.N + bb.N - 1;
         size_t so = 0;
-        L.S = take(so, diags * L.pitch * 4); L.MXYW = take(so, diags * L.pitch * 16);
+        L.S = take(so, (size_t)a.N * (((size_t)bb.N + 3) & ~(size_t)3) * 4 + 64); L.MXYW = take(so, diags * L.pitch * 16);
         L.Tbuf = take(so, sizeof(float) * n * bb.N); L.u = take(so, 4 * a.N); L.v = take(so, 4 * bb.N);
         L.alt_score = take(so, 4 * std::max(a.N, bb.N)); L.alt_prev = take(so, 4 * std::max(a.N, bb.N));
         scratch_need[k] = so;
@@ -165,7 +166,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         const pgm_graph* gs[2] = {&g1[k], &g2[k]};
         const JobLayout& L = b->lay[k];
         GraphJobDev& J = b->jobs[k];
-        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.cap = L.cap;
+        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
         dynprog_scores(g1[k], g2[k], models[k], *opts, J.sc);
         const float rinit = J.sc[8], rext = J.sc[9];
         float* s1 = (float*)(hin + L.sites1); float* s2 = (float*)(hin + L.sites2);
@@ -205,6 +206,13 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 if (node >= 1 && node <= g.N - 2) deg_sum[w] += (uint64_t)(q - ptr[node]);
             }
             ptr[g.N] = q;
+            NodeInfo* ni = (NodeInfo*)(hin + (w == 0 ? L.ni1 : L.ni2));
+            for (int node = 0; node < g.N; ++node) {
+                const int cnt = ptr[node + 1] - ptr[node];
+                ni[node].ptr = ptr[node];
+                ni[node].cnt = cnt | ((cnt && rep[ptr[node]]) ? (int)0x80000000 : 0);     // sign bit: first pred is a repeat edge
+                ni[node].idx0 = cnt ? idx[ptr[node]] : 0; ni[node].val0 = cnt ? val[ptr[node]] : 0.f;
+            }
         }
         b->cell_updates[k] = deg_sum[0] * deg_sum[1];
         b->total_updates += b->cell_updates[k];
@@ -216,6 +224,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.p1_rep = (const uint8_t*)(din + L.p1_rep); J.p1_alt = (const float*)(din + L.p1_alt);
         J.p2_ptr = (const int*)(din + L.p2_ptr); J.p2_idx = (const int*)(din + L.p2_idx); J.p2_val = (const float*)(din + L.p2_val);
         J.p2_rep = (const uint8_t*)(din + L.p2_rep); J.p2_alt = (const float*)(din + L.p2_alt);
+        J.ni1 = (const NodeInfo*)(din + L.ni1); J.ni2 = (const NodeInfo*)(din + L.ni2);
         J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.Tbuf = (float*)(sb + L.Tbuf);
         J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
         J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev);
@@ -238,10 +247,11 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
     const GraphJobDev* dj = b->d_jobs.as<GraphJobDev>();
     for (auto& sb : b->sub) {
         const int nj = sb.second - sb.first;
-        int mx1 = 0, mx2 = 0, mxd = 0;
+        int mx1 = 0, mx2 = 0, mxd = 0, mxn = 0, mxp = 0;
         for (int k = sb.first; k < sb.second; ++k) {
             mx1 = std::max(mx1, b->jobs[k].N1); mx2 = std::max(mx2, b->jobs[k].N2);
             mxd = std::max(mxd, std::min(b->jobs[k].N1, b->jobs[k].N2));
+            mxn = std::max(mxn, b->jobs[k].N1 + b->jobs[k].N2); mxp = std::max(mxp, b->jobs[k].pitch);
         }
         int rc; void* tok;
         pgm_ctx_time_begin(c, 3, &tok);
@@ -249,9 +259,9 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
         else rc = launch_emission_exact(st, b->n_states, nj, dj + sb.first, mx1, mx2);
         pgm_ctx_time_end(c, tok);
         if (rc) return rc;
-        const int threads = mxd <= 128 ? 128 : (mxd <= 256 ? 256 : (mxd <= 512 ? 512 : 1024));
         pgm_ctx_time_begin(c, 4, &tok);
-        rc = launch_graph_fill(st, nj, dj + sb.first, threads);
+        (void)mxd; (void)mxn; (void)mxp;
+        rc = launch_graph_fill(st, nj, dj + sb.first, mx1, mx2);
         pgm_ctx_time_end(c, tok);
         if (rc) return rc;
         pgm_ctx_time_begin(c, 5, &tok);
@@ -329,17 +339,13 @@ int pgm_emission_scores(pgm_ctx* c, int n, const pgm_graph* g1, const pgm_graph*
     else rc = launch_emission_exact(st, n, 1, b->d_jobs.as<GraphJobDev>(), g1->N, g2->N);
     if (!rc) {
         const GraphJobDev& J = b->jobs[0];
-        const size_t diags = (size_t)J.N1 + J.N2 - 1;
-        std::vector<float> sk(diags * J.pitch);
+        std::vector<float> sk((size_t)J.N1 * J.ldS);
         cudaError_t e = cudaMemcpyAsync(sk.data(), J.S, sk.size() * 4, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) { pgm_set_error("CUDA error: %s", cudaGetErrorString(e)); rc = PGM_ERR_CUDA; }
         else
             for (int x = 0; x < J.N2; ++x)
-                for (int y = 0; y < J.N1; ++y) {
-                    const int d = y + x, ylo = std::max(0, d - (J.N2 - 1));
-                    S[y + (size_t)J.N1 * x] = sk[(size_t)d * J.pitch + (y - ylo)];
-                }
+                for (int y = 0; y < J.N1; ++y) S[y + (size_t)J.N1 * x] = sk[(size_t)y * J.ldS + x];
     }
     pgm_graph_batch_destroy(c, b);
     return rc;

@@ -16,9 +16,9 @@
 //     groups), written with plain stores + fence.proxy.async -- K is tiny, so TMA would buy nothing
 //   * one elected thread issues K'/8 tcgen05.mma (kind::tf32, M=128, N=128, K=8) and commits to an
 //     mbarrier; the 4 warps then pull their 32 TMEM lanes with tcgen05.ld (32x32b.x32), apply the
-//     epilogue  S = ls_log2( num / (u(y) v(x)) ) + match_init  with the reference's exact rational log2,
-//     transpose 32x32 blocks through shared memory and store along anti-diagonals, i.e. coalesced in
-//     the DP's skewed layout.
+//     epilogue  S = ls_log2( num / (u(y) v(x)) ) + match_init  with the reference's rational log2 and
+//     store their row's 32 columns as eight 16-byte stores (S is row-major by graph-1 node, which is
+//     exactly the TMEM lane = row ownership, so no transpose is needed).
 //
 // The GEMM has arithmetic intensity n/2 flop per output byte, so it is bound by the S write, not by the
 // tensor pipe; the point of the tensor cores here is that the 2*n flop/cell leave the
@@ -37,7 +37,7 @@ __device__ __forceinline__ float ls_log2_add_t(float x, float add) {
     const uint32_t bits = __float_as_uint(x);
     const float e = (float)((int)(bits >> 23) - 126);
     const float d = __uint_as_float(((bits << 9) >> 9) ^ 0x3f000000u);
-    float vd = __fdiv_rn(b, __fsub_rn(d, c));
+    float vd = __fdividef(b, __fsub_rn(d, c));                // tolerance flavour: fast divide
     const float ve = __fadd_rn(e, a);
     vd = __fadd_rn(vd, add);
     return __fadd_rn(vd, ve);
@@ -76,38 +76,40 @@ emission_tensor_kernel(int n, int tiles_x, const GraphJobDev* __restrict__ jobs)
     float* sB = (float*)(smem + (size_t)ET_M * KP * 4);         // ET_N x KP
     __shared__ __align__(8) uint64_t mbar;
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float sV[ET_N];
+    __shared__ float sRV[ET_N];                                  // 1 / v(x)
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = tid >> 5;
 
-    // ---- stage operands (hi/lo split, K-concatenated) ----
+    // ---- stage operands (hi/lo split, K-concatenated); node vectors are n contiguous floats: coalesced ----
     {
-        for (int i = tid; i < ET_M * KP; i += ET_THREADS) { sA[i] = 0.f; sB[i] = 0.f; }
-        __syncthreads();
-        const int y = y0 + tid, x = x0 + tid;
-        if (y < N1) {
-            const float* g = J.sites1 + (size_t)n * y;
-            for (int a = 0; a < n; ++a) {
-                const float v = g[a];
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                const float lo = __fsub_rn(v, hi);
-                *(float*)((char*)sA + op_offset(tid, a, ET_M)) = hi;
-                *(float*)((char*)sA + op_offset(tid, n + a, ET_M)) = hi;
-                *(float*)((char*)sA + op_offset(tid, 2 * n + a, ET_M)) = lo;
-            }
+        const int rowsA = min(ET_M, N1 - y0), rowsB = min(ET_N, N2 - x0);
+        const float* gA = J.sites1 + (size_t)n * y0;
+        const float* gB = J.Tbuf + (size_t)n * x0;
+        for (int i = tid; i < ET_M * n; i += ET_THREADS) {
+            const int r = i / n, a = i - r * n;
+            const float v = (r < rowsA) ? gA[i] : 0.f;
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            const float lo = __fsub_rn(v, hi);
+            *(float*)((char*)sA + op_offset(r, a, ET_M)) = hi;
+            *(float*)((char*)sA + op_offset(r, n + a, ET_M)) = hi;
+            *(float*)((char*)sA + op_offset(r, 2 * n + a, ET_M)) = lo;
         }
-        if (x < N2) {
-            const float* g = J.Tbuf + (size_t)n * x;
-            for (int a = 0; a < n; ++a) {
-                const float v = g[a];
-                const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-                const float lo = __fsub_rn(v, hi);
-                *(float*)((char*)sB + op_offset(tid, a, ET_N)) = hi;
-                *(float*)((char*)sB + op_offset(tid, n + a, ET_N)) = lo;
-                *(float*)((char*)sB + op_offset(tid, 2 * n + a, ET_N)) = hi;
-            }
-            sV[tid] = J.v[x];
-        } else sV[tid] = 1.f;
+        for (int i = tid; i < ET_N * n; i += ET_THREADS) {
+            const int r = i / n, a = i - r * n;
+            const float v = (r < rowsB) ? gB[i] : 0.f;
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            const float lo = __fsub_rn(v, hi);
+            *(float*)((char*)sB + op_offset(r, a, ET_N)) = hi;
+            *(float*)((char*)sB + op_offset(r, n + a, ET_N)) = lo;
+            *(float*)((char*)sB + op_offset(r, 2 * n + a, ET_N)) = hi;
+        }
+        for (int i = tid; i < ET_M * (KP - 3 * n); i += ET_THREADS) {      // zero the K padding
+            const int r = i / (KP - 3 * n), k = 3 * n + (i - r * (KP - 3 * n));
+            *(float*)((char*)sA + op_offset(r, k, ET_M)) = 0.f;
+            *(float*)((char*)sB + op_offset(r, k, ET_N)) = 0.f;
+        }
+        const int x = x0 + tid;
+        sRV[tid] = (x < N2) ? __frcp_rn(J.v[x]) : 1.f;
     }
     // ---- TMEM allocation (warp 0) + mbarrier init ----
     if (warp == 0) {
@@ -155,15 +157,15 @@ emission_tensor_kernel(int n, int tiles_x, const GraphJobDev* __restrict__ jobs)
     }
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
 
-    // ---- epilogue: TMEM -> registers -> log-odds -> transpose through smem -> diagonal-coalesced stores ----
-    float* tile = (float*)smem + warp * (32 * 33);               // operands are dead: reuse their shared memory
+    // ---- epilogue: TMEM -> registers -> log-odds -> 16-byte row-major stores ----
     const int y = y0 + tid;
-    const float uy = (y < N1) ? J.u[y] : 1.f;
+    const float ruy = (y < N1) ? __frcp_rn(J.u[y]) : 1.f;
     const float add = J.sc[2];
-    const int pitch = J.pitch;
-    __syncthreads();                                             // everyone past the wait before smem is reused
+    const int ldS = J.ldS;
+    const bool warp_has_rows = (y0 + warp * 32) < N1;            // warp-uniform: skip fully out-of-range row groups
 #pragma unroll 1
     for (int cb = 0; cb < ET_N / 32; ++cb) {
+        if (!warp_has_rows || x0 + cb * 32 >= N2) break;
         uint32_t r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
         asm volatile(
@@ -175,23 +177,20 @@ emission_tensor_kernel(int n, int tiles_x, const GraphJobDev* __restrict__ jobs)
               "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (y < N1) {
+            float* dst = J.S + (size_t)y * ldS + x0 + cb * 32;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const float q = __fdiv_rn(__uint_as_float(r[j]), __fmul_rn(uy, sV[cb * 32 + j]));
-            tile[lane * 33 + j] = ls_log2_add_t(q, add);
-        }
-        __syncwarp();
-        const int yb = y0 + warp * 32, xb = x0 + cb * 32;
-        for (int dd = 0; dd < 63; ++dd) {
-            const int xx = dd - lane;
-            const int yy = yb + lane, xg = xb + xx;
-            if (xx >= 0 && xx < 32 && yy < N1 && xg < N2) {
-                const int d = yy + xg;
-                const int ylo = max(0, d - (N2 - 1));
-                J.S[(size_t)d * pitch + (yy - ylo)] = tile[lane * 33 + xx];
+            for (int j4 = 0; j4 < 8; ++j4) {
+                if (x0 + cb * 32 + j4 * 4 < ldS) {                 // ldS is a multiple of 4: whole float4 in range
+                    float4 o;
+                    o.x = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 0]) * ruy * sRV[cb * 32 + j4 * 4 + 0], add);
+                    o.y = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 1]) * ruy * sRV[cb * 32 + j4 * 4 + 1], add);
+                    o.z = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 2]) * ruy * sRV[cb * 32 + j4 * 4 + 2], add);
+                    o.w = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 3]) * ruy * sRV[cb * 32 + j4 * 4 + 3], add);
+                    *reinterpret_cast<float4*>(dst + j4 * 4) = o;
+                }
             }
         }
-        __syncwarp();
     }
     // ---- teardown ----
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -205,7 +204,7 @@ int launch_emission_prep(cudaStream_t st, int n, int n_jobs, const GraphJobDev* 
 template <int KP>
 static int launch_t(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int tiles_x, int tiles_y) {
     const size_t smem = (size_t)(ET_M + ET_N) * KP * 4;
-    const size_t need = smem > 4 * 32 * 33 * 4 ? smem : 4 * 32 * 33 * 4;
+    const size_t need = smem;
     PGM_CUDA(cudaFuncSetAttribute(emission_tensor_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
     dim3 grid(tiles_x * tiles_y, n_jobs);
     emission_tensor_kernel<KP><<<grid, ET_THREADS, need, st>>>(n, tiles_x, d_jobs);

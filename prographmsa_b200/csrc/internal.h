@@ -113,6 +113,8 @@ int launch_ml_from_counts(cudaStream_t st, const MlDev& ml, int64_t n_pairs, con
                           const double* d_seqlen, double* d_dist, double* d_var, unsigned long long* d_evals);
 
 // ---- HP-1 (hp1_*.cu) ------------------------------------------------------------------------------
+struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred list start, count (sign bit = first pred is a repeat edge), first entry inline
+
 struct GraphJobDev {        // one alignGraphs job, all pointers into the batch's device arena
     int N1, N2;
     int pitch;                  // skewed-layout pitch (>= N1): cell (y,x) lives at (y+x)*pitch + y
@@ -125,8 +127,10 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     const int* p2_ptr; const int* p2_idx; const float* p2_val; const uint8_t* p2_rep;
     // alternative-path preds (values with repeat_init = repeat_ext = +inf; GraphAlign.h:165-198)
     const float* p1_alt; const float* p2_alt;
+    const NodeInfo* ni1; const NodeInfo* ni2;   // N1 / N2 entries
     float sc[10];               // DynProgScores
-    float* S;                   // skewed
+    float* S;                   // row-major by graph-1 node: S(y,x) at y*ldS + x (a DP thread streams its own row)
+    int ldS;                    // N2 rounded up to a multiple of 4
     float4* MXYW;               // skewed {M,X,Y,W}
     float* Tbuf;                // n * N2 scratch: T = M^T g2
     float* u; float* v;         // g1^T pi (N1), pi^T g2 (N2)
@@ -138,5 +142,4 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
 
 int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, int max_N1, int max_N2);
 int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const GraphJobDev* h_jobs);
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs);
 int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs);

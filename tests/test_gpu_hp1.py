@@ -181,3 +181,20 @@ def test_tensor_alignments_within_tolerance(ga, po):
     progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
     print("tensor-mode tracebacks identical: %d / %d jobs" % (stats["identical"], stats["jobs"]))
     assert stats["identical"] >= stats["jobs"] - 2          # near-tie flips are reported, not hidden
+
+
+def test_large_batch_is_deterministic_and_correct(ga, po):
+    """600 jobs in one batch (several CTAs per SM, multiple waves): identical results on two runs and
+    agreement with the oracle on a sample -- guards the asynchronous S prefetch ring of the fill kernel"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    m = mf.getModel(0.5, 0.5)
+    jobs = []
+    for k in range(600):
+        a, b = synth.random_pair(180 + (k % 7) * 11, 0.5, mf, seed=1000 + k)
+        jobs.append((sequence_graph(a, 20), sequence_graph(b, 20), m))
+    r1 = ga.alignGraphsBatch(jobs, opts)
+    r2 = ga.alignGraphsBatch(jobs, opts)
+    assert [r["score"] for r in r1] == [r["score"] for r in r2]
+    for k in range(0, 600, 37):
+        _same_alignment(r1[k], po.align_graphs(jobs[k][0], jobs[k][1], m, opts))
