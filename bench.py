@@ -278,7 +278,7 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
 
 def run_ours(args):
     import torch
-    from prographmsa_b200 import _lib, alphabet, distance
+    from prographmsa_b200 import _lib, alphabet, distance, sharding
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -295,8 +295,8 @@ def run_ours(args):
     keep = []
     prm = distance.make_ml_params(mf, opts, keep)
     P = N_SEQ * (N_SEQ - 1) // 2
-    per = (P + world - 1) // world                         # equal-sized shards (the last one is padded)
-    pb, pe = min(P, rank * per), min(P, (rank + 1) * per)
+    per = sharding.shard_size(N_SEQ, world)                # equal-sized shards (the last one is padded)
+    pb, pe = sharding.pair_shard(N_SEQ, rank, world)
     cells_total = 0
     L = np.diff(offsets.astype(np.int64))
     for i in range(N_SEQ):
