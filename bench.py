@@ -285,6 +285,7 @@ def run_ours(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ["NCCL_DEBUG"] = "WARN"                  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pk = peaks()
     opts, mf, seqs, names, _ = make_family()

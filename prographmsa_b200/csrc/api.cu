@@ -33,6 +33,8 @@ struct pgm_ctx {
     DevBuf d_off, d_codes, d_descs, d_tasks, d_ftasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
            d_counts, d_scores, d_misc, d_rows, d_seqlen;
     HostPinned h_stage;
+    // buffer pool for HP-1 batches: cudaMalloc / cudaMallocHost of GB-sized arenas per call would dominate e2e
+    std::vector<DevBuf> pool_dev; std::vector<HostPinned> pool_host;
 };
 
 // ---- timing ----------------------------------------------------------------------------------------
@@ -105,6 +107,8 @@ void pgm_destroy(pgm_ctx* c) {
                       &c->d_list_len, &c->d_gaps, &c->d_dist, &c->d_var, &c->d_counts, &c->d_scores, &c->d_misc, &c->d_rows,
                       &c->d_seqlen}) b->release();
     c->h_stage.release();
+    for (auto& b : c->pool_dev) b.release();
+    for (auto& b : c->pool_host) b.release();
     for (auto e : c->event_pool) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -462,3 +466,22 @@ pgm_timing* pgm_ctx_timing(pgm_ctx* c) { return &c->timing; }
 void pgm_ctx_reset_timing(pgm_ctx* c) { reset_timing(c); }
 void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok) { *tok = new ScopedKernelTimer(c, kind); }
 void pgm_ctx_time_end(pgm_ctx* c, void* tok) { (void)c; delete (ScopedKernelTimer*)tok; }
+
+// ---- buffer pool (HP-1 arenas) ----------------------------------------------------------------------
+template <class B> static int pool_take(std::vector<B>& pool, size_t bytes, B& out) {
+    int best = -1;
+    for (int i = 0; i < (int)pool.size(); ++i)
+        if (pool[i].cap >= bytes && (best < 0 || pool[i].cap < pool[best].cap)) best = i;
+    if (best >= 0) { out = pool[best]; pool.erase(pool.begin() + best); return 0; }
+    if (!pool.empty()) {                       // too small: drop the largest one instead of hoarding memory
+        int big = 0;
+        for (int i = 1; i < (int)pool.size(); ++i) if (pool[i].cap > pool[big].cap) big = i;
+        pool[big].release(); pool.erase(pool.begin() + big);
+    }
+    out = B();
+    return out.reserve(bytes);
+}
+int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out) { return pool_take(c->pool_dev, bytes, out); }
+int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out) { return pool_take(c->pool_host, bytes, out); }
+void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b) { if (b.p) { if (c && c->pool_dev.size() < 16) c->pool_dev.push_back(b); else b.release(); } b = DevBuf(); }
+void pgm_ctx_give_host(pgm_ctx* c, HostPinned& b) { if (b.p) { if (c && c->pool_host.size() < 16) c->pool_host.push_back(b); else b.release(); } b = HostPinned(); }

@@ -17,6 +17,10 @@ void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
 int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2);
+int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
+int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
+void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
+void pgm_ctx_give_host(pgm_ctx* c, HostPinned& b);
 
 namespace {
 
@@ -73,7 +77,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct JobLayout {                // byte offsets into the upload arena / scratch arena / output arena
     size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2;
-    size_t S, MXYW, Tbuf, u, v, alt_score, alt_prev;     // scratch
+    size_t S, MXYW, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev;     // scratch
     size_t map1, map2, result;                           // output
     int np1, np2, cap, pitch;
 };
@@ -138,6 +142,11 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         size_t so = 0;
         L.S = take(so, (size_t)a.N * (((size_t)bb.N + 3) & ~(size_t)3) * 4 + 64); L.MXYW = take(so, diags * L.pitch * 16);
         L.Tbuf = take(so, sizeof(float) * n * bb.N); L.u = take(so, 4 * a.N); L.v = take(so, 4 * bb.N);
+        if (opts->emission_mode == PGM_EMISSION_TENSOR) {
+            const size_t kp = (size_t)((3 * n + 7) & ~7);
+            L.Aimg = take(so, (size_t)((a.N + 127) / 128) * 128 * kp * 4);
+            L.Bimg = take(so, (size_t)((bb.N + 127) / 128) * 128 * kp * 4);
+        } else { L.Aimg = L.Bimg = 0; }
         L.alt_score = take(so, 4 * std::max(a.N, bb.N)); L.alt_prev = take(so, 4 * std::max(a.N, bb.N));
         scratch_need[k] = so;
         b->max_N1 = std::max(b->max_N1, a.N); b->max_N2 = std::max(b->max_N2, bb.N);
@@ -155,10 +164,10 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         if (n_jobs > begin) b->sub.push_back({begin, n_jobs});
     }
     int rc;
-    if ((rc = b->h_in.reserve(std::max<size_t>(in_off, 1))) || (rc = b->d_in.reserve(std::max<size_t>(in_off, 1))) ||
-        (rc = b->d_out.reserve(std::max<size_t>(out_off, 1))) || (rc = b->h_out.reserve(std::max<size_t>(out_off, 1))) ||
-        (rc = b->d_scratch.reserve(std::max<size_t>(b->scratch_bytes_used, 1))) ||
-        (rc = b->d_jobs.reserve(std::max<size_t>(sizeof(GraphJobDev) * n_jobs, 1)))) { pgm_graph_batch_destroy(c, b); return rc; }
+    if ((rc = pgm_ctx_take_host(c, std::max<size_t>(in_off, 1), b->h_in)) || (rc = pgm_ctx_take_dev(c, std::max<size_t>(in_off, 1), b->d_in)) ||
+        (rc = pgm_ctx_take_dev(c, std::max<size_t>(out_off, 1), b->d_out)) || (rc = pgm_ctx_take_host(c, std::max<size_t>(out_off, 1), b->h_out)) ||
+        (rc = pgm_ctx_take_dev(c, std::max<size_t>(b->scratch_bytes_used, 1), b->d_scratch)) ||
+        (rc = pgm_ctx_take_dev(c, std::max<size_t>(sizeof(GraphJobDev) * n_jobs, 1), b->d_jobs))) { pgm_graph_batch_destroy(c, b); return rc; }
     b->out_bytes = out_off;
     char* hin = b->h_in.as<char>();
     char* din = b->d_in.as<char>(); char* dsc = b->d_scratch.as<char>(); char* dout = b->d_out.as<char>();
@@ -227,6 +236,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.ni1 = (const NodeInfo*)(din + L.ni1); J.ni2 = (const NodeInfo*)(din + L.ni2);
         J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.Tbuf = (float*)(sb + L.Tbuf);
         J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
+        J.Aimg = (float*)(sb + L.Aimg); J.Bimg = (float*)(sb + L.Bimg);
         J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev);
         J.map1 = (int*)(dout + L.map1); J.map2 = (int*)(dout + L.map2); J.result = (int*)(dout + L.result);
     }
@@ -308,8 +318,8 @@ int pgm_graph_batch_fetch(pgm_ctx* c, pgm_graph_batch* b, pgm_alignment* out) {
 void pgm_graph_batch_destroy(pgm_ctx* c, pgm_graph_batch* b) {
     if (!b) return;
     if (c) { cudaSetDevice(pgm_ctx_device(c)); cudaStreamSynchronize(pgm_ctx_stream(c)); }
-    b->d_in.release(); b->d_scratch.release(); b->d_out.release(); b->d_jobs.release();
-    b->h_in.release(); b->h_out.release();
+    pgm_ctx_give_dev(c, b->d_in); pgm_ctx_give_dev(c, b->d_scratch); pgm_ctx_give_dev(c, b->d_out); pgm_ctx_give_dev(c, b->d_jobs);
+    pgm_ctx_give_host(c, b->h_in); pgm_ctx_give_host(c, b->h_out);
     delete b;
 }
 

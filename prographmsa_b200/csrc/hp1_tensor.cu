@@ -61,153 +61,230 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
     return d;
 }
 
-// grid = (tiles_x * tiles_y of the largest job, n_jobs); block = 128
+// ---- mbarrier / bulk-copy helpers ---------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* b, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+// bounded wait: a lost arrival must never hang the GPU; returns false on timeout
+__device__ __forceinline__ bool mbar_wait(uint64_t* b, uint32_t parity) {
+    uint32_t done = 0, spins = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(smem_u32(b)), "r"(parity) : "memory");
+        if (++spins > (1u << 24)) return false;
+    }
+    return true;
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Operand images: the prep kernel writes, per 128-row tile, the exact shared-memory image of the UMMA
+// operand (hi/lo split, K-concatenated, canonical K-major no-swizzle layout), so the GEMM kernel stages a
+// tile with ONE bulk async copy (cp.async.bulk + mbarrier complete_tx) and no register traffic.
+//   block (tile, job): tiles [0, tiles_y) are A tiles (graph 1 rows), the rest B tiles (graph 2 columns)
 template <int KP>
-__global__ void __launch_bounds__(ET_THREADS)
-emission_tensor_kernel(int n, int tiles_x, const GraphJobDev* __restrict__ jobs) {
+__global__ void __launch_bounds__(ET_M)
+emission_images_kernel(int n, int tiles_y, int tiles_x, const GraphJobDev* __restrict__ jobs) {
+    const GraphJobDev& J = jobs[blockIdx.y];
+    extern __shared__ float sm[];                     // Mf (n*n) + pif (n)
+    float* sM = sm; float* sPi = sm + n * n;
+    for (int i = threadIdx.x; i < n * n; i += blockDim.x) sM[i] = J.Mf[i];
+    for (int i = threadIdx.x; i < n; i += blockDim.x) sPi[i] = J.pif[i];
+    __syncthreads();
+    const int t = blockIdx.x, r = threadIdx.x;
+    const bool isA = t < tiles_y;
+    const int tile = isA ? t : t - tiles_y;
+    const int N = isA ? J.N1 : J.N2;
+    if (tile * ET_M >= N) return;
+    const int node = tile * ET_M + r;
+    char* img = (char*)(isA ? J.Aimg : J.Bimg) + (size_t)tile * ET_M * KP * 4;
+    float vals[64];                                   // n <= 61
+    if (node < N) {
+        const float* g = (isA ? J.sites1 : J.sites2) + (size_t)n * node;
+        if (isA) {
+            float s = 0.f;
+            for (int a = 0; a < n; ++a) { vals[a] = g[a]; s = __fadd_rn(s, __fmul_rn(g[a], sPi[a])); }
+            J.u[node] = s;
+        } else {
+            for (int a = 0; a < n; ++a) {             // T(a,x) = sum_b M(b,a) g2(b,x)
+                float s = 0.f;
+                for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sM[b * n + a], g[b]));
+                vals[a] = s;
+            }
+            float s = 0.f;
+            for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sPi[b], g[b]));
+            J.v[node] = s;
+        }
+    } else {
+        for (int a = 0; a < n; ++a) vals[a] = 0.f;
+    }
+    for (int a = 0; a < n; ++a) {
+        const float v = vals[a];
+        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        const float lo = __fsub_rn(v, hi);
+        // A' = [hi | hi | lo],  B' = [hi ; lo ; hi]
+        *(float*)(img + op_offset(r, a, ET_M)) = hi;
+        *(float*)(img + op_offset(r, n + a, ET_M)) = isA ? hi : lo;
+        *(float*)(img + op_offset(r, 2 * n + a, ET_M)) = isA ? lo : hi;
+    }
+    for (int k = 3 * n; k < KP; ++k) *(float*)(img + op_offset(r, k, ET_M)) = 0.f;
+}
+
+// Persistent GEMM + epilogue: one CTA per (job, 128-row tile of graph 1), looping over graph 2's 128-column
+// tiles.  Warp roles: 0 = bulk-copy producer, 1 = TMEM owner + single-thread MMA issuer, 2..5 = epilogue
+// (TMEM lanes 32*(warp%4)).  B operand tiles and TMEM accumulators are double-buffered so the copy of tile
+// i+1, the MMA of tile i+1 and the epilogue of tile i overlap.
+#define ETP_THREADS 192
+template <int KP, int BST>
+__global__ void __launch_bounds__(ETP_THREADS)
+emission_tensor_kernel(int tiles_y, const GraphJobDev* __restrict__ jobs) {
     const GraphJobDev& J = jobs[blockIdx.y];
     const int N1 = J.N1, N2 = J.N2;
-    const int ty = blockIdx.x / tiles_x, tx = blockIdx.x - ty * tiles_x;
-    const int y0 = ty * ET_M, x0 = tx * ET_N;
-    if (y0 >= N1 || x0 >= N2) return;
+    const int y0 = blockIdx.x * ET_M;
+    if (y0 >= N1) return;
+    const int ntx = (N2 + ET_N - 1) / ET_N;
+    constexpr uint32_t IMG = ET_M * KP * 4;
 
     extern __shared__ __align__(128) unsigned char smem[];
-    float* sA = (float*)smem;                                   // ET_M x KP, canonical layout
-    float* sB = (float*)(smem + (size_t)ET_M * KP * 4);         // ET_N x KP
-    __shared__ __align__(8) uint64_t mbar;
+    unsigned char* sA = smem;
+    unsigned char* sB = smem + IMG;                               // BST stages
+    __shared__ __align__(8) uint64_t a_full, b_full[2], b_empty[2], t_full[2], t_empty[2];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float sRV[ET_N];                                  // 1 / v(x)
+    __shared__ float sRV[2][ET_N];
+    __shared__ int s_fail;
 
-    const int tid = threadIdx.x, warp = tid >> 5;
-
-    // ---- stage operands (hi/lo split, K-concatenated); node vectors are n contiguous floats: coalesced ----
-    {
-        const int rowsA = min(ET_M, N1 - y0), rowsB = min(ET_N, N2 - x0);
-        const float* gA = J.sites1 + (size_t)n * y0;
-        const float* gB = J.Tbuf + (size_t)n * x0;
-        for (int i = tid; i < ET_M * n; i += ET_THREADS) {
-            const int r = i / n, a = i - r * n;
-            const float v = (r < rowsA) ? gA[i] : 0.f;
-            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            const float lo = __fsub_rn(v, hi);
-            *(float*)((char*)sA + op_offset(r, a, ET_M)) = hi;
-            *(float*)((char*)sA + op_offset(r, n + a, ET_M)) = hi;
-            *(float*)((char*)sA + op_offset(r, 2 * n + a, ET_M)) = lo;
-        }
-        for (int i = tid; i < ET_N * n; i += ET_THREADS) {
-            const int r = i / n, a = i - r * n;
-            const float v = (r < rowsB) ? gB[i] : 0.f;
-            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-            const float lo = __fsub_rn(v, hi);
-            *(float*)((char*)sB + op_offset(r, a, ET_N)) = hi;
-            *(float*)((char*)sB + op_offset(r, n + a, ET_N)) = lo;
-            *(float*)((char*)sB + op_offset(r, 2 * n + a, ET_N)) = hi;
-        }
-        for (int i = tid; i < ET_M * (KP - 3 * n); i += ET_THREADS) {      // zero the K padding
-            const int r = i / (KP - 3 * n), k = 3 * n + (i - r * (KP - 3 * n));
-            *(float*)((char*)sA + op_offset(r, k, ET_M)) = 0.f;
-            *(float*)((char*)sB + op_offset(r, k, ET_N)) = 0.f;
-        }
-        const int x = x0 + tid;
-        sRV[tid] = (x < N2) ? __frcp_rn(J.v[x]) : 1.f;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        mbar_init(&a_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); mbar_init(&t_full[s], 1); mbar_init(&t_empty[s], 4); }
+        s_fail = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
     }
-    // ---- TMEM allocation (warp 0) + mbarrier init ----
-    if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "n"(ET_N));
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_slot)), "n"(2 * ET_N));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n");
     }
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&mbar)));
-        asm volatile("fence.mbarrier_init.release.cluster;\n");
-    }
-    // generic-proxy smem writes -> visible to the async proxy (tensor core reads)
-    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    bool ok = true;
 
-    // ---- MMA issue (one thread) ----
-    if (tid == 0) {
-        // instruction descriptor: D = F32 (1<<4), A = B = TF32 (2<<7, 2<<10), K-major both, N>>3 at [17,23), M>>4 at [24,29)
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ET_N >> 3) << 17) | ((uint32_t)(ET_M >> 4) << 24);
-        const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB);
-        const uint32_t lboA = ET_M * 16, lboB = ET_N * 16, sbo = 128;
-#pragma unroll 1
-        for (int ks = 0; ks < KP / 8; ++ks) {
-            const uint64_t adesc = make_desc(a_base + (uint32_t)(2 * ks) * lboA, lboA, sbo);
-            const uint64_t bdesc = make_desc(b_base + (uint32_t)(2 * ks) * lboB, lboB, sbo);
-            const uint32_t accum = ks > 0 ? 1u : 0u;
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_base), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-                : "memory");
-        }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(&mbar)) : "memory");
-    }
-    // ---- wait for the accumulator ----
-    {
-        uint32_t done = 0, spins = 0;
-        while (!done) {
-            asm volatile(
-                "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
-                : "=r"(done) : "r"(smem_u32(&mbar)), "r"(0u) : "memory");
-            if (++spins > (1u << 22)) { J.result[0] = PGM_ERR_CUDA; break; }   // never hang the GPU on a lost commit
-        }
-    }
-    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-
-    // ---- epilogue: TMEM -> registers -> log-odds -> 16-byte row-major stores ----
-    const int y = y0 + tid;
-    const float ruy = (y < N1) ? __frcp_rn(J.u[y]) : 1.f;
-    const float add = J.sc[2];
-    const int ldS = J.ldS;
-    const bool warp_has_rows = (y0 + warp * 32) < N1;            // warp-uniform: skip fully out-of-range row groups
-#pragma unroll 1
-    for (int cb = 0; cb < ET_N / 32; ++cb) {
-        if (!warp_has_rows || x0 + cb * 32 >= N2) break;
-        uint32_t r[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
-            "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-              "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
-              "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
-              "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-        if (y < N1) {
-            float* dst = J.S + (size_t)y * ldS + x0 + cb * 32;
-#pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-                if (x0 + cb * 32 + j4 * 4 < ldS) {                 // ldS is a multiple of 4: whole float4 in range
-                    float4 o;
-                    o.x = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 0]) * ruy * sRV[cb * 32 + j4 * 4 + 0], add);
-                    o.y = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 1]) * ruy * sRV[cb * 32 + j4 * 4 + 1], add);
-                    o.z = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 2]) * ruy * sRV[cb * 32 + j4 * 4 + 2], add);
-                    o.w = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 3]) * ruy * sRV[cb * 32 + j4 * 4 + 3], add);
-                    *reinterpret_cast<float4*>(dst + j4 * 4) = o;
-                }
+    if (warp == 0) {
+        if (lane == 0) {                                          // ---- producer ----
+            mbar_expect_tx(&a_full, IMG);
+            bulk_g2s(sA, (const char*)J.Aimg + (size_t)blockIdx.x * IMG, IMG, &a_full);
+            for (int i = 0; i < ntx && ok; ++i) {
+                const int s = i % BST;
+                if (i >= BST) ok = mbar_wait(&b_empty[s], ((i / BST) - 1) & 1);
+                mbar_expect_tx(&b_full[s], IMG);
+                bulk_g2s(sB + (size_t)s * IMG, (const char*)J.Bimg + (size_t)i * IMG, IMG, &b_full[s]);
             }
         }
+    } else if (warp == 1) {
+        if (lane == 0) {                                          // ---- MMA issuer ----
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(ET_N >> 3) << 17) | ((uint32_t)(ET_M >> 4) << 24);
+            const uint32_t lbo = ET_M * 16, sbo = 128;
+            ok = mbar_wait(&a_full, 0);
+            for (int i = 0; i < ntx && ok; ++i) {
+                const int s = i % BST, ts = i & 1;
+                ok = mbar_wait(&b_full[s], (i / BST) & 1);
+                if (ok && i >= 2) ok = mbar_wait(&t_empty[ts], ((i >> 1) - 1) & 1);
+                if (!ok) break;
+                asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+                const uint32_t a_base = smem_u32(sA), b_base = smem_u32(sB + (size_t)s * IMG);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(ts * ET_N);
+#pragma unroll 1
+                for (int ks = 0; ks < KP / 8; ++ks) {
+                    const uint64_t adesc = make_desc(a_base + (uint32_t)(2 * ks) * lbo, lbo, sbo);
+                    const uint64_t bdesc = make_desc(b_base + (uint32_t)(2 * ks) * lbo, lbo, sbo);
+                    const uint32_t accum = ks > 0 ? 1u : 0u;
+                    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+                                 ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+                }
+                umma_commit(&b_empty[s]);                         // shared-memory stage free once these MMAs retire
+                umma_commit(&t_full[ts]);                         // accumulator ready
+            }
+        }
+    } else {                                                      // ---- epilogue warps 2..5 ----
+        const int q = warp & 3;                                   // TMEM lane quarter this warp may touch
+        const int row = q * 32 + lane, y = y0 + row;
+        const float ruy = (y < N1) ? __frcp_rn(J.u[y]) : 1.f;
+        const float add = J.sc[2];
+        const int ldS = J.ldS;
+        const bool warp_has_rows = (y0 + q * 32) < N1;
+        const int et = tid - 64;                                  // 0..127
+        for (int i = 0; i < ntx && ok; ++i) {
+            const int ts = i & 1, x0 = i * ET_N;
+            { const int x = x0 + et; sRV[ts][et] = (x < N2) ? __frcp_rn(J.v[x]) : 1.f; }
+            asm volatile("bar.sync 1, 128;\n" ::: "memory");
+            ok = mbar_wait(&t_full[ts], (i >> 1) & 1);
+            if (!ok) break;
+            asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll 1
+            for (int cb = 0; cb < ET_N / 32; ++cb) {
+                if (!warp_has_rows || x0 + cb * 32 >= N2) break;
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * ET_N + cb * 32);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,"
+                    "%24,%25,%26,%27,%28,%29,%30,%31}, [%32];\n"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+                      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+                      "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+                      "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+                if (y < N1) {
+                    float* dst = J.S + (size_t)y * ldS + x0 + cb * 32;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        if (x0 + cb * 32 + j4 * 4 < ldS) {         // ldS is a multiple of 4: whole float4 in range
+                            float4 o;
+                            o.x = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 0]) * ruy * sRV[ts][cb * 32 + j4 * 4 + 0], add);
+                            o.y = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 1]) * ruy * sRV[ts][cb * 32 + j4 * 4 + 1], add);
+                            o.z = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 2]) * ruy * sRV[ts][cb * 32 + j4 * 4 + 2], add);
+                            o.w = ls_log2_add_t(__uint_as_float(r[j4 * 4 + 3]) * ruy * sRV[ts][cb * 32 + j4 * 4 + 3], add);
+                            *reinterpret_cast<float4*>(dst + j4 * 4) = o;
+                        }
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[ts]);             // 4 arrivals (one per epilogue warp) free the accumulator
+        }
     }
-    // ---- teardown ----
+    if (!ok) s_fail = 1;
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(ET_N));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(2 * ET_N));
+    if (tid == 0 && s_fail) J.result[0] = PGM_ERR_CUDA;           // surfaces as a failed job, never as a hang
 }
 
-// prep kernel of the exact flavour (T = M^T g2, u, v) lives in hp1_emission.cu
-int launch_emission_prep(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int maxN);
-
-template <int KP>
+template <int KP, int BST>
 static int launch_t(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int tiles_x, int tiles_y) {
-    const size_t smem = (size_t)(ET_M + ET_N) * KP * 4;
-    const size_t need = smem;
-    PGM_CUDA(cudaFuncSetAttribute(emission_tensor_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-    dim3 grid(tiles_x * tiles_y, n_jobs);
-    emission_tensor_kernel<KP><<<grid, ET_THREADS, need, st>>>(n, tiles_x, d_jobs);
+    {
+        dim3 grid(tiles_y + tiles_x, n_jobs);
+        emission_images_kernel<KP><<<grid, ET_M, sizeof(float) * (n * n + n), st>>>(n, tiles_y, tiles_x, d_jobs);
+        PGM_CUDA(cudaGetLastError());
+    }
+    const size_t smem = (size_t)(1 + BST) * ET_M * KP * 4;
+    PGM_CUDA(cudaFuncSetAttribute(emission_tensor_kernel<KP, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(tiles_y, n_jobs);
+    emission_tensor_kernel<KP, BST><<<grid, ETP_THREADS, smem, st>>>(tiles_y, d_jobs);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -216,13 +293,11 @@ int launch_emission_tensor(cudaStream_t st, int n, int n_jobs, const GraphJobDev
     if (n_jobs == 0) return 0;
     int mx1 = 0, mx2 = 0;
     for (int k = 0; k < n_jobs; ++k) { mx1 = mx1 > h_jobs[k].N1 ? mx1 : h_jobs[k].N1; mx2 = mx2 > h_jobs[k].N2 ? mx2 : h_jobs[k].N2; }
-    int rc = launch_emission_prep(st, n, n_jobs, d_jobs, mx1 > mx2 ? mx1 : mx2);
-    if (rc) return rc;
     const int tiles_y = (mx1 + ET_M - 1) / ET_M, tiles_x = (mx2 + ET_N - 1) / ET_N;
     const int kp = (3 * n + 7) & ~7;
-    if (kp <= 16) return launch_t<16>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
-    if (kp <= 64) return launch_t<64>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
-    if (kp <= 184) return launch_t<184>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
+    if (kp <= 16) return launch_t<16, 2>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
+    if (kp <= 64) return launch_t<64, 2>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
+    if (kp <= 184) return launch_t<184, 1>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
     pgm_set_error("tensor emission supports n_states <= 61");
     return PGM_ERR_ARG;
 }

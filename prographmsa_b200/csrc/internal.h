@@ -133,6 +133,7 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     int ldS;                    // N2 rounded up to a multiple of 4
     float4* MXYW;               // skewed {M,X,Y,W}
     float* Tbuf;                // n * N2 scratch: T = M^T g2
+    float* Aimg; float* Bimg;   // tensor flavour: per-128-row-tile UMMA operand images (ceil(N/128) * 128 * KP floats)
     float* u; float* v;         // g1^T pi (N1), pi^T g2 (N2)
     int* map1; int* map2;       // output mappings (capacity cap), written reversed then flipped
     int cap;
