@@ -228,9 +228,15 @@ struct Tracer {
     }
 };
 
+// One WARP per job.  All 32 lanes run the walk redundantly (identical values, so the duplicate stores are
+// benign and every load is a broadcast); the lanes earn their keep on DIAGONAL RUNS: in state M at chain
+// nodes the next cell is forced to be (y-1, x-1), so lane k fetches cell (y-k, x-k) and its nodes, the warp
+// finds with two ballots how far the run extends, and up to 32 path steps are emitted at once instead of
+// one dependent load chain per step.
 __global__ void __launch_bounds__(32)
 graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
-    const int job = blockIdx.x * blockDim.x + threadIdx.x;
+    const int job = blockIdx.x;
+    const int lane = threadIdx.x;
     if (job >= n_jobs) return;
     const GraphJobDev& J = jobs[job];
     const int N1 = J.N1, N2 = J.N2, pitch = J.pitch;
@@ -285,6 +291,43 @@ graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
     const int PF = 8;                                   // prefetch distance (steps) along the diagonal
     while (x != 0 || y != 0) {
         if (++guard > guard_max) { status = PGM_ERR_BACKTRACK; break; }
+        if (state == 0 && isfinite(cur)) {
+            // ---- diagonal run: lane -> k = lane+1, position (y-k, x-k), reached from (y-k+1, x-k+1) ----
+            const int k = lane + 1, yk = y - k, xk = x - k;
+            bool tr = false, stM = false; int st = 3; float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (yk >= 0 && xk >= 0) {
+                const NodeInfo a1 = J.ni1[yk + 1], a2 = J.ni2[xk + 1];          // the nodes whose predecessor is followed
+                const float sv = J.S[(size_t)(yk + 1) * J.ldS + (xk + 1)];
+                c = C[skew(yk, xk, N2, pitch)];
+                tr = a1.cnt == 1 && a1.idx0 == yk && a2.cnt == 1 && a2.idx0 == xk && isfinite(a1.val0) && isfinite(a2.val0) &&
+                     isfinite(sv) && isfinite(c.w);
+                if (yk == 0 && xk == 0) st = 4;                                 // start node: the walk ends here
+                else if (c.w == c.x) st = 0; else if (c.w == c.z) st = 2; else if (c.w == c.y) st = 1;
+                stM = (st == 0);
+            }
+            const unsigned mtr = __ballot_sync(0xffffffffu, tr), mM = __ballot_sync(0xffffffffu, stM);
+            const unsigned cond = mtr & ((mM << 1) | 1u);                        // step k needs state M at k-1
+            const int R = (cond == 0xffffffffu) ? 32 : (__ffs(~cond) - 1);
+            if (R > 0) {
+                const int stR = __shfl_sync(0xffffffffu, st, R - 1);
+                if (stR == 3) { status = PGM_ERR_BACKTRACK; break; }            // reference: error("backtracking failed")
+                if (lane < R && st != 4) {
+                    const int pos = T.len + lane;
+                    if (pos < J.cap) {
+                        J.map1[pos] = (st == 1) ? -1 : yk;
+                        J.map2[pos] = (st == 2) ? -1 : xk;
+                    }
+                }
+                T.len += (stR == 4) ? R - 1 : R;
+                const float cx = __shfl_sync(0xffffffffu, c.x, R - 1), cy = __shfl_sync(0xffffffffu, c.y, R - 1),
+                            cz = __shfl_sync(0xffffffffu, c.z, R - 1);
+                y -= R; x -= R;
+                if (stR != 4) { state = stR; cur = (stR == 0) ? cx : (stR == 1 ? cy : cz); }
+                trx = false; try_ = false; nx = x; ny = y; nstate = state; nscore = cur;
+                guard += R;
+                continue;
+            }
+        }
         {   // the path is mostly diagonal: pull the lines it will touch PF steps from now into L2
             const int py = y - PF, px = x - PF;
             if (py > 0 && px > 0) {
@@ -387,7 +430,7 @@ int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, in
 
 int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs) {
     if (n_jobs == 0) return 0;
-    graph_trace_kernel<<<(n_jobs + 31) / 32, 32, 0, st>>>(n_jobs, d_jobs);
+    graph_trace_kernel<<<n_jobs, 32, 0, st>>>(n_jobs, d_jobs);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
