@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <cmath>
+#include <cstdlib>
 
 static thread_local char g_err[1024] = "";
 void pgm_set_error(const char* fmt, ...) {
@@ -23,6 +24,7 @@ struct pgm_ctx {
     cudaStream_t stream = nullptr;
     uint64_t scratch_bytes = 8ull << 30;
     bool timing_on = false;
+    bool force_nw32 = false;             // PGM_NW_FORCE_32BIT=1: never use the 16-bit forward flavour (tests / A-B runs)
     pgm_timing timing{};
     std::vector<TimedSection> sections;       // pending (resolved at sync)
     std::vector<cudaEvent_t> event_pool;
@@ -93,6 +95,7 @@ int pgm_create(int device, pgm_ctx** out) {
     }
     pgm_ctx* c = new pgm_ctx();
     c->device = device;
+    { const char* e = getenv("PGM_NW_FORCE_32BIT"); c->force_nw32 = e && e[0] == '1'; }
     PGM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c;
     return 0;
@@ -212,6 +215,12 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     rc = c->d_off.reserve((size_t)(N + 1) * 4); if (rc) return rc;
     PGM_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, c->stream));
 
+    // 16-bit flavour constants (hp2_nw.cu): potential slope H, bias, and the value bound that decides eligibility
+    int smax = 0, smin = 0;
+    for (size_t i = 0; i < tab8.size(); ++i) { smax = std::max(smax, (int)tab8[i]); smin = std::min(smin, (int)tab8[i]); }
+    int u16_h = std::max(std::max(-(4 * go + 1), -4 * ge), 0); u16_h = (u16_h + 3) & ~3;
+    const int u16_bias = 16 * (std::abs(go) + std::abs(ge)) + 64;
+    const bool u16_table_ok = (4 * smin + 3 + 2 * u16_h >= 0) && go <= 0 && ge <= 0 && !c->force_nw32;
     // tasks = up to 32 consecutive pairs of one row; chunks = runs of tasks that fit the traceback budget
     const uint64_t tb_budget_words = std::max<uint64_t>(c->scratch_bytes / 4, 1u << 20);
     std::vector<NwTask>& tasks = c->h_tasks;
@@ -238,6 +247,13 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
                 }
                 NwTask t; t.i = (uint32_t)i; t.j0 = (uint32_t)j0; t.j1 = (uint32_t)j1; t.out_base = (uint32_t)(p - pb);
                 t.tb_base = tb_words; t.list_base = (uint32_t)list_entries; t.C = C;
+                if (u16_table_ok && L1 >= 1 && L1 <= 512) {      // 16-bit flavour: single band, non-empty rows, values < 65536
+                    uint32_t l2max = 0, l2min = 0xffffffffu;
+                    for (int64_t jq = j0; jq < j1; ++jq) { const uint32_t l = offsets[jq + 1] - offsets[jq]; l2max = std::max(l2max, l); l2min = std::min(l2min, l); }
+                    const uint64_t bound = (uint64_t)4 * smax * std::min<uint32_t>(L1, l2max) + (uint64_t)u16_h * (L1 + l2max) + u16_bias +
+                                           4 * smax + 2 * u16_h + 64;
+                    if (l2min >= 1 && bound < 65536) t.C |= NW_MODE_U16;
+                }
                 tasks.push_back(t);
                 tb_words += w; list_entries += span;
                 cells += (uint64_t)(L1 + 1) * (span + (uint64_t)(j1 - j0));      // sum (L1+1)(L2+1)
@@ -266,7 +282,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
         {
             ScopedKernelTimer t(c, K_NW_FWD);
             rc = launch_nw_forward(c->stream, ntasks, n, max_bands, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tab.as<int8_t>(),
-                                   go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores);
+                                   go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores, u16_h, u16_bias);
             if (rc) return rc;
         }
         {

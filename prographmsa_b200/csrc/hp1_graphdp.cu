@@ -23,6 +23,7 @@
 #include "internal.h"
 #include <math_constants.h>
 #include <algorithm>
+#include <cstdlib>
 
 __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
     const int d = y + x;
@@ -413,7 +414,11 @@ static int launch_fill_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs,
 int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2) {
     if (n_jobs == 0) return 0;
     const int rows = max_n1 > 1 ? max_n1 - 1 : 1;                   // rows 0 .. N1-2
-    const int rpt = rows <= 1024 ? 1 : (rows <= 2048 ? 2 : 4);
+    // rows per thread: on an anti-diagonal sweep only ~half the rows are active at a time, so giving a thread
+    // several rows (y, y+T, ..) halves the number of idle warps that still pay the per-diagonal loop overhead
+    int rpt = rows <= 1024 ? 1 : (rows <= 2048 ? 2 : 4);       // measured: 1 row per thread is best while it fits
+    if (const char* e = getenv("PGM_FILL_RPT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) rpt = v; }
+    while ((rows + rpt - 1) / rpt > 1024) rpt *= 2;
     if (rows > 4096) { pgm_set_error("graph 1 has %d nodes; the wavefront kernel supports up to 4097", max_n1); return PGM_ERR_ARG; }
     const int threads = std::min(1024, std::max(64, ((rows + rpt - 1) / rpt + 31) & ~31));
     const int ring_pitch = (max_n1 + 3) & ~3;

@@ -25,6 +25,15 @@
 // IS the traceback direction.  The int8 profile stores 4*T+3 directly.  Per cell this is two fused
 // add-max (VIADDMNMX), one 3-input max, one mask and the adds -- no ISETP/SEL chain.
 //
+// 16-bit SIMD flavour (nw_forward_body_u16): when the scores fit, a warp aligns TWO pairs that share seq1
+// at once, one per 16-bit half of every register (VIADDMNMX.U16x2 / VIMNMX3.U16x2).  To keep the plain
+// adds on the FMA pipe as ordinary 32-bit integer multiply-adds, no carry may ever cross the halves, so
+// all quantities are stored unsigned with a potential:  V^(y,x) = 4 V(y,x) + tag + H (x+y) + BIAS,
+// with H >= -(4 go + 1), -4 ge so that every additive constant (gap open / extend, profile entry) is
+// non-negative; the potential is the same for the three candidates of a cell, so maxima, ties and
+// therefore directions are unchanged.  The host only selects this flavour when the largest possible value
+// stays below 65536 (api.cu); otherwise the 32-bit flavour runs.
+//
 // Integer arithmetic only: bit-exact against the oracle.
 #include "internal.h"
 
@@ -149,6 +158,111 @@ nw_forward_body(const NwTask& task, const uint8_t* __restrict__ codes, const uin
     }
 }
 
+template <int C>
+__device__ __forceinline__ void
+nw_forward_body_u16(const NwTask& task, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
+                    const int8_t* __restrict__ tab, int n1, int go, int ge, uint32_t* __restrict__ tb,
+                    int32_t* __restrict__ scores_out, int k_one, int k_four, int H, int BIAS) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    int8_t* s_tab = (int8_t*)smem;
+    const int tab_bytes = (n1 * n1 + 15) & ~15;
+    uint16_t* prof = (uint16_t*)(smem + tab_bytes);          // [r][lane][16] halfwords: 4*T + 3 + 2H
+
+    const uint32_t s1_off = off[task.i];
+    const int L1 = (int)(off[task.i + 1] - s1_off);
+    const uint8_t* __restrict__ s1 = codes + s1_off;
+    for (int i = threadIdx.x; i < n1 * n1; i += NW_THREADS) s_tab[i] = tab[i];
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n1 * 512; idx += NW_THREADS) {
+        const int r = idx >> 9, lk = idx & 511, ln = lk >> 4, k = lk & 15;
+        const int x = ln * C + k;
+        prof[idx] = (k < C && x < L1) ? (uint16_t)(4 * (int)s_tab[r + n1 * (int)s1[x]] + 3 + 2 * H) : (uint16_t)0;
+    }
+    __syncthreads();
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int go4 = 4 * go, ge4 = 4 * ge;
+    auto pack2 = [](int v) -> uint32_t { return (uint32_t)v | ((uint32_t)v << 16); };
+    const uint32_t gex2 = pack2(ge4 + H), gox2 = pack2(go4 + 2 + H), goy2 = pack2(go4 + 1 + H);
+    const uint32_t u_one = (uint32_t)k_one, u_four = (uint32_t)k_four, u_mone = (uint32_t)(-k_one);
+    const int nl = (L1 + C - 1) / C;
+
+    for (uint32_t jj = task.j0 + 2 * warp; jj < task.j1; jj += 2 * NW_WARPS) {
+        const bool hasB = jj + 1 < task.j1;
+        const NwPair da = nw_pair(task, jj, off), db = nw_pair(task, hasB ? jj + 1 : jj, off);
+        const int L2a = (int)da.L2, L2b = (int)db.L2, L2m = max(L2a, L2b);
+        const uint8_t* __restrict__ s2a = codes + da.s2_off;
+        const uint8_t* __restrict__ s2b = codes + db.s2_off;
+        const int nsteps = L2m + nl - 1;
+        const int x0 = lane * C;
+        uint32_t Wup[C], Yup[C];
+#pragma unroll
+        for (int k = 0; k < C; ++k) { Wup[k] = pack2(4 * (go + (x0 + k) * ge) + H * (x0 + k + 1) + BIAS); Yup[k] = 0u; }
+        uint32_t Wdiag = (x0 == 0) ? pack2(BIAS) : pack2(4 * (go + (x0 - 1) * ge) + H * x0 + BIAS);
+        uint32_t Wlast = 0, Xlast = 0, rcur = 0;
+        uint32_t inW = pack2(go4 + H + BIAS);                 // W^(1,0)
+        const uint32_t inWstep = pack2(ge4 + H);
+        uint32_t inR = (uint32_t)s2a[0] | ((uint32_t)s2b[0] << 16);
+        const unsigned char* pb = (const unsigned char*)prof + lane * 32;
+        uint32_t* __restrict__ tba = tb + da.tb_off + lane;
+        uint32_t* __restrict__ tbb = tb + db.tb_off + lane;
+        uint32_t capA = 0, capB = 0;
+        const int kk = L1 - 1 - x0;                           // this lane owns column L1 iff 0 <= kk < C
+        for (int t = 0; t < nsteps; ++t) {
+            uint32_t Wl = __shfl_up_sync(0xffffffffu, Wlast, 1);
+            uint32_t Xl = __shfl_up_sync(0xffffffffu, Xlast, 1);
+            uint32_t r = __shfl_up_sync(0xffffffffu, rcur, 1);
+            if (lane == 0) { Wl = inW; Xl = 0u; r = inR; }
+            {
+                const int ya = min(t + 2, L2a), yb = min(t + 2, L2b);
+                inR = (uint32_t)s2a[ya - 1] | ((uint32_t)s2b[yb - 1] << 16);
+                inW += inWstep;
+            }
+            const int row = t - lane;                          // 0-based row of this lane at this step
+            if ((unsigned)row < (unsigned)L2m) {
+                const unsigned char* pa_ = pb + (r & 0xffffu) * 1024u;
+                const unsigned char* pb_ = pb + (r >> 16) * 1024u;
+                const uint4 a0 = *reinterpret_cast<const uint4*>(pa_), a1 = *reinterpret_cast<const uint4*>(pa_ + 16);
+                const uint4 b0 = *reinterpret_cast<const uint4*>(pb_), b1 = *reinterpret_cast<const uint4*>(pb_ + 16);
+                const uint32_t Aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                const uint32_t Bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                uint32_t Wleft = Wl, Xleft = Xl, dg = Wdiag, bits = 0, F = 0;
+#pragma unroll
+                for (int k = 0; k < C; ++k) {
+                    const uint32_t s = __byte_perm(Aw[k >> 1], Bw[k >> 1], (k & 1) ? 0x7632 : 0x5410);
+                    const uint32_t wd = dg * u_one + s;
+                    const uint32_t xv = __viaddmax_u16x2(Xleft, gex2, Wleft * u_one + gox2);
+                    const uint32_t yv = __viaddmax_u16x2(Yup[k], gex2, Wup[k] * u_one + goy2);
+                    const uint32_t wt = __vimax3_u16x2(xv, yv, wd);
+                    const uint32_t wn = wt & 0xfffcfffcu;
+                    bits = bits * u_four + (wn * u_mone + wt);  // per half: tag 3 diag, 2 left, 1 up
+                    if (k == 7) { F = bits; bits = 0; }
+                    dg = Wup[k];
+                    Wup[k] = wn; Yup[k] = yv;
+                    Wleft = wn; Xleft = xv;
+                }
+                if (C < 8) { F = bits; bits = 0; }
+                Wdiag = Wl;
+                Wlast = Wleft; Xlast = Xleft; rcur = r;
+                if (row < L2a) tba[(size_t)t * 32] = __byte_perm(F, bits, 0x5410);
+                if (hasB && row < L2b) tbb[(size_t)t * 32] = __byte_perm(F, bits, 0x7632);
+                if (scores_out != nullptr && kk >= 0 && kk < C) {
+                    uint32_t v = 0;
+#pragma unroll
+                    for (int k = 0; k < C; ++k) if (k == kk) v = Wup[k];
+                    if (row == L2a - 1) capA = v & 0xffffu;
+                    if (row == L2b - 1) capB = v >> 16;
+                }
+            }
+        }
+        if (scores_out != nullptr && kk >= 0 && kk < C) {
+            scores_out[da.out_idx] = ((int)capA - H * (L1 + L2a) - BIAS) >> 2;
+            if (hasB) scores_out[db.out_idx] = ((int)capB - H * (L1 + L2b) - BIAS) >> 2;
+        }
+        __syncwarp();
+    }
+}
+
 // One thread per pair (one warp per task): follow the 2-bit tags from (L2,L1) until x==0 or y==0
 // (DistanceFactoryAlign.h:99-123).  Emits the matched state pairs (s1*n+s2, both < n) and the
 // number of gap openings.
@@ -161,7 +275,8 @@ nw_walk_kernel(int n_tasks, int n, const uint8_t* __restrict__ codes, const uint
     const NwTask task = tasks[ti];
     const uint32_t j = task.j0 + (threadIdx.x & 31);
     if (j >= task.j1) return;
-    const int C = (int)task.C;
+    const int C = (int)(task.C & 0xff);
+    const bool u16 = (task.C & NW_MODE_U16) != 0;
     const NwPair d = nw_pair(task, j, off);
     const uint8_t* __restrict__ s1 = codes + d.s1_off;
     const uint8_t* __restrict__ s2 = codes + d.s2_off;
@@ -178,7 +293,9 @@ nw_walk_kernel(int n_tasks, int n, const uint8_t* __restrict__ codes, const uint
         const int lane = rem / C, k = rem - lane * C;
         const int t = y - 1 + lane;
         const uint32_t w = __ldg(tbp + ((size_t)b * steps + t) * 32 + lane);
-        const uint32_t tag = (w >> (2 * (C - 1 - k))) & 3u;       // 3 diagonal, 2 left (X), 1 up (Y)
+        // 32-bit flavour: cell k at bit 2(C-1-k).  16-bit flavour: cells 0..7 in the low half, 8.. in the high half
+        const int sh = !u16 ? 2 * (C - 1 - k) : (k < 8 ? 2 * (min(C, 8) - 1 - k) : 16 + 2 * (C - 1 - k));
+        const uint32_t tag = (w >> sh) & 3u;                       // 3 diagonal, 2 left (X), 1 up (Y)
         if (tag == 3u) {
             const int c1 = s1[xz], c2 = s2[y - 1];
             if (c1 < n && c2 < n) lp[nl++] = (uint16_t)(c1 * n + c2);
@@ -204,10 +321,18 @@ __global__ void __launch_bounds__(NW_THREADS)
 nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
                   const NwTask* __restrict__ tasks, const int8_t* __restrict__ tab, int n1, int go, int ge,
                   uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out,
-                  int k_one, int k_four) {
+                  int k_one, int k_four, int u16_h, int u16_bias) {
     const NwTask task = tasks[blockIdx.x];
+    if (task.C & NW_MODE_U16) {
+#define CASE(c) case c: nw_forward_body_u16<c>(task, codes, off, tab, n1, go, ge, tb, scores_out, k_one, k_four, u16_h, u16_bias); break;
+        switch (task.C & 0xff) {
+            CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
+        }
+#undef CASE
+        return;
+    }
 #define CASE(c) case c: nw_forward_body<c>(task, codes, off, tab, n1, go, ge, tb, colbuf, colbuf_stride, scores_out, k_one, k_four); break;
-    switch (task.C) {
+    switch (task.C & 0xff) {
         CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
     }
 #undef CASE
@@ -215,14 +340,15 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
 
 int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
                       const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
-                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores) {
+                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores, int u16_h, int u16_bias) {
     if (n_tasks == 0) return 0;
     const int n1 = n_states + 1;
-    const size_t smem = ((n1 * n1 + 15) & ~15) + (size_t)max_bands * n1 * 512;
+    const size_t prof32 = (size_t)max_bands * n1 * 512, prof16 = (size_t)n1 * 1024;
+    const size_t smem = ((n1 * n1 + 15) & ~15) + (prof32 > prof16 ? prof32 : prof16);
     if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
     PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nw_forward_kernel<<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_off, d_tasks, d_tab, n1, go, ge, d_tb,
-                                                        d_colbuf, colbuf_stride, d_scores, 1, 4);
+                                                        d_colbuf, colbuf_stride, d_scores, 1, 4, u16_h, u16_bias);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }

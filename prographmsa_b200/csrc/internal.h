@@ -68,6 +68,7 @@ struct NwTask {             // 32 B: the pairs (i, j0 .. j1-1); one CTA builds s
     uint32_t list_base;         // offset of pair (i, j0)'s matched-state list (uint16 entries)
     uint32_t C;                 // columns per lane of the forward kernel that wrote this task's traceback
 };
+#define NW_MODE_U16 0x100u      // NwTask::C flag: traceback written by the 16-bit two-pairs-per-warp flavour
 #define NW_TASK_PAIRS 32        // pairs per task (4 per warp of the forward kernel, 1 per lane of the walk)
 
 // Everything else about a pair is derived on the device from the offsets array (a prefix sum of the
@@ -76,7 +77,7 @@ struct NwTask {             // 32 B: the pairs (i, j0 .. j1-1); one CTA builds s
 //   list_off(i,j) = list_base + (off[j] - off[j0])            (capacity L2 >= matched pairs)
 struct NwPair { uint32_t s1_off, s2_off, L1, L2, out_idx, list_off; uint64_t tb_off; };
 __device__ __forceinline__ NwPair nw_pair(const NwTask& t, uint32_t j, const uint32_t* __restrict__ off) {
-    const uint32_t C = t.C;
+    const uint32_t C = t.C & 0xffu;
     NwPair p;
     p.s1_off = off[t.i]; p.L1 = off[t.i + 1] - p.s1_off;
     p.s2_off = off[j]; p.L2 = off[j + 1] - p.s2_off;
@@ -98,7 +99,7 @@ struct MlDev {              // ML constants + eigen-basis in device memory
 // kernels (hp2_nw.cu / hp2_ml.cu); all launch on `st`
 int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
                       const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
-                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores);
+                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores, int u16_h, int u16_bias);
 int launch_nw_walk(cudaStream_t st, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
                    const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
                    int* d_err);

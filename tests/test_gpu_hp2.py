@@ -234,3 +234,21 @@ def test_config2_size_properties(dist_mod):
     cuts = np.linspace(0, P, 9).astype(np.int64)
     parts = [fac.pair_range(lst, int(a), int(b))[0] for a, b in zip(cuts[:-1], cuts[1:])]
     assert np.array_equal(np.concatenate(parts), D[iu])
+
+
+def test_nw_32bit_flavour_matches_16bit(dist_mod, po, monkeypatch):
+    """the 32-bit forward kernel (long sequences / large scores) and the 16-bit two-pairs-per-warp kernel
+    must produce identical counts, gap openings, scores and distances"""
+    from prographmsa_b200 import _lib
+    opts = Options(mldist_flag=True, nwdist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, _ = synth.simulate_family(33, 260, mf, seed=77, indel_rate=0.03)     # odd count: a lone pair per task
+    lst = list(seqs.values())
+    P = 33 * 32 // 2
+    a = dist_mod.DistanceFactoryAlign(mf, opts).pair_range(lst, 0, P, want_counts=True)
+    monkeypatch.setenv("PGM_NW_FORCE_32BIT", "1")
+    ctx = _lib.Context(0)
+    b = dist_mod.DistanceFactoryAlign(mf, opts, ctx).pair_range(lst, 0, P, want_counts=True)
+    ctx.close()
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
