@@ -122,6 +122,12 @@ int pgm_prealigned_ml_pair_range_dev(pgm_ctx* ctx, const pgm_ml_params* prm,
 int pgm_prealigned_ml_all_pairs(pgm_ctx* ctx, const pgm_ml_params* prm,
                                 const uint8_t* rows, int N, int L_aln, double* dist, double* var);
 
+/* k-mer angle distances: DistanceFactoryAngle<A,K>::computePwDistances
+ * (DistanceFactoryAngle.h:54-131).  K = 2 for AA / codon, 6 for DNA (DistanceFactory.cpp:14,32,50).
+ * ml_flag = cmdlineopts.mldist_flag || mldist_gap_flag.  dist / var: full N*N matrices (host).            */
+int pgm_angle_all_pairs(pgm_ctx* ctx, int n_states, int K, const uint8_t* codes, const uint32_t* offsets, int N,
+                        int ml_flag, double* dist, double* var);
+
 /* computeDistance on caller-supplied count matrices (n*n int32 each, counts[s1*n+s2]).            */
 int pgm_ml_distances(pgm_ctx* ctx, const pgm_ml_params* prm, int64_t n_pairs,
                      const int32_t* counts, const uint32_t* gaps, const double* seqlen,

@@ -389,6 +389,40 @@ int orc_prealigned_ml_all_pairs(const uint8_t* rows, int N, int L, int n, const 
     return 0;
 }
 
+void orc_angle_all_pairs(const uint8_t* codes, const uint32_t* off, int N, int n, int K, int ml_flag, double* dist, double* var) {
+    size_t dims = 1;
+    for (int k = 0; k < K; ++k) dims *= n;
+    std::vector<double> cnt((size_t)N * dims, 0.0), inv(N), A((size_t)N * dims);
+    for (int i = 0; i < N; ++i) {
+        const int L = off[i + 1] - off[i];
+        std::vector<int> chars(K, -1);
+        for (int j = 0; j < L; ++j) {
+            for (int k = 1; k < K; ++k) chars[k - 1] = chars[k];
+            const int c = codes[off[i] + j];
+            chars[K - 1] = (c >= n) ? -1 : c;
+            long index = 0;
+            for (int k = 0; k < K; ++k) { if (chars[k] == -1) { index = -1; break; } index = index * n + chars[k]; }
+            if (index != -1) cnt[(size_t)i * dims + index] += 1;
+        }
+        double ss = 0;
+        for (size_t k = 0; k < dims; ++k) ss += cnt[(size_t)i * dims + k] * cnt[(size_t)i * dims + k];
+        inv[i] = 1.0 / std::sqrt(ss);
+        for (size_t k = 0; k < dims; ++k) A[(size_t)i * dims + k] = inv[i] * cnt[(size_t)i * dims + k];   // D * C2^T
+    }
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) {
+            double s = 0;
+            for (size_t k = 0; k < dims; ++k) s += A[(size_t)i * dims + k] * cnt[(size_t)j * dims + k];       // (D C2^T) C2
+            double d = s * inv[j];                                                                                // ... D
+            d = -1.0 * std::log((d * d + 0.4) / 1.4);
+            if (!ml_flag) { d = std::exp(d); d = -0.5 * (5.0 * d - std::sqrt(45.0 * d * d - 20.0 * d)) * (1.0 / d); }
+            const double li = off[i + 1] - off[i], lj = off[j + 1] - off[j];
+            double v = (1.0 / ((li + lj) / 2)) * d;
+            v = std::max(v, 1e-5);
+            dist[(size_t)i * N + j] = d; var[(size_t)i * N + j] = v;
+        }
+}
+
 double orc_average_alignment_length(const orc_graph* g) { return average_alignment_length(g); }
 
 void orc_dynprog_scores(const orc_graph* g1, const orc_graph* g2, const orc_dp_model* m, const orc_dp_opts* o, float out[10]) {

@@ -130,6 +130,16 @@ def prealigned_ml_all_pairs(rows, n, Q, pi, opts):
     return dist, var
 
 
+def angle_all_pairs(code_seqs, n, K, ml_flag):
+    N = len(code_seqs)
+    off = np.zeros(N + 1, dtype=np.uint32)
+    off[1:] = np.cumsum([len(s) for s in code_seqs])
+    codes = np.concatenate([np.asarray(s, dtype=np.uint8) for s in code_seqs]) if off[-1] else np.zeros(1, np.uint8)
+    dist = np.zeros((N, N)); var = np.zeros((N, N))
+    lib().orc_angle_all_pairs(_p(codes), _p(off), N, n, K, int(ml_flag), _p(dist), _p(var))
+    return dist, var
+
+
 def expm(Q, t):
     Q = np.ascontiguousarray(Q, dtype=np.float64)
     P = np.zeros_like(Q)

@@ -59,7 +59,7 @@ SYMBOLS = [
     "pgm_enable_timing", "pgm_get_timing",
     "pgm_nw_ml_pair_range", "pgm_nw_ml_pair_range_dev", "pgm_nw_ml_all_pairs",
     "pgm_prealigned_ml_pair_range", "pgm_prealigned_ml_pair_range_dev", "pgm_prealigned_ml_all_pairs",
-    "pgm_ml_distances",
+    "pgm_ml_distances", "pgm_angle_all_pairs",
     "pgm_align_graphs_batch", "pgm_graph_batch_create", "pgm_graph_batch_run", "pgm_graph_batch_fetch",
     "pgm_graph_batch_destroy", "pgm_dynprog_scores", "pgm_emission_scores",
 ]

@@ -438,6 +438,30 @@ int pgm_prealigned_ml_all_pairs(pgm_ctx* c, const pgm_ml_params* prm, const uint
     return 0;
 }
 
+int pgm_angle_all_pairs(pgm_ctx* c, int n, int K, const uint8_t* codes, const uint32_t* offsets, int N, int ml_flag,
+                        double* dist, double* var) {
+    if (!c || !offsets || N < 0 || K < 1 || n < 2) { pgm_set_error("bad arguments"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(c->device));
+    reset_timing(c);
+    if (N == 0) return 0;
+    long long dims = 1;
+    for (int k = 0; k < K; ++k) { dims *= n; if (dims > 8192) { pgm_set_error("n_states^K = %lld exceeds 8192", dims); return PGM_ERR_ARG; } }
+    for (int k = 0; k < N; ++k) if (offsets[k + 1] - offsets[k] > 65535u) { pgm_set_error("sequence longer than 65535"); return PGM_ERR_ARG; }
+    const size_t total = offsets[N];
+    int rc;
+    if ((rc = c->d_codes.reserve(std::max<size_t>(total, 1))) || (rc = c->d_off.reserve((size_t)(N + 1) * 4)) ||
+        (rc = c->d_counts.reserve((size_t)N * dims * 2)) || (rc = c->d_seqlen.reserve((size_t)N * 8)) ||
+        (rc = c->d_dist.reserve((size_t)N * N * 8)) || (rc = c->d_var.reserve((size_t)N * N * 8))) return rc;
+    PGM_CUDA(cudaMemcpyAsync(c->d_codes.p, codes, total, cudaMemcpyHostToDevice, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(c->d_off.p, offsets, (size_t)(N + 1) * 4, cudaMemcpyHostToDevice, c->stream));
+    rc = launch_angle(c->stream, n, K, (int)dims, N, c->d_codes.as<uint8_t>(), c->d_off.as<uint32_t>(), c->d_counts.as<uint16_t>(),
+                      c->d_seqlen.as<double>(), ml_flag, c->d_dist.as<double>(), c->d_var.as<double>());
+    if (rc) return rc;
+    PGM_CUDA(cudaMemcpyAsync(dist, c->d_dist.p, (size_t)N * N * 8, cudaMemcpyDeviceToHost, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(var, c->d_var.p, (size_t)N * N * 8, cudaMemcpyDeviceToHost, c->stream));
+    return pgm_sync(c);
+}
+
 int pgm_ml_distances(pgm_ctx* c, const pgm_ml_params* prm, int64_t np, const int32_t* counts, const uint32_t* gaps,
                      const double* seqlen, double* dist, double* var) {
     if (!c || !prm) { pgm_set_error("ctx/prm is NULL"); return PGM_ERR_ARG; }

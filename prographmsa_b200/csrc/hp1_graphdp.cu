@@ -31,7 +31,7 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
     return (size_t)d * pitch + (y - ylo);
 }
 
-#define GF_RING 4            // anti-diagonals of {M,X,Y,W} kept in shared memory (must be a power of two)
+#define GF_RING 8            // anti-diagonals of {M,X,Y,W} kept in shared memory (power of two): covers skip edges spanning <= 5 nodes
 // S is row-major by y; each (thread,row) streams its own row 16 bytes (4 columns) at a time with cp.async,
 // 8 columns (= 8 anti-diagonals) ahead, into a private ring of four float4 slots
 
@@ -54,11 +54,19 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, int ring_pitch) {
     float4* ring = (float4*)gsm;                                                    // [GF_RING][ring_pitch], indexed by y
     float4* sring = (float4*)(gsm + (size_t)GF_RING * ring_pitch * sizeof(float4)); // [4][RPT*T], private slots per (thread,row)
     NodeInfo* s2 = (NodeInfo*)(sring + 4 * RPT * T);
+    // STAGE: graph 2's node infos and both predecessor lists live in shared memory, so the rare multi-predecessor
+    // cell (met by SOME row on almost every anti-diagonal) does not put global-memory latency on the sweep's critical path
+    int* sp1i = (int*)(s2 + N2); float* sp1v = (float*)(sp1i + J.np1);
+    int* sp2i = (int*)(sp1v + J.np1); float* sp2v = (float*)(sp2i + J.np2);
     if (STAGE) {
         for (int i = tid; i < N2; i += T) s2[i] = J.ni2[i];
+        for (int i = tid; i < J.np1; i += T) { sp1i[i] = J.p1_idx[i]; sp1v[i] = J.p1_val[i]; }
+        for (int i = tid; i < J.np2; i += T) { sp2i[i] = J.p2_idx[i]; sp2v[i] = J.p2_val[i]; }
         __syncthreads();
     }
     const NodeInfo* __restrict__ I2 = STAGE ? s2 : J.ni2;
+    const int* __restrict__ P1I = STAGE ? sp1i : J.p1_idx; const float* __restrict__ P1V = STAGE ? sp1v : J.p1_val;
+    const int* __restrict__ P2I = STAGE ? sp2i : J.p2_idx; const float* __restrict__ P2V = STAGE ? sp2v : J.p2_val;
 
     auto cell = [&](int yy, int xx, int d) -> float4 {          // any earlier cell: ring when recent, else HBM/L2
         const int dd = yy + xx;
@@ -111,8 +119,8 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, int ring_pitch) {
                 else {
                     const int cnt = ny[r].cnt & 0x7fffffff;
                     for (int ky = 0; ky < cnt; ++ky) {
-                        const int yp = ky ? J.p1_idx[ny[r].ptr + ky] : ny[r].idx0;
-                        const float ey = ky ? J.p1_val[ny[r].ptr + ky] : ny[r].val0;
+                        const int yp = ky ? P1I[ny[r].ptr + ky] : ny[r].idx0;
+                        const float ey = ky ? P1V[ny[r].ptr + ky] : ny[r].val0;
                         const float4 c = cell(yp, 0, d);
                         ys = fmaxf(ys, __fsub_rn(fmaxf(__fadd_rn(c.z, gap_extend), __fadd_rn(c.w, start_gap)), ey));
                     }
@@ -123,8 +131,8 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, int ring_pitch) {
                 if (y == 0) {
                     const int cnt = nx.cnt & 0x7fffffff;
                     for (int kx = 0; kx < cnt; ++kx) {
-                        const int xp = kx ? J.p2_idx[nx.ptr + kx] : nx.idx0;
-                        const float ex = kx ? J.p2_val[nx.ptr + kx] : nx.val0;
+                        const int xp = kx ? P2I[nx.ptr + kx] : nx.idx0;
+                        const float ex = kx ? P2V[nx.ptr + kx] : nx.val0;
                         const float4 c = cell(0, xp, d);
                         xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(c.y, gap_extend), __fadd_rn(c.w, start_gap)), ex));
                     }
@@ -144,13 +152,13 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, int ring_pitch) {
                     } else {
                         const int c1 = ny[r].cnt & 0x7fffffff, c2 = nx.cnt & 0x7fffffff;
                         for (int ky = 0; ky < c1; ++ky) {
-                            const int yp = ky ? J.p1_idx[ny[r].ptr + ky] : ny[r].idx0;
-                            const float ey = ky ? J.p1_val[ny[r].ptr + ky] : ny[r].val0;
+                            const int yp = ky ? P1I[ny[r].ptr + ky] : ny[r].idx0;
+                            const float ey = ky ? P1V[ny[r].ptr + ky] : ny[r].val0;
                             const float4 cu = cell(yp, x, d);                        // (yp, x): Y, W
                             const float Sy = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
                             for (int kx = 0; kx < c2; ++kx) {
-                                const int xp = kx ? J.p2_idx[nx.ptr + kx] : nx.idx0;
-                                const float ex = kx ? J.p2_val[nx.ptr + kx] : nx.val0;
+                                const int xp = kx ? P2I[nx.ptr + kx] : nx.idx0;
+                                const float ex = kx ? P2V[nx.ptr + kx] : nx.val0;
                                 const float4 cd = cell(yp, xp, d);                   // (yp, xp): W
                                 const float4 cl = cell(y, xp, d);                    // (y, xp): X, W
                                 const float Sm = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
@@ -411,7 +419,7 @@ static int launch_fill_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs,
 }
 
 // max_n1 / max_n2: largest graph-1 / graph-2 node counts in this launch
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2) {
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2, int max_np) {
     if (n_jobs == 0) return 0;
     const int rows = max_n1 > 1 ? max_n1 - 1 : 1;                   // rows 0 .. N1-2
     // rows per thread: on an anti-diagonal sweep only ~half the rows are active at a time, so giving a thread
@@ -423,7 +431,7 @@ int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, in
     const int threads = std::min(1024, std::max(64, ((rows + rpt - 1) / rpt + 31) & ~31));
     const int ring_pitch = (max_n1 + 3) & ~3;
     const size_t ring = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * rpt * threads * sizeof(float4);
-    const size_t info = (size_t)max_n2 * sizeof(NodeInfo);
+    const size_t info = (size_t)max_n2 * sizeof(NodeInfo) + (size_t)max_np * 8 + 64;
     if (ring > 227 * 1024) { pgm_set_error("graph too large for the shared-memory diagonal ring (N1 = %d)", max_n1); return PGM_ERR_ARG; }
     const bool stage = ring + info <= 200 * 1024;
     const size_t smem = ring + (stage ? info : 0);

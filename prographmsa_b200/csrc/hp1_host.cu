@@ -16,7 +16,7 @@ void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok);
 void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2);
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2, int max_np);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
 void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
@@ -234,6 +234,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.p2_ptr = (const int*)(din + L.p2_ptr); J.p2_idx = (const int*)(din + L.p2_idx); J.p2_val = (const float*)(din + L.p2_val);
         J.p2_rep = (const uint8_t*)(din + L.p2_rep); J.p2_alt = (const float*)(din + L.p2_alt);
         J.ni1 = (const NodeInfo*)(din + L.ni1); J.ni2 = (const NodeInfo*)(din + L.ni2);
+        J.np1 = L.np1; J.np2 = L.np2;
         J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.Tbuf = (float*)(sb + L.Tbuf);
         J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
         J.Aimg = (float*)(sb + L.Aimg); J.Bimg = (float*)(sb + L.Bimg);
@@ -257,11 +258,12 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
     const GraphJobDev* dj = b->d_jobs.as<GraphJobDev>();
     for (auto& sb : b->sub) {
         const int nj = sb.second - sb.first;
-        int mx1 = 0, mx2 = 0, mxd = 0, mxn = 0, mxp = 0;
+        int mx1 = 0, mx2 = 0, mxd = 0, mxn = 0, mxp = 0, mxnp = 0;
         for (int k = sb.first; k < sb.second; ++k) {
             mx1 = std::max(mx1, b->jobs[k].N1); mx2 = std::max(mx2, b->jobs[k].N2);
             mxd = std::max(mxd, std::min(b->jobs[k].N1, b->jobs[k].N2));
             mxn = std::max(mxn, b->jobs[k].N1 + b->jobs[k].N2); mxp = std::max(mxp, b->jobs[k].pitch);
+            mxnp = std::max(mxnp, b->jobs[k].np1 + b->jobs[k].np2);
         }
         int rc; void* tok;
         pgm_ctx_time_begin(c, 3, &tok);
@@ -271,7 +273,7 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
         if (rc) return rc;
         pgm_ctx_time_begin(c, 4, &tok);
         (void)mxd; (void)mxn; (void)mxp;
-        rc = launch_graph_fill(st, nj, dj + sb.first, mx1, mx2);
+        rc = launch_graph_fill(st, nj, dj + sb.first, mx1, mx2, mxnp);
         pgm_ctx_time_end(c, tok);
         if (rc) return rc;
         pgm_ctx_time_begin(c, 5, &tok);

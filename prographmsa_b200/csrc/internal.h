@@ -113,6 +113,9 @@ int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t 
 int launch_ml_from_counts(cudaStream_t st, const MlDev& ml, int64_t n_pairs, const int32_t* d_counts, const uint32_t* d_gaps,
                           const double* d_seqlen, double* d_dist, double* d_var, unsigned long long* d_evals);
 
+int launch_angle(cudaStream_t st, int n, int K, int dims, int N, const uint8_t* d_codes, const uint32_t* d_off,
+                 uint16_t* d_counts, double* d_norm2, int ml_flag, double* d_dist, double* d_var);
+
 // ---- HP-1 (hp1_*.cu) ------------------------------------------------------------------------------
 struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred list start, count (sign bit = first pred is a repeat edge), first entry inline
 
@@ -129,6 +132,7 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     // alternative-path preds (values with repeat_init = repeat_ext = +inf; GraphAlign.h:165-198)
     const float* p1_alt; const float* p2_alt;
     const NodeInfo* ni1; const NodeInfo* ni2;   // N1 / N2 entries
+    int np1, np2;                               // total predecessor-list entries of graph 1 / graph 2
     float sc[10];               // DynProgScores
     float* S;                   // row-major by graph-1 node: S(y,x) at y*ldS + x (a DP thread streams its own row)
     int ldS;                    // N2 rounded up to a multiple of 4

@@ -86,8 +86,7 @@ class DistanceFactory:
         if not prealigned:
             if opts.nwdist_flag:
                 return DistanceFactoryAlign(model_factory, opts, ctx)
-            raise NotImplementedError("DistanceFactoryAngle (k-mer angle distances) is outside the hot path "
-                                      "(SURVEY.md §8f N1); pass -a / nwdist_flag")
+            return DistanceFactoryAngle(model_factory, opts, ctx)
         return DistanceFactoryPrealigned(model_factory, opts, ctx)
 
 
@@ -169,6 +168,27 @@ class DistanceFactoryPrealigned(DistanceFactory):
         dm = DistanceMatrix(N)
         _lib.check(_lib.lib().pgm_prealigned_ml_all_pairs(self.ctx.handle, C.byref(prm), _p(arr) if arr.size else None, N, L,
                                                           _p(dm.distances), _p(dm.variances)))
+        return dm
+
+
+class DistanceFactoryAngle(DistanceFactory):
+    """k-mer angle distances on the GPU (DistanceFactoryAngle<A,K>, DistanceFactoryAngle.h:24-131);
+    K = 2 for AA and codon, 6 for DNA (DistanceFactory.cpp:14,32,50)."""
+
+    def computePwDistances(self, sequences, order):
+        alpha = self.model_factory.alphabet
+        K = 6 if alpha is DNA else 2
+        seqs = []
+        for name in order:
+            if name not in sequences:
+                raise KeyError(name)
+            seqs.append(np.minimum(np.asarray(sequences[name], dtype=np.uint8), alpha.DIM))
+        codes, offsets = pack_sequences(seqs)
+        N = len(seqs)
+        dm = DistanceMatrix(N)
+        ml = int(self.opts.mldist_flag or self.opts.mldist_gap_flag)
+        _lib.check(_lib.lib().pgm_angle_all_pairs(self.ctx.handle, alpha.DIM, K, _p(codes), _p(offsets), N, ml,
+                                                  _p(dm.distances), _p(dm.variances)))
         return dm
 
 

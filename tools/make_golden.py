@@ -104,5 +104,29 @@ def main():
         json.dump(dict(generator="tools/make_golden.py", binary="ProGraphMSA_64 (2013-07-09 rev 5e7b708)", families=alis), f, indent=1)
 
 
+def pipelines():
+    """whole runs (initial tree from k-mer angle or NW+ML distances, two guide-tree iterations, final
+    alignment): `-i 2 -f` text + `-T --all_trees`.  (50, 300, -m) is BASELINE.json configs[0]."""
+    out = []
+    for n, L, seed, flags in [(8, 60, 5, ["-m"]), (20, 120, 6, ["-m"]), (20, 120, 6, ["-a", "-m"]), (50, 300, 7, ["-m"])]:
+        opts = Options(mldist_flag=True, nwdist_flag=("-a" in flags))
+        mf = model.getDefault(opts)
+        seqs, _ = synth.simulate_family(n, L, mf, seed=seed, indel_rate=0.03, forbid_first=10)
+        strs = {k: to_str(v) for k, v in seqs.items()}
+        fa = "".join(">%s\n%s\n" % (k, v) for k, v in strs.items())
+        trees, _ = run(flags + ["-i", "2", "-T", "--all_trees"], fa)
+        ali, _ = run(flags + ["-i", "2", "-f"], fa)
+        parsed = parse_fasta(ali)
+        out.append(dict(n=n, L=L, seed=seed, flags=flags, seqs=strs, trees=trees.strip().splitlines(),
+                        aligned=parsed, order=list(parsed)))
+        print("pipeline", n, L, flags, "trees", len(out[-1]["trees"]), file=sys.stderr)
+    with open(os.path.join(ROOT, "tests", "golden", "pipelines.json"), "w") as f:
+        json.dump(dict(generator="tools/make_golden.py", binary="ProGraphMSA_64 (2013-07-09 rev 5e7b708)", runs=out), f, indent=1)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "pipelines":
+        pipelines()
+        sys.exit(0)
     main()
+    pipelines()
