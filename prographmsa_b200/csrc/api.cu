@@ -227,36 +227,81 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     std::vector<size_t> chunk_end;                      // task index where each chunk ends
     std::vector<uint64_t> chunk_tb, chunk_list, chunk_cells;
     tasks.clear();
+    int u16_max_rows = 0;                               // longest row sequence of any 16-bit task (sizes the residue staging)
     {
         int64_t i, j; pair_from_index_host(pb, N, i, j);
         int64_t p = pb;
         uint64_t tb_words = 0, list_entries = 0, cells = 0;
+        auto len_of = [&](int64_t k) -> uint32_t { return offsets[k + 1] - offsets[k]; };
+        // can rows with at most Lcol columns run the 16-bit flavour against the row sequences [j0, j1)?
+        auto u16_ok = [&](uint32_t Lcol_min, uint32_t Lcol_max, int64_t j0, int64_t j1, uint32_t& l2max) -> bool {
+            l2max = 0;
+            if (!u16_table_ok || Lcol_min < 1 || Lcol_max > 512) return false;
+            uint32_t l2min = 0xffffffffu;
+            for (int64_t jq = j0; jq < j1; ++jq) { const uint32_t l = len_of(jq); l2max = std::max(l2max, l); l2min = std::min(l2min, l); }
+            const uint64_t bound = (uint64_t)4 * smax * std::min<uint32_t>(Lcol_max, l2max) + (uint64_t)u16_h * (Lcol_max + l2max) + u16_bias +
+                                   4 * smax + 2 * u16_h + 64;
+            return l2min >= 1 && bound < 65536;
+        };
+        auto close_chunk_if_full = [&](uint64_t w, uint64_t span) {
+            if (tb_words > 0 && (tb_words + w > tb_budget_words || list_entries + span > 0xf0000000ull)) {
+                chunk_end.push_back(tasks.size()); chunk_tb.push_back(tb_words); chunk_list.push_back(list_entries);
+                chunk_cells.push_back(cells);
+                tb_words = 0; list_entries = 0; cells = 0;
+            }
+        };
+        auto tb_need = [&](uint32_t L1, uint32_t C, int64_t j0, int64_t j1) -> uint64_t {
+            const uint32_t nb = (L1 + 32u * C - 1u) / (32u * C);
+            return (uint64_t)nb * 32u * ((uint64_t)(offsets[j1] - offsets[j0]) + 31u * (uint64_t)(j1 - j0));
+        };
+        auto push_task = [&](int64_t row, int64_t j0, int64_t j1, int64_t out_base, uint32_t Cflags) {
+            const uint32_t L1 = len_of(row);
+            const uint64_t span = offsets[j1] - offsets[j0];
+            NwTask t; t.i = (uint32_t)row; t.j0 = (uint32_t)j0; t.j1 = (uint32_t)j1; t.out_base = (uint32_t)out_base;
+            t.tb_base = tb_words; t.list_base = (uint32_t)list_entries; t.C = Cflags;
+            tasks.push_back(t);
+            tb_words += tb_need(L1, Cflags & 0xffu, j0, j1); list_entries += span;
+            cells += (uint64_t)(L1 + 1) * (span + (uint64_t)(j1 - j0));          // sum (L1+1)(L2+1)
+        };
         while (p < pe) {
             const int64_t row_end = std::min<int64_t>(N, j + (pe - p));          // exclusive j bound within this row
-            const uint32_t L1 = offsets[i + 1] - offsets[i];
-            const uint32_t C = (uint32_t)nw_pick_C((int)L1);                     // per row: keeps all 32 lanes busy
-            const uint32_t nb = (L1 + 32u * C - 1u) / (32u * C);
+            const uint32_t L1 = len_of(i);
+            // twin rows: row i runs to its end and row i+1 is covered completely -> both rows share their j blocks
+            const bool twin_rows = row_end == N && i + 2 < N && j <= i + 2 && p + (N - j) + (N - i - 2) <= pe;
+            if (twin_rows) {
+                const uint32_t L1b = len_of(i + 1);
+                const int64_t pA = p - pb, pB = pA + (N - j);                    // packed index of (i, j) and of (i+1, i+2)
+                for (int64_t j0 = j; j0 < N; j0 += NW_TASK_PAIRS) {
+                    const int64_t j1 = std::min<int64_t>(N, j0 + NW_TASK_PAIRS), jb0 = std::max<int64_t>(j0, i + 2);
+                    uint32_t l2max;
+                    if (jb0 < j1 && u16_ok(std::min(L1, L1b), std::max(L1, L1b), j0, j1, l2max)) {
+                        const uint32_t C = (uint32_t)nw_pick_C((int)std::max(L1, L1b));
+                        close_chunk_if_full(tb_need(L1, C, j0, j1) + tb_need(L1b, C, jb0, j1), offsets[j1] - offsets[j0] + offsets[j1] - offsets[jb0]);
+                        push_task(i, j0, j1, pA + (j0 - j), C | NW_MODE_U16 | NW_TWIN_A);
+                        push_task(i + 1, jb0, j1, pB + (jb0 - (i + 2)), C | NW_MODE_U16 | NW_TWIN_B);
+                        u16_max_rows = std::max<int>(u16_max_rows, (int)l2max);
+                    } else {
+                        for (int h = 0; h < 2; ++h) {
+                            const int64_t row = i + h, ja = h ? jb0 : j0;
+                            if (ja >= j1) continue;
+                            const uint32_t Lr = len_of(row);
+                            uint32_t C = (uint32_t)nw_pick_C((int)Lr);
+                            if (u16_ok(Lr, Lr, ja, j1, l2max)) { C |= NW_MODE_U16; u16_max_rows = std::max<int>(u16_max_rows, (int)l2max); }
+                            close_chunk_if_full(tb_need(Lr, C & 0xffu, ja, j1), offsets[j1] - offsets[ja]);
+                            push_task(row, ja, j1, h ? pB + (ja - (i + 2)) : pA + (ja - j), C);
+                        }
+                    }
+                }
+                p += (N - j) + (N - i - 2);
+                i += 2; j = i + 1;
+                continue;
+            }
             for (int64_t j0 = j; j0 < row_end; j0 += NW_TASK_PAIRS) {
                 const int64_t j1 = std::min<int64_t>(row_end, j0 + NW_TASK_PAIRS);
-                const uint64_t span = offsets[j1] - offsets[j0];
-                const uint64_t w = (uint64_t)nb * 32u * (span + 31u * (uint64_t)(j1 - j0));
-                if (tb_words > 0 && (tb_words + w > tb_budget_words || list_entries + span > 0xf0000000ull)) {
-                    chunk_end.push_back(tasks.size()); chunk_tb.push_back(tb_words); chunk_list.push_back(list_entries);
-                    chunk_cells.push_back(cells);
-                    tb_words = 0; list_entries = 0; cells = 0;
-                }
-                NwTask t; t.i = (uint32_t)i; t.j0 = (uint32_t)j0; t.j1 = (uint32_t)j1; t.out_base = (uint32_t)(p - pb);
-                t.tb_base = tb_words; t.list_base = (uint32_t)list_entries; t.C = C;
-                if (u16_table_ok && L1 >= 1 && L1 <= 512) {      // 16-bit flavour: single band, non-empty rows, values < 65536
-                    uint32_t l2max = 0, l2min = 0xffffffffu;
-                    for (int64_t jq = j0; jq < j1; ++jq) { const uint32_t l = offsets[jq + 1] - offsets[jq]; l2max = std::max(l2max, l); l2min = std::min(l2min, l); }
-                    const uint64_t bound = (uint64_t)4 * smax * std::min<uint32_t>(L1, l2max) + (uint64_t)u16_h * (L1 + l2max) + u16_bias +
-                                           4 * smax + 2 * u16_h + 64;
-                    if (l2min >= 1 && bound < 65536) t.C |= NW_MODE_U16;
-                }
-                tasks.push_back(t);
-                tb_words += w; list_entries += span;
-                cells += (uint64_t)(L1 + 1) * (span + (uint64_t)(j1 - j0));      // sum (L1+1)(L2+1)
+                uint32_t C = (uint32_t)nw_pick_C((int)L1), l2max;              // per row: keeps all 32 lanes busy
+                if (u16_ok(L1, L1, j0, j1, l2max)) { C |= NW_MODE_U16; u16_max_rows = std::max<int>(u16_max_rows, (int)l2max); }
+                close_chunk_if_full(tb_need(L1, C & 0xffu, j0, j1), offsets[j1] - offsets[j0]);
+                push_task(i, j0, j1, p - pb, C);
                 p += j1 - j0;
             }
             ++i; j = i + 1;
@@ -282,7 +327,8 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
         {
             ScopedKernelTimer t(c, K_NW_FWD);
             rc = launch_nw_forward(c->stream, ntasks, n, max_bands, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tab.as<int8_t>(),
-                                   go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores, u16_h, u16_bias);
+                                   go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores, u16_h, u16_bias,
+                                   u16_max_rows);
             if (rc) return rc;
         }
         {

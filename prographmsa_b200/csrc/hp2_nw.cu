@@ -25,7 +25,7 @@
 // IS the traceback direction.  The int8 profile stores 4*T+3 directly.  Per cell this is two fused
 // add-max (VIADDMNMX), one 3-input max, one mask and the adds -- no ISETP/SEL chain.
 //
-// 16-bit SIMD flavour (nw_forward_body_u16): when the scores fit, a warp aligns TWO pairs that share seq1
+// 16-bit SIMD flavour (nw_forward_body_twin): when the scores fit, a warp aligns TWO pairs that share seq2
 // at once, one per 16-bit half of every register (VIADDMNMX.U16x2 / VIMNMX3.U16x2).  To keep the plain
 // adds on the FMA pipe as ordinary 32-bit integer multiply-adds, no carry may ever cross the halves, so
 // all quantities are stored unsigned with a potential:  V^(y,x) = 4 V(y,x) + tag + H (x+y) + BIAS,
@@ -46,8 +46,8 @@ __device__ __forceinline__ void
 nw_forward_body(const NwTask& task, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
                 const int8_t* __restrict__ tab, int n1, int go, int ge,
                 uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out,
-                int k_one, int k_four) {
-    // k_one == 1, k_four == 4 at run time: opaque multipliers that make the plain adds below integer
+                int k_one, int k_four, int k_mone) {
+    // k_one == 1, k_four == 4, k_mone == -1 at run time: opaque multipliers that make the plain adds below integer
     // multiply-adds, i.e. FMA-pipe instructions, so the ALU pipe (which carries the max/logic ops and
     // is the kernel's limiter) and the FMA pipe are both busy
     extern __shared__ __align__(16) unsigned char smem[];
@@ -80,7 +80,6 @@ nw_forward_body(const NwTask& task, const uint8_t* __restrict__ codes, const uin
     const int go4 = 4 * go, ge4 = 4 * ge;
     const int gox = go4 + 2, goy = go4 + 1;                   // gap-open into X (tag 2) / into Y (tag 1)
     const int XINF = 4 * NW_MINFTY + 2, YINF = 4 * NW_MINFTY + 1;
-    const int k_mone = -k_one;
 
     for (uint32_t j = task.j0 + warp; j < task.j1; j += NW_WARPS) {
         const NwPair d = nw_pair(task, j, off);
@@ -158,108 +157,146 @@ nw_forward_body(const NwTask& task, const uint8_t* __restrict__ codes, const uin
     }
 }
 
+// 16-bit twin flavour.  The CTA owns the rows (column sequences) of TWO tasks A = (i, j0..j1) and B = (i', j0'..j1)
+// and every warp aligns the pairs (i, j) and (i', j) at once, A in the low and B in the high 16 bits of each
+// register.  Because both halves share the row sequence j, the CTA's profile can hold both substitution scores
+// of a cell in ONE word, prof[r][q][lane] (uint4 = 4 columns x (A | B << 16)), so a cell pair costs 9 instructions
+// (5 multiply-adds on the FMA pipe, 4 max/logic on the ALU pipe) and no byte permutes.  The row residues are
+// staged per warp in shared memory, pre-multiplied by the profile's row pitch.
+#define NW_TWIN_ROW_BYTES 2048u                               // profile bytes per residue: 4 x 32 lanes x 16 B
+
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+
 template <int C>
 __device__ __forceinline__ void
-nw_forward_body_u16(const NwTask& task, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
-                    const int8_t* __restrict__ tab, int n1, int go, int ge, uint32_t* __restrict__ tb,
-                    int32_t* __restrict__ scores_out, int k_one, int k_four, int H, int BIAS) {
+nw_forward_body_twin(const NwTask& ta, const NwTask* __restrict__ tasks, const uint8_t* __restrict__ codes,
+                     const uint32_t* __restrict__ off, const int8_t* __restrict__ tab, int n1, int go, int ge,
+                     uint32_t* __restrict__ tb, int32_t* __restrict__ scores_out, uint32_t rs_stride,
+                     int k_one, int k_four, int k_mone, int H, int BIAS) {
     extern __shared__ __align__(16) unsigned char smem[];
     int8_t* s_tab = (int8_t*)smem;
     const int tab_bytes = (n1 * n1 + 15) & ~15;
-    uint16_t* prof = (uint16_t*)(smem + tab_bytes);          // [r][lane][16] halfwords: 4*T + 3 + 2H
+    uint32_t* prof = (uint32_t*)(smem + tab_bytes);          // [r][q][lane][4] words
+    uint32_t* rs_all = prof + (size_t)n1 * (NW_TWIN_ROW_BYTES / 4);
 
-    const uint32_t s1_off = off[task.i];
-    const int L1 = (int)(off[task.i + 1] - s1_off);
-    const uint8_t* __restrict__ s1 = codes + s1_off;
+    const bool twin = (ta.C & NW_TWIN_A) != 0;
+    NwTask tbk = ta;
+    if (twin) tbk = tasks[blockIdx.x + 1];
+    const uint32_t s1a_off = off[ta.i], s1b_off = off[tbk.i];
+    const int L1a = (int)(off[ta.i + 1] - s1a_off), L1b = twin ? (int)(off[tbk.i + 1] - s1b_off) : 0;
+    const uint8_t* __restrict__ s1a = codes + s1a_off;
+    const uint8_t* __restrict__ s1b = codes + s1b_off;
     for (int i = threadIdx.x; i < n1 * n1; i += NW_THREADS) s_tab[i] = tab[i];
     __syncthreads();
     for (int idx = threadIdx.x; idx < n1 * 512; idx += NW_THREADS) {
-        const int r = idx >> 9, lk = idx & 511, ln = lk >> 4, k = lk & 15;
-        const int x = ln * C + k;
-        prof[idx] = (k < C && x < L1) ? (uint16_t)(4 * (int)s_tab[r + n1 * (int)s1[x]] + 3 + 2 * H) : (uint16_t)0;
+        const int r = idx >> 9, q = (idx >> 7) & 3, ln = (idx >> 2) & 31, w = idx & 3;
+        const int k = 4 * q + w, x = ln * C + k;
+        uint32_t v = 0;
+        if (k < C) {
+            if (x < L1a) v = (uint32_t)(4 * (int)s_tab[r + n1 * (int)s1a[x]] + 3 + 2 * H);
+            if (x < L1b) v |= (uint32_t)(4 * (int)s_tab[r + n1 * (int)s1b[x]] + 3 + 2 * H) << 16;
+        }
+        prof[idx] = v;
     }
     __syncthreads();
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* rs = rs_all + (size_t)warp * rs_stride;         // rs[32 + row] = residue(row) * row pitch
     const int go4 = 4 * go, ge4 = 4 * ge;
     auto pack2 = [](int v) -> uint32_t { return (uint32_t)v | ((uint32_t)v << 16); };
-    const uint32_t gex2 = pack2(ge4 + H), gox2 = pack2(go4 + 2 + H), goy2 = pack2(go4 + 1 + H);
-    const uint32_t u_one = (uint32_t)k_one, u_four = (uint32_t)k_four, u_mone = (uint32_t)(-k_one);
-    const int nl = (L1 + C - 1) / C;
+    uint32_t gex2 = pack2(ge4 + H), gox2 = pack2(go4 + 2 + H), goy2 = pack2(go4 + 1 + H);
+    uint32_t u_one = (uint32_t)k_one, u_four = (uint32_t)k_four, u_mone = (uint32_t)k_mone;
+    // pin the loop constants in registers (otherwise they are re-derived from the parameters every step)
+    asm volatile("" : "+r"(gex2), "+r"(gox2), "+r"(goy2), "+r"(u_one), "+r"(u_four), "+r"(u_mone));
+    const int L1m = max(L1a, L1b);
+    const int nl = (L1m + C - 1) / C;
+    const int x0 = lane * C;
+    uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)lane * 16u;
+    uint32_t inWstep = pack2(ge4 + H);
+    asm volatile("" : "+r"(prof_lane), "+r"(inWstep));
+    const uint32_t off_a0 = off[ta.j0], off_b0 = off[tbk.j0];
 
-    for (uint32_t jj = task.j0 + 2 * warp; jj < task.j1; jj += 2 * NW_WARPS) {
-        const bool hasB = jj + 1 < task.j1;
-        const NwPair da = nw_pair(task, jj, off), db = nw_pair(task, hasB ? jj + 1 : jj, off);
-        const int L2a = (int)da.L2, L2b = (int)db.L2, L2m = max(L2a, L2b);
-        const uint8_t* __restrict__ s2a = codes + da.s2_off;
-        const uint8_t* __restrict__ s2b = codes + db.s2_off;
-        const int nsteps = L2m + nl - 1;
-        const int x0 = lane * C;
+    for (uint32_t j = ta.j0 + warp; j < ta.j1; j += NW_WARPS) {
+        const uint32_t s2_off = off[j];
+        const int L2 = (int)(off[j + 1] - s2_off);
+        const uint8_t* __restrict__ s2 = codes + s2_off;
+        const bool hasB = twin && j >= tbk.j0;
+        __syncwarp();
+        for (int q = lane; q < L2; q += 32) rs[32 + q] = (uint32_t)s2[q] * NW_TWIN_ROW_BYTES;
+        __syncwarp();
+        uint32_t* __restrict__ pa = tb + ta.tb_base + 32ull * ((uint64_t)(s2_off - off_a0) + 31u * (j - ta.j0)) + lane;
+        uint32_t* __restrict__ pb = pa;
+        if (hasB) pb = tb + tbk.tb_base + 32ull * ((uint64_t)(s2_off - off_b0) + 31u * (j - tbk.j0)) + lane;
+
+        const int nsteps = L2 + nl - 1;
         uint32_t Wup[C], Yup[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) { Wup[k] = pack2(4 * (go + (x0 + k) * ge) + H * (x0 + k + 1) + BIAS); Yup[k] = 0u; }
         uint32_t Wdiag = (x0 == 0) ? pack2(BIAS) : pack2(4 * (go + (x0 - 1) * ge) + H * x0 + BIAS);
-        uint32_t Wlast = 0, Xlast = 0, rcur = 0;
+        uint32_t Wlast = 0, Xlast = 0;
         uint32_t inW = pack2(go4 + H + BIAS);                 // W^(1,0)
-        const uint32_t inWstep = pack2(ge4 + H);
-        uint32_t inR = (uint32_t)s2a[0] | ((uint32_t)s2b[0] << 16);
-        const unsigned char* pb = (const unsigned char*)prof + lane * 32;
-        uint32_t* __restrict__ tba = tb + da.tb_off + lane;
-        uint32_t* __restrict__ tbb = tb + db.tb_off + lane;
-        uint32_t capA = 0, capB = 0;
-        const int kk = L1 - 1 - x0;                           // this lane owns column L1 iff 0 <= kk < C
+        const uint32_t* rp = rs + 32 - lane;                  // &rs[32 + row] for row = t - lane
+        uint32_t rnext = rp[0];
+        int row = -lane;
         for (int t = 0; t < nsteps; ++t) {
             uint32_t Wl = __shfl_up_sync(0xffffffffu, Wlast, 1);
             uint32_t Xl = __shfl_up_sync(0xffffffffu, Xlast, 1);
-            uint32_t r = __shfl_up_sync(0xffffffffu, rcur, 1);
-            if (lane == 0) { Wl = inW; Xl = 0u; r = inR; }
-            {
-                const int ya = min(t + 2, L2a), yb = min(t + 2, L2b);
-                inR = (uint32_t)s2a[ya - 1] | ((uint32_t)s2b[yb - 1] << 16);
-                inW += inWstep;
-            }
-            const int row = t - lane;                          // 0-based row of this lane at this step
-            if ((unsigned)row < (unsigned)L2m) {
-                const unsigned char* pa_ = pb + (r & 0xffffu) * 1024u;
-                const unsigned char* pb_ = pb + (r >> 16) * 1024u;
-                const uint4 a0 = *reinterpret_cast<const uint4*>(pa_), a1 = *reinterpret_cast<const uint4*>(pa_ + 16);
-                const uint4 b0 = *reinterpret_cast<const uint4*>(pb_), b1 = *reinterpret_cast<const uint4*>(pb_ + 16);
-                const uint32_t Aw[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const uint32_t Bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-                uint32_t Wleft = Wl, Xleft = Xl, dg = Wdiag, bits = 0, F = 0;
+            if (lane == 0) { Wl = inW; Xl = 0u; }
+            inW += inWstep;
+            const uint32_t rcur = rnext;
+            ++rp;
+            rnext = *rp;                                      // next row's residue (slots past L2 are never used)
+            if ((unsigned)row < (unsigned)L2) {
+                const uint32_t pbase = prof_lane + rcur;
+                uint32_t sw[16];
+                {
+                    const uint4 v = lds128(pbase);
+                    sw[0] = v.x; sw[1] = v.y; sw[2] = v.z; sw[3] = v.w;
+                }
+                if (C > 4) { const uint4 v = lds128(pbase + 512u); sw[4] = v.x; sw[5] = v.y; sw[6] = v.z; sw[7] = v.w; }
+                if (C > 8) { const uint4 v = lds128(pbase + 1024u); sw[8] = v.x; sw[9] = v.y; sw[10] = v.z; sw[11] = v.w; }
+                if (C > 12) { const uint4 v = lds128(pbase + 1536u); sw[12] = v.x; sw[13] = v.y; sw[14] = v.z; sw[15] = v.w; }
+                // phase 1: everything that only needs the previous row
+                uint32_t wd[C];
+                wd[0] = Wdiag * u_one + sw[0];
+#pragma unroll
+                for (int k = 1; k < C; ++k)                     // every third add stays on the ALU pipe: pipe balance
+                    wd[k] = (k % 3 == 1) ? Wup[k - 1] + sw[k] : Wup[k - 1] * u_one + sw[k];
+#pragma unroll
+                for (int k = 0; k < C; ++k) Yup[k] = __viaddmax_u16x2(Yup[k], gex2, Wup[k] * u_one + goy2);
+                // phase 2: the chain along the row
+                uint32_t Wleft = Wl, Xleft = Xl, bits = 0, F = 0;
 #pragma unroll
                 for (int k = 0; k < C; ++k) {
-                    const uint32_t s = __byte_perm(Aw[k >> 1], Bw[k >> 1], (k & 1) ? 0x7632 : 0x5410);
-                    const uint32_t wd = dg * u_one + s;
-                    const uint32_t xv = __viaddmax_u16x2(Xleft, gex2, Wleft * u_one + gox2);
-                    const uint32_t yv = __viaddmax_u16x2(Yup[k], gex2, Wup[k] * u_one + goy2);
-                    const uint32_t wt = __vimax3_u16x2(xv, yv, wd);
-                    const uint32_t wn = wt & 0xfffcfffcu;
-                    bits = bits * u_four + (wn * u_mone + wt);  // per half: tag 3 diag, 2 left, 1 up
+                    Xleft = __viaddmax_u16x2(Xleft, gex2, Wleft * u_one + gox2);
+                    const uint32_t wt = __vimax3_u16x2(Xleft, Yup[k], wd[k]);
+                    Wleft = wt & 0xfffcfffcu;
+                    bits = Wleft * u_mone + (bits * u_four + wt);   // per half: tag 3 diag, 2 left, 1 up
+                    Wup[k] = Wleft;
                     if (k == 7) { F = bits; bits = 0; }
-                    dg = Wup[k];
-                    Wup[k] = wn; Yup[k] = yv;
-                    Wleft = wn; Xleft = xv;
                 }
                 if (C < 8) { F = bits; bits = 0; }
                 Wdiag = Wl;
-                Wlast = Wleft; Xlast = Xleft; rcur = r;
-                if (row < L2a) tba[(size_t)t * 32] = __byte_perm(F, bits, 0x5410);
-                if (hasB && row < L2b) tbb[(size_t)t * 32] = __byte_perm(F, bits, 0x7632);
-                if (scores_out != nullptr && kk >= 0 && kk < C) {
-                    uint32_t v = 0;
-#pragma unroll
-                    for (int k = 0; k < C; ++k) if (k == kk) v = Wup[k];
-                    if (row == L2a - 1) capA = v & 0xffffu;
-                    if (row == L2b - 1) capB = v >> 16;
-                }
+                Wlast = Wleft; Xlast = Xleft;
+                *pa = __byte_perm(F, bits, 0x5410);
+                if (hasB) *pb = __byte_perm(F, bits, 0x7632);
             }
+            ++row;
+            pa += 32; pb += 32;
         }
-        if (scores_out != nullptr && kk >= 0 && kk < C) {
-            scores_out[da.out_idx] = ((int)capA - H * (L1 + L2a) - BIAS) >> 2;
-            if (hasB) scores_out[db.out_idx] = ((int)capB - H * (L1 + L2b) - BIAS) >> 2;
+        if (scores_out != nullptr) {
+            // every lane stopped after its row L2, so Wup holds W^(L2, .)
+            const int ka = L1a - 1 - x0, kb = L1b - 1 - x0;
+            uint32_t va = 0, vb = 0;
+#pragma unroll
+            for (int k = 0; k < C; ++k) { if (k == ka) va = Wup[k] & 0xffffu; if (k == kb) vb = Wup[k] >> 16; }
+            if (ka >= 0 && ka < C) scores_out[ta.out_base + (j - ta.j0)] = ((int)va - H * (L1a + L2) - BIAS) >> 2;
+            if (hasB && kb >= 0 && kb < C) scores_out[tbk.out_base + (j - tbk.j0)] = ((int)vb - H * (L1b + L2) - BIAS) >> 2;
         }
-        __syncwarp();
     }
 }
 
@@ -321,17 +358,18 @@ __global__ void __launch_bounds__(NW_THREADS)
 nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
                   const NwTask* __restrict__ tasks, const int8_t* __restrict__ tab, int n1, int go, int ge,
                   uint32_t* __restrict__ tb, int32_t* colbuf, uint32_t colbuf_stride, int32_t* __restrict__ scores_out,
-                  int k_one, int k_four, int u16_h, int u16_bias) {
+                  int k_one, int k_four, int k_mone, int u16_h, int u16_bias, uint32_t rs_stride) {
     const NwTask task = tasks[blockIdx.x];
+    if (task.C & NW_TWIN_B) return;                            // aligned by the CTA of the preceding task
     if (task.C & NW_MODE_U16) {
-#define CASE(c) case c: nw_forward_body_u16<c>(task, codes, off, tab, n1, go, ge, tb, scores_out, k_one, k_four, u16_h, u16_bias); break;
+#define CASE(c) case c: nw_forward_body_twin<c>(task, tasks, codes, off, tab, n1, go, ge, tb, scores_out, rs_stride, k_one, k_four, k_mone, u16_h, u16_bias); break;
         switch (task.C & 0xff) {
             CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
         }
 #undef CASE
         return;
     }
-#define CASE(c) case c: nw_forward_body<c>(task, codes, off, tab, n1, go, ge, tb, colbuf, colbuf_stride, scores_out, k_one, k_four); break;
+#define CASE(c) case c: nw_forward_body<c>(task, codes, off, tab, n1, go, ge, tb, colbuf, colbuf_stride, scores_out, k_one, k_four, k_mone); break;
     switch (task.C & 0xff) {
         CASE(4) CASE(6) CASE(8) CASE(10) CASE(12) CASE(13) CASE(14) CASE(16)
     }
@@ -340,15 +378,18 @@ nw_forward_kernel(const uint8_t* __restrict__ codes, const uint32_t* __restrict_
 
 int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
                       const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
-                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores, int u16_h, int u16_bias) {
+                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores, int u16_h, int u16_bias,
+                      int u16_max_rows) {
     if (n_tasks == 0) return 0;
     const int n1 = n_states + 1;
-    const size_t prof32 = (size_t)max_bands * n1 * 512, prof16 = (size_t)n1 * 1024;
+    const uint32_t rs_stride = (uint32_t)((u16_max_rows + 64 + 3) & ~3);   // 32 slots before row 0, >= 1 after the last row
+    const size_t prof32 = (size_t)max_bands * n1 * 512;
+    const size_t prof16 = u16_max_rows > 0 ? (size_t)n1 * NW_TWIN_ROW_BYTES + (size_t)NW_WARPS * rs_stride * 4 : 0;
     const size_t smem = ((n1 * n1 + 15) & ~15) + (prof32 > prof16 ? prof32 : prof16);
     if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
     PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     nw_forward_kernel<<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_off, d_tasks, d_tab, n1, go, ge, d_tb,
-                                                        d_colbuf, colbuf_stride, d_scores, 1, 4, u16_h, u16_bias);
+                                                        d_colbuf, colbuf_stride, d_scores, 1, 4, -1, u16_h, u16_bias, rs_stride);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -69,6 +69,8 @@ struct NwTask {             // 32 B: the pairs (i, j0 .. j1-1); one CTA builds s
     uint32_t C;                 // columns per lane of the forward kernel that wrote this task's traceback
 };
 #define NW_MODE_U16 0x100u      // NwTask::C flag: traceback written by the 16-bit two-pairs-per-warp flavour
+#define NW_TWIN_A   0x200u      // ... and the NEXT task (same j1, row i') is aligned by this task's CTA, in the high halves
+#define NW_TWIN_B   0x400u      // ... this task is the second of such a twin: the forward kernel skips its CTA
 #define NW_TASK_PAIRS 32        // pairs per task (4 per warp of the forward kernel, 1 per lane of the walk)
 
 // Everything else about a pair is derived on the device from the offsets array (a prefix sum of the
@@ -99,7 +101,8 @@ struct MlDev {              // ML constants + eigen-basis in device memory
 // kernels (hp2_nw.cu / hp2_ml.cu); all launch on `st`
 int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands, const uint8_t* d_codes,
                       const uint32_t* d_off, const NwTask* d_tasks, const int8_t* d_tab, int go, int ge,
-                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores, int u16_h, int u16_bias);
+                      uint32_t* d_tb, int32_t* d_colbuf, uint32_t colbuf_stride, int32_t* d_scores, int u16_h, int u16_bias,
+                      int u16_max_rows);
 int launch_nw_walk(cudaStream_t st, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
                    const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
                    int* d_err);
