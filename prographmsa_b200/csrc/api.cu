@@ -250,9 +250,9 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
                 tb_words = 0; list_entries = 0; cells = 0;
             }
         };
-        auto tb_need = [&](uint32_t L1, uint32_t C, int64_t j0, int64_t j1) -> uint64_t {
-            const uint32_t nb = (L1 + 32u * C - 1u) / (32u * C);
-            return (uint64_t)nb * 32u * ((uint64_t)(offsets[j1] - offsets[j0]) + 31u * (uint64_t)(j1 - j0));
+        auto tb_need = [&](uint32_t L1, uint32_t Cflags, int64_t j0, int64_t j1) -> uint64_t {
+            const uint32_t C = Cflags & 0xffu, nb = (L1 + 32u * C - 1u) / (32u * C);
+            return nw_tb_words((Cflags & NW_MODE_U16) != 0, nb, offsets[j1] - offsets[j0], (uint64_t)(j1 - j0));
         };
         auto push_task = [&](int64_t row, int64_t j0, int64_t j1, int64_t out_base, uint32_t Cflags) {
             const uint32_t L1 = len_of(row);
@@ -260,7 +260,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
             NwTask t; t.i = (uint32_t)row; t.j0 = (uint32_t)j0; t.j1 = (uint32_t)j1; t.out_base = (uint32_t)out_base;
             t.tb_base = tb_words; t.list_base = (uint32_t)list_entries; t.C = Cflags;
             tasks.push_back(t);
-            tb_words += tb_need(L1, Cflags & 0xffu, j0, j1); list_entries += span;
+            tb_words += tb_need(L1, Cflags, j0, j1); list_entries += span;
             cells += (uint64_t)(L1 + 1) * (span + (uint64_t)(j1 - j0));          // sum (L1+1)(L2+1)
         };
         while (p < pe) {
@@ -276,7 +276,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
                     uint32_t l2max;
                     if (jb0 < j1 && u16_ok(std::min(L1, L1b), std::max(L1, L1b), j0, j1, l2max)) {
                         const uint32_t C = (uint32_t)nw_pick_C((int)std::max(L1, L1b));
-                        close_chunk_if_full(tb_need(L1, C, j0, j1) + tb_need(L1b, C, jb0, j1), offsets[j1] - offsets[j0] + offsets[j1] - offsets[jb0]);
+                        close_chunk_if_full(tb_need(L1, C | NW_MODE_U16, j0, j1) + tb_need(L1b, C | NW_MODE_U16, jb0, j1), offsets[j1] - offsets[j0] + offsets[j1] - offsets[jb0]);
                         push_task(i, j0, j1, pA + (j0 - j), C | NW_MODE_U16 | NW_TWIN_A);
                         push_task(i + 1, jb0, j1, pB + (jb0 - (i + 2)), C | NW_MODE_U16 | NW_TWIN_B);
                         u16_max_rows = std::max<int>(u16_max_rows, (int)l2max);
@@ -287,7 +287,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
                             const uint32_t Lr = len_of(row);
                             uint32_t C = (uint32_t)nw_pick_C((int)Lr);
                             if (u16_ok(Lr, Lr, ja, j1, l2max)) { C |= NW_MODE_U16; u16_max_rows = std::max<int>(u16_max_rows, (int)l2max); }
-                            close_chunk_if_full(tb_need(Lr, C & 0xffu, ja, j1), offsets[j1] - offsets[ja]);
+                            close_chunk_if_full(tb_need(Lr, C, ja, j1), offsets[j1] - offsets[ja]);
                             push_task(row, ja, j1, h ? pB + (ja - (i + 2)) : pA + (ja - j), C);
                         }
                     }
@@ -300,7 +300,7 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
                 const int64_t j1 = std::min<int64_t>(row_end, j0 + NW_TASK_PAIRS);
                 uint32_t C = (uint32_t)nw_pick_C((int)L1), l2max;              // per row: keeps all 32 lanes busy
                 if (u16_ok(L1, L1, j0, j1, l2max)) { C |= NW_MODE_U16; u16_max_rows = std::max<int>(u16_max_rows, (int)l2max); }
-                close_chunk_if_full(tb_need(L1, C & 0xffu, j0, j1), offsets[j1] - offsets[j0]);
+                close_chunk_if_full(tb_need(L1, C, j0, j1), offsets[j1] - offsets[j0]);
                 push_task(i, j0, j1, p - pb, C);
                 p += j1 - j0;
             }

@@ -52,6 +52,43 @@ __device__ __forceinline__ void pair_from_index(long long p, int N, int& i, int&
 // Each lane register-blocks EB entries so the broadcast loads of the per-k weights are shared.
 #define ML_EB 4
 
+// One register block of the likelihood sums: lane handles entries q0 + lane + 32 r, r < EB.  The two quotients
+// of the reference (P'/P and (P''P - P'^2)/P^2) share one reciprocal.
+template <int EB, bool ATAB>
+__device__ __forceinline__ void
+ml_eval_block(const uint32_t* __restrict__ hist, uint32_t q0, uint32_t nnz, int lane, int n, int astride,
+              const double* __restrict__ sA, const double* __restrict__ sV, const double* __restrict__ sVi,
+              const double* __restrict__ wb, double& f, double& ff) {
+    int ia[EB], ib[EB]; double cnt[EB], a0[EB], a1[EB], a2[EB];
+#pragma unroll
+    for (int r = 0; r < EB; ++r) {
+        const uint32_t q = q0 + lane + 32 * r;
+        const uint32_t h = (q < nnz) ? hist[q] : 0u;
+        const int idx = (int)(h >> 20);
+        cnt[r] = (double)(h & 0xfffffu);
+        if (ATAB) { ia[r] = idx * astride; ib[r] = 0; }
+        else { const int i = idx / n; ia[r] = i * n; ib[r] = idx - i * n; }
+        a0[r] = a1[r] = a2[r] = 0;
+    }
+    for (int k = 0; k < n; ++k) {
+        const double2 w01 = *reinterpret_cast<const double2*>(wb + 4 * k);
+        const double w2 = wb[4 * k + 2];
+#pragma unroll
+        for (int r = 0; r < EB; ++r) {
+            const double a = ATAB ? sA[ia[r] + k] : sV[ia[r] + k] * sVi[k * n + ib[r]];
+            a0[r] = fma(a, w01.x, a0[r]); a1[r] = fma(a, w01.y, a1[r]); a2[r] = fma(a, w2, a2[r]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < EB; ++r)
+        if (cnt[r] != 0) {
+            const double inv = __drcp_rn(a0[r]);
+            const double g = a1[r] * inv;                       // P'/P
+            f = fma(cnt[r], g, f);
+            ff = fma(cnt[r], fma(a2[r], inv, -g * g), ff);      // P''/P - (P'/P)^2
+        }
+}
+
 template <int FRONT, bool ATAB, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out, double* __restrict__ var_out,
@@ -190,33 +227,15 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
                         }
                         __syncwarp();
                         f = 0; ff = 0;
-                        for (uint32_t q0 = 0; q0 < nnz; q0 += 32 * ML_EB) {
-                            int ia[ML_EB], ib[ML_EB]; double cnt[ML_EB], a0[ML_EB], a1[ML_EB], a2[ML_EB];
-#pragma unroll
-                            for (int r = 0; r < ML_EB; ++r) {
-                                const uint32_t q = q0 + lane + 32 * r;
-                                const uint32_t h = (q < nnz) ? hist[q] : 0u;
-                                const int idx = (int)(h >> 20);
-                                cnt[r] = (double)(h & 0xfffffu);
-                                if (ATAB) { ia[r] = idx * astride; ib[r] = 0; }
-                                else { const int i = idx / n; ia[r] = i * n; ib[r] = idx - i * n; }
-                                a0[r] = a1[r] = a2[r] = 0;
-                            }
-                            for (int k = 0; k < n; ++k) {
-                                const double2 w01 = *reinterpret_cast<const double2*>(wb + 4 * k);
-                                const double w2 = wb[4 * k + 2];
-#pragma unroll
-                                for (int r = 0; r < ML_EB; ++r) {
-                                    const double a = ATAB ? sA[ia[r] + k] : sV[ia[r] + k] * sVi[k * n + ib[r]];
-                                    a0[r] = fma(a, w01.x, a0[r]); a1[r] = fma(a, w01.y, a1[r]); a2[r] = fma(a, w2, a2[r]);
-                                }
-                            }
-#pragma unroll
-                            for (int r = 0; r < ML_EB; ++r)
-                                if (cnt[r] != 0) {
-                                    f += cnt[r] * a1[r] / a0[r];
-                                    ff += (cnt[r] * (a2[r] * a0[r] - a1[r] * a1[r])) / (a0[r] * a0[r]);
-                                }
+                        uint32_t q0 = 0;
+                        for (; q0 + 32 * ML_EB <= nnz; q0 += 32 * ML_EB)
+                            ml_eval_block<ML_EB, ATAB>(hist, q0, nnz, lane, n, astride, sA, sV, sVi, wb, f, ff);
+                        switch ((nnz - q0 + 31) >> 5) {         // the tail gets the smallest register block that covers it
+                            case 1: ml_eval_block<1, ATAB>(hist, q0, nnz, lane, n, astride, sA, sV, sVi, wb, f, ff); break;
+                            case 2: ml_eval_block<2, ATAB>(hist, q0, nnz, lane, n, astride, sA, sV, sVi, wb, f, ff); break;
+                            case 3: ml_eval_block<3, ATAB>(hist, q0, nnz, lane, n, astride, sA, sV, sVi, wb, f, ff); break;
+                            case 4: ml_eval_block<4, ATAB>(hist, q0, nnz, lane, n, astride, sA, sV, sVi, wb, f, ff); break;
+                            default: break;
                         }
                         f = warp_sum(f); ff = warp_sum(ff);
                         ++my_evals;

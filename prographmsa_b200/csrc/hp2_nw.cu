@@ -171,6 +171,18 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
     return v;
 }
 
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.u32 [%0], %1;" :: "r"(addr), "r"(v) : "memory");
+}
+// write this lane's eight staged steps (one 32-byte sector) of an 8-step block
+__device__ __forceinline__ void nw_flush_block(uint32_t tile_lane, uint32_t* __restrict__ dst) {
+    uint32_t w[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w[q]) : "r"(tile_lane + 128u * q) : "memory");
+    reinterpret_cast<uint4*>(dst)[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    reinterpret_cast<uint4*>(dst)[1] = make_uint4(w[4], w[5], w[6], w[7]);
+}
+
 template <int C>
 __device__ __forceinline__ void
 nw_forward_body_twin(const NwTask& ta, const NwTask* __restrict__ tasks, const uint8_t* __restrict__ codes,
@@ -181,7 +193,8 @@ nw_forward_body_twin(const NwTask& ta, const NwTask* __restrict__ tasks, const u
     int8_t* s_tab = (int8_t*)smem;
     const int tab_bytes = (n1 * n1 + 15) & ~15;
     uint32_t* prof = (uint32_t*)(smem + tab_bytes);          // [r][q][lane][4] words
-    uint32_t* rs_all = prof + (size_t)n1 * (NW_TWIN_ROW_BYTES / 4);
+    uint32_t* tiles = prof + (size_t)n1 * (NW_TWIN_ROW_BYTES / 4);   // per warp [half][step & 7][lane] words
+    uint32_t* rs_all = tiles + NW_WARPS * 512;
 
     const bool twin = (ta.C & NW_TWIN_A) != 0;
     NwTask tbk = ta;
@@ -217,7 +230,8 @@ nw_forward_body_twin(const NwTask& ta, const NwTask* __restrict__ tasks, const u
     const int x0 = lane * C;
     uint32_t prof_lane = (uint32_t)__cvta_generic_to_shared(prof) + (uint32_t)lane * 16u;
     uint32_t inWstep = pack2(ge4 + H);
-    asm volatile("" : "+r"(prof_lane), "+r"(inWstep));
+    uint32_t tile_lane = (uint32_t)__cvta_generic_to_shared(tiles + warp * 512) + (uint32_t)lane * 4u;
+    asm volatile("" : "+r"(prof_lane), "+r"(inWstep), "+r"(tile_lane));
     const uint32_t off_a0 = off[ta.j0], off_b0 = off[tbk.j0];
 
     for (uint32_t j = ta.j0 + warp; j < ta.j1; j += NW_WARPS) {
@@ -228,9 +242,11 @@ nw_forward_body_twin(const NwTask& ta, const NwTask* __restrict__ tasks, const u
         __syncwarp();
         for (int q = lane; q < L2; q += 32) rs[32 + q] = (uint32_t)s2[q] * NW_TWIN_ROW_BYTES;
         __syncwarp();
-        uint32_t* __restrict__ pa = tb + ta.tb_base + 32ull * ((uint64_t)(s2_off - off_a0) + 31u * (j - ta.j0)) + lane;
+        // this lane's sector of the pair's first 8-step block (layout: internal.h)
+        uint32_t* __restrict__ pa = tb + ta.tb_base + 32ull * (((uint64_t)(s2_off - off_a0) + NW_U16_STEP_SLACK * (j - ta.j0) + 7u) & ~7ull) + lane * 8;
         uint32_t* __restrict__ pb = pa;
-        if (hasB) pb = tb + tbk.tb_base + 32ull * ((uint64_t)(s2_off - off_b0) + 31u * (j - tbk.j0)) + lane;
+        if (hasB) pb = tb + tbk.tb_base + 32ull * (((uint64_t)(s2_off - off_b0) + NW_U16_STEP_SLACK * (j - tbk.j0) + 7u) & ~7ull) + lane * 8;
+        uint32_t toff = 0;                                    // (t & 7) * 128: byte offset of this step's tile row
 
         const int nsteps = L2 + nl - 1;
         uint32_t Wup[C], Yup[C];
@@ -282,11 +298,20 @@ nw_forward_body_twin(const NwTask& ta, const NwTask* __restrict__ tasks, const u
                 if (C < 8) { F = bits; bits = 0; }
                 Wdiag = Wl;
                 Wlast = Wleft; Xlast = Xleft;
-                *pa = __byte_perm(F, bits, 0x5410);
-                if (hasB) *pb = __byte_perm(F, bits, 0x7632);
+                sts32(tile_lane + toff, __byte_perm(F, bits, 0x5410));
+                sts32(tile_lane + toff + 1024u, __byte_perm(F, bits, 0x7632));
             }
             ++row;
-            pa += 32; pb += 32;
+            if (toff == 896u) {
+                nw_flush_block(tile_lane, pa);
+                if (hasB) nw_flush_block(tile_lane + 1024u, pb);
+                pa += 256; pb += 256;
+            }
+            toff = (toff + 128u) & 1023u;
+        }
+        if (toff != 0u) {
+            nw_flush_block(tile_lane, pa);
+            if (hasB) nw_flush_block(tile_lane + 1024u, pb);
         }
         if (scores_out != nullptr) {
             // every lane stopped after its row L2, so Wup holds W^(L2, .)
@@ -320,34 +345,33 @@ nw_walk_kernel(int n_tasks, int n, const uint8_t* __restrict__ codes, const uint
     const uint32_t* __restrict__ tbp = tb + d.tb_off;
     uint16_t* __restrict__ lp = list + d.list_off;
     const int steps = (int)d.L2 + 31;
-    const int bandw = 32 * C;
     int x = (int)d.L1, y = (int)d.L2;
-    uint32_t gaps = 0, nl = 0;
-    bool o1 = false, o2 = false;
+    uint32_t gaps = 0, nl = 0, prev = 3u;
+    // (band, lane, k) of column x, kept incrementally: no divisions inside the chain
+    int band = 0, lane = 0, k = 0;
+    if (x > 0) { const int xz = x - 1, bandw = 32 * C; band = xz / bandw; const int rem = xz - band * bandw; lane = rem / C; k = rem - lane * C; }
+    const int c8 = min(C, 8);
+    bool pend = false;                                          // a diagonal step whose residues are still in flight
+    int pc1 = 0, pc2 = 0;
     while (x != 0 && y != 0) {
-        const int xz = x - 1;
-        const int b = xz / bandw, rem = xz - b * bandw;
-        const int lane = rem / C, k = rem - lane * C;
         const int t = y - 1 + lane;
-        const uint32_t w = __ldg(tbp + ((size_t)b * steps + t) * 32 + lane);
+        const uint32_t* wp = u16 ? tbp + ((((uint32_t)t >> 3) * 32u + (uint32_t)lane) << 3) + (t & 7)
+                                 : tbp + ((size_t)band * steps + t) * 32 + lane;
+        const uint32_t w = __ldg(wp);
+        if (pend && pc1 < n && pc2 < n) lp[nl++] = (uint16_t)(pc1 * n + pc2);   // previous step's pair: its loads overlap this one's
         // 32-bit flavour: cell k at bit 2(C-1-k).  16-bit flavour: cells 0..7 in the low half, 8.. in the high half
-        const int sh = !u16 ? 2 * (C - 1 - k) : (k < 8 ? 2 * (min(C, 8) - 1 - k) : 16 + 2 * (C - 1 - k));
+        const int sh = !u16 ? 2 * (C - 1 - k) : (k < 8 ? 2 * (c8 - 1 - k) : 16 + 2 * (C - 1 - k));
         const uint32_t tag = (w >> sh) & 3u;                       // 3 diagonal, 2 left (X), 1 up (Y)
-        if (tag == 3u) {
-            const int c1 = s1[xz], c2 = s2[y - 1];
-            if (c1 < n && c2 < n) lp[nl++] = (uint16_t)(c1 * n + c2);
-            o1 = o2 = false; --x; --y;
-        } else if (tag == 2u) {
-            if (!o1) ++gaps;
-            o1 = true; o2 = false; --x;
-        } else if (tag == 1u) {
-            if (!o2) ++gaps;
-            o1 = false; o2 = true; --y;
-        } else {
-            *err = 1;                                          // reference: error("error while backtracking")
-            break;
-        }
+        if (tag == 0u) { *err = 1; pend = false; break; }          // reference: error("error while backtracking")
+        pend = (tag == 3u);
+        if (pend) { pc1 = s1[x - 1]; pc2 = s2[y - 1]; }
+        gaps += (tag != 3u && tag != prev) ? 1u : 0u;              // a left-run or an up-run opens
+        prev = tag;
+        const int dx = (int)(tag >> 1), dy = (int)(tag & 1u);
+        x -= dx; y -= dy; k -= dx;
+        if (k < 0) { k = C - 1; if (--lane < 0) { lane = 31; --band; } }
     }
+    if (pend && pc1 < n && pc2 < n) lp[nl++] = (uint16_t)(pc1 * n + pc2);
     list_len[d.out_idx] = nl;
     gaps_out[d.out_idx] = gaps;
 }
@@ -384,7 +408,7 @@ int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands,
     const int n1 = n_states + 1;
     const uint32_t rs_stride = (uint32_t)((u16_max_rows + 64 + 3) & ~3);   // 32 slots before row 0, >= 1 after the last row
     const size_t prof32 = (size_t)max_bands * n1 * 512;
-    const size_t prof16 = u16_max_rows > 0 ? (size_t)n1 * NW_TWIN_ROW_BYTES + (size_t)NW_WARPS * rs_stride * 4 : 0;
+    const size_t prof16 = u16_max_rows > 0 ? (size_t)n1 * NW_TWIN_ROW_BYTES + (size_t)NW_WARPS * (512 + rs_stride) * 4 : 0;
     const size_t smem = ((n1 * n1 + 15) & ~15) + (prof32 > prof16 ? prof32 : prof16);
     if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
     PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -74,10 +74,18 @@ struct NwTask {             // 32 B: the pairs (i, j0 .. j1-1); one CTA builds s
 #define NW_TASK_PAIRS 32        // pairs per task (4 per warp of the forward kernel, 1 per lane of the walk)
 
 // Everything else about a pair is derived on the device from the offsets array (a prefix sum of the
-// lengths), so no per-pair descriptor is ever built or copied:
-//   tb_off(i,j)   = tb_base   + nb(L1) * 32 * ((off[j] - off[j0]) + 31 * (j - j0))
-//   list_off(i,j) = list_base + (off[j] - off[j0])            (capacity L2 >= matched pairs)
+// lengths), so no per-pair descriptor is ever built or copied.  With span = off[j] - off[j0]:
+//   32-bit flavour: tb_off(i,j) = tb_base + nb(L1) * 32 * (span + 31 * (j - j0)),   word (band, step t, lane) at
+//                   ((band * (L2 + 31) + t) * 32 + lane
+//   16-bit flavour: tb_off(i,j) = tb_base + 32 * roundup8(span + 46 * (j - j0)),    word (step t, lane) at
+//                   ((t >> 3) * 32 + lane) * 8 + (t & 7): eight consecutive steps of a lane share one 32-byte
+//                   sector, which is what the walk (mostly diagonal: same lane, t - 1) wants to read
+//   list_off(i,j) = list_base + span                             (capacity L2 >= matched pairs)
+#define NW_U16_STEP_SLACK 46u   // per-pair step budget L2 + 46 >= roundup8(L2 + 31) + 7 (alignment of the start)
 struct NwPair { uint32_t s1_off, s2_off, L1, L2, out_idx, list_off; uint64_t tb_off; };
+__host__ __device__ __forceinline__ uint64_t nw_tb_words(bool u16, uint32_t nb, uint64_t span, uint64_t cnt) {
+    return u16 ? 32ull * (span + NW_U16_STEP_SLACK * cnt + 8u) : (uint64_t)nb * 32u * (span + 31u * cnt);
+}
 __device__ __forceinline__ NwPair nw_pair(const NwTask& t, uint32_t j, const uint32_t* __restrict__ off) {
     const uint32_t C = t.C & 0xffu;
     NwPair p;
@@ -85,7 +93,8 @@ __device__ __forceinline__ NwPair nw_pair(const NwTask& t, uint32_t j, const uin
     p.s2_off = off[j]; p.L2 = off[j + 1] - p.s2_off;
     const uint32_t nb = (p.L1 + 32u * C - 1u) / (32u * C);
     const uint32_t span = (p.s2_off - off[t.j0]);
-    p.tb_off = t.tb_base + (uint64_t)nb * 32u * ((uint64_t)span + 31u * (j - t.j0));
+    if (t.C & NW_MODE_U16) p.tb_off = t.tb_base + 32ull * (((uint64_t)span + NW_U16_STEP_SLACK * (j - t.j0) + 7u) & ~7ull);
+    else p.tb_off = t.tb_base + (uint64_t)nb * 32u * ((uint64_t)span + 31u * (j - t.j0));
     p.list_off = t.list_base + span;
     p.out_idx = t.out_base + (j - t.j0);
     return p;
