@@ -24,6 +24,7 @@ struct pgm_ctx {
     cudaStream_t stream = nullptr;
     uint64_t scratch_bytes = 8ull << 30;
     bool timing_on = false;
+    bool cached_symmetric = false, ml_no_merge = false;   // PGM_ML_NO_MERGE=1: keep (i,j) and (j,i) counts separate (A-B runs)
     bool force_nw32 = false;             // PGM_NW_FORCE_32BIT=1: never use the 16-bit forward flavour (tests / A-B runs)
     pgm_timing timing{};
     std::vector<TimedSection> sections;       // pending (resolved at sync)
@@ -96,6 +97,7 @@ int pgm_create(int device, pgm_ctx** out) {
     pgm_ctx* c = new pgm_ctx();
     c->device = device;
     { const char* e = getenv("PGM_NW_FORCE_32BIT"); c->force_nw32 = e && e[0] == '1'; }
+    { const char* e = getenv("PGM_ML_NO_MERGE"); c->ml_no_merge = e && e[0] == '1'; }
     PGM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     *out = c;
     return 0;
@@ -152,6 +154,21 @@ static int prepare_model(pgm_ctx* c, const pgm_ml_params* prm, MlDev& ml) {
         std::vector<double> buf(2 * nn + n);
         rc = pgm_eigen_basis(prm->Q, n, buf.data(), buf.data() + 2 * nn, buf.data() + nn);
         if (rc) return rc;
+        // is P_ij(t) / P_ji(t) independent of t?  (true for reversible Q; ECM is only reversible to ~1e-6)
+        {
+            const double* V = buf.data(); const double* Vi = buf.data() + nn;
+            double amax = 0, dev = 0;
+            for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) amax = std::max(amax, std::fabs(V[i * n + k] * Vi[k * n + j]));
+            for (int i = 0; i < n && dev <= 1e-11 * amax; ++i)
+                for (int j = i + 1; j < n; ++j) {
+                    double num = 0, den = 0;                         // least-squares ratio c_ij over k
+                    for (int k = 0; k < n; ++k) { const double a = V[i * n + k] * Vi[k * n + j], b = V[j * n + k] * Vi[k * n + i]; num += a * b; den += b * b; }
+                    const double cij = den > 0 ? num / den : 0;
+                    for (int k = 0; k < n; ++k) dev = std::max(dev, std::fabs(V[i * n + k] * Vi[k * n + j] - cij * V[j * n + k] * Vi[k * n + i]));
+                    if (!(cij > 0)) dev = amax;
+                }
+            c->cached_symmetric = dev <= 1e-11 * amax;
+        }
         PGM_CUDA(cudaMemcpyAsync(c->d_model.p, buf.data(), buf.size() * 8, cudaMemcpyHostToDevice, c->stream));
         PGM_CUDA(cudaStreamSynchronize(c->stream));
         c->cachedQ.assign(prm->Q, prm->Q + nn); c->cached_n = n;
@@ -159,6 +176,7 @@ static int prepare_model(pgm_ctx* c, const pgm_ml_params* prm, MlDev& ml) {
     ml.n = n;
     ml.V = c->d_model.as<double>(); ml.Vi = ml.V + nn; ml.sigma = ml.V + 2 * nn;
     ml.mldist_flag = prm->mldist_flag; ml.mldist_gap_flag = prm->mldist_gap_flag;
+    ml.symmetric = (need_basis && c->cached_symmetric && !c->ml_no_merge) ? 1 : 0;
     ml.indel_rate = prm->indel_rate; ml.min_dist = prm->min_dist; ml.max_dist = prm->max_dist;
     ml.cutoff_dist = prm->cutoff_dist; ml.DIST_MAX = prm->DIST_MAX; ml.VAR_MAX = prm->VAR_MAX; ml.VAR_MIN = prm->VAR_MIN;
     return 0;

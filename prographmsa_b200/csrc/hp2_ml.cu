@@ -184,8 +184,11 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
         uint32_t nnz = 0;
         for (int base = 0; base < nn; base += 32) {
             const int idx = base + lane;
-            const uint32_t c = (idx < nn) ? hist[idx] : 0u;
-            if (c) { total += c; if (idx / n == idx % n) ident += c; }
+            uint32_t c = (idx < nn) ? hist[idx] : 0u;
+            const int ci = idx / n, cj = idx - ci * n;
+            if (c) { total += c; if (ci == cj) ident += c; }
+            // reversible model: P'/P and P''/P are the same for (i,j) and (j,i), so the two counts share one entry
+            if (ml.symmetric && idx < nn) { if (ci > cj) c = 0u; else if (ci < cj) c += hist[cj * n + ci]; }
             const uint32_t m = __ballot_sync(0xffffffffu, c != 0);
             __syncwarp();
             if (c) hist[nnz + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)idx << 20) | c;

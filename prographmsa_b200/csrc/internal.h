@@ -104,6 +104,7 @@ struct MlDev {              // ML constants + eigen-basis in device memory
     int n;
     const double *V, *Vi, *sigma;   // n*n row-major, n*n row-major, n
     int mldist_flag, mldist_gap_flag;
+    int symmetric;                  // V(i,k) Vi(k,j) = c_ij V(j,k) Vi(k,i) for all k (reversible Q): (i,j) and (j,i) counts can be merged
     double indel_rate, min_dist, max_dist, cutoff_dist, DIST_MAX, VAR_MAX, VAR_MIN;
 };
 
