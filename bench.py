@@ -404,11 +404,16 @@ def run_ours(args):
             ml_evaluations_per_step=acc["ml_evaluations"] / args.steps,
             clocks=clocks,
             roofline=dict(bound="hbm", kernel="nw_forward_kernel", achieved=alg_bytes_launch / fwd_ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
-                          frac=alg_bytes_launch / fwd_ms / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                          frac=alg_bytes_launch / fwd_ms / 1e6 / pk["hbm_gbs"],
+                          # dram__bytes_read.sum + dram__bytes_write.sum of this kernel on this workload at N=1 (6.33 MB + 6.971 GB),
+                          # from the ncu --set full capture summarised in profiles/r1_final_hp2.txt; not re-measured per run
+                          traffic=(6.978e9 if world == 1 else None), peak_source=pk["source"],
                           launch_ms=fwd_ms, algorithmic_bytes_per_launch=alg_bytes_launch),
             roofline_issue=dict(bound="sm integer issue", kernel="nw_forward_kernel", achieved=9.0 * cells_launch / fwd_ms / 1e9,
                                 peak=lane_ops / 1e12, unit="Tlane-op/s", frac=9.0 * cells_launch / fwd_ms / 1e9 / (lane_ops / 1e12),
-                                note="algorithmic work = 9 int ops/cell (SURVEY.md §8d); peak = 148 SM x 128 lanes x sm_max_mhz",
+                                note="algorithmic work = 9 int32 ops/cell (SURVEY.md §8d); peak = 148 SM x 128 lanes x sm_max_mhz. The 16-bit twin "
+                                     "flavour retires two cells per lane-op (9 instructions per cell PAIR), so this is a fraction of the 32-bit-op bound, "
+                                     "not of issue slots: ncu shows 74 % of issue slots busy (profiles/r1_final_hp2.txt)",
                                 gcups_kernel=cells_launch / fwd_ms / 1e6),
         )
         if world == 1:
