@@ -10,11 +10,13 @@
  * Interfaces replaced (unchanged signatures):
  *   DistanceFactory<A>::computePwDistances(sequences, order)         DistanceFactory.h:44-51
  *   DistanceFactoryAlign<A> / DistanceFactoryPrealigned<A>           DistanceFactoryAlign.h:8-27, DistanceFactoryPrealigned.h:8-19
+ *   DistanceFactoryAngle<A, K>                                        DistanceFactoryAngle.h:16-131
  */
 #ifndef GPUDISTANCEFACTORY_H_
 #define GPUDISTANCEFACTORY_H_
 
 #include "DistanceFactory.h"
+#include "DistanceFactoryAngle.h"
 #include "ModelFactory.h"
 #include "main.h"
 #include "debug.h"
@@ -125,7 +127,31 @@ public:
     }
 };
 
+/* k-mer angle distances (the default initial-tree factory).  The reference maps letters with mapChar()
+ * (DistanceFactoryAngle.h:36-52); invalid letters take the last code, ALPHABET::DIM - 1. */
+template <class ALPHABET, int K>
+class GpuDistanceFactoryAngle : public DistanceFactoryAngle<ALPHABET, K> {
+public:
+    GpuDistanceFactoryAngle() : DistanceFactoryAngle<ALPHABET, K>() {}
+    virtual DistanceMatrix computePwDistances(const std::map<std::string, sequence_t<ALPHABET> >& sequences,
+                                              const std::vector<std::string>& order) {
+        const int N = (int)order.size(), n = ALPHABET::DIM;
+        std::vector<uint8_t> codes; std::vector<uint32_t> off(N + 1, 0);
+        for (int k = 0; k < N; ++k) {
+            const sequence_t<ALPHABET>& s = sequences.find(order[k])->second;
+            for (size_t c = 0; c < s.length(); ++c) codes.push_back((uint8_t)this->mapChar(s[c]));
+            off[k + 1] = (uint32_t)codes.size();
+        }
+        std::vector<double> d((size_t)N * N), v((size_t)N * N);
+        if (pgm_angle_all_pairs(pgm_shim::context(), n, K, codes.empty() ? NULL : &codes[0], &off[0], N,
+                                cmdlineopts.mldist_flag || cmdlineopts.mldist_gap_flag, &d[0], &v[0]) != 0)
+            error("%s", pgm_last_error());
+        return pgm_shim::to_matrix(N, d, v);
+    }
+};
+
 /* In DistanceFactory.cpp (getDefault, :8-55) replace
+ *     new DistanceFactoryAngle<A, K>()                 by  new GpuDistanceFactoryAngle<A, K>()
  *     new DistanceFactoryAlign<A>(model_factory)       by  new GpuDistanceFactoryAlign<A>(model_factory)
  *     new DistanceFactoryPrealigned<A>(model_factory)  by  new GpuDistanceFactoryPrealigned<A>(model_factory)   */
 #endif
