@@ -127,8 +127,8 @@ public:
     }
 };
 
-/* k-mer angle distances (the default initial-tree factory).  The reference maps letters with mapChar()
- * (DistanceFactoryAngle.h:36-52); invalid letters take the last code, ALPHABET::DIM - 1. */
+/* k-mer angle distances (the default initial-tree factory).  A k-mer containing an invalid state (value() < 0 or
+ * >= DIM) is not counted (DistanceFactoryAngle.h:76-91): such states are passed as code 255 (any code >= n_states). */
 template <class ALPHABET, int K>
 class GpuDistanceFactoryAngle : public DistanceFactoryAngle<ALPHABET, K> {
 public:
@@ -139,7 +139,7 @@ public:
         std::vector<uint8_t> codes; std::vector<uint32_t> off(N + 1, 0);
         for (int k = 0; k < N; ++k) {
             const sequence_t<ALPHABET>& s = sequences.find(order[k])->second;
-            for (size_t c = 0; c < s.length(); ++c) codes.push_back((uint8_t)this->mapChar(s[c]));
+            for (size_t c = 0; c < s.size(); ++c) { const int v = s[c].value(); codes.push_back((uint8_t)((v < 0 || v >= n) ? 255 : v)); }
             off[k + 1] = (uint32_t)codes.size();
         }
         std::vector<double> d((size_t)N * N), v((size_t)N * N);
