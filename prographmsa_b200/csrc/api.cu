@@ -245,6 +245,10 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     std::vector<size_t> chunk_end;                      // task index where each chunk ends
     std::vector<uint64_t> chunk_tb, chunk_list, chunk_cells;
     tasks.clear();
+    // small pair ranges (a shard of a strongly-scaled matrix): smaller tasks keep >= ~2 waves of forward CTAs, and the walk
+    // runs 8 instead of 32 independent chains per warp (a warp-step waits for the slowest lane's DRAM access)
+    const int64_t task_pairs = np >= 38000 ? NW_TASK_PAIRS : (np >= 19000 ? 16 : 8);
+    const int walk_lanes = np >= 70000 ? 32 : 8;
     int u16_max_rows = 0;                               // longest row sequence of any 16-bit task (sizes the residue staging)
     {
         int64_t i, j; pair_from_index_host(pb, N, i, j);
@@ -252,7 +256,13 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
         uint64_t tb_words = 0, list_entries = 0, cells = 0;
         auto len_of = [&](int64_t k) -> uint32_t { return offsets[k + 1] - offsets[k]; };
         // can rows with at most Lcol columns run the 16-bit flavour against the row sequences [j0, j1)?
+        // shortcut: if even the longest sequence against the longest sequence fits 16 bits, no per-block scan is needed
+        uint32_t g_lmax = 0, g_lmin = 0xffffffffu;
+        for (int k = 0; k < N; ++k) { g_lmax = std::max(g_lmax, len_of(k)); g_lmin = std::min(g_lmin, len_of(k)); }
+        const bool u16_all = u16_table_ok && g_lmin >= 1 && g_lmax <= 512 &&
+                             (uint64_t)4 * smax * g_lmax + (uint64_t)u16_h * 2 * g_lmax + u16_bias + 4 * smax + 2 * u16_h + 64 < 65536;
         auto u16_ok = [&](uint32_t Lcol_min, uint32_t Lcol_max, int64_t j0, int64_t j1, uint32_t& l2max) -> bool {
+            if (u16_all) { l2max = g_lmax; return true; }
             l2max = 0;
             if (!u16_table_ok || Lcol_min < 1 || Lcol_max > 512) return false;
             uint32_t l2min = 0xffffffffu;
@@ -289,8 +299,8 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
             if (twin_rows) {
                 const uint32_t L1b = len_of(i + 1);
                 const int64_t pA = p - pb, pB = pA + (N - j);                    // packed index of (i, j) and of (i+1, i+2)
-                for (int64_t j0 = j; j0 < N; j0 += NW_TASK_PAIRS) {
-                    const int64_t j1 = std::min<int64_t>(N, j0 + NW_TASK_PAIRS), jb0 = std::max<int64_t>(j0, i + 2);
+                for (int64_t j0 = j; j0 < N; j0 += task_pairs) {
+                    const int64_t j1 = std::min<int64_t>(N, j0 + task_pairs), jb0 = std::max<int64_t>(j0, i + 2);
                     uint32_t l2max;
                     if (jb0 < j1 && u16_ok(std::min(L1, L1b), std::max(L1, L1b), j0, j1, l2max)) {
                         const uint32_t C = (uint32_t)nw_pick_C((int)std::max(L1, L1b));
@@ -314,8 +324,8 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
                 i += 2; j = i + 1;
                 continue;
             }
-            for (int64_t j0 = j; j0 < row_end; j0 += NW_TASK_PAIRS) {
-                const int64_t j1 = std::min<int64_t>(row_end, j0 + NW_TASK_PAIRS);
+            for (int64_t j0 = j; j0 < row_end; j0 += task_pairs) {
+                const int64_t j1 = std::min<int64_t>(row_end, j0 + task_pairs);
                 uint32_t C = (uint32_t)nw_pick_C((int)L1), l2max;              // per row: keeps all 32 lanes busy
                 if (u16_ok(L1, L1, j0, j1, l2max)) { C |= NW_MODE_U16; u16_max_rows = std::max<int>(u16_max_rows, (int)l2max); }
                 close_chunk_if_full(tb_need(L1, C, j0, j1), offsets[j1] - offsets[j0]);
@@ -352,13 +362,13 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
         {
             ScopedKernelTimer t(c, K_NW_WALK);
             rc = launch_nw_walk(c->stream, ntasks, n, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tb.as<uint32_t>(),
-                                c->d_list.as<uint16_t>(), c->d_list_len.as<uint32_t>(), d_gaps, d_err);
+                                c->d_list.as<uint16_t>(), c->d_list_len.as<uint32_t>(), d_gaps, d_err, walk_lanes);
             if (rc) return rc;
         }
         {
             ScopedKernelTimer t(c, K_ML);
             rc = launch_ml_from_lists(c->stream, ml, ntasks, c->d_off.as<uint32_t>(), dt, c->d_list.as<uint16_t>(),
-                                      c->d_list_len.as<uint32_t>(), d_gaps, d_dist, d_var, d_counts, d_evals);
+                                      c->d_list_len.as<uint32_t>(), d_gaps, d_dist, d_var, d_counts, d_evals, (int)task_pairs);
             if (rc) return rc;
         }
         c->timing.nw_cells += chunk_cells[k];

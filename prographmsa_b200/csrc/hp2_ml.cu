@@ -22,7 +22,7 @@ enum { FRONT_LIST = 0, FRONT_ROWS = 1, FRONT_COUNTS = 2 };
 
 struct MlFront {
     // LIST
-    const NwTask* tasks; const uint32_t* off; const uint16_t* list; const uint32_t* list_len; const uint32_t* gaps_in;
+    const NwTask* tasks; const uint32_t* off; const uint16_t* list; const uint32_t* list_len; const uint32_t* gaps_in; int task_pairs;
     // ROWS
     const uint8_t* rows; int N; int L; long long pair_begin;
     // COUNTS
@@ -126,8 +126,9 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
 
         if (FRONT == FRONT_LIST) {
             // p enumerates (task, slot); slots past the task's last pair are empty
-            const NwTask task = fr.tasks[p >> 5];
-            const uint32_t j = task.j0 + (uint32_t)(p & 31);
+            const long long ti = p / fr.task_pairs;
+            const NwTask task = fr.tasks[ti];
+            const uint32_t j = task.j0 + (uint32_t)(p - ti * fr.task_pairs);
             if (j >= task.j1) continue;
             const NwPair d = nw_pair(task, j, fr.off);
             out_idx = d.out_idx;
@@ -282,12 +283,18 @@ static int launch_ml_t(cudaStream_t st, const MlDev& ml, const MlFront& fr, long
     const int n = ml.n, nn = n * n;
     const size_t smem = sizeof(double) * ((ATAB ? (size_t)nn * (n + 1) : 2 * (size_t)nn) + ((n + 1) & ~1) + (size_t)WARPS * n * 4) +
                         sizeof(uint32_t) * (size_t)WARPS * nn;
-    PGM_CUDA(cudaFuncSetAttribute(ml_kernel<FRONT, ATAB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int dev = 0, sms = 148, per_sm = 1;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ml_kernel<FRONT, ATAB, WARPS>, WARPS * 32, smem);
-    if (per_sm < 1) per_sm = 1;
+    // attribute / occupancy queries are driver calls: do them once per (instantiation, shared-memory size), not per launch
+    static size_t cached_smem = 0; static int cached_sms = 148, cached_per_sm = 1;
+    if (cached_smem != smem) {
+        PGM_CUDA(cudaFuncSetAttribute(ml_kernel<FRONT, ATAB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, ml_kernel<FRONT, ATAB, WARPS>, WARPS * 32, smem);
+        if (cached_per_sm < 1) cached_per_sm = 1;
+        cached_smem = smem;
+    }
+    const int sms = cached_sms, per_sm = cached_per_sm;
     long long want = (n_pairs + WARPS - 1) / WARPS;
     long long grid = (long long)sms * per_sm;
     if (grid > want) grid = want;
@@ -307,11 +314,11 @@ static int launch_ml(cudaStream_t st, const MlDev& ml, const MlFront& fr, long l
 
 int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
                          const uint16_t* d_list, const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist,
-                         double* d_var, int32_t* d_counts, unsigned long long* d_evals) {
+                         double* d_var, int32_t* d_counts, unsigned long long* d_evals, int task_pairs) {
     MlFront fr{};
     fr.tasks = d_tasks; fr.off = d_off; fr.list = d_list; fr.list_len = d_list_len; fr.gaps_in = d_gaps;
-    fr.counts_out = d_counts;
-    return launch_ml<FRONT_LIST>(st, ml, fr, (long long)n_tasks * NW_TASK_PAIRS, d_dist, d_var, d_evals);
+    fr.counts_out = d_counts; fr.task_pairs = task_pairs;
+    return launch_ml<FRONT_LIST>(st, ml, fr, (long long)n_tasks * task_pairs, d_dist, d_var, d_evals);
 }
 
 int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,

@@ -331,11 +331,13 @@ nw_forward_body_twin(const NwTask& ta, const NwTask* __restrict__ tasks, const u
 __global__ void __launch_bounds__(128)
 nw_walk_kernel(int n_tasks, int n, const uint8_t* __restrict__ codes, const uint32_t* __restrict__ off,
                const NwTask* __restrict__ tasks, const uint32_t* __restrict__ tb, uint16_t* __restrict__ list,
-               uint32_t* __restrict__ list_len, uint32_t* __restrict__ gaps_out, int* __restrict__ err) {
-    const int ti = blockIdx.x * 4 + (threadIdx.x >> 5);
-    if (ti >= n_tasks) return;
+               uint32_t* __restrict__ list_len, uint32_t* __restrict__ gaps_out, int* __restrict__ err, int lpw) {
+    // lpw pairs per warp (32 or 8): 32 / lpw warps share a task
+    const int wpt = 32 / lpw, gw = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int ti = gw / wpt;
+    if (ti >= n_tasks || (int)(threadIdx.x & 31) >= lpw) return;
     const NwTask task = tasks[ti];
-    const uint32_t j = task.j0 + (threadIdx.x & 31);
+    const uint32_t j = task.j0 + (uint32_t)((gw - ti * wpt) * lpw) + (threadIdx.x & 31);
     if (j >= task.j1) return;
     const int C = (int)(task.C & 0xff);
     const bool u16 = (task.C & NW_MODE_U16) != 0;
@@ -411,7 +413,8 @@ int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands,
     const size_t prof16 = u16_max_rows > 0 ? (size_t)n1 * NW_TWIN_ROW_BYTES + (size_t)NW_WARPS * (512 + rs_stride) * 4 : 0;
     const size_t smem = ((n1 * n1 + 15) & ~15) + (prof32 > prof16 ? prof32 : prof16);
     if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
-    PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr_smem = 0;                               // the attribute call is a driver round trip: only when the size grows
+    if (smem > attr_smem) { PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
     nw_forward_kernel<<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_off, d_tasks, d_tab, n1, go, ge, d_tb,
                                                         d_colbuf, colbuf_stride, d_scores, 1, 4, -1, u16_h, u16_bias, rs_stride);
     PGM_CUDA(cudaGetLastError());
@@ -420,10 +423,12 @@ int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands,
 
 int launch_nw_walk(cudaStream_t st, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
                    const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
-                   int* d_err) {
+                   int* d_err, int lanes_per_warp) {
     if (n_tasks == 0) return 0;
-    nw_walk_kernel<<<(n_tasks + 3) / 4, 128, 0, st>>>(n_tasks, n_states, d_codes, d_off, d_tasks, d_tb, d_list,
-                                                      d_list_len, d_gaps, d_err);
+    const int lpw = lanes_per_warp == 8 ? 8 : 32;
+    const long long warps = (long long)n_tasks * (32 / lpw);
+    nw_walk_kernel<<<(unsigned)((warps + 3) / 4), 128, 0, st>>>(n_tasks, n_states, d_codes, d_off, d_tasks, d_tb, d_list,
+                                                                d_list_len, d_gaps, d_err, lpw);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }

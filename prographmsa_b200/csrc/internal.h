@@ -115,11 +115,11 @@ int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands,
                       int u16_max_rows);
 int launch_nw_walk(cudaStream_t st, int n_tasks, int n_states, const uint8_t* d_codes, const uint32_t* d_off,
                    const NwTask* d_tasks, const uint32_t* d_tb, uint16_t* d_list, uint32_t* d_list_len, uint32_t* d_gaps,
-                   int* d_err);
+                   int* d_err, int lanes_per_warp);
 // front-end LIST: histogram from matched-state lists; ROWS: scan two MSA rows
 int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
                          const uint16_t* d_list, const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist,
-                         double* d_var, int32_t* d_counts, unsigned long long* d_evals);
+                         double* d_var, int32_t* d_counts, unsigned long long* d_evals, int task_pairs);
 int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,
                         const uint8_t* d_rows, double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps,
                         unsigned long long* d_evals);
