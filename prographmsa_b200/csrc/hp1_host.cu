@@ -3,6 +3,8 @@
 // host, predecessor lists in PredIterator order with their edge values (Graph.h:172-248), one packed
 // host->device arena per batch, sub-batching by the scratch budget, result fetch.
 #include "internal.h"
+#include <atomic>
+#include <thread>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -171,7 +173,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     b->out_bytes = out_off;
     char* hin = b->h_in.as<char>();
     char* din = b->d_in.as<char>(); char* dsc = b->d_scratch.as<char>(); char* dout = b->d_out.as<char>();
-    for (int k = 0; k < n_jobs; ++k) {
+    // Packing a job (double -> float sites, predecessor lists, node infos, DynProgScores) touches only that job's slices of
+    // the arenas, so the jobs are packed by a few host threads.
+    auto pack_job = [&](int k) {
         const pgm_graph* gs[2] = {&g1[k], &g2[k]};
         const JobLayout& L = b->lay[k];
         GraphJobDev& J = b->jobs[k];
@@ -224,8 +228,6 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             }
         }
         b->cell_updates[k] = deg_sum[0] * deg_sum[1];
-        b->total_updates += b->cell_updates[k];
-        b->total_cells += (uint64_t)J.N1 * J.N2;
         char* sb = dsc + scratch_base[k];
         J.sites1 = (const float*)(din + L.sites1); J.sites2 = (const float*)(din + L.sites2);
         J.Mf = (const float*)(din + L.Mf); J.pif = (const float*)(din + L.pif);
@@ -240,6 +242,19 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.Aimg = (float*)(sb + L.Aimg); J.Bimg = (float*)(sb + L.Bimg);
         J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev);
         J.map1 = (int*)(dout + L.map1); J.map2 = (int*)(dout + L.map2); J.result = (int*)(dout + L.result);
+    };
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        const int nthreads = (int)std::max(1u, std::min<unsigned>(std::min<unsigned>(hw ? hw : 1u, 16u), (unsigned)(n_jobs / 8 + 1)));
+        if (nthreads <= 1) { for (int k = 0; k < n_jobs; ++k) pack_job(k); }
+        else {
+            std::atomic<int> next(0);
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; ++t)
+                pool.emplace_back([&] { for (int k = next.fetch_add(1); k < n_jobs; k = next.fetch_add(1)) pack_job(k); });
+            for (auto& th : pool) th.join();
+        }
+        for (int k = 0; k < n_jobs; ++k) { b->total_updates += b->cell_updates[k]; b->total_cells += (uint64_t)b->jobs[k].N1 * b->jobs[k].N2; }
     }
     if (n_jobs) {
         PGM_CUDA(cudaMemcpyAsync(b->d_in.p, b->h_in.p, in_off, cudaMemcpyHostToDevice, st));

@@ -29,6 +29,7 @@ class Graph:
 
     # Graph.h:81-90 setEdgesFromMap: stored = min(cost, 1e4) - 1e4 in float
     def _set_edges(self, edges):
+        self._pgm_struct = None                     # cached C view (graphalign.c_graph) is stale once arrays change
         items = sorted(edges.items())
         rowptr = np.zeros(self.N + 1, dtype=np.int32)
         col = np.empty(len(items), dtype=np.int32)
@@ -42,6 +43,7 @@ class Graph:
 
     def _set_stored_edges(self, triplets):
         """triplets: list of (to, from, stored float32) -- keeps stored values verbatim."""
+        self._pgm_struct = None
         items = sorted(triplets)
         rowptr = np.zeros(self.N + 1, dtype=np.int32)
         for to, _, _ in items:
@@ -51,6 +53,7 @@ class Graph:
         self.e_val = np.array([v for _, _, v in items], dtype=np.float32)
 
     def _set_repeats(self, repeats):
+        self._pgm_struct = None
         items = sorted(repeats.items())
         rowptr = np.zeros(self.N + 1, dtype=np.int32)
         for (to, _), _u in items:

@@ -17,18 +17,37 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _addr(a):
+    return a.__array_interface__["data"][0]
+
+
 def c_graph(g, keep):
+    """pgm_graph view of a Graph.  The struct is cached on the graph (its arrays never change after construction)."""
     keep.append(g)
-    has_rep = g.r_col.size > 0
-    return _lib.Graph(g.N, _p(g.sites), _p(g.e_rowptr), _p(g.e_col), _p(g.e_val),
-                      _p(g.r_rowptr), _p(g.r_col) if has_rep else None, _p(g.r_units) if has_rep else None)
+    c = getattr(g, "_pgm_struct", None)
+    if c is None:
+        has_rep = g.r_col.size > 0
+        c = _lib.Graph(g.N, _addr(g.sites), _addr(g.e_rowptr), _addr(g.e_col), _addr(g.e_val),
+                       _addr(g.r_rowptr), _addr(g.r_col) if has_rep else None, _addr(g.r_units) if has_rep else None)
+        try:
+            g._pgm_struct = c
+        except AttributeError:
+            pass
+    return c
 
 
 def c_model(model, keep):
-    M = np.ascontiguousarray(model.M, dtype=np.float64)
-    pi = np.ascontiguousarray(model.pi, dtype=np.float64)
-    keep += [M, pi]
-    return _lib.DPModel(_p(M), _p(pi), model.distance, model.epsilon, model.delta)
+    c = getattr(model, "_pgm_struct", None)
+    if c is None:
+        M = np.ascontiguousarray(model.M, dtype=np.float64)
+        pi = np.ascontiguousarray(model.pi, dtype=np.float64)
+        c = (_lib.DPModel(_addr(M), _addr(pi), model.distance, model.epsilon, model.delta), M, pi)
+        try:
+            model._pgm_struct = c
+        except AttributeError:
+            pass
+    keep.append(c)
+    return c[0]
 
 
 def c_opts(opts, emission_mode=EMISSION_EXACT):
@@ -58,20 +77,22 @@ class GraphBatch:
 
     def fetch(self):
         out = (_lib.Alignment * max(1, self.n_jobs))()
-        bufs = []
+        offs = np.zeros(self.n_jobs + 1, dtype=np.int64)
+        np.cumsum(self.caps, out=offs[1:])
+        buf = np.zeros((2, max(1, int(offs[-1]))), dtype=np.int32)           # every job's two mappings, one allocation
+        base1, base2 = _addr(buf[0]), _addr(buf[1])
         for k in range(self.n_jobs):
-            m1 = np.zeros(self.caps[k], dtype=np.int32); m2 = np.zeros(self.caps[k], dtype=np.int32)
-            bufs.append((m1, m2))
-            out[k].mapping1 = _p(m1); out[k].mapping2 = _p(m2); out[k].capacity = self.caps[k]
+            o = int(offs[k]) * 4
+            out[k].mapping1 = base1 + o; out[k].mapping2 = base2 + o; out[k].capacity = self.caps[k]
         rc = _lib.lib().pgm_graph_batch_fetch(self.ctx.handle, self._h, out)
         if rc == -4:
             raise RuntimeError("backtracking failed")
         _lib.check(rc)
         res = []
         for k in range(self.n_jobs):
-            ln = out[k].length
+            ln = out[k].length; o = int(offs[k])
             res.append(dict(score=float(out[k].score), n_tr_indels=int(out[k].n_tr_indels),
-                            mapping1=bufs[k][0][:ln].astype(np.int64), mapping2=bufs[k][1][:ln].astype(np.int64),
+                            mapping1=buf[0, o:o + ln].astype(np.int64), mapping2=buf[1, o:o + ln].astype(np.int64),
                             cell_updates=int(out[k].cell_updates)))
         return res
 
