@@ -41,8 +41,8 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 // previous two ring rows at index y-1 (no skew arithmetic).  STAGE: graph 2's node infos in shared memory.
 template <bool STAGE, int RPT>
 __global__ void __launch_bounds__(1024)
-graph_fill_kernel(const GraphJobDev* __restrict__ jobs, int ring_pitch) {
-    const GraphJobDev& J = jobs[blockIdx.x];
+graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch) {
+    const GraphJobDev& J = jobs[order[blockIdx.x]];
     const int N1 = J.N1, N2 = J.N2, pitch = J.pitch;
     const float gap_init = J.sc[0], gap_extend = J.sc[1], start_gap = J.sc[6], start_init = J.sc[7];
     const float NINF = -CUDART_INF_F;
@@ -411,15 +411,17 @@ graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
 }
 
 template <bool STAGE, int RPT>
-static int launch_fill_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int threads, int ring_pitch, size_t smem) {
+static int launch_fill_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int threads, int ring_pitch, size_t smem) {
     PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<STAGE, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_fill_kernel<STAGE, RPT><<<n_jobs, threads, smem, st>>>(d_jobs, ring_pitch);
+    graph_fill_kernel<STAGE, RPT><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
 
 // max_n1 / max_n2: largest graph-1 / graph-2 node counts in this launch
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2, int max_np) {
+// d_order: the n_jobs job indices this launch sweeps (the host groups jobs of similar graph-1 length, because block size
+// and shared memory -- hence CTAs per SM -- are set by the launch's largest job)
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np) {
     if (n_jobs == 0) return 0;
     const int rows = max_n1 > 1 ? max_n1 - 1 : 1;                   // rows 0 .. N1-2
     // rows per thread: on an anti-diagonal sweep only ~half the rows are active at a time, so giving a thread
@@ -435,7 +437,7 @@ int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, in
     if (ring > 227 * 1024) { pgm_set_error("graph too large for the shared-memory diagonal ring (N1 = %d)", max_n1); return PGM_ERR_ARG; }
     const bool stage = ring + info <= 200 * 1024;
     const size_t smem = ring + (stage ? info : 0);
-#define GO(S_, R_) return launch_fill_t<S_, R_>(st, n_jobs, d_jobs, threads, ring_pitch, smem)
+#define GO(S_, R_) return launch_fill_t<S_, R_>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem)
     if (stage) { if (rpt == 1) GO(true, 1); if (rpt == 2) GO(true, 2); GO(true, 4); }
     if (rpt == 1) GO(false, 1); if (rpt == 2) GO(false, 2); GO(false, 4);
 #undef GO

@@ -18,7 +18,7 @@ void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok);
 void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, int max_n1, int max_n2, int max_np);
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
 void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
@@ -86,6 +86,10 @@ struct JobLayout {                // byte offsets into the upload arena / scratc
 
 } // namespace
 
+// side streams for concurrent fill launches: one set per device, created on first use and kept for the process
+struct SideStreams { std::vector<cudaStream_t> streams; std::vector<cudaEvent_t> join; cudaEvent_t fork = nullptr; };
+static SideStreams& side_streams(int device) { static SideStreams s[64]; return s[device & 63]; }
+
 struct pgm_graph_batch {
     int n_states = 0, n_jobs = 0, emission_mode = 0;
     std::vector<GraphJobDev> jobs;          // host copy with DEVICE pointers
@@ -95,6 +99,12 @@ struct pgm_graph_batch {
     HostPinned h_in, h_out;
     size_t out_bytes = 0;
     std::vector<std::pair<int, int>> sub;   // [begin, end) job ranges that fit the scratch budget
+    // Fill schedule.  The fill kernel's block size and shared memory -- hence CTAs per SM -- are set by the LARGEST job
+    // of a launch, so each sub-batch is swept as a few launches of similar graph-1 length (largest first), on
+    // separate streams so that a class with few jobs does not leave the GPU idle.
+    struct FillLaunch { int sub, offset, count, max_n1, max_n2, max_np; };
+    std::vector<int> order;                 // job indices relative to their sub-batch, grouped by FillLaunch
+    std::vector<FillLaunch> fills;
     size_t scratch_bytes_used = 0;
     int max_N1 = 0, max_N2 = 0;
     uint64_t total_updates = 0, total_cells = 0;
@@ -169,7 +179,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     if ((rc = pgm_ctx_take_host(c, std::max<size_t>(in_off, 1), b->h_in)) || (rc = pgm_ctx_take_dev(c, std::max<size_t>(in_off, 1), b->d_in)) ||
         (rc = pgm_ctx_take_dev(c, std::max<size_t>(out_off, 1), b->d_out)) || (rc = pgm_ctx_take_host(c, std::max<size_t>(out_off, 1), b->h_out)) ||
         (rc = pgm_ctx_take_dev(c, std::max<size_t>(b->scratch_bytes_used, 1), b->d_scratch)) ||
-        (rc = pgm_ctx_take_dev(c, std::max<size_t>(sizeof(GraphJobDev) * n_jobs, 1), b->d_jobs))) { pgm_graph_batch_destroy(c, b); return rc; }
+        (rc = pgm_ctx_take_dev(c, std::max<size_t>((sizeof(GraphJobDev) + sizeof(int)) * n_jobs, 1), b->d_jobs))) { pgm_graph_batch_destroy(c, b); return rc; }
     b->out_bytes = out_off;
     char* hin = b->h_in.as<char>();
     char* din = b->d_in.as<char>(); char* dsc = b->d_scratch.as<char>(); char* dout = b->d_out.as<char>();
@@ -256,8 +266,32 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         }
         for (int k = 0; k < n_jobs; ++k) { b->total_updates += b->cell_updates[k]; b->total_cells += (uint64_t)b->jobs[k].N1 * b->jobs[k].N2; }
     }
+    {   // fill schedule: thread-count classes (graph-1 rows rounded up); a class boundary where occupancy changes
+        static const int cls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
+        b->order.resize(n_jobs);
+        for (size_t si = 0; si < b->sub.size(); ++si) {
+            const auto& sbr = b->sub[si];
+            std::vector<int> idx;
+            for (int k = sbr.first; k < sbr.second; ++k) idx.push_back(k - sbr.first);
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int bq) { return b->jobs[sbr.first + a].N1 > b->jobs[sbr.first + bq].N1; });
+            std::copy(idx.begin(), idx.end(), b->order.begin() + sbr.first);
+            auto class_of = [&](int n1) { int q = 0; while (n1 - 1 > cls[q]) ++q; return q; };
+            size_t p = 0;
+            while (p < idx.size()) {
+                const int q = class_of(b->jobs[sbr.first + idx[p]].N1);
+                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, 0, 0, 0};
+                while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]].N1) == q) {
+                    const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
+                    f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2); f.max_np = std::max(f.max_np, J.np1 + J.np2);
+                    ++f.count; ++p;
+                }
+                b->fills.push_back(f);
+            }
+        }
+    }
     if (n_jobs) {
         PGM_CUDA(cudaMemcpyAsync(b->d_in.p, b->h_in.p, in_off, cudaMemcpyHostToDevice, st));
+        PGM_CUDA(cudaMemcpyAsync(b->d_jobs.as<char>() + sizeof(GraphJobDev) * n_jobs, b->order.data(), sizeof(int) * n_jobs, cudaMemcpyHostToDevice, st));
         PGM_CUDA(cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(GraphJobDev) * n_jobs, cudaMemcpyHostToDevice, st));
         PGM_CUDA(cudaStreamSynchronize(st));
     }
@@ -271,7 +305,9 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
     cudaStream_t st = pgm_ctx_stream(c);
     pgm_ctx_reset_timing(c);
     const GraphJobDev* dj = b->d_jobs.as<GraphJobDev>();
-    for (auto& sb : b->sub) {
+    const int* d_order_all = (const int*)(b->d_jobs.as<char>() + sizeof(GraphJobDev) * b->n_jobs);
+    for (size_t si = 0; si < b->sub.size(); ++si) {
+        const auto& sb = b->sub[si];
         const int nj = sb.second - sb.first;
         int mx1 = 0, mx2 = 0, mxd = 0, mxn = 0, mxp = 0, mxnp = 0;
         for (int k = sb.first; k < sb.second; ++k) {
@@ -287,8 +323,31 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
         pgm_ctx_time_end(c, tok);
         if (rc) return rc;
         pgm_ctx_time_begin(c, 4, &tok);
-        (void)mxd; (void)mxn; (void)mxp;
-        rc = launch_graph_fill(st, nj, dj + sb.first, mx1, mx2, mxnp);
+        (void)mxd; (void)mxn; (void)mxp; (void)mxnp;
+        {   // one launch per size class; the first on the main stream, the others forked onto side streams and joined
+            std::vector<const pgm_graph_batch::FillLaunch*> fl;
+            for (auto& f : b->fills) if (f.sub == (int)si) fl.push_back(&f);
+            rc = 0;
+            SideStreams& ss = side_streams(pgm_ctx_device(c));
+            const size_t n_side = fl.size() > 1 ? std::min<size_t>(fl.size() - 1, 3) : 0;
+            if (n_side) {
+                if (!ss.fork) PGM_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+                while (ss.streams.size() < n_side) {
+                    cudaStream_t s2; PGM_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); ss.streams.push_back(s2);
+                    cudaEvent_t e2; PGM_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); ss.join.push_back(e2);
+                }
+                PGM_CUDA(cudaEventRecord(ss.fork, st));
+                for (size_t q = 0; q < n_side; ++q) PGM_CUDA(cudaStreamWaitEvent(ss.streams[q], ss.fork, 0));
+            }
+            for (size_t q = 0; q < fl.size() && !rc; ++q) {
+                cudaStream_t sq = (q == 0 || !n_side) ? st : ss.streams[(q - 1) % n_side];
+                rc = launch_graph_fill(sq, fl[q]->count, dj + sb.first, d_order_all + sb.first + fl[q]->offset, fl[q]->max_n1, fl[q]->max_n2, fl[q]->max_np);
+            }
+            for (size_t q = 0; q < n_side; ++q) {
+                PGM_CUDA(cudaEventRecord(ss.join[q], ss.streams[q]));
+                PGM_CUDA(cudaStreamWaitEvent(st, ss.join[q], 0));
+            }
+        }
         pgm_ctx_time_end(c, tok);
         if (rc) return rc;
         pgm_ctx_time_begin(c, 5, &tok);
