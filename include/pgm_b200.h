@@ -42,7 +42,7 @@ void pgm_destroy(pgm_ctx* ctx);
 int pgm_sync(pgm_ctx* ctx);
 const char* pgm_last_error(void);
 int pgm_abi_version(void);
-/* scratch budget for packed traceback bits etc. (default 8 GiB); work is chunked to fit */
+/* scratch budget for packed traceback bits etc. (default 16 GiB); work is chunked to fit */
 int pgm_set_scratch_bytes(pgm_ctx* ctx, uint64_t bytes);
 /* cudaStream_t the ctx launches on (so callers can record events on it) */
 void* pgm_stream(pgm_ctx* ctx);

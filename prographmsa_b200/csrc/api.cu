@@ -22,7 +22,7 @@ struct TimedSection { cudaEvent_t a = nullptr, b = nullptr; int kind = 0; };
 struct pgm_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    uint64_t scratch_bytes = 8ull << 30;
+    uint64_t scratch_bytes = 16ull << 30;          // of 180 GB HBM; pgm_set_scratch_bytes changes it
     bool timing_on = false;
     bool cached_symmetric = false, ml_no_merge = false;   // PGM_ML_NO_MERGE=1: keep (i,j) and (j,i) counts separate (A-B runs)
     bool force_nw32 = false;             // PGM_NW_FORCE_32BIT=1: never use the 16-bit forward flavour (tests / A-B runs)

@@ -347,6 +347,9 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
                 PGM_CUDA(cudaEventRecord(ss.join[q], ss.streams[q]));
                 PGM_CUDA(cudaStreamWaitEvent(st, ss.join[q], 0));
             }
+            // the timing sections count one launch each; the emission section holds two kernels, the fill section one per class
+            pgm_ctx_timing(c)->emission_launches += 1;
+            pgm_ctx_timing(c)->graph_fill_launches += (uint32_t)(fl.size() ? fl.size() - 1 : 0);
         }
         pgm_ctx_time_end(c, tok);
         if (rc) return rc;
