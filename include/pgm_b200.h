@@ -128,6 +128,23 @@ int pgm_prealigned_ml_all_pairs(pgm_ctx* ctx, const pgm_ml_params* prm,
 int pgm_angle_all_pairs(pgm_ctx* ctx, int n_states, int K, const uint8_t* codes, const uint32_t* offsets, int N,
                         int ml_flag, double* dist, double* var);
 
+/* ---- N2: profile part of mergeGraphs (GraphAlign.h:569-620) ------------------------------
+ * For every merged node: P * g of the child node(s), Hadamard product when both exist, L2 normalisation.
+ * All jobs of one guide-tree level go in one call.  Edge construction stays on the host. */
+typedef struct {
+    int N1, N2;                 /* nodes of the two child graphs                                        */
+    const double* sites1;       /* N1 * n_states, node-major (Graph::sites column = node)               */
+    const double* sites2;       /* N2 * n_states                                                        */
+    const double* P1;           /* n*n row-major, Model::P of the first  child's branch                 */
+    const double* P2;           /* n*n row-major, Model::P of the second child's branch                 */
+    int len;                    /* merged nodes                                                         */
+    const int32_t* rm1;         /* per merged node: index into graph 1, or -1                           */
+    const int32_t* rm2;         /* per merged node: index into graph 2, or -1                           */
+    const uint8_t* matched;     /* 0: node skipped by the alignment path (uses P1, GraphAlign.h:591)    */
+    double* out;                /* len * n_states                                                       */
+} pgm_merge_job;
+int pgm_merge_profiles_batch(pgm_ctx* ctx, int n_states, int n_jobs, const pgm_merge_job* jobs);
+
 /* computeDistance on caller-supplied count matrices (n*n int32 each, counts[s1*n+s2]).            */
 int pgm_ml_distances(pgm_ctx* ctx, const pgm_ml_params* prm, int64_t n_pairs,
                      const int32_t* counts, const uint32_t* gaps, const double* seqlen,

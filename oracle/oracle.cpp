@@ -423,6 +423,30 @@ void orc_angle_all_pairs(const uint8_t* codes, const uint32_t* off, int N, int n
         }
 }
 
+// mergeGraphs, profile part (GraphAlign.h:569-620): P * g as a sequential-k mul/add per output state, Hadamard product,
+// L2 normalisation (skipped for an all-zero profile)
+void orc_merge_profiles(int n, const double* sites1, const double* sites2, const double* P1, const double* P2,
+                        int len, const int32_t* rm1, const int32_t* rm2, const uint8_t* matched, double* out) {
+    std::vector<double> a(n), b(n);
+    auto matvec = [&](const double* P, const double* g, std::vector<double>& r) {
+        for (int i = 0; i < n; ++i) { double s = 0; for (int k = 0; k < n; ++k) s = s + P[i * n + k] * g[k]; r[i] = s; }
+    };
+    for (int i = 0; i < len; ++i) {
+        double* o = out + (size_t)i * n;
+        if (!matched[i]) {
+            matvec(P1, rm1[i] >= 0 ? sites1 + (size_t)rm1[i] * n : sites2 + (size_t)rm2[i] * n, a);
+        } else if (rm1[i] >= 0 && rm2[i] >= 0) {
+            matvec(P1, sites1 + (size_t)rm1[i] * n, a); matvec(P2, sites2 + (size_t)rm2[i] * n, b);
+            for (int k = 0; k < n; ++k) a[k] = a[k] * b[k];
+        } else if (rm1[i] >= 0) matvec(P1, sites1 + (size_t)rm1[i] * n, a);
+        else matvec(P2, sites2 + (size_t)rm2[i] * n, a);
+        double ss = 0;
+        for (int k = 0; k < n; ++k) ss = ss + a[k] * a[k];
+        const double nrm = std::sqrt(ss);
+        for (int k = 0; k < n; ++k) o[k] = nrm == 0 ? a[k] : a[k] / nrm;
+    }
+}
+
 double orc_average_alignment_length(const orc_graph* g) { return average_alignment_length(g); }
 
 void orc_dynprog_scores(const orc_graph* g1, const orc_graph* g2, const orc_dp_model* m, const orc_dp_opts* o, float out[10]) {

@@ -140,6 +140,17 @@ def angle_all_pairs(code_seqs, n, K, ml_flag):
     return dist, var
 
 
+def merge_profiles(sites1, sites2, P1, P2, rm1, rm2, matched):
+    sites1 = np.ascontiguousarray(sites1, dtype=np.float64); sites2 = np.ascontiguousarray(sites2, dtype=np.float64)
+    P1 = np.ascontiguousarray(P1, dtype=np.float64); P2 = np.ascontiguousarray(P2, dtype=np.float64)
+    rm1 = np.ascontiguousarray(rm1, dtype=np.int32); rm2 = np.ascontiguousarray(rm2, dtype=np.int32)
+    matched = np.ascontiguousarray(matched, dtype=np.uint8)
+    n = sites1.shape[1]
+    out = np.zeros((len(rm1), n))
+    lib().orc_merge_profiles(n, _p(sites1), _p(sites2), _p(P1), _p(P2), len(rm1), _p(rm1), _p(rm2), _p(matched), _p(out))
+    return out
+
+
 def expm(Q, t):
     Q = np.ascontiguousarray(Q, dtype=np.float64)
     P = np.zeros_like(Q)

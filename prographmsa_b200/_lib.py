@@ -36,6 +36,11 @@ class DPOpts(C.Structure):
                 ("repeatext_prob", C.c_double), ("emission_mode", C.c_int)]
 
 
+class MergeJob(C.Structure):
+    _fields_ = [("N1", C.c_int), ("N2", C.c_int), ("sites1", C.c_void_p), ("sites2", C.c_void_p), ("P1", C.c_void_p), ("P2", C.c_void_p),
+                ("len", C.c_int), ("rm1", C.c_void_p), ("rm2", C.c_void_p), ("matched", C.c_void_p), ("out", C.c_void_p)]
+
+
 class Alignment(C.Structure):
     _fields_ = [("score", C.c_float), ("n_tr_indels", C.c_uint32), ("mapping1", C.c_void_p), ("mapping2", C.c_void_p),
                 ("capacity", C.c_int32), ("length", C.c_int32), ("status", C.c_int32), ("cell_updates", C.c_uint64)]
@@ -55,7 +60,7 @@ class Timing(C.Structure):
 
 # every symbol include/pgm_b200.h declares (tests check the .so exports all of them)
 SYMBOLS = [
-    "pgm_create", "pgm_destroy", "pgm_sync", "pgm_last_error", "pgm_abi_version", "pgm_set_scratch_bytes", "pgm_stream",
+    "pgm_merge_profiles_batch", "pgm_create", "pgm_destroy", "pgm_sync", "pgm_last_error", "pgm_abi_version", "pgm_set_scratch_bytes", "pgm_stream",
     "pgm_enable_timing", "pgm_get_timing",
     "pgm_nw_ml_pair_range", "pgm_nw_ml_pair_range_dev", "pgm_nw_ml_all_pairs",
     "pgm_prealigned_ml_pair_range", "pgm_prealigned_ml_pair_range_dev", "pgm_prealigned_ml_all_pairs",

@@ -199,34 +199,54 @@ def _normalized(p):
     return p if nrm == 0 else p / nrm
 
 
-def merge_graphs(g1: Graph, g2: Graph, mapping1, mapping2, model1, model2, support1, support2, altsplice_prob):
-    """mergeGraphs (GraphAlign.h:551-727).  Returns (graph, mapping1, mapping2, is_matched).
-    Reference quirks kept: unmatched g2 nodes use model1.P (:591); is_matched[] is indexed with
-    child-graph indices (:692-695,711-714)."""
-    nodes, rm1, rm2, matched = [], [], [], []
+def merge_plan(mapping1, mapping2):
+    """Which child nodes every node of the merged graph comes from (GraphAlign.h:569-620, the loop structure):
+    -> (rm1, rm2, matched) lists; matched[i] is False for nodes the alignment path skipped."""
+    rm1, rm2, matched = [], [], []
     i1 = i2 = 0
-    P1, P2 = model1.P, model2.P
     for k1, k2 in zip(mapping1, mapping2):
         k1, k2 = int(k1), int(k2)
         if k1 != NOGAP:
             while i1 != k1:
-                nodes.append(_normalized(P1 @ g1.sites[i1])); rm1.append(i1); rm2.append(NOGAP); matched.append(False)
+                rm1.append(i1); rm2.append(NOGAP); matched.append(False)
                 i1 += 1
             i1 += 1
         if k2 != NOGAP:
             while i2 != k2:
-                nodes.append(_normalized(P1 @ g2.sites[i2])); rm1.append(NOGAP); rm2.append(i2); matched.append(False)
+                rm1.append(NOGAP); rm2.append(i2); matched.append(False)
                 i2 += 1
             i2 += 1
-        if k1 != NOGAP and k2 != NOGAP:
+        if k1 == NOGAP and k2 == NOGAP:
+            raise AssertionError("error in mapping")
+        rm1.append(k1); rm2.append(k2); matched.append(True)
+    return rm1, rm2, matched
+
+
+def merge_profiles_host(g1, g2, P1, P2, rm1, rm2, matched):
+    """Profile of every merged node on the host (numpy).  Reference quirk kept: skipped g2 nodes use model1.P (:591)."""
+    nodes = []
+    for k1, k2, m in zip(rm1, rm2, matched):
+        if not m:
+            p = P1 @ (g1.sites[k1] if k1 != NOGAP else g2.sites[k2])
+        elif k1 != NOGAP and k2 != NOGAP:
             p = (P1 @ g1.sites[k1]) * (P2 @ g2.sites[k2])
         elif k1 != NOGAP:
             p = P1 @ g1.sites[k1]
-        elif k2 != NOGAP:
-            p = P2 @ g2.sites[k2]
         else:
-            raise AssertionError("error in mapping")
-        nodes.append(_normalized(p)); rm1.append(k1); rm2.append(k2); matched.append(True)
+            p = P2 @ g2.sites[k2]
+        nodes.append(_normalized(p))
+    return nodes
+
+
+def merge_graphs(g1: Graph, g2: Graph, mapping1, mapping2, model1, model2, support1, support2, altsplice_prob, nodes=None):
+    """mergeGraphs (GraphAlign.h:551-727).  Returns (graph, mapping1, mapping2, is_matched).
+    Reference quirks kept: unmatched g2 nodes use model1.P (:591); is_matched[] is indexed with
+    child-graph indices (:692-695,711-714).  nodes: profiles computed elsewhere (pgm_merge_profiles_batch) for the
+    plan merge_plan(mapping1, mapping2), else they are computed here with numpy."""
+    rm1, rm2, matched = merge_plan(mapping1, mapping2)
+    if nodes is None:
+        nodes = merge_profiles_host(g1, g2, model1.P, model2.P, rm1, rm2, matched)
+    assert len(nodes) == len(rm1)
 
     edges, repeats = {}, {}
     last_xy = last_x = last_y = last_mapped = 0

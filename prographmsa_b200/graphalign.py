@@ -140,3 +140,24 @@ def emission_scores(g1, g2, model, match_init, emission_mode=EMISSION_EXACT, ctx
     _lib.check(_lib.lib().pgm_emission_scores(ctx.handle, g1.n, C.byref(a), C.byref(b), C.byref(m), C.c_float(match_init),
                                               int(emission_mode), _p(S)))
     return S.T
+
+
+def merge_profiles_batch(jobs, ctx=None):
+    """Profile part of mergeGraphs (GraphAlign.h:569-620) for all merges of one tree level on the GPU.
+    jobs: [(g1, g2, P1, P2, rm1, rm2, matched)] with the plan of graph.merge_plan -> [len x n float64 arrays]."""
+    ctx = ctx or _lib.default_context()
+    if not jobs:
+        return []
+    n = jobs[0][0].n
+    J = (_lib.MergeJob * len(jobs))()
+    keep, outs = [], []
+    for k, (g1, g2, P1, P2, rm1, rm2, matched) in enumerate(jobs):
+        P1 = np.ascontiguousarray(P1, dtype=np.float64); P2 = np.ascontiguousarray(P2, dtype=np.float64)
+        a = np.ascontiguousarray(rm1, dtype=np.int32); b = np.ascontiguousarray(rm2, dtype=np.int32)
+        m = np.ascontiguousarray(matched, dtype=np.uint8)
+        out = np.zeros((len(a), n))
+        keep += [g1, g2, P1, P2, a, b, m]
+        outs.append(out)
+        J[k] = _lib.MergeJob(g1.N, g2.N, _addr(g1.sites), _addr(g2.sites), _addr(P1), _addr(P2), len(a), _addr(a), _addr(b), _addr(m), _addr(out))
+    _lib.check(_lib.lib().pgm_merge_profiles_batch(ctx.handle, n, len(jobs), J))
+    return outs

@@ -36,6 +36,9 @@ class GpuBackend:
     def batch_align(self, jobs, opts):
         return self._g.alignGraphsBatch(jobs, opts, self.mode, self.ctx)
 
+    def batch_merge(self, jobs):
+        return self._g.merge_profiles_batch(jobs, self.ctx)
+
 
 def do_align(seq_strings, opts: Options, backend_factory, alphabet=_alpha.AA, iters=2, return_trees=False):
     """seq_strings: name -> residue string.  -> (name -> aligned string in tree order, [newick of every tree])."""
@@ -55,7 +58,8 @@ def do_align(seq_strings, opts: Options, backend_factory, alphabet=_alpha.AA, it
     trees.append(tree.newick())
     result = old = None
     for i in range(iters):
-        result = _prog.progressive_alignment(seqs, _tree.to_progressive(tree), mf, opts, batch_align_fn=be.batch_align)
+        result = _prog.progressive_alignment(seqs, _tree.to_progressive(tree), mf, opts, batch_align_fn=be.batch_align,
+                                              batch_merge_fn=getattr(be, "batch_merge", None))
         aligned = {k: v for k, v in result.aligned.items() if not k.startswith("(")}
         if i > 0 and old is not None and all(np.array_equal(aligned[k], old[k]) for k in aligned):
             break
@@ -63,7 +67,8 @@ def do_align(seq_strings, opts: Options, backend_factory, alphabet=_alpha.AA, it
         tree = _tree.tree_nj(anames, be.prealigned_distances(aligned, anames), opts.edge_halflife)
         trees.append(tree.newick())
         old = aligned
-    result = _prog.progressive_alignment(seqs, _tree.to_progressive(tree), mf, opts, batch_align_fn=be.batch_align)
+    result = _prog.progressive_alignment(seqs, _tree.to_progressive(tree), mf, opts, batch_align_fn=be.batch_align,
+                                              batch_merge_fn=getattr(be, "batch_merge", None))
 
     out = {}
     for k in tree.leaf_order():

@@ -14,7 +14,7 @@ import re
 import numpy as np
 
 from .alphabet import GAP
-from .graph import Graph, CleanedGraph, sequence_graph, merge_graphs, NOGAP
+from .graph import Graph, CleanedGraph, sequence_graph, merge_graphs, merge_plan, NOGAP
 
 
 class TreeNode:
@@ -129,15 +129,23 @@ def prepare_job(r1, r2, d1, d2, model_factory, opts):
     return dict(model=model, model1=model1, model2=model2, cg1=cg1, cg2=cg2)
 
 
-def finish_job(r1, r2, job, ali, s1, s2, opts):
-    """...and everything after it (ProgressiveAlignment.h:440-468)."""
+def merge_job(r1, r2, job, ali):
+    """The mergeGraphs profile job of an aligned node: (g1, g2, P1, P2, rm1, rm2, matched) for merge_profiles_batch."""
+    m1 = job["cg1"].uncleanMapping(ali["mapping1"])
+    m2 = job["cg2"].uncleanMapping(ali["mapping2"])
+    rm1, rm2, matched = merge_plan(m1, m2)
+    return (r1.graph, r2.graph, job["model1"].P, job["model2"].P, rm1, rm2, matched)
+
+
+def finish_job(r1, r2, job, ali, s1, s2, opts, nodes=None):
+    """...and everything after it (ProgressiveAlignment.h:440-468).  nodes: merged-node profiles computed elsewhere."""
     res = Result()
     res.score = ali["score"]
     res.n_tr_indels = ali["n_tr_indels"] + r1.n_tr_indels + r2.n_tr_indels
     m1 = job["cg1"].uncleanMapping(ali["mapping1"])
     m2 = job["cg2"].uncleanMapping(ali["mapping2"])
     graph, am1, am2, _ = merge_graphs(r1.graph, r2.graph, m1, m2, job["model1"], job["model2"], s1, s2,
-                                      opts.altsplice_prob)
+                                      opts.altsplice_prob, nodes=nodes)
     res.graph = graph
     res.aligned.update(_extend_rows(graph.N, am1, r1.aligned))
     res.aligned.update(_extend_rows(graph.N, am2, r2.aligned))
@@ -148,7 +156,7 @@ def finish_job(r1, r2, job, ali, s1, s2, opts):
 
 
 def progressive_alignment(sequences, tree, model_factory, opts, align_fn=None, repeats=None,
-                          batch_align_fn=None, stats=None):
+                          batch_align_fn=None, stats=None, batch_merge_fn=None):
     """-> Result for the root.  sequences: name -> uint8 codes."""
     n = model_factory.alphabet.DIM
     if batch_align_fn is None:
@@ -188,10 +196,14 @@ def progressive_alignment(sequences, tree, model_factory, opts, align_fn=None, r
             r1, r2 = results[id(nd.children[0])], results[id(nd.children[1])]
             jobs.append(prepare_job(r1, r2, nd.children[0].length, nd.children[1].length, model_factory, opts))
         alis = batch_align_fn([(j["cg1"], j["cg2"], j["model"]) for j in jobs], opts)
-        for nd, job, ali in zip(nodes, jobs, alis):
+        profiles = [None] * len(jobs)
+        if batch_merge_fn is not None:                      # mergeGraphs' profile part for the whole level in one call
+            profiles = batch_merge_fn([merge_job(results[id(nd.children[0])], results[id(nd.children[1])], job, ali)
+                                       for nd, job, ali in zip(nodes, jobs, alis)])
+        for nd, job, ali, prof in zip(nodes, jobs, alis, profiles):
             r1, r2 = results.pop(id(nd.children[0])), results.pop(id(nd.children[1]))
             if stats is not None:
                 stats.append(dict(N1=job["cg1"].N, N2=job["cg2"].N, score=ali["score"], level=h,
                                   cell_updates=job["cg1"].total_pred_pairs(job["cg2"])))
-            results[id(nd)] = finish_job(r1, r2, job, ali, nd.children[0].support, nd.children[1].support, opts)
+            results[id(nd)] = finish_job(r1, r2, job, ali, nd.children[0].support, nd.children[1].support, opts, nodes=prof)
     return results[id(tree)]

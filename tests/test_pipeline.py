@@ -114,3 +114,54 @@ def test_angle_distances_vs_oracle():
         off = ~np.eye(len(names), dtype=bool)
         np.testing.assert_allclose(dm.distances[off], d_ref[off], rtol=1e-12, atol=1e-15)
         np.testing.assert_allclose(dm.variances[off], v_ref[off], rtol=1e-12, atol=1e-15)
+
+
+# ---- N2: profile part of mergeGraphs (GraphAlign.h:569-620) ---------------------------------------------------------------
+def _merge_cases():
+    """Merge jobs of a small progressive pass (aligned with the oracle): [(g1, g2, P1, P2, rm1, rm2, matched)]."""
+    from oracle import pyoracle as po
+    from prographmsa_b200 import model, synth, progressive
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(12, 60, mf, seed=5, indel_rate=0.05)
+    jobs = []
+
+    def align(g1, g2, m, o):
+        return po.align_graphs(g1, g2, m, o)
+    orig = progressive.finish_job
+
+    def spy(r1, r2, job, ali, s1, s2, o, nodes=None):
+        jobs.append(progressive.merge_job(r1, r2, job, ali))
+        return orig(r1, r2, job, ali, s1, s2, o, nodes=nodes)
+    progressive.finish_job = spy
+    try:
+        progressive.progressive_alignment(seqs, progressive.from_synth(root), mf, opts, align_fn=align)
+    finally:
+        progressive.finish_job = orig
+    return jobs
+
+
+def test_merge_profiles_oracle_vs_numpy_host():
+    from oracle import pyoracle as po
+    from prographmsa_b200 import graph
+    jobs = _merge_cases()
+    assert len(jobs) == 11 and any(not all(j[6]) for j in jobs)            # some merges skip nodes (the P1 quirk, :591)
+    for g1, g2, P1, P2, rm1, rm2, matched in jobs:
+        ref = np.array(graph.merge_profiles_host(g1, g2, P1, P2, rm1, rm2, matched))
+        got = po.merge_profiles(g1.sites, g2.sites, P1, P2, rm1, rm2, matched)
+        np.testing.assert_allclose(got, ref, rtol=1e-13, atol=1e-300)      # numpy's BLAS sums in another order
+        nz = np.linalg.norm(got, axis=1) > 0
+        np.testing.assert_allclose(np.linalg.norm(got[nz], axis=1), 1.0, rtol=1e-14)
+
+
+@pytest.mark.gpu
+def test_merge_profiles_gpu_bit_exact_vs_oracle():
+    from oracle import pyoracle as po
+    from prographmsa_b200 import graphalign
+    jobs = _merge_cases()
+    outs = graphalign.merge_profiles_batch(jobs)
+    assert len(outs) == len(jobs)
+    for (g1, g2, P1, P2, rm1, rm2, matched), got in zip(jobs, outs):
+        ref = po.merge_profiles(g1.sites, g2.sites, P1, P2, rm1, rm2, matched)
+        assert got.shape == ref.shape and np.array_equal(got, ref)         # sequential-k FP64 mul/add on both sides
+    assert graphalign.merge_profiles_batch([]) == []
