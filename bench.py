@@ -252,7 +252,8 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 upd, cells = t["graph_cell_updates"], t["graph_cells"]
             ms = sum(a.elapsed_time(b) for a, b in ev) / steps
             res = gb.fetch()
-            # e2e: host graphs in, mappings out, per step
+            # e2e: host graphs in, mappings out, per step (one untimed call first: buffer pools, side streams)
+            graphalign.alignGraphsBatch(jobs, opts, mode, ctx)
             t0 = time.perf_counter()
             for _ in range(max(1, steps // 2)):
                 graphalign.alignGraphsBatch(jobs, opts, mode, ctx)
@@ -267,7 +268,8 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 gpu_launches=tm["launches"],
                 roofline=dict(bound="hbm", kernel="graph_fill_kernel", achieved=alg_bytes / fill_ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
                               frac=alg_bytes / fill_ms / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
-                              note="algorithmic bytes = 20 B/cell (4 B S read + 16 B MXYW write); the wavefront is dependency-latency bound"),
+                              note="algorithmic bytes = 20 B/cell (4 B S read + 16 B MXYW write); one job's sweep is a chain of ~830 barriers, "
+                                   "so the kernel is latency-bound per job, not HBM-bound (profiles/r1_final_hp1.txt)"),
                 score_checksum=float(sum(r["score"] for r in res)))
         finally:
             gb.close()

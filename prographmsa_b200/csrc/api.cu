@@ -248,7 +248,8 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     // small pair ranges (a shard of a strongly-scaled matrix): smaller tasks keep >= ~2 waves of forward CTAs, and the walk
     // runs 8 instead of 32 independent chains per warp (a warp-step waits for the slowest lane's DRAM access)
     const int64_t task_pairs = np >= 38000 ? NW_TASK_PAIRS : (np >= 19000 ? 16 : 8);
-    const int walk_lanes = np >= 70000 ? 32 : 8;
+    int walk_lanes = np >= 70000 ? 32 : 8;
+    if (const char* e = getenv("PGM_WALK_LANES")) { const int v = atoi(e); if (v == 8 || v == 32) walk_lanes = v; }
     int u16_max_rows = 0;                               // longest row sequence of any 16-bit task (sizes the residue staging)
     {
         int64_t i, j; pair_from_index_host(pb, N, i, j);
