@@ -32,6 +32,7 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 }
 
 #define GF_RING 8            // anti-diagonals of {M,X,Y,W} kept in shared memory (power of two): covers skip edges spanning <= 5 nodes
+#define GF_RING_LONG 4       // ... for graphs too long for 8 (>= 4: rows d, d-1, d-2 are live at once); S is then read directly
 // S is row-major by y; each (thread,row) streams its own row 16 bytes (4 columns) at a time with cp.async,
 // 8 columns (= 8 anti-diagonals) ahead, into a private ring of four float4 slots
 
@@ -39,7 +40,7 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 // thread meets (y,0), (y,1), ... on consecutive anti-diagonals, so the LEFT neighbour (y, x-1) and the
 // row's own predecessor info stay in registers; the UP / DIAGONAL neighbours (y-1, .) come from the
 // previous two ring rows at index y-1 (no skew arithmetic).  STAGE: graph 2's node infos in shared memory.
-template <bool STAGE, int RPT>
+template <bool STAGE, int RPT, int RING, bool SPF>
 __global__ void __launch_bounds__(1024)
 graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch) {
     const GraphJobDev& J = jobs[order[blockIdx.x]];
@@ -51,9 +52,9 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
     const int T = (int)blockDim.x, tid = (int)threadIdx.x;
 
     extern __shared__ __align__(16) unsigned char gsm[];
-    float4* ring = (float4*)gsm;                                                    // [GF_RING][ring_pitch], indexed by y
-    float4* sring = (float4*)(gsm + (size_t)GF_RING * ring_pitch * sizeof(float4)); // [4][RPT*T], private slots per (thread,row)
-    NodeInfo* s2 = (NodeInfo*)(sring + 4 * RPT * T);
+    float4* ring = (float4*)gsm;                                                    // [RING][ring_pitch], indexed by y
+    float4* sring = (float4*)(gsm + (size_t)RING * ring_pitch * sizeof(float4));    // SPF: [4][RPT*T], private slots per (thread,row)
+    NodeInfo* s2 = (NodeInfo*)(sring + (SPF ? 4 * RPT * T : 0));
     // STAGE: graph 2's node infos and both predecessor lists live in shared memory, so the rare multi-predecessor
     // cell (met by SOME row on almost every anti-diagonal) does not put global-memory latency on the sweep's critical path
     int* sp1i = (int*)(s2 + N2); float* sp1v = (float*)(sp1i + J.np1);
@@ -70,7 +71,7 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
 
     auto cell = [&](int yy, int xx, int d) -> float4 {          // any earlier cell: ring when recent, else HBM/L2
         const int dd = yy + xx;
-        if (d - dd < GF_RING) return ring[(dd & (GF_RING - 1)) * ring_pitch + yy];
+        if (d - dd < RING) return ring[(dd & (RING - 1)) * ring_pitch + yy];
         return C[(size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)))];
     };
 
@@ -92,7 +93,7 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
         const int y = tid + r * T;
-        if (y >= 1 && y <= N1 - 2) { fetch_s4(r, y, 0); if (4 < ldS) fetch_s4(r, y, 4); }
+        if (SPF && y >= 1 && y <= N1 - 2) { fetch_s4(r, y, 0); if (4 < ldS) fetch_s4(r, y, 4); }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");      // the first rows need these within < 8 diagonals
@@ -101,14 +102,14 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int y = tid + r * T, x = d - y;
-            if (y >= 1 && y <= N1 - 2 && x >= 0 && (x & 3) == 0 && x + 8 < ldS) fetch_s4(r, y, x + 8);
+            if (SPF && y >= 1 && y <= N1 - 2 && x >= 0 && (x & 3) == 0 && x + 8 < ldS) fetch_s4(r, y, x + 8);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         asm volatile("cp.async.wait_group 7;\n" ::: "memory");             // everything issued >= 8 diagonals ago has landed
         const int ylo = max(0, d - (N2 - 1));
-        float4* rcur = ring + (d & (GF_RING - 1)) * ring_pitch;
-        const float4* row1 = ring + ((d - 1) & (GF_RING - 1)) * ring_pitch;
-        const float4* row2 = ring + ((d - 2) & (GF_RING - 1)) * ring_pitch;
+        float4* rcur = ring + (d & (RING - 1)) * ring_pitch;
+        const float4* row1 = ring + ((d - 1) & (RING - 1)) * ring_pitch;
+        const float4* row2 = ring + ((d - 2) & (RING - 1)) * ring_pitch;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int y = tid + r * T, x = d - y;
@@ -138,7 +139,8 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
                     }
                     w = xs;
                 } else {
-                    const float s = reinterpret_cast<const float*>(sring + ((x >> 2) & 3) * (RPT * T) + r * T + tid)[x & 3];
+                    const float s = SPF ? reinterpret_cast<const float*>(sring + ((x >> 2) & 3) * (RPT * T) + r * T + tid)[x & 3]
+                                        : __ldg(S + (size_t)y * ldS + x);
                     if (ysimple[r] && nx.cnt == 1 && nx.idx0 == x - 1) {
                         // fast path (chain nodes, the overwhelming majority): one adjacent regular predecessor each
                         const float ey = ny[r].val0, ex = nx.val0;
@@ -410,10 +412,10 @@ graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
     J.result[0] = status; J.result[1] = T.len; J.result[2] = (int)n_tr;
 }
 
-template <bool STAGE, int RPT>
+template <bool STAGE, int RPT, int RING, bool SPF>
 static int launch_fill_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int threads, int ring_pitch, size_t smem) {
-    PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<STAGE, RPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_fill_kernel<STAGE, RPT><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch);
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<STAGE, RPT, RING, SPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_fill_kernel<STAGE, RPT, RING, SPF><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -432,12 +434,17 @@ int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, co
     if (rows > 4096) { pgm_set_error("graph 1 has %d nodes; the wavefront kernel supports up to 4097", max_n1); return PGM_ERR_ARG; }
     const int threads = std::min(1024, std::max(64, ((rows + rpt - 1) / rpt + 31) & ~31));
     const int ring_pitch = (max_n1 + 3) & ~3;
-    const size_t ring = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * rpt * threads * sizeof(float4);
     const size_t info = (size_t)max_n2 * sizeof(NodeInfo) + (size_t)max_np * 8 + 64;
-    if (ring > 227 * 1024) { pgm_set_error("graph too large for the shared-memory diagonal ring (N1 = %d)", max_n1); return PGM_ERR_ARG; }
+    // regular flavour: 8-diagonal ring + cp.async S prefetch slots; long graphs: 4-diagonal ring, S read directly
+    const size_t ring8 = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * rpt * threads * sizeof(float4);
+    const size_t ring4 = (size_t)GF_RING_LONG * ring_pitch * sizeof(float4);
+    const bool regular = ring8 <= 227 * 1024;
+    const size_t ring = regular ? ring8 : ring4;
+    if (ring > 227 * 1024) { pgm_set_error("graph too large for the shared-memory diagonal ring (N1 = %d, limit ~3500)", max_n1); return PGM_ERR_ARG; }
     const bool stage = ring + info <= 200 * 1024;
     const size_t smem = ring + (stage ? info : 0);
-#define GO(S_, R_) return launch_fill_t<S_, R_>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem)
+#define GO(S_, R_) do { if (regular) return launch_fill_t<S_, R_, GF_RING, true>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); \
+                        return launch_fill_t<S_, R_, GF_RING_LONG, false>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); } while (0)
     if (stage) { if (rpt == 1) GO(true, 1); if (rpt == 2) GO(true, 2); GO(true, 4); }
     if (rpt == 1) GO(false, 1); if (rpt == 2) GO(false, 2); GO(false, 4);
 #undef GO

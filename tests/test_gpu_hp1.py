@@ -66,6 +66,27 @@ def test_leaf_pair_alignment_identical(ga, po, L, t, seed):
     _same_alignment(ga.alignGraphs(g1, g2, m, opts), po.align_graphs(g1, g2, m, opts))
 
 
+@pytest.mark.parametrize("L", [1100, 1500, 2300])
+def test_long_graphs_identical(ga, po, L):
+    """graph 1 beyond 1024 rows: several rows per thread; beyond ~1400 rows the fill kernel switches to its 4-diagonal
+    ring and reads S directly (BASELINE config 3 has 1500-nt sequences)"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    a, b = synth.random_pair(L, 0.4, mf, seed=L)
+    g1, g2 = sequence_graph(a, 20), sequence_graph(b, 20)
+    m = mf.getModel(0.4, 0.4)
+    _same_alignment(ga.alignGraphs(g1, g2, m, opts), po.align_graphs(g1, g2, m, opts))
+
+
+def test_too_long_graph_is_an_error_not_a_crash(ga):
+    from prographmsa_b200._lib import PgmError
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    a, b = synth.random_pair(4200, 0.4, mf, seed=1)
+    with pytest.raises(PgmError):
+        ga.alignGraphs(sequence_graph(a, 20), sequence_graph(b, 20), mf.getModel(0.4, 0.4), opts)
+
+
 def test_empty_sequences(ga, po):
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
