@@ -219,6 +219,22 @@ int pgm_dynprog_scores(int n_states, const pgm_graph* g1, const pgm_graph* g2, c
 int pgm_emission_scores(pgm_ctx* ctx, int n_states, const pgm_graph* g1, const pgm_graph* g2,
                         const pgm_dp_model* model, float match_init, int emission_mode, float* S);
 
+/* ---- native HOST glue around the graph DP (csrc/host_graph.cpp; no GPU work, callable without a device) -------
+ * What the reference does in C++ between two alignGraphs calls, on the same CSR arrays as pgm_graph:
+ * CleanedGraph (CleanedGraph.h:38-146), the node plan of mergeGraphs (GraphAlign.h:569-620) and its edge
+ * construction (GraphAlign.h:622-727, Graph.h:81-100).  Outputs are caller-allocated; capacities in the comments. */
+int pgm_host_clean_graph(const pgm_graph* g, double repeatext_prob,
+                         int32_t* keep /* N */, int* new_N,
+                         int32_t* e_rowptr /* N+1 */, int32_t* e_col /* E */, float* e_val /* E */,
+                         int32_t* r_rowptr /* N+1 */, int32_t* r_col /* R */, uint32_t* r_units /* R */);
+int pgm_host_merge_plan(const int64_t* mapping1, const int64_t* mapping2, int len,
+                        int32_t* rm1 /* N1+N2 */, int32_t* rm2 /* N1+N2 */, uint8_t* matched /* N1+N2 */, int* out_len);
+int pgm_host_merge_edges(const pgm_graph* g1, const pgm_graph* g2, int len,
+                         const int32_t* rm1, const int32_t* rm2, const uint8_t* matched,
+                         double support1, double support2, double altsplice_prob,
+                         int32_t* e_rowptr /* len+1 */, int32_t* e_col /* E1+E2+4*len */, float* e_val, int* n_edges,
+                         int32_t* r_rowptr /* len+1 */, int32_t* r_col /* R1+R2 */, uint32_t* r_units, int* n_repeats);
+
 #ifdef __cplusplus
 }
 #endif

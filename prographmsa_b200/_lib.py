@@ -67,6 +67,7 @@ SYMBOLS = [
     "pgm_ml_distances", "pgm_angle_all_pairs",
     "pgm_align_graphs_batch", "pgm_graph_batch_create", "pgm_graph_batch_run", "pgm_graph_batch_fetch",
     "pgm_graph_batch_destroy", "pgm_dynprog_scores", "pgm_emission_scores",
+    "pgm_host_clean_graph", "pgm_host_merge_plan", "pgm_host_merge_edges",
 ]
 
 
@@ -81,6 +82,11 @@ def lib():
         _lib.pgm_stream.restype = C.c_void_p
         _lib.pgm_destroy.restype = None
         _lib.pgm_graph_batch_destroy.restype = None
+        vp, ip = C.c_void_p, C.POINTER(C.c_int)
+        _lib.pgm_host_clean_graph.argtypes = [vp, C.c_double, vp, ip, vp, vp, vp, vp, vp, vp]
+        _lib.pgm_host_merge_plan.argtypes = [vp, vp, C.c_int, vp, vp, vp, ip]
+        _lib.pgm_host_merge_edges.argtypes = [vp, vp, C.c_int, vp, vp, vp, C.c_double, C.c_double, C.c_double,
+                                              vp, vp, vp, ip, vp, vp, vp, ip]
     return _lib
 
 

@@ -6,11 +6,41 @@ and GraphAlign.h:539-727 (mergeGraphs).  The device consumes exactly these array
 (include/pgm_b200.h `pgm_graph`): ``sites`` DIM x N column-major double, two CSR matrices whose
 rows are *to*-nodes and whose entries are ascending *from*-nodes.
 """
+import ctypes as C
 import math
+import os
 import numpy as np
+
+from . import _lib
 
 MAX_EDGE_COST = np.float32(10000.0)
 NOGAP = -1
+
+# The graph surgery between two alignGraphs calls exists twice: the Python below is the readable restatement of the
+# reference (and what the oracle-backed CPU tests pin against the reference binary); csrc/host_graph.cpp is the same
+# logic in C++ behind the C ABI (pgm_host_*), used whenever the library is built.  tests/test_cpu_host.py compares the
+# two array by array; PGM_HOST_GLUE=python forces the Python path.
+NATIVE = os.environ.get("PGM_HOST_GLUE", "native") != "python" and os.path.exists(_lib.LIB_PATH)
+
+
+def _addr(a):
+    return a.__array_interface__["data"][0]
+
+
+def c_graph(g, keep=None):
+    """pgm_graph view of a Graph.  The struct is cached on the graph (its arrays never change after construction)."""
+    if keep is not None:
+        keep.append(g)
+    c = getattr(g, "_pgm_struct", None)
+    if c is None:
+        has_rep = g.r_col.size > 0
+        c = _lib.Graph(g.N, _addr(g.sites), _addr(g.e_rowptr), _addr(g.e_col), _addr(g.e_val),
+                       _addr(g.r_rowptr), _addr(g.r_col) if has_rep else None, _addr(g.r_units) if has_rep else None)
+        try:
+            g._pgm_struct = c
+        except AttributeError:
+            pass
+    return c
 
 
 def _f32(x):
@@ -108,15 +138,23 @@ class Graph:
 def sequence_graph(codes, n) -> Graph:
     """SequenceGraph(seq) (SequenceGraph.h:44-104 + Graph.h:35-46): one-hot (or uniform 1/n for a
     non-valid state) profile, chain edges of cost 0."""
+    codes = np.asarray(codes)
     L = len(codes)
     sites = np.zeros((L + 2, n), dtype=np.float64)
-    for i, c in enumerate(codes):
-        if c < n:
-            sites[i + 1, c] = 1.0
-        else:
-            sites[i + 1, :] = 1.0 / n
-    edges = {(i + 1, i): np.float32(0.0) for i in range(L + 1)}
-    return Graph(sites, edges)
+    valid = codes < n
+    pos = np.nonzero(valid)[0]
+    sites[pos + 1, codes[pos]] = 1.0
+    sites[np.nonzero(~valid)[0] + 1, :] = 1.0 / n
+    g = Graph.__new__(Graph)
+    g._pgm_struct = None
+    g.sites, g.N, g.n = sites, L + 2, n
+    # chain edges (i+1 <- i) of cost 0: stored value min(0, 1e4) - 1e4 (Graph.h:85)
+    g.e_rowptr = np.concatenate([[0], np.arange(L + 2)]).astype(np.int32)
+    g.e_col = np.arange(L + 1, dtype=np.int32)
+    g.e_val = np.full(L + 1, -MAX_EDGE_COST, dtype=np.float32)
+    g.r_rowptr = np.zeros(L + 3, dtype=np.int32)
+    g.r_col = np.zeros(0, dtype=np.int32); g.r_units = np.zeros(0, dtype=np.uint32)
+    return g
 
 
 class CleanedGraph(Graph):
@@ -124,6 +162,9 @@ class CleanedGraph(Graph):
     0-unit repeats; remember the index mapping for uncleanMapping (:153-160)."""
 
     def __init__(self, original: Graph, repeatext_prob: float):
+        if NATIVE:
+            self._init_native(original, repeatext_prob)
+            return
         N = original.N
         repeat_ext = np.float32(np.inf) if repeatext_prob == 0 else np.float32(0.0)
 
@@ -179,6 +220,27 @@ class CleanedGraph(Graph):
         self._set_repeats(reps)
         self.outmapping = keep.astype(np.int64)
 
+    def _init_native(self, original, repeatext_prob):
+        N, E, R = original.N, original.e_col.size, original.r_col.size
+        keep = np.empty(N, dtype=np.int32)
+        e_rowptr = np.empty(N + 1, dtype=np.int32); e_col = np.empty(E, dtype=np.int32); e_val = np.empty(E, dtype=np.float32)
+        r_rowptr = np.empty(N + 1, dtype=np.int32); r_col = np.empty(R, dtype=np.int32); r_units = np.empty(R, dtype=np.uint32)
+        new_N = C.c_int(0)
+        g = c_graph(original)
+        _lib.check(_lib.lib().pgm_host_clean_graph(C.byref(g), C.c_double(repeatext_prob), _addr(keep), C.byref(new_N),
+                                                   _addr(e_rowptr), _addr(e_col), _addr(e_val),
+                                                   _addr(r_rowptr), _addr(r_col), _addr(r_units)))
+        n = new_N.value
+        keep = keep[:n]
+        self._pgm_struct = None
+        self.sites = original.sites if n == N else np.ascontiguousarray(original.sites[keep])
+        self.N, self.n = self.sites.shape
+        self.e_rowptr = e_rowptr[:n + 1]; ne = int(e_rowptr[n])
+        self.e_col, self.e_val = e_col[:ne], e_val[:ne]
+        self.r_rowptr = r_rowptr[:n + 1]; nr = int(r_rowptr[n])
+        self.r_col, self.r_units = r_col[:nr], r_units[:nr]
+        self.outmapping = keep.astype(np.int64)
+
     def uncleanMapping(self, mapping):
         m = np.asarray(mapping, dtype=np.int64).copy()
         ok = m != NOGAP
@@ -202,6 +264,13 @@ def _normalized(p):
 def merge_plan(mapping1, mapping2):
     """Which child nodes every node of the merged graph comes from (GraphAlign.h:569-620, the loop structure):
     -> (rm1, rm2, matched) lists; matched[i] is False for nodes the alignment path skipped."""
+    if NATIVE:
+        m1 = np.ascontiguousarray(mapping1, dtype=np.int64); m2 = np.ascontiguousarray(mapping2, dtype=np.int64)
+        cap = 2 * len(m1) + 2 + int(max(m1.max(initial=0), 0)) + int(max(m2.max(initial=0), 0))
+        rm1 = np.empty(cap, dtype=np.int32); rm2 = np.empty(cap, dtype=np.int32); matched = np.empty(cap, dtype=np.uint8)
+        n = C.c_int(0)
+        _lib.check(_lib.lib().pgm_host_merge_plan(_addr(m1), _addr(m2), len(m1), _addr(rm1), _addr(rm2), _addr(matched), C.byref(n)))
+        return rm1[:n.value], rm2[:n.value], matched[:n.value]
     rm1, rm2, matched = [], [], []
     i1 = i2 = 0
     for k1, k2 in zip(mapping1, mapping2):
@@ -247,6 +316,8 @@ def merge_graphs(g1: Graph, g2: Graph, mapping1, mapping2, model1, model2, suppo
     if nodes is None:
         nodes = merge_profiles_host(g1, g2, model1.P, model2.P, rm1, rm2, matched)
     assert len(nodes) == len(rm1)
+    if NATIVE:
+        return _merge_graphs_native(g1, g2, rm1, rm2, matched, nodes, support1, support2, altsplice_prob)
 
     edges, repeats = {}, {}
     last_xy = last_x = last_y = last_mapped = 0
@@ -299,3 +370,28 @@ def merge_graphs(g1: Graph, g2: Graph, mapping1, mapping2, model1, model2, suppo
                     _update_edge(repeats, y, x, units)
     graph = Graph(np.array(nodes), edges, repeats)
     return graph, np.array(rm1, dtype=np.int64), np.array(rm2, dtype=np.int64), matched
+
+
+def _merge_graphs_native(g1, g2, rm1, rm2, matched, nodes, support1, support2, altsplice_prob):
+    """Edge part of mergeGraphs through pgm_host_merge_edges; the merged Graph is assembled from the returned CSR."""
+    rm1 = np.ascontiguousarray(rm1, dtype=np.int32); rm2 = np.ascontiguousarray(rm2, dtype=np.int32)
+    mt = np.ascontiguousarray(matched, dtype=np.uint8)
+    ln = len(rm1)
+    ecap = g1.e_col.size + g2.e_col.size + 4 * ln + 4
+    rcap = g1.r_col.size + g2.r_col.size + 1
+    e_rowptr = np.empty(ln + 1, dtype=np.int32); e_col = np.empty(ecap, dtype=np.int32); e_val = np.empty(ecap, dtype=np.float32)
+    r_rowptr = np.empty(ln + 1, dtype=np.int32); r_col = np.empty(rcap, dtype=np.int32); r_units = np.empty(rcap, dtype=np.uint32)
+    ne, nr = C.c_int(0), C.c_int(0)
+    a, b = c_graph(g1), c_graph(g2)
+    _lib.check(_lib.lib().pgm_host_merge_edges(C.byref(a), C.byref(b), ln, _addr(rm1), _addr(rm2), _addr(mt),
+                                               C.c_double(support1), C.c_double(support2), C.c_double(altsplice_prob),
+                                               _addr(e_rowptr), _addr(e_col), _addr(e_val), C.byref(ne),
+                                               _addr(r_rowptr), _addr(r_col), _addr(r_units), C.byref(nr)))
+    g = Graph.__new__(Graph)
+    g._pgm_struct = None
+    g.sites = np.ascontiguousarray(nodes, dtype=np.float64)
+    g.N, g.n = g.sites.shape
+    assert g.N >= 2 and not g.sites[0].any() and not g.sites[-1].any()
+    g.e_rowptr, g.e_col, g.e_val = e_rowptr, e_col[:ne.value], e_val[:ne.value]
+    g.r_rowptr, g.r_col, g.r_units = r_rowptr, r_col[:nr.value], r_units[:nr.value]
+    return g, rm1.astype(np.int64), rm2.astype(np.int64), mt.astype(bool)

@@ -8,6 +8,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
+from .graph import c_graph
 
 EMISSION_EXACT = 0
 EMISSION_TENSOR = 1
@@ -19,21 +20,6 @@ def _p(a):
 
 def _addr(a):
     return a.__array_interface__["data"][0]
-
-
-def c_graph(g, keep):
-    """pgm_graph view of a Graph.  The struct is cached on the graph (its arrays never change after construction)."""
-    keep.append(g)
-    c = getattr(g, "_pgm_struct", None)
-    if c is None:
-        has_rep = g.r_col.size > 0
-        c = _lib.Graph(g.N, _addr(g.sites), _addr(g.e_rowptr), _addr(g.e_col), _addr(g.e_val),
-                       _addr(g.r_rowptr), _addr(g.r_col) if has_rep else None, _addr(g.r_units) if has_rep else None)
-        try:
-            g._pgm_struct = c
-        except AttributeError:
-            pass
-    return c
 
 
 def c_model(model, keep):

@@ -134,3 +134,68 @@ def test_two_rank_sharding_reassembles_full_matrix_gloo(tmp_path):
                        capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert r.stdout.count("ok") == 2
+
+
+# ---- native host glue (csrc/host_graph.cpp) vs its Python specification (graph.py) -----------------------------
+def _graph_arrays(g):
+    return [g.sites, g.e_rowptr, g.e_col, g.e_val, g.r_rowptr, g.r_col, g.r_units]
+
+
+def _run_progressive(native, seqs, tree, mf, opts, repeats=None):
+    from prographmsa_b200 import graph, progressive
+    old = graph.NATIVE
+    graph.NATIVE = native
+    try:
+        seen = []
+
+        def align(a, b, m, o):
+            seen.append((a, b))
+            return po.align_graphs(a, b, m, o)
+        res = progressive.progressive_alignment(seqs, tree, mf, opts, align_fn=align, repeats=repeats)
+        return res, seen
+    finally:
+        graph.NATIVE = old
+
+
+@pytest.mark.parametrize("seed,indel", [(3, 0.02), (5, 0.08)])
+def test_native_host_glue_equals_python_specification(seed, indel):
+    """CleanedGraph, merge plan and merged-graph edges: every array of every graph of a progressive pass is identical
+    whether the C++ glue (pgm_host_*) or the Python restatement built it."""
+    from prographmsa_b200 import progressive
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(12, 90, mf, seed=seed, indel_rate=indel)
+    tree = progressive.from_synth(root)
+    r_nat, seen_nat = _run_progressive(True, seqs, tree, mf, opts)
+    r_py, seen_py = _run_progressive(False, seqs, tree, mf, opts)
+    assert len(seen_nat) == len(seen_py) == 11
+    for (a1, b1), (a2, b2) in zip(seen_nat, seen_py):
+        for x, y in zip(_graph_arrays(a1) + _graph_arrays(b1) + [a1.outmapping, b1.outmapping],
+                        _graph_arrays(a2) + _graph_arrays(b2) + [a2.outmapping, b2.outmapping]):
+            assert x.dtype == y.dtype and np.array_equal(x, y)
+    for x, y in zip(_graph_arrays(r_nat.graph), _graph_arrays(r_py.graph)):
+        assert np.array_equal(x, y)
+    assert all(np.array_equal(r_nat.aligned[k], r_py.aligned[k]) for k in r_py.aligned)
+
+
+def test_native_host_glue_with_repeat_edges():
+    """tandem-repeat edges through CleanedGraph (repeatext_prob = 0 drops multi-unit repeats) and mergeGraphs."""
+    from prographmsa_b200 import progressive
+    rng = np.random.default_rng(12)
+    unit = rng.integers(0, 20, 7).astype(np.uint8)
+    f1, f2 = rng.integers(0, 20, 15).astype(np.uint8), rng.integers(0, 20, 12).astype(np.uint8)
+    seqs = {"a": np.concatenate([f1, np.tile(unit, 5), f2]), "b": np.concatenate([f1, np.tile(unit, 3), f2]),
+            "c": np.concatenate([f1, np.tile(unit, 4), f2[:9]])}
+    reps = {k: [dict(start=len(f1), tr_hom=list(range(7)) * nu)] for k, nu in (("a", 5), ("b", 3), ("c", 4))}
+    tree = progressive.parse_newick("((a:0.1,b:0.12):0.05,c:0.2);")
+    for opts in (Options(mldist_flag=True), Options(mldist_flag=True, repeatext_prob=0.0)):
+        mf = model.getDefault(opts)
+        r_nat, seen_nat = _run_progressive(True, seqs, tree, mf, opts, reps)
+        r_py, seen_py = _run_progressive(False, seqs, tree, mf, opts, reps)
+        assert seen_nat[0][0].r_col.size > 0 or opts.repeatext_prob == 0.0
+        for (a1, b1), (a2, b2) in zip(seen_nat, seen_py):
+            for x, y in zip(_graph_arrays(a1) + _graph_arrays(b1), _graph_arrays(a2) + _graph_arrays(b2)):
+                assert np.array_equal(x, y)
+        for x, y in zip(_graph_arrays(r_nat.graph), _graph_arrays(r_py.graph)):
+            assert np.array_equal(x, y)
+        assert r_nat.n_tr_indels == r_py.n_tr_indels
