@@ -1,0 +1,224 @@
+// hp1_graphdp_diag.cu -- K5, latency-optimised flavour: the anti-diagonal wavefront fill (one thread per graph-1 row,
+// one cell per thread and barrier).  It does ~3x the instructions per cell of the blocked kernel in hp1_graphdp.cu, but a
+// job's sweep is N1 + N2 short steps with hundreds of threads at work, and multi-predecessor cells cost it almost nothing,
+// so it is the faster one for graphs with many non-chain nodes (the upper levels of a guide tree) and for small batches.
+// hp1_host.cu picks the flavour per job (GraphJobDev::layout); the traceback reads either cell layout.
+//
+// Recurrences, evaluation order and the reference lines are those of hp1_graphdp.cu (GraphAlign.h:205-280).
+#include "internal.h"
+#include <math_constants.h>
+#include <algorithm>
+#include <cstdlib>
+
+__device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
+    const int d = y + x;
+    const int ylo = max(0, d - (N2 - 1));
+    return (size_t)d * pitch + (y - ylo);
+}
+
+#define GF_RING 8            // anti-diagonals of {M,X,Y,W} kept in shared memory (power of two): covers skip edges spanning <= 5 nodes
+#define GF_RING_LONG 4       // ... for graphs too long for 8 (>= 4: rows d, d-1, d-2 are live at once); S is then read directly
+// S is row-major by y; each (thread,row) streams its own row 16 bytes (4 columns) at a time with cp.async,
+// 8 columns (= 8 anti-diagonals) ahead, into a private ring of four float4 slots
+
+// Thread <-> ROW mapping: thread t owns rows y = t + r*blockDim (r < RPT).  Along the sweep the same
+// thread meets (y,0), (y,1), ... on consecutive anti-diagonals, so the LEFT neighbour (y, x-1) and the
+// row's own predecessor info stay in registers; the UP / DIAGONAL neighbours (y-1, .) come from the
+// previous two ring rows at index y-1 (no skew arithmetic).  STAGE: graph 2's node infos in shared memory.
+template <bool STAGE, int RPT, int RING, bool SPF>
+__global__ void __launch_bounds__(1024)
+graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch) {
+    const GraphJobDev& J = jobs[order[blockIdx.x]];
+    const int N1 = J.N1, N2 = J.N2, pitch = J.pitch;
+    const float gap_init = J.sc[0], gap_extend = J.sc[1], start_gap = J.sc[6], start_init = J.sc[7];
+    const float NINF = -CUDART_INF_F;
+    float4* __restrict__ C = J.MXYW;
+    const float* __restrict__ S = J.S;
+    const int T = (int)blockDim.x, tid = (int)threadIdx.x;
+
+    extern __shared__ __align__(16) unsigned char gsm[];
+    float4* ring = (float4*)gsm;                                                    // [RING][ring_pitch], indexed by y
+    float4* sring = (float4*)(gsm + (size_t)RING * ring_pitch * sizeof(float4));    // SPF: [4][RPT*T], private slots per (thread,row)
+    NodeInfo* s2 = (NodeInfo*)(sring + (SPF ? 4 * RPT * T : 0));
+    // STAGE: graph 2's node infos and both predecessor lists live in shared memory, so the rare multi-predecessor
+    // cell (met by SOME row on almost every anti-diagonal) does not put global-memory latency on the sweep's critical path
+    int* sp1i = (int*)(s2 + N2); float* sp1v = (float*)(sp1i + J.np1);
+    int* sp2i = (int*)(sp1v + J.np1); float* sp2v = (float*)(sp2i + J.np2);
+    if (STAGE) {
+        for (int i = tid; i < N2; i += T) s2[i] = J.ni2[i];
+        for (int i = tid; i < J.np1; i += T) { sp1i[i] = J.p1_idx[i]; sp1v[i] = J.p1_val[i]; }
+        for (int i = tid; i < J.np2; i += T) { sp2i[i] = J.p2_idx[i]; sp2v[i] = J.p2_val[i]; }
+        __syncthreads();
+    }
+    const NodeInfo* __restrict__ I2 = STAGE ? s2 : J.ni2;
+    const int* __restrict__ P1I = STAGE ? sp1i : J.p1_idx; const float* __restrict__ P1V = STAGE ? sp1v : J.p1_val;
+    const int* __restrict__ P2I = STAGE ? sp2i : J.p2_idx; const float* __restrict__ P2V = STAGE ? sp2v : J.p2_val;
+
+    auto cell = [&](int yy, int xx, int d) -> float4 {          // any earlier cell: ring when recent, else HBM/L2
+        const int dd = yy + xx;
+        if (d - dd < RING) return ring[(dd & (RING - 1)) * ring_pitch + yy];
+        return C[(size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)))];
+    };
+
+    NodeInfo ny[RPT]; bool ysimple[RPT]; float4 left[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int y = tid + r * T;
+        ny[r] = (y <= N1 - 2) ? J.ni1[y] : NodeInfo{0, 0, 0, 0.f};
+        ysimple[r] = (ny[r].cnt == 1 && ny[r].idx0 == y - 1);
+        left[r] = make_float4(NINF, NINF, NINF, NINF);
+    }
+    const int dmax = (N1 - 2) + (N2 - 2);
+    const int ldS = J.ldS;
+    auto fetch_s4 = [&](int r, int y, int xq) {                  // S(y, xq..xq+3) -> sring[(xq/4)&3][r*T+tid], asynchronously
+        const float* src = S + (size_t)y * ldS + xq;
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sring + ((xq >> 2) & 3) * (RPT * T) + r * T + tid);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+    };
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+        const int y = tid + r * T;
+        if (SPF && y >= 1 && y <= N1 - 2) { fetch_s4(r, y, 0); if (4 < ldS) fetch_s4(r, y, 4); }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");      // the first rows need these within < 8 diagonals
+
+    for (int d = 0; d <= dmax; ++d) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int y = tid + r * T, x = d - y;
+            if (SPF && y >= 1 && y <= N1 - 2 && x >= 0 && (x & 3) == 0 && x + 8 < ldS) fetch_s4(r, y, x + 8);
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+        asm volatile("cp.async.wait_group 7;\n" ::: "memory");             // everything issued >= 8 diagonals ago has landed
+        const int ylo = max(0, d - (N2 - 1));
+        float4* rcur = ring + (d & (RING - 1)) * ring_pitch;
+        const float4* row1 = ring + ((d - 1) & (RING - 1)) * ring_pitch;
+        const float4* row2 = ring + ((d - 2) & (RING - 1)) * ring_pitch;
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) {
+            const int y = tid + r * T, x = d - y;
+            if (y > N1 - 2 || x < 0 || x > N2 - 2) continue;
+            float m = NINF, xs = NINF, ys = NINF, w = NINF;
+            if (x == 0) {
+                if (y == 0) w = start_init;
+                else {
+                    const int cnt = ny[r].cnt & 0x7fffffff;
+                    for (int ky = 0; ky < cnt; ++ky) {
+                        const int yp = ky ? P1I[ny[r].ptr + ky] : ny[r].idx0;
+                        const float ey = ky ? P1V[ny[r].ptr + ky] : ny[r].val0;
+                        const float4 c = cell(yp, 0, d);
+                        ys = fmaxf(ys, __fsub_rn(fmaxf(__fadd_rn(c.z, gap_extend), __fadd_rn(c.w, start_gap)), ey));
+                    }
+                    w = ys;
+                }
+            } else {
+                const NodeInfo nx = I2[x];
+                if (y == 0) {
+                    const int cnt = nx.cnt & 0x7fffffff;
+                    for (int kx = 0; kx < cnt; ++kx) {
+                        const int xp = kx ? P2I[nx.ptr + kx] : nx.idx0;
+                        const float ex = kx ? P2V[nx.ptr + kx] : nx.val0;
+                        const float4 c = cell(0, xp, d);
+                        xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(c.y, gap_extend), __fadd_rn(c.w, start_gap)), ex));
+                    }
+                    w = xs;
+                } else {
+                    const float s = SPF ? reinterpret_cast<const float*>(sring + ((x >> 2) & 3) * (RPT * T) + r * T + tid)[x & 3]
+                                        : __ldg(S + (size_t)y * ldS + x);
+                    if (ysimple[r] && nx.cnt == 1 && nx.idx0 == x - 1) {
+                        // fast path (chain nodes, the overwhelming majority): one adjacent regular predecessor each
+                        const float ey = ny[r].val0, ex = nx.val0;
+                        const float4 cu = row1[y - 1];                               // (y-1, x)
+                        const float4 cd = row2[y - 1];                               // (y-1, x-1)
+                        const float4 cl = left[r];                                   // (y, x-1): this thread, last diagonal
+                        ys = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
+                        m = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
+                        xs = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
+                        w = fmaxf(m, fmaxf(xs, ys));
+                    } else {
+                        const int c1 = ny[r].cnt & 0x7fffffff, c2 = nx.cnt & 0x7fffffff;
+                        for (int ky = 0; ky < c1; ++ky) {
+                            const int yp = ky ? P1I[ny[r].ptr + ky] : ny[r].idx0;
+                            const float ey = ky ? P1V[ny[r].ptr + ky] : ny[r].val0;
+                            const float4 cu = cell(yp, x, d);                        // (yp, x): Y, W
+                            const float Sy = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
+                            for (int kx = 0; kx < c2; ++kx) {
+                                const int xp = kx ? P2I[nx.ptr + kx] : nx.idx0;
+                                const float ex = kx ? P2V[nx.ptr + kx] : nx.val0;
+                                const float4 cd = cell(yp, xp, d);                   // (yp, xp): W
+                                const float4 cl = cell(y, xp, d);                    // (y, xp): X, W
+                                const float Sm = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
+                                const float Sx = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
+                                const float Sw = fmaxf(Sm, fmaxf(Sx, Sy));
+                                m = fmaxf(m, Sm); xs = fmaxf(xs, Sx); ys = fmaxf(ys, Sy); w = fmaxf(w, Sw);
+                            }
+                        }
+                    }
+                }
+            }
+            const float4 out = make_float4(m, xs, ys, w);
+            left[r] = out;
+            rcur[y] = out;
+            C[(size_t)d * pitch + (y - ylo)] = out;
+        }
+        __syncthreads();
+    }
+    // end-node match (GraphAlign.h:262-280)
+    if (tid == 0) {
+        const float end_match = J.sc[3], end_gap = J.sc[4], end_skip = J.sc[5];
+        float Wend = NINF;
+        for (int ky = J.p1_ptr[N1 - 1]; ky < J.p1_ptr[N1]; ++ky)
+            for (int kx = J.p2_ptr[N2 - 1]; kx < J.p2_ptr[N2]; ++kx) {
+                const int yp = J.p1_idx[ky], xp = J.p2_idx[kx];
+                const float ey = J.p1_val[ky], ex = J.p2_val[kx];
+                if (xp == 0 && yp == 0) {
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(end_skip, ey), ex), Wend);
+                } else {
+                    const float4 c = C[skew(yp, xp, N2, pitch)];
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.y, end_gap), ey), ex), Wend);
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.z, end_gap), ey), ex), Wend);
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.x, end_match), ey), ex), Wend);
+                }
+            }
+        ((float*)J.result)[3] = Wend;
+    }
+}
+
+template <bool STAGE, int RPT, int RING, bool SPF>
+static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int threads, int ring_pitch, size_t smem) {
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, RPT, RING, SPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_fill_diag_kernel<STAGE, RPT, RING, SPF><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch);
+    PGM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// max_n1 / max_n2: largest graph-1 / graph-2 node counts in this launch
+// d_order: the n_jobs job indices this launch sweeps (the host groups jobs of similar graph-1 length, because block size
+// and shared memory -- hence CTAs per SM -- are set by the launch's largest job)
+int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np) {
+    if (n_jobs == 0) return 0;
+    const int rows = max_n1 > 1 ? max_n1 - 1 : 1;                   // rows 0 .. N1-2
+    // rows per thread: on an anti-diagonal sweep only ~half the rows are active at a time, so giving a thread
+    // several rows (y, y+T, ..) halves the number of idle warps that still pay the per-diagonal loop overhead
+    int rpt = rows <= 1024 ? 1 : (rows <= 2048 ? 2 : 4);       // measured: 1 row per thread is best while it fits
+    if (const char* e = getenv("PGM_FILL_RPT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) rpt = v; }
+    while ((rows + rpt - 1) / rpt > 1024) rpt *= 2;
+    if (rows > 4096) { pgm_set_error("graph 1 has %d nodes; the wavefront kernel supports up to 4097", max_n1); return PGM_ERR_ARG; }
+    const int threads = std::min(1024, std::max(64, ((rows + rpt - 1) / rpt + 31) & ~31));
+    const int ring_pitch = (max_n1 + 3) & ~3;
+    const size_t info = (size_t)max_n2 * sizeof(NodeInfo) + (size_t)max_np * 8 + 64;
+    // regular flavour: 8-diagonal ring + cp.async S prefetch slots; long graphs: 4-diagonal ring, S read directly
+    const size_t ring8 = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * rpt * threads * sizeof(float4);
+    const size_t ring4 = (size_t)GF_RING_LONG * ring_pitch * sizeof(float4);
+    const bool regular = ring8 <= 227 * 1024;
+    const size_t ring = regular ? ring8 : ring4;
+    if (ring > 227 * 1024) { pgm_set_error("graph too large for the shared-memory diagonal ring (N1 = %d, limit ~3500)", max_n1); return PGM_ERR_ARG; }
+    const bool stage = ring + info <= 200 * 1024;
+    const size_t smem = ring + (stage ? info : 0);
+#define GO(S_, R_) do { if (regular) return launch_fill_diag_t<S_, R_, GF_RING, true>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); \
+                        return launch_fill_diag_t<S_, R_, GF_RING_LONG, false>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); } while (0)
+    if (stage) { if (rpt == 1) GO(true, 1); if (rpt == 2) GO(true, 2); GO(true, 4); }
+    if (rpt == 1) GO(false, 1); if (rpt == 2) GO(false, 2); GO(false, 4);
+#undef GO
+}

@@ -18,7 +18,8 @@ void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok);
 void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
+int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
 void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
@@ -78,10 +79,10 @@ void dynprog_scores(const pgm_graph& g1, const pgm_graph& g2, const pgm_dp_model
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct JobLayout {                // byte offsets into the upload arena / scratch arena / output arena
-    size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2;
+    size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2, colinfo, blkstart;
     size_t S, MXYW, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev;     // scratch
     size_t map1, map2, result;                           // output
-    int np1, np2, cap, pitch;
+    int np1, np2, cap, pitch, nb, layout;
 };
 
 } // namespace
@@ -100,9 +101,9 @@ struct pgm_graph_batch {
     size_t out_bytes = 0;
     std::vector<std::pair<int, int>> sub;   // [begin, end) job ranges that fit the scratch budget
     // Fill schedule.  The fill kernel's block size and shared memory -- hence CTAs per SM -- are set by the LARGEST job
-    // of a launch, so each sub-batch is swept as a few launches of similar graph-1 length (largest first), on
+    // of a launch, so each sub-batch is swept as a few launches of similar graph-2 length (largest first), on
     // separate streams so that a class with few jobs does not leave the GPU idle.
-    struct FillLaunch { int sub, offset, count, max_n1, max_n2, max_np; };
+    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np; };
     std::vector<int> order;                 // job indices relative to their sub-batch, grouped by FillLaunch
     std::vector<FillLaunch> fills;
     size_t scratch_bytes_used = 0;
@@ -131,6 +132,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     b->lay.resize(n_jobs); b->jobs.resize(n_jobs); b->cell_updates.resize(n_jobs);
     size_t in_off = 0, out_off = 0;
     std::vector<size_t> scratch_need(n_jobs);
+    int force_layout = -1, diag_min_generic = 8;                  // PGM_FILL_LAYOUT=block|diag forces one kernel (tests, profiling)
+    if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : -1);
+    if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
     for (int k = 0; k < n_jobs; ++k) {
         const pgm_graph &a = g1[k], &bb = g2[k];
         if (a.N < 2 || bb.N < 2) { delete b; pgm_set_error("job %d: graphs need at least start and end nodes", k); return PGM_ERR_ARG; }
@@ -138,7 +142,28 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.np1 = a.e_rowptr[a.N] + (a.r_rowptr ? a.r_rowptr[a.N] : 0);
         L.np2 = bb.e_rowptr[bb.N] + (bb.r_rowptr ? bb.r_rowptr[bb.N] : 0);
         L.cap = 2 * (a.N + bb.N) + 8;
-        L.pitch = (int)align_up((size_t)std::min(a.N, bb.N), 32);
+        // column blocks of graph 2 (columns 0 .. N2-2) for the blocked fill kernel: a block never leaves its aligned group
+        // of GF_K columns, and a column whose node is not a chain node (exactly one predecessor, the regular edge from
+        // x-1) starts a block, so that inside a block every column's only predecessor is its left neighbour
+        auto non_chain = [](const pgm_graph& g, int x) {
+            const int nreg = g.e_rowptr[x + 1] - g.e_rowptr[x];
+            const int nrep = g.r_rowptr ? g.r_rowptr[x + 1] - g.r_rowptr[x] : 0;
+            return !(nreg == 1 && nrep == 0 && g.e_col[g.e_rowptr[x]] == x - 1);
+        };
+        int nblk = 0, generic = 0;
+        for (int x = 0; x <= bb.N - 2; ++x) {
+            const bool nc = x >= 1 && non_chain(bb, x);
+            generic += nc;
+            if ((x & (GF_K - 1)) == 0 || nc) ++nblk;
+        }
+        for (int y = 1; y <= a.N - 2; ++y) generic += non_chain(a, y);
+        L.nb = nblk;
+        // Which fill kernel: the blocked sweep is ~2x faster on chain-dominated graphs (the bulk of a guide tree's cells); the
+        // anti-diagonal sweep pays almost nothing for multi-predecessor nodes and has the shorter critical path on the few
+        // large, branchy graphs near the root.  It also takes the graphs whose graph 2 is too long for the blocked kernel.
+        L.layout = (generic > diag_min_generic || nblk > GF_MAX_NB) ? GF_LAYOUT_DIAG : GF_LAYOUT_BLOCK;
+        if (force_layout >= 0 && !(force_layout == GF_LAYOUT_BLOCK && nblk > GF_MAX_NB)) L.layout = force_layout;
+        L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 8);
         auto take = [&](size_t& off, size_t bytes) { size_t r = off; off = align_up(off + bytes, 128); return r; };
         L.sites1 = take(in_off, sizeof(float) * n * a.N);
         L.sites2 = take(in_off, sizeof(float) * n * bb.N);
@@ -149,10 +174,12 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.p2_ptr = take(in_off, 4 * (bb.N + 1)); L.p2_idx = take(in_off, 4 * L.np2); L.p2_val = take(in_off, 4 * L.np2);
         L.p2_alt = take(in_off, 4 * L.np2); L.p2_rep = take(in_off, L.np2);
         L.ni1 = take(in_off, sizeof(NodeInfo) * a.N); L.ni2 = take(in_off, sizeof(NodeInfo) * bb.N);
+        L.colinfo = take(in_off, 2 * (size_t)bb.N); L.blkstart = take(in_off, 2 * ((size_t)L.nb + 1));
         L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 16);
-        const size_t diags = (size_t)a.N + bb.N - 1;
+        const size_t mxyw_cells = L.layout == GF_LAYOUT_DIAG ? ((size_t)a.N + bb.N - 1) * L.pitch
+                                                             : ((size_t)(a.N - 1) + L.nb - 1) * GF_K * L.pitch;
         size_t so = 0;
-        L.S = take(so, (size_t)a.N * (((size_t)bb.N + 3) & ~(size_t)3) * 4 + 64); L.MXYW = take(so, diags * L.pitch * 16);
+        L.S = take(so, (size_t)a.N * (((size_t)bb.N + 3) & ~(size_t)3) * 4 + 64); L.MXYW = take(so, mxyw_cells * 16);
         L.Tbuf = take(so, sizeof(float) * n * bb.N); L.u = take(so, 4 * a.N); L.v = take(so, 4 * bb.N);
         if (opts->emission_mode == PGM_EMISSION_TENSOR) {
             const size_t kp = (size_t)((3 * n + 7) & ~7);
@@ -189,7 +216,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         const pgm_graph* gs[2] = {&g1[k], &g2[k]};
         const JobLayout& L = b->lay[k];
         GraphJobDev& J = b->jobs[k];
-        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
+        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.nb = L.nb; J.layout = L.layout; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
         dynprog_scores(g1[k], g2[k], models[k], *opts, J.sc);
         const float rinit = J.sc[8], rext = J.sc[9];
         float* s1 = (float*)(hin + L.sites1); float* s2 = (float*)(hin + L.sites2);
@@ -237,6 +264,18 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 ni[node].idx0 = cnt ? idx[ptr[node]] : 0; ni[node].val0 = cnt ? val[ptr[node]] : 0.f;
             }
         }
+        {   // column blocks of graph 2, from the node infos just built (same rule as the sizing pass above)
+            const NodeInfo* ni = (const NodeInfo*)(hin + L.ni2);
+            uint16_t* ci = (uint16_t*)(hin + L.colinfo); uint16_t* bs = (uint16_t*)(hin + L.blkstart);
+            int blk = -1;
+            for (int x = 0; x <= g2[k].N - 2; ++x) {
+                const bool chain = x == 0 || (ni[x].cnt == 1 && ni[x].idx0 == x - 1);
+                if ((x & (GF_K - 1)) == 0 || !chain) { ++blk; bs[blk] = (uint16_t)x; }
+                ci[x] = (uint16_t)((blk << GF_LOGK) | (x & (GF_K - 1)));
+            }
+            bs[blk + 1] = (uint16_t)(g2[k].N - 1);
+            ci[g2[k].N - 1] = 0;
+        }
         b->cell_updates[k] = deg_sum[0] * deg_sum[1];
         char* sb = dsc + scratch_base[k];
         J.sites1 = (const float*)(din + L.sites1); J.sites2 = (const float*)(din + L.sites2);
@@ -246,6 +285,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.p2_ptr = (const int*)(din + L.p2_ptr); J.p2_idx = (const int*)(din + L.p2_idx); J.p2_val = (const float*)(din + L.p2_val);
         J.p2_rep = (const uint8_t*)(din + L.p2_rep); J.p2_alt = (const float*)(din + L.p2_alt);
         J.ni1 = (const NodeInfo*)(din + L.ni1); J.ni2 = (const NodeInfo*)(din + L.ni2);
+        J.colinfo = (const uint16_t*)(din + L.colinfo); J.blkstart = (const uint16_t*)(din + L.blkstart);
         J.np1 = L.np1; J.np2 = L.np2;
         J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.Tbuf = (float*)(sb + L.Tbuf);
         J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
@@ -266,23 +306,33 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         }
         for (int k = 0; k < n_jobs; ++k) { b->total_updates += b->cell_updates[k]; b->total_cells += (uint64_t)b->jobs[k].N1 * b->jobs[k].N2; }
     }
-    {   // fill schedule: thread-count classes (graph-1 rows rounded up); a class boundary where occupancy changes
-        static const int cls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
+    {   // fill schedule: per kernel flavour, block-size classes (blocked: column blocks per row rounded up to warps;
+        // diagonal: graph-1 rows); longest sweeps first
         b->order.resize(n_jobs);
+        static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
+        auto class_of = [&](const GraphJobDev& J) {
+            if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
+            const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
+        };
         for (size_t si = 0; si < b->sub.size(); ++si) {
             const auto& sbr = b->sub[si];
             std::vector<int> idx;
             for (int k = sbr.first; k < sbr.second; ++k) idx.push_back(k - sbr.first);
-            std::stable_sort(idx.begin(), idx.end(), [&](int a, int bq) { return b->jobs[sbr.first + a].N1 > b->jobs[sbr.first + bq].N1; });
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int bq) {
+                const GraphJobDev &A = b->jobs[sbr.first + a], &B = b->jobs[sbr.first + bq];
+                const int ca = class_of(A), cb = class_of(B);
+                if (ca != cb) return ca > cb;
+                return A.N1 + A.N2 > B.N1 + B.N2;
+            });
             std::copy(idx.begin(), idx.end(), b->order.begin() + sbr.first);
-            auto class_of = [&](int n1) { int q = 0; while (n1 - 1 > cls[q]) ++q; return q; };
             size_t p = 0;
             while (p < idx.size()) {
-                const int q = class_of(b->jobs[sbr.first + idx[p]].N1);
-                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, 0, 0, 0};
-                while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]].N1) == q) {
+                const int q = class_of(b->jobs[sbr.first + idx[p]]);
+                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, b->jobs[sbr.first + idx[p]].layout, 0, 0, 0, 0, 0};
+                while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]]) == q) {
                     const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
-                    f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2); f.max_np = std::max(f.max_np, J.np1 + J.np2);
+                    f.max_nb = std::max(f.max_nb, J.nb); f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2);
+                    f.max_np2 = std::max(f.max_np2, J.np2); f.max_np = std::max(f.max_np, J.np1 + J.np2);
                     ++f.count; ++p;
                 }
                 b->fills.push_back(f);
@@ -329,7 +379,7 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             for (auto& f : b->fills) if (f.sub == (int)si) fl.push_back(&f);
             rc = 0;
             SideStreams& ss = side_streams(pgm_ctx_device(c));
-            const size_t n_side = fl.size() > 1 ? std::min<size_t>(fl.size() - 1, 3) : 0;
+            const size_t n_side = fl.size() > 1 ? std::min<size_t>(fl.size() - 1, 15) : 0;   // every class on its own stream: a long sweep must not queue behind another
             if (n_side) {
                 if (!ss.fork) PGM_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
                 while (ss.streams.size() < n_side) {
@@ -341,7 +391,10 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             }
             for (size_t q = 0; q < fl.size() && !rc; ++q) {
                 cudaStream_t sq = (q == 0 || !n_side) ? st : ss.streams[(q - 1) % n_side];
-                rc = launch_graph_fill(sq, fl[q]->count, dj + sb.first, d_order_all + sb.first + fl[q]->offset, fl[q]->max_n1, fl[q]->max_n2, fl[q]->max_np);
+                const int* ord = d_order_all + sb.first + fl[q]->offset;
+                rc = fl[q]->layout == GF_LAYOUT_DIAG
+                         ? launch_graph_fill_diag(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_n1, fl[q]->max_n2, fl[q]->max_np)
+                         : launch_graph_fill(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_nb, fl[q]->max_n2, fl[q]->max_np2);
             }
             for (size_t q = 0; q < n_side; ++q) {
                 PGM_CUDA(cudaEventRecord(ss.join[q], ss.streams[q]));

@@ -132,9 +132,20 @@ int launch_angle(cudaStream_t st, int n, int K, int dims, int N, const uint8_t* 
 // ---- HP-1 (hp1_*.cu) ------------------------------------------------------------------------------
 struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred list start, count (sign bit = first pred is a repeat edge), first entry inline
 
+#define GF_LAYOUT_BLOCK 0
+#define GF_LAYOUT_DIAG 1
+#define GF_K 8               // columns a fill-kernel thread sweeps per step (one block of a row)
+#define GF_LOGK 3
+#define GF_MAX_NB 512        // most column blocks per row the fill kernel's shared memory holds (graph 2 up to ~4000 nodes)
+
 struct GraphJobDev {        // one alignGraphs job, all pointers into the batch's device arena
     int N1, N2;
-    int pitch;                  // skewed-layout pitch (>= N1): cell (y,x) lives at (y+x)*pitch + y
+    int layout;                 // cell layout of MXYW = which fill kernel sweeps the job: GF_LAYOUT_BLOCK or GF_LAYOUT_DIAG
+    int nb;                     // column blocks per row (columns 0 .. N2-2 cut into blocks of <= GF_K; a non-chain node starts a block)
+    int pitch;                  // block-skewed layout (hp1_graphdp.cu): cell (y,x) at (((y + blk(x))*GF_K + off(x))*pitch + y%nb;
+                                // diagonal layout (hp1_graphdp_diag.cu): (y+x)*pitch + y - max(0, y+x-(N2-1))
+    const uint16_t* colinfo;    // N2 entries: (blk(x) << GF_LOGK) | off(x)
+    const uint16_t* blkstart;   // nb + 1 entries: first column of each block, blkstart[nb] = N2 - 1
     const float* sites1;        // n * N1 (float cast of Graph::sites), column-major
     const float* sites2;        // n * N2
     const float* Mf;            // n*n row-major float cast of Model::M
@@ -149,7 +160,7 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     float sc[10];               // DynProgScores
     float* S;                   // row-major by graph-1 node: S(y,x) at y*ldS + x (a DP thread streams its own row)
     int ldS;                    // N2 rounded up to a multiple of 4
-    float4* MXYW;               // skewed {M,X,Y,W}
+    float4* MXYW;               // block-skewed {M,X,Y,W}, (N1-1 + nb-1) * GF_K * pitch cells
     float* Tbuf;                // n * N2 scratch: T = M^T g2
     float* Aimg; float* Bimg;   // tensor flavour: per-128-row-tile UMMA operand images (ceil(N/128) * 128 * KP floats)
     float* u; float* v;         // g1^T pi (N1), pi^T g2 (N2)

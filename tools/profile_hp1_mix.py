@@ -1,0 +1,69 @@
+#!/usr/bin/env python3
+"""Fill-kernel timing of the bench's progressive-pass jobs, split by how many non-chain columns graph 2 has."""
+import sys, os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import numpy as np
+from prographmsa_b200 import model, synth, graphalign, progressive, _lib
+from prographmsa_b200.options import Options
+
+n_seq = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+rep = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+opts = Options(mldist_flag=True)
+mf = model.getDefault(opts)
+seqs, root = synth.simulate_family(n_seq, 400, mf, seed=2)
+tree = progressive.from_synth(root)
+ctx = _lib.default_context()
+jobs = []
+def batch(js, o):
+    jobs.extend(js)
+    return graphalign.alignGraphsBatch(js, o, ctx=ctx)
+progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
+
+def nonchain(g):
+    n = 0
+    for y in range(1, g.N - 1):
+        ks = g.e_col[g.e_rowptr[y]:g.e_rowptr[y + 1]]; rs = g.r_col[g.r_rowptr[y]:g.r_rowptr[y + 1]]
+        if not (len(ks) == 1 and len(rs) == 0 and ks[0] == y - 1):
+            n += 1
+    return n
+info = [(nonchain(a), nonchain(b), a.N, b.N) for a, b, m in jobs]
+ctx.enable_timing(True)
+def run(sel, label):
+    js = [jobs[i] for i in sel] * rep
+    if not js:
+        return
+    gb = graphalign.GraphBatch(js, opts, 0, ctx)
+    for _ in range(3):
+        gb.run(); ctx.sync()
+    t = ctx.timing()
+    cells = sum(info[i][2] * info[i][3] for i in sel) * rep
+    print("%-34s jobs %4d cells %.3g: fill %.3f ms (%.1f GCUPS) trace %.3f ms" % (label, len(js), cells, t["graph_fill_ms"], cells / t["graph_fill_ms"] / 1e6, t["graph_trace_ms"]))
+    gb.close()
+idx = list(range(len(jobs)))
+only = sys.argv[3] if len(sys.argv) > 3 else None
+if only == "few":
+    run([i for i in idx if 0 < max(info[i][0], info[i][1]) <= 8], "1..8 non-chain nodes"); sys.exit(0)
+if only == "big":
+    run(sorted(idx, key=lambda i: -info[i][2] * info[i][3])[:1], "largest job"); sys.exit(0)
+for lay in (None,):
+    if lay: os.environ["PGM_FILL_LAYOUT"] = lay
+    print("--- PGM_FILL_LAYOUT =", lay)
+    run(idx, "all")
+    run([i for i in idx if info[i][0] == 0 and info[i][1] == 0], "pure chain x chain")
+    run([i for i in idx if 0 < info[i][0] + info[i][1] <= 4], "1..4 non-chain nodes")
+    run([i for i in idx if 4 < info[i][0] + info[i][1] <= 8], "5..8 non-chain nodes")
+    run([i for i in idx if 8 < info[i][0] + info[i][1] <= 16], "9..16 non-chain nodes")
+    run([i for i in idx if 16 < info[i][0] + info[i][1] <= 40], "17..40 non-chain nodes")
+    run([i for i in idx if info[i][0] + info[i][1] > 40], ">40 non-chain nodes")
+os.environ.pop("PGM_FILL_LAYOUT", None)
+for th in (2, 4, 6, 8, 12, 16, 30):
+    os.environ["PGM_FILL_DIAG_MIN"] = str(th)
+    run(idx, "all, diag if > %d non-chain" % th)
+sys.exit(0)
+run([i for i in idx if info[i][0] == 0 and info[i][1] == 0], "pure chain x chain")
+run([i for i in idx if 0 < max(info[i][0], info[i][1]) <= 8], "1..8 non-chain nodes")
+run([i for i in idx if 8 < max(info[i][0], info[i][1]) <= 30], "9..30 non-chain nodes")
+run([i for i in idx if max(info[i][0], info[i][1]) > 30], ">30 non-chain nodes")
+big = sorted(idx, key=lambda i: -info[i][2] * info[i][3])[:4]
+for i in big:
+    run([i], "single job N1 %d N2 %d nc %d/%d" % (info[i][2], info[i][3], info[i][0], info[i][1]))
