@@ -242,6 +242,19 @@ void ls_log_add(float* data, float add, unsigned len) {
     }
 }
 
+// The two normalisers g1^T pi and pi^T g2 (GraphAlign.h:154) are Eigen matrix-vector products.  Pinning against the
+// reference binary on a 1000-sequence family (tools/make_golden_large.py) showed that they are NOT summed sequentially
+// like the GEMM: the binary reproduces only with Eigen's SSE2 row-major gemv order -- four lane sums over
+// k = lane, lane+4, ..., the horizontal add (l0 + l2) + (l1 + l3), then any n % 4 tail sequentially.  The difference
+// is one ulp of S on non-one-hot profile columns and decides exact score ties (e.g. which N of "NN" takes the gap).
+static float dot_gemv(const float* a, const float* b, int n) {
+    float lane[4] = {0, 0, 0, 0};
+    const int n4 = n & ~3;
+    for (int k = 0; k < n4; k += 4) for (int l = 0; l < 4; ++l) lane[l] = lane[l] + a[k + l] * b[k + l];
+    float s = (lane[0] + lane[2]) + (lane[1] + lane[3]);
+    for (int k = n4; k < n; ++k) s = s + a[k] * b[k];
+    return s;
+}
 // GraphAlign.h:145-163: float casts, S = (g1^T (M^T g2)) ./ ((g1^T pi)(pi^T g2)), then ls_log_add
 void precompute_scores(const orc_graph* g1, const orc_graph* g2, const orc_dp_model* m, float match_init, float* S) {
     const int n = m->n, N1 = g1->N, N2 = g2->N;
@@ -254,14 +267,14 @@ void precompute_scores(const orc_graph* g1, const orc_graph* g2, const orc_dp_mo
             for (int b = 0; b < n; ++b) s = s + Mf[b * n + a] * (float)g2->sites[b + (size_t)n * x];
             T[a + (size_t)n * x] = s;
         }
-        float s = 0;
-        for (int b = 0; b < n; ++b) s = s + pif[b] * (float)g2->sites[b + (size_t)n * x];
-        v[x] = s;
+        std::vector<float> col(n);
+        for (int b = 0; b < n; ++b) col[b] = (float)g2->sites[b + (size_t)n * x];
+        v[x] = dot_gemv(col.data(), pif.data(), n);
     }
     for (int y = 0; y < N1; ++y) {
-        float s = 0;
-        for (int a = 0; a < n; ++a) s = s + (float)g1->sites[a + (size_t)n * y] * pif[a];
-        u[y] = s;
+        std::vector<float> col(n);
+        for (int a = 0; a < n; ++a) col[a] = (float)g1->sites[a + (size_t)n * y];
+        u[y] = dot_gemv(col.data(), pif.data(), n);
     }
     for (int x = 0; x < N2; ++x)
         for (int y = 0; y < N1; ++y) {

@@ -44,15 +44,11 @@ emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs) {
             for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sM[b * n + a], g[b]));
             J.Tbuf[a + (size_t)n * k] = s;
         }
-        float s = 0.f;
-        for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sPi[b], g[b]));
-        J.v[k] = s;
+        J.v[k] = dot_gemv_order(g, sPi, n);
     }
     if (k < J.N1) {
         const float* g = J.sites1 + (size_t)n * k;
-        float s = 0.f;
-        for (int a = 0; a < n; ++a) s = __fadd_rn(s, __fmul_rn(g[a], sPi[a]));
-        J.u[k] = s;
+        J.u[k] = dot_gemv_order(g, sPi, n);
     }
 }
 

@@ -113,18 +113,15 @@ emission_images_kernel(int n, int tiles_y, int tiles_x, const GraphJobDev* __res
     if (node < N) {
         const float* g = (isA ? J.sites1 : J.sites2) + (size_t)n * node;
         if (isA) {
-            float s = 0.f;
-            for (int a = 0; a < n; ++a) { vals[a] = g[a]; s = __fadd_rn(s, __fmul_rn(g[a], sPi[a])); }
-            J.u[node] = s;
+            for (int a = 0; a < n; ++a) vals[a] = g[a];
+            J.u[node] = dot_gemv_order(g, sPi, n);
         } else {
             for (int a = 0; a < n; ++a) {             // T(a,x) = sum_b M(b,a) g2(b,x)
                 float s = 0.f;
                 for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sM[b * n + a], g[b]));
                 vals[a] = s;
             }
-            float s = 0.f;
-            for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sPi[b], g[b]));
-            J.v[node] = s;
+            J.v[node] = dot_gemv_order(g, sPi, n);
         }
     } else {
         for (int a = 0; a < n; ++a) vals[a] = 0.f;

@@ -170,6 +170,22 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     int* result;                // [0]=status [1]=length [2]=n_tr_indels ; score at ((float*)result)[3]
 };
 
+#ifdef __CUDACC__
+// g^T pi in the order of Eigen's SSE2 row-major gemv kernel (what the reference binary does for the two normalisers of
+// GraphAlign.h:154; pinned against the binary on a 1000-sequence family): four lane sums, (l0 + l2) + (l1 + l3), sequential tail
+__device__ __forceinline__ float dot_gemv_order(const float* __restrict__ g, const float* __restrict__ pi, int n) {
+    float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+    const int n4 = n & ~3;
+    for (int k = 0; k < n4; k += 4) {
+        l0 = __fadd_rn(l0, __fmul_rn(g[k], pi[k])); l1 = __fadd_rn(l1, __fmul_rn(g[k + 1], pi[k + 1]));
+        l2 = __fadd_rn(l2, __fmul_rn(g[k + 2], pi[k + 2])); l3 = __fadd_rn(l3, __fmul_rn(g[k + 3], pi[k + 3]));
+    }
+    float s = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
+    for (int k = n4; k < n; ++k) s = __fadd_rn(s, __fmul_rn(g[k], pi[k]));
+    return s;
+}
+#endif
+
 int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, int max_N1, int max_N2);
 int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const GraphJobDev* h_jobs);
 int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs);

@@ -93,3 +93,23 @@ def test_pair_alignment_matches_binary():
         res = progressive.progressive_alignment(seqs, tree, mf, opts, align_fn=po.align_graphs)
         got = {k: AA.decode(v) for k, v in res.aligned.items()}
         assert got == rec["alignment_i0"], rec["t"]
+
+
+def test_oracle_progressive_pass_1000_sequences_matches_reference_binary():
+    """a whole progressive pass over 1000 x 500 aa under a fixed tree (999 alignGraphs + mergeGraphs nodes): the oracle
+    reproduces the reference binary's alignment (SHA-256 in large.json).  This is the case that pinned the summation
+    order of the two emission normalisers (oracle.cpp dot_gemv)."""
+    import hashlib
+    from prographmsa_b200 import synth, progressive
+    from oracle import pyoracle as po
+    rec = [r for r in golden("large.json")["runs"] if r["n"] == 1000][0]
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(rec["n"], rec["L"], mf, seed=rec["seed"], forbid_first=10)
+    tree = progressive.parse_newick(root.newick(6) + ";")
+    res = progressive.progressive_alignment(seqs, tree, mf, opts,
+                                            batch_align_fn=lambda jobs, o: [po.align_graphs(a, b, m, o) for a, b, m in jobs])
+    h = hashlib.sha256()
+    for k in sorted(res.aligned):
+        h.update(k.encode()); h.update(b"\n"); h.update(alphabet.AA.decode(res.aligned[k]).encode()); h.update(b"\n")
+    assert h.hexdigest() == rec["sha256"]
