@@ -25,11 +25,20 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 // thread meets (y,0), (y,1), ... on consecutive anti-diagonals, so the LEFT neighbour (y, x-1) and the
 // row's own predecessor info stay in registers; the UP / DIAGONAL neighbours (y-1, .) come from the
 // previous two ring rows at index y-1 (no skew arithmetic).  STAGE: graph 2's node infos in shared memory.
-template <bool STAGE, int RPT, int RING, bool SPF>
+//
+// BANDED (graph 1 too long for one CTA's ring): the rows are cut into bands of blockDim rows, one CTA per band, all
+// co-resident.  Every dependency of a cell lies on a strictly earlier global anti-diagonal, so band b may sweep
+// diagonal d once every earlier band has finished its cells on diagonals < d: each band publishes the number of
+// diagonals it has completed (fence + flag, every 4 diagonals) and waits on the earlier bands' flags (every 8).
+// Cells of other bands are read from HBM/L2 (the {M,X,Y,W} array itself is the exchange buffer).
+template <bool STAGE, int RPT, int RING, bool SPF, bool BANDED>
 __global__ void __launch_bounds__(1024)
-graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch) {
-    const GraphJobDev& J = jobs[order[blockIdx.x]];
+graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch, int max_bands) {
+    const GraphJobDev& J = jobs[order[BANDED ? blockIdx.x / max_bands : blockIdx.x]];
+    const int band = BANDED ? (int)blockIdx.x % max_bands : 0;
+    if (BANDED && band >= J.bands) return;
     const int N1 = J.N1, N2 = J.N2, pitch = J.pitch;
+    const int y0 = BANDED ? band * (int)blockDim.x * RPT : 0;                      // first row of this band
     const float gap_init = J.sc[0], gap_extend = J.sc[1], start_gap = J.sc[6], start_init = J.sc[7];
     const float NINF = -CUDART_INF_F;
     float4* __restrict__ C = J.MXYW;
@@ -54,21 +63,24 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     const int* __restrict__ P1I = STAGE ? sp1i : J.p1_idx; const float* __restrict__ P1V = STAGE ? sp1v : J.p1_val;
     const int* __restrict__ P2I = STAGE ? sp2i : J.p2_idx; const float* __restrict__ P2V = STAGE ? sp2v : J.p2_val;
 
-    auto cell = [&](int yy, int xx, int d) -> float4 {          // any earlier cell: ring when recent, else HBM/L2
+    auto cell = [&](int yy, int xx, int d) -> float4 {          // any earlier cell: ring when recent (and of this band), else HBM/L2
         const int dd = yy + xx;
-        if (d - dd < RING) return ring[(dd & (RING - 1)) * ring_pitch + yy];
-        return C[(size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)))];
+        if (d - dd < RING && (!BANDED || yy >= y0)) return ring[(dd & (RING - 1)) * ring_pitch + (yy - y0)];
+        const float4* p = C + (size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)));
+        return BANDED ? __ldcg(p) : *p;
     };
 
     NodeInfo ny[RPT]; bool ysimple[RPT]; float4 left[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-        const int y = tid + r * T;
+        const int y = y0 + tid + r * T;
         ny[r] = (y <= N1 - 2) ? J.ni1[y] : NodeInfo{0, 0, 0, 0.f};
-        ysimple[r] = (ny[r].cnt == 1 && ny[r].idx0 == y - 1);
+        ysimple[r] = (ny[r].cnt == 1 && ny[r].idx0 == y - 1) && !(BANDED && band > 0 && y == y0);   // row y0-1 is another band's
         left[r] = make_float4(NINF, NINF, NINF, NINF);
     }
-    const int dmax = (N1 - 2) + (N2 - 2);
+    const int band_rows = T * RPT;
+    const int ylast = BANDED ? min(N1 - 2, y0 + band_rows - 1) : N1 - 2;           // last row of this band
+    const int dmin = y0, dmax = ylast + (N2 - 2);
     const int ldS = J.ldS;
     auto fetch_s4 = [&](int r, int y, int xq) {                  // S(y, xq..xq+3) -> sring[(xq/4)&3][r*T+tid], asynchronously
         const float* src = S + (size_t)y * ldS + xq;
@@ -77,16 +89,27 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     };
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-        const int y = tid + r * T;
+        const int y = y0 + tid + r * T;
         if (SPF && y >= 1 && y <= N1 - 2) { fetch_s4(r, y, 0); if (4 < ldS) fetch_s4(r, y, 4); }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");      // the first rows need these within < 8 diagonals
 
-    for (int d = 0; d <= dmax; ++d) {
+    for (int d = dmin; d <= dmax; ++d) {
+        if (BANDED && band > 0 && ((d - dmin) & 7) == 0) {      // the earlier bands must be past the next 8 diagonals
+            if (tid == 0) {
+                for (int bq = 0; bq < band; ++bq) {
+                    const int last_q = min(N1 - 2, (bq + 1) * band_rows - 1) + (N2 - 2);
+                    const int need = min(d + 8, last_q + 1);
+                    while (*(volatile int*)(J.progress + bq) < need) __nanosleep(64);
+                }
+                __threadfence();
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            const int y = tid + r * T, x = d - y;
+            const int y = y0 + tid + r * T, x = d - y;
             if (SPF && y >= 1 && y <= N1 - 2 && x >= 0 && (x & 3) == 0 && x + 8 < ldS) fetch_s4(r, y, x + 8);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
@@ -97,7 +120,7 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         const float4* row2 = ring + ((d - 2) & (RING - 1)) * ring_pitch;
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
-            const int y = tid + r * T, x = d - y;
+            const int y = y0 + tid + r * T, x = d - y;
             if (y > N1 - 2 || x < 0 || x > N2 - 2) continue;
             float m = NINF, xs = NINF, ys = NINF, w = NINF;
             if (x == 0) {
@@ -129,8 +152,8 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                     if (ysimple[r] && nx.cnt == 1 && nx.idx0 == x - 1) {
                         // fast path (chain nodes, the overwhelming majority): one adjacent regular predecessor each
                         const float ey = ny[r].val0, ex = nx.val0;
-                        const float4 cu = row1[y - 1];                               // (y-1, x)
-                        const float4 cd = row2[y - 1];                               // (y-1, x-1)
+                        const float4 cu = row1[y - y0 - 1];                          // (y-1, x)
+                        const float4 cd = row2[y - y0 - 1];                          // (y-1, x-1)
                         const float4 cl = left[r];                                   // (y, x-1): this thread, last diagonal
                         ys = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
                         m = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
@@ -159,13 +182,17 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
             }
             const float4 out = make_float4(m, xs, ys, w);
             left[r] = out;
-            rcur[y] = out;
+            rcur[y - y0] = out;
             C[(size_t)d * pitch + (y - ylo)] = out;
         }
         __syncthreads();
+        if (BANDED && tid == 0 && (((d - dmin) & 3) == 3 || d == dmax)) {
+            __threadfence();                                     // the CTA's stores of diagonals <= d, ordered by the barrier, before the flag
+            *(volatile int*)(J.progress + band) = d + 1;
+        }
     }
-    // end-node match (GraphAlign.h:262-280)
-    if (tid == 0) {
+    // end-node match (GraphAlign.h:262-280); banded: the last band has waited for all the others
+    if (tid == 0 && (!BANDED || band == J.bands - 1)) {
         const float end_match = J.sc[3], end_gap = J.sc[4], end_skip = J.sc[5];
         float Wend = NINF;
         for (int ky = J.p1_ptr[N1 - 1]; ky < J.p1_ptr[N1]; ++ky)
@@ -175,7 +202,7 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                 if (xp == 0 && yp == 0) {
                     Wend = fmaxf(__fsub_rn(__fsub_rn(end_skip, ey), ex), Wend);
                 } else {
-                    const float4 c = C[skew(yp, xp, N2, pitch)];
+                    const float4 c = __ldcg(C + skew(yp, xp, N2, pitch));
                     Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.y, end_gap), ey), ex), Wend);
                     Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.z, end_gap), ey), ex), Wend);
                     Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.x, end_match), ey), ex), Wend);
@@ -187,9 +214,26 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
 
 template <bool STAGE, int RPT, int RING, bool SPF>
 static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int threads, int ring_pitch, size_t smem) {
-    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, RPT, RING, SPF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_fill_diag_kernel<STAGE, RPT, RING, SPF><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch);
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, RPT, RING, SPF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_fill_diag_kernel<STAGE, RPT, RING, SPF, false><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch, 1);
     PGM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// Long graphs: bands of GF_BAND_ROWS rows, one CTA each.  All CTAs of a launch must be resident at once (they wait on each
+// other's flags), so a launch holds at most one CTA per SM; the jobs' progress flags are zeroed by the caller.
+int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms) {
+    if (n_jobs == 0) return 0;
+    const int threads = GF_BAND_ROWS;
+    const int ring_pitch = GF_BAND_ROWS;
+    const size_t smem = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * threads * sizeof(float4);
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<false, 1, GF_RING, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int per = std::max(1, n_sms / max_bands);               // jobs per launch
+    for (int j = 0; j < n_jobs; j += per) {
+        const int nj = std::min(per, n_jobs - j);
+        graph_fill_diag_kernel<false, 1, GF_RING, true, true><<<nj * max_bands, threads, smem, st>>>(d_jobs, d_order + j, ring_pitch, max_bands);
+        PGM_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -20,6 +20,7 @@ pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
 int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
 int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
+int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
 void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
@@ -80,9 +81,9 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct JobLayout {                // byte offsets into the upload arena / scratch arena / output arena
     size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2, colinfo, blkstart;
-    size_t S, MXYW, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev;     // scratch
+    size_t S, MXYW, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev, progress;     // scratch
     size_t map1, map2, result;                           // output
-    int np1, np2, cap, pitch, nb, layout;
+    int np1, np2, cap, pitch, nb, layout, bands;
 };
 
 } // namespace
@@ -103,7 +104,7 @@ struct pgm_graph_batch {
     // Fill schedule.  The fill kernel's block size and shared memory -- hence CTAs per SM -- are set by the LARGEST job
     // of a launch, so each sub-batch is swept as a few launches of similar graph-2 length (largest first), on
     // separate streams so that a class with few jobs does not leave the GPU idle.
-    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np; };
+    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands; };
     std::vector<int> order;                 // job indices relative to their sub-batch, grouped by FillLaunch
     std::vector<FillLaunch> fills;
     size_t scratch_bytes_used = 0;
@@ -140,6 +141,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     for (int k = 0; k < n_jobs; ++k) {
         const pgm_graph &a = g1[k], &bb = g2[k];
         if (a.N < 2 || bb.N < 2) { delete b; pgm_set_error("job %d: graphs need at least start and end nodes", k); return PGM_ERR_ARG; }
+        if (a.N > 60000 || bb.N > 60000) { delete b; pgm_set_error("job %d: graphs of more than 60000 nodes are not supported (%d x %d)", k, a.N, bb.N); return PGM_ERR_ARG; }
         JobLayout& L = b->lay[k];
         L.np1 = a.e_rowptr[a.N] + (a.r_rowptr ? a.r_rowptr[a.N] : 0);
         L.np2 = bb.e_rowptr[bb.N] + (bb.r_rowptr ? bb.r_rowptr[bb.N] : 0);
@@ -167,6 +169,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         // on chain graphs (measured, 400 x 400 nodes alone on an SM: 0.31 ms against 0.49 ms).
         L.layout = (generic > diag_min_generic || nblk > GF_MAX_NB || n_jobs < small_batch) ? GF_LAYOUT_DIAG : GF_LAYOUT_BLOCK;
         if (force_layout >= 0 && !(force_layout == GF_LAYOUT_BLOCK && nblk > GF_MAX_NB)) L.layout = force_layout;
+        L.bands = (L.layout == GF_LAYOUT_DIAG && a.N >= GF_BAND_MIN_N1) ? (a.N - 1 + GF_BAND_ROWS - 1) / GF_BAND_ROWS : 1;
         L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 8);
         auto take = [&](size_t& off, size_t bytes) { size_t r = off; off = align_up(off + bytes, 128); return r; };
         L.sites1 = take(in_off, sizeof(float) * n * a.N);
@@ -191,6 +194,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             L.Bimg = take(so, (size_t)((bb.N + 127) / 128) * 128 * kp * 4);
         } else { L.Aimg = L.Bimg = 0; }
         L.alt_score = take(so, 4 * std::max(a.N, bb.N)); L.alt_prev = take(so, 4 * std::max(a.N, bb.N));
+        L.progress = take(so, 4 * (size_t)L.bands);
         scratch_need[k] = so;
         b->max_N1 = std::max(b->max_N1, a.N); b->max_N2 = std::max(b->max_N2, bb.N);
     }
@@ -220,7 +224,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         const pgm_graph* gs[2] = {&g1[k], &g2[k]};
         const JobLayout& L = b->lay[k];
         GraphJobDev& J = b->jobs[k];
-        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.nb = L.nb; J.layout = L.layout; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
+        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.nb = L.nb; J.layout = L.layout; J.bands = L.bands; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
         dynprog_scores(g1[k], g2[k], models[k], *opts, J.sc);
         const float rinit = J.sc[8], rext = J.sc[9];
         float* s1 = (float*)(hin + L.sites1); float* s2 = (float*)(hin + L.sites2);
@@ -294,7 +298,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.Tbuf = (float*)(sb + L.Tbuf);
         J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
         J.Aimg = (float*)(sb + L.Aimg); J.Bimg = (float*)(sb + L.Bimg);
-        J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev);
+        J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev); J.progress = (int*)(sb + L.progress);
         J.map1 = (int*)(dout + L.map1); J.map2 = (int*)(dout + L.map2); J.result = (int*)(dout + L.result);
     };
     {
@@ -315,6 +319,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         b->order.resize(n_jobs);
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
         auto class_of = [&](const GraphJobDev& J) {
+            if (J.bands > 1) return 200;                                       // banded anti-diagonal sweep: its own launches
             if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
             const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
         };
@@ -332,11 +337,12 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             size_t p = 0;
             while (p < idx.size()) {
                 const int q = class_of(b->jobs[sbr.first + idx[p]]);
-                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, b->jobs[sbr.first + idx[p]].layout, 0, 0, 0, 0, 0};
+                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, b->jobs[sbr.first + idx[p]].layout, 0, 0, 0, 0, 0, 1};
                 while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]]) == q) {
                     const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
                     f.max_nb = std::max(f.max_nb, J.nb); f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2);
                     f.max_np2 = std::max(f.max_np2, J.np2); f.max_np = std::max(f.max_np, J.np1 + J.np2);
+                    f.max_bands = std::max(f.max_bands, J.bands);
                     ++f.count; ++p;
                 }
                 b->fills.push_back(f);
@@ -396,6 +402,15 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             for (size_t q = 0; q < fl.size() && !rc; ++q) {
                 cudaStream_t sq = (q == 0 || !n_side) ? st : ss.streams[(q - 1) % n_side];
                 const int* ord = d_order_all + sb.first + fl[q]->offset;
+                if (fl[q]->max_bands > 1) {
+                    for (int jq = 0; jq < fl[q]->count; ++jq) {         // zero the bands' progress flags
+                        const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + fl[q]->offset + jq]];
+                        PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * Jq.bands, sq));
+                    }
+                    int n_sms = 148; cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, pgm_ctx_device(c));
+                    rc = launch_graph_fill_banded(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_bands, n_sms);
+                    continue;
+                }
                 rc = fl[q]->layout == GF_LAYOUT_DIAG
                          ? launch_graph_fill_diag(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_n1, fl[q]->max_n2, fl[q]->max_np)
                          : launch_graph_fill(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_nb, fl[q]->max_n2, fl[q]->max_np2);

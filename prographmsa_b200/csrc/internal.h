@@ -132,6 +132,8 @@ int launch_angle(cudaStream_t st, int n, int K, int dims, int N, const uint8_t* 
 // ---- HP-1 (hp1_*.cu) ------------------------------------------------------------------------------
 struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred list start, count (sign bit = first pred is a repeat edge), first entry inline
 
+#define GF_BAND_ROWS 1024     // rows per band (= threads per CTA) of the banded anti-diagonal kernel
+#define GF_BAND_MIN_N1 3074    // graph 1 from this many nodes on is swept in bands
 #define GF_LAYOUT_BLOCK 0
 #define GF_LAYOUT_DIAG 1
 #define GF_K 8               // columns a fill-kernel thread sweeps per step (one block of a row)
@@ -140,6 +142,8 @@ struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred
 
 struct GraphJobDev {        // one alignGraphs job, all pointers into the batch's device arena
     int N1, N2;
+    int bands;                  // > 1: graph 1 is swept in bands of GF_BAND_ROWS rows by the banded anti-diagonal kernel
+    int* progress;              // bands flags (scratch, zeroed before every sweep): anti-diagonals completed per band
     int layout;                 // cell layout of MXYW = which fill kernel sweeps the job: GF_LAYOUT_BLOCK or GF_LAYOUT_DIAG
     int nb;                     // column blocks per row (columns 0 .. N2-2 cut into blocks of <= GF_K; a non-chain node starts a block)
     int pitch;                  // block-skewed layout (hp1_graphdp.cu): cell (y,x) at (((y + blk(x))*GF_K + off(x))*pitch + y%nb;

@@ -66,10 +66,11 @@ def test_leaf_pair_alignment_identical(ga, po, L, t, seed):
     _same_alignment(ga.alignGraphs(g1, g2, m, opts), po.align_graphs(g1, g2, m, opts))
 
 
-@pytest.mark.parametrize("L", [1100, 1500, 2300])
+@pytest.mark.parametrize("L", [1100, 1500, 2300, 3300, 4200])
 def test_long_graphs_identical(ga, po, L):
-    """graph 1 beyond 1024 rows: several rows per thread; beyond ~1400 rows the fill kernel switches to its 4-diagonal
-    ring and reads S directly (BASELINE config 3 has 1500-nt sequences)"""
+    """graph 1 beyond 1024 rows: several rows per thread; beyond ~1400 rows the anti-diagonal kernel switches to its
+    4-diagonal ring and reads S directly (BASELINE config 3 has 1500-nt sequences); from 3074 nodes on the rows are swept
+    in bands of 1024 by co-resident CTAs that hand over through HBM (the root of a 5000-sequence tree has > 6000 nodes)"""
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
     a, b = synth.random_pair(L, 0.4, mf, seed=L)
@@ -82,7 +83,7 @@ def test_too_long_graph_is_an_error_not_a_crash(ga):
     from prographmsa_b200._lib import PgmError
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
-    a, b = synth.random_pair(4200, 0.4, mf, seed=1)
+    a, b = synth.random_pair(61000, 0.01, mf, seed=1)
     with pytest.raises(PgmError):
         ga.alignGraphs(sequence_graph(a, 20), sequence_graph(b, 20), mf.getModel(0.4, 0.4), opts)
 
