@@ -219,6 +219,16 @@ int pgm_dynprog_scores(int n_states, const pgm_graph* g1, const pgm_graph* g2, c
 int pgm_emission_scores(pgm_ctx* ctx, int n_states, const pgm_graph* g1, const pgm_graph* g2,
                         const pgm_dp_model* model, float match_init, int emission_mode, float* S);
 
+/* ---- N3: BioNJ join loop on the GPU (csrc/nj_bionj.cu) ------------------------------------------------------------
+ * Replaces the O(N^3) part of TreeNJ<A>::buildNJTree (reference TreeNJ.cpp:132-281) for N taxa: D, V are the N*N
+ * row-major symmetric distance / variance matrices (diagonals are ignored).  Join k (k < N-3) merges the taxa at the
+ * CURRENT indices join_i1[k] < join_i2[k] (index i2 is removed, later indices shift down, the new cluster takes i1)
+ * with branch lengths join_d1[k], join_d2[k].  D_rest receives the remaining rest_dim x rest_dim (<= 3) distance
+ * matrix, row-major, from which the caller places the last taxa as the reference does (TreeNJ.cpp:236-281).        */
+int pgm_bionj_joins(pgm_ctx* ctx, int N, const double* D, const double* V,
+                    int32_t* join_i1, int32_t* join_i2, double* join_d1, double* join_d2 /* N-3 each */,
+                    double* D_rest /* min(N,3)^2 */, int* rest_dim);
+
 /* ---- native HOST glue around the graph DP (csrc/host_graph.cpp; no GPU work, callable without a device) -------
  * What the reference does in C++ between two alignGraphs calls, on the same CSR arrays as pgm_graph:
  * CleanedGraph (CleanedGraph.h:38-146), the node plan of mergeGraphs (GraphAlign.h:569-620) and its edge

@@ -1,0 +1,221 @@
+// nj_bionj.cu -- BioNJ join loop on the GPU.  Replaces the O(N^3) part of
+// TreeNJ<A>::buildNJTree (reference TreeNJ.cpp:132-281): per join the clamped matrices, the column sums, the argmin of
+// the Q criterion, the BioNJ lambda and the reduced distance / variance matrices.  The tree objects, names and the
+// final <= 3 taxa stay on the host (tree.py / TreeNJ in the reference).
+//
+// The arithmetic follows the host specification (tree.py build_nj_tree) operation by operation in FP64 without
+// contraction, so the join sequence and the branch lengths are bit-identical to it:
+//   D <- max(D, 1e-4), V <- max(V, 1e-5), zero diagonals          (only the row/column written by the last join changes)
+//   sums[j] = sum_i D[i][j], sequentially in i                    (tiles staged in shared memory, one adding thread per column)
+//   Q[i][j] = 0.5 D[i][j] - (0.5 / (dim - 2)) (sums[j] + sums[i]); first minimum in column-major order
+//   d1, d2, lambda (its row difference summed sequentially), new row, then row/column i2 removed by compaction
+// The whole loop is enqueued without a host synchronisation: the join parameters live in device memory.
+#include "internal.h"
+#include <math_constants.h>
+#include <algorithm>
+
+struct pgm_ctx;
+cudaStream_t pgm_ctx_stream(pgm_ctx* c);
+int pgm_ctx_device(pgm_ctx* c);
+int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
+void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
+
+namespace {
+
+inline size_t align_up_sz(size_t v, size_t a) { return (v + a - 1) / a * a; }
+constexpr double NJ_MIN_DIST = 1e-4, NJ_MIN_VAR = 1e-5;
+constexpr int ARGMIN_BLOCKS = 592, ARGMIN_THREADS = 256;
+
+struct NjParams { int i1, i2; double d1, d2, lam, v12; };
+struct NjCand { double q; unsigned long long flat; };
+
+// clamp: the first join touches everything, later joins only the row / column written by the previous join
+__global__ void __launch_bounds__(256)
+nj_clamp_kernel(double* __restrict__ D, double* __restrict__ V, int dim, int P, const NjParams* __restrict__ prm, int first) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int i, j;
+    if (first) { if (e >= (size_t)dim * dim) return; i = (int)(e / dim); j = (int)(e - (size_t)i * dim); }
+    else {
+        if (e >= 2 * (size_t)dim) return;
+        const int t = prm->i1, k = (int)(e >> 1);
+        if (e & 1) { i = t; j = k; } else { i = k; j = t; }
+    }
+    const size_t o = (size_t)i * P + j;
+    D[o] = (i == j) ? 0.0 : fmax(D[o], NJ_MIN_DIST);
+    V[o] = (i == j) ? 0.0 : fmax(V[o], NJ_MIN_VAR);
+}
+
+// sums[j] = sum_i D[i][j], sequentially in i.  A CTA owns 32 columns: eight warps stream 32 x 128 tiles into shared memory
+// (coalesced rows), then one thread per column adds its 128 values in order, so the order is that of a scalar loop while
+// the loads are wide.
+#define CS_ROWS 128
+__global__ void __launch_bounds__(256)
+nj_colsum_kernel(const double* __restrict__ D, int dim, int P, double* __restrict__ sums) {
+    __shared__ double tile[CS_ROWS][33];
+    const int j0 = blockIdx.x * 32, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    double s = 0.0;
+    for (int i0 = 0; i0 < dim; i0 += CS_ROWS) {
+        for (int r = w; r < CS_ROWS; r += 8) {
+            const int i = i0 + r, j = j0 + lane;
+            tile[r][lane] = (i < dim && j < dim) ? D[(size_t)i * P + j] : 0.0;
+        }
+        __syncthreads();
+        if (w == 0) {
+            const int rows = min(CS_ROWS, dim - i0);
+            for (int r = 0; r < rows; ++r) s = s + tile[r][lane];
+        }
+        __syncthreads();
+    }
+    if (w == 0 && j0 + lane < dim) sums[j0 + lane] = s;
+}
+
+__device__ __forceinline__ bool nj_better(double q, unsigned long long f, double bq, unsigned long long bf) {
+    return q < bq || (q == bq && f < bf);
+}
+
+// Q criterion: per-block minimum, ties to the smallest column-major index (Eigen minCoeff / numpy argmin order)
+__global__ void __launch_bounds__(ARGMIN_THREADS)
+nj_argmin_kernel(const double* __restrict__ D, int dim, int P, const double* __restrict__ sums, NjCand* __restrict__ part) {
+    const double c = 0.5 / ((double)dim - 2.0);
+    double bq = CUDART_INF; unsigned long long bf = ~0ull;
+    for (int i = blockIdx.x; i < dim; i += gridDim.x) {
+        const double si = sums[i];
+        for (int j = threadIdx.x; j < dim; j += blockDim.x) {
+            if (i == j) continue;
+            const double q = 0.5 * D[(size_t)i * P + j] - c * (sums[j] + si);
+            const unsigned long long f = (unsigned long long)j * dim + i;
+            if (nj_better(q, f, bq, bf)) { bq = q; bf = f; }
+        }
+    }
+    __shared__ double sq[ARGMIN_THREADS]; __shared__ unsigned long long sf[ARGMIN_THREADS];
+    sq[threadIdx.x] = bq; sf[threadIdx.x] = bf;
+    __syncthreads();
+    for (int st = ARGMIN_THREADS / 2; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st && nj_better(sq[threadIdx.x + st], sf[threadIdx.x + st], sq[threadIdx.x], sf[threadIdx.x])) {
+            sq[threadIdx.x] = sq[threadIdx.x + st]; sf[threadIdx.x] = sf[threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[blockIdx.x].q = sq[0]; part[blockIdx.x].flat = sf[0]; }
+}
+
+// one block: final argmin over the partials, then the join's scalars (TreeNJ.cpp:176-214 / tree.py)
+#define JN_CHUNK 2048
+__global__ void __launch_bounds__(ARGMIN_THREADS)
+nj_join_kernel(const double* __restrict__ D, const double* __restrict__ V, int dim, int P, const double* __restrict__ sums,
+               const NjCand* __restrict__ part, int n_part, NjParams* __restrict__ prm, int join,
+               int32_t* __restrict__ j1, int32_t* __restrict__ j2, double* __restrict__ jd1, double* __restrict__ jd2) {
+    __shared__ double sq[ARGMIN_THREADS]; __shared__ unsigned long long sf[ARGMIN_THREADS];
+    __shared__ double diff[JN_CHUNK];
+    __shared__ int s_i1, s_i2;
+    double bq = CUDART_INF; unsigned long long bf = ~0ull;
+    for (int k = threadIdx.x; k < n_part; k += blockDim.x) if (nj_better(part[k].q, part[k].flat, bq, bf)) { bq = part[k].q; bf = part[k].flat; }
+    sq[threadIdx.x] = bq; sf[threadIdx.x] = bf;
+    __syncthreads();
+    for (int st = ARGMIN_THREADS / 2; st > 0; st >>= 1) {
+        if ((int)threadIdx.x < st && nj_better(sq[threadIdx.x + st], sf[threadIdx.x + st], sq[threadIdx.x], sf[threadIdx.x])) {
+            sq[threadIdx.x] = sq[threadIdx.x + st]; sf[threadIdx.x] = sf[threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int i2 = (int)(sf[0] % (unsigned long long)dim), i1 = (int)(sf[0] / (unsigned long long)dim);   // (row, col)
+        if (i2 < i1) { const int t = i1; i1 = i2; i2 = t; }
+        s_i1 = i1; s_i2 = i2;
+    }
+    __syncthreads();
+    const int i1 = s_i1, i2 = s_i2;
+    // sum_k (V[i2][k] - V[i1][k]) sequentially in k: the differences are staged by the whole block, added by one thread
+    double s = 0.0;
+    for (int k0 = 0; k0 < dim; k0 += JN_CHUNK) {
+        for (int k = threadIdx.x; k < JN_CHUNK && k0 + k < dim; k += blockDim.x)
+            diff[k] = V[(size_t)i2 * P + k0 + k] - V[(size_t)i1 * P + k0 + k];
+        __syncthreads();
+        if (threadIdx.x == 0) { const int m = min(JN_CHUNK, dim - k0); for (int k = 0; k < m; ++k) s = s + diff[k]; }
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    const double d12 = D[(size_t)i1 * P + i2];
+    double d1 = (d12 + (sums[i1] - sums[i2]) / ((double)dim - 2.0)) / 2.0;
+    d1 = fmin(fmax(d1, NJ_MIN_DIST), d12);
+    const double d2 = fmax(D[(size_t)i2 * P + i1] - d1, NJ_MIN_DIST);
+    const double v12 = V[(size_t)i1 * P + i2];
+    double lam = (v12 != 0.0) ? 0.5 + s / ((double)(2 * (dim - 2)) * v12) : CUDART_NAN;
+    lam = isnan(lam) ? 0.5 : fmin(fmax(0.0, lam), 1.0);
+    prm->i1 = i1; prm->i2 = i2; prm->d1 = d1; prm->d2 = d2; prm->lam = lam; prm->v12 = v12;
+    j1[join] = i1; j2[join] = i2; jd1[join] = d1; jd2[join] = d2;
+}
+
+// reduced matrices: row/column i2 removed, row/column i1 replaced by the BioNJ combination
+__global__ void __launch_bounds__(256)
+nj_reduce_kernel(const double* __restrict__ Ds, const double* __restrict__ Vs, double* __restrict__ Dd, double* __restrict__ Vd,
+                 int dim, int P, const NjParams* __restrict__ prm) {
+    const int i1 = prm->i1, i2 = prm->i2;
+    const double d1 = prm->d1, d2 = prm->d2, lam = prm->lam, v12 = prm->v12;
+    const int nd = dim - 1;
+    const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+    if (c >= nd) return;
+    const int rs = r + (r >= i2), cs = c + (c >= i2);
+    double d, v;
+    if (r == i1 || c == i1) {
+        const int ks = (r == i1) ? cs : rs;                      // the other taxon, source index
+        if (r == c) { d = 0.0; v = 0.0; }
+        else {
+            d = lam * (Ds[(size_t)i1 * P + ks] - d1) + (1.0 - lam) * (Ds[(size_t)i2 * P + ks] - d2);
+            v = lam * Vs[(size_t)i1 * P + ks] + (1.0 - lam) * Vs[(size_t)i2 * P + ks] - lam * (1.0 - lam) * v12;
+        }
+    } else { d = Ds[(size_t)rs * P + cs]; v = Vs[(size_t)rs * P + cs]; }
+    Dd[(size_t)r * P + c] = d; Vd[(size_t)r * P + c] = v;
+}
+
+} // namespace
+
+extern "C" int pgm_bionj_joins(pgm_ctx* c, int N, const double* D, const double* V, int32_t* join_i1, int32_t* join_i2,
+                               double* join_d1, double* join_d2, double* D_rest, int* rest_dim) {
+    if (!c || !D || !V || !rest_dim || !D_rest || N < 1) { pgm_set_error("bad arguments"); return PGM_ERR_ARG; }
+    const int n_joins = N > 3 ? N - 3 : 0;
+    if (n_joins && (!join_i1 || !join_i2 || !join_d1 || !join_d2)) { pgm_set_error("NULL join arrays"); return PGM_ERR_ARG; }
+    *rest_dim = N - n_joins;
+    if (n_joins == 0) { for (int i = 0; i < N * N; ++i) D_rest[i] = D[i]; return 0; }
+    PGM_CUDA(cudaSetDevice(pgm_ctx_device(c)));
+    cudaStream_t st = pgm_ctx_stream(c);
+    const size_t mat = (size_t)N * N * sizeof(double);
+    DevBuf buf;
+    const size_t small = align_up_sz((size_t)N * 8, 256) + align_up_sz(sizeof(NjCand) * ARGMIN_BLOCKS, 256) + 256 +
+                         2 * align_up_sz((size_t)n_joins * 4, 256) + 2 * align_up_sz((size_t)n_joins * 8, 256);
+    int rc = pgm_ctx_take_dev(c, 4 * mat + small, buf);
+    if (rc) return rc;
+    char* p = buf.as<char>();
+    double* Dm[2] = {(double*)p, (double*)(p + mat)}; double* Vm[2] = {(double*)(p + 2 * mat), (double*)(p + 3 * mat)};
+    p += 4 * mat;
+    double* sums = (double*)p; p += align_up_sz((size_t)N * 8, 256);
+    NjCand* part = (NjCand*)p; p += align_up_sz(sizeof(NjCand) * ARGMIN_BLOCKS, 256);
+    NjParams* prm = (NjParams*)p; p += 256;
+    int32_t* dj1 = (int32_t*)p; p += align_up_sz((size_t)n_joins * 4, 256);
+    int32_t* dj2 = (int32_t*)p; p += align_up_sz((size_t)n_joins * 4, 256);
+    double* dd1 = (double*)p; p += align_up_sz((size_t)n_joins * 8, 256);
+    double* dd2 = (double*)p;
+    cudaError_t e = cudaMemcpyAsync(Dm[0], D, mat, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Vm[0], V, mat, cudaMemcpyHostToDevice, st);
+    int cur = 0, dim = N;
+    for (int join = 0; join < n_joins && e == cudaSuccess; ++join, --dim) {
+        const size_t n_clamp = join == 0 ? (size_t)dim * dim : 2 * (size_t)dim;
+        nj_clamp_kernel<<<(unsigned)((n_clamp + 255) / 256), 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, prm, join == 0);
+        nj_colsum_kernel<<<(dim + 31) / 32, 256, 0, st>>>(Dm[cur], dim, N, sums);
+        const int nblk = std::min(ARGMIN_BLOCKS, dim);
+        nj_argmin_kernel<<<nblk, ARGMIN_THREADS, 0, st>>>(Dm[cur], dim, N, sums, part);
+        nj_join_kernel<<<1, ARGMIN_THREADS, 0, st>>>(Dm[cur], Vm[cur], dim, N, sums, part, nblk, prm, join, dj1, dj2, dd1, dd2);
+        nj_reduce_kernel<<<dim3((dim - 1 + 255) / 256, dim - 1), 256, 0, st>>>(Dm[cur], Vm[cur], Dm[cur ^ 1], Vm[cur ^ 1], dim, N, prm);
+        cur ^= 1;
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(join_i1, dj1, (size_t)n_joins * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(join_i2, dj2, (size_t)n_joins * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(join_d1, dd1, (size_t)n_joins * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(join_d2, dd2, (size_t)n_joins * 8, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpy2DAsync(D_rest, (size_t)dim * 8, Dm[cur], (size_t)N * 8, (size_t)dim * 8, dim, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    pgm_ctx_give_dev(c, buf);
+    if (e != cudaSuccess) { pgm_set_error("CUDA error in BioNJ: %s", cudaGetErrorString(e)); cudaGetLastError(); return PGM_ERR_CUDA; }
+    return 0;
+}

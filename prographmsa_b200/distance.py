@@ -204,3 +204,20 @@ def ml_distances(model_factory, opts, counts, gaps, seqlen, ctx=None):
     dist = np.zeros(max(P, 1)); var = np.zeros(max(P, 1))
     _lib.check(_lib.lib().pgm_ml_distances(ctx.handle, C.byref(prm), C.c_int64(P), _p(counts), _p(gaps), _p(seqlen), _p(dist), _p(var)))
     return dist[:P], var[:P]
+
+
+def bionj_joins(D, V, ctx=None):
+    """The BioNJ join loop on the GPU (pgm_bionj_joins): same contract as tree.nj_joins_host."""
+    ctx = ctx or _lib.default_context()
+    D = np.ascontiguousarray(D, dtype=np.float64); V = np.ascontiguousarray(V, dtype=np.float64)
+    N = D.shape[0]
+    nj = max(0, N - 3)
+    j1 = np.zeros(max(1, nj), np.int32); j2 = np.zeros(max(1, nj), np.int32)
+    d1 = np.zeros(max(1, nj)); d2 = np.zeros(max(1, nj))
+    rest = np.zeros(9); rdim = C.c_int(0)
+    _lib.check(_lib.lib().pgm_bionj_joins(ctx.handle, N, D.ctypes.data_as(C.c_void_p), V.ctypes.data_as(C.c_void_p),
+                                          j1.ctypes.data_as(C.c_void_p), j2.ctypes.data_as(C.c_void_p),
+                                          d1.ctypes.data_as(C.c_void_p), d2.ctypes.data_as(C.c_void_p),
+                                          rest.ctypes.data_as(C.c_void_p), C.byref(rdim)))
+    r = rdim.value
+    return [(int(j1[k]), int(j2[k]), float(d1[k]), float(d2[k])) for k in range(nj)], rest[:r * r].reshape(r, r).copy()

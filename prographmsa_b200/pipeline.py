@@ -39,6 +39,9 @@ class GpuBackend:
     def batch_merge(self, jobs):
         return self._g.merge_profiles_batch(jobs, self.ctx)
 
+    def nj_joins(self, D, V):
+        return self._d.bionj_joins(D, V, self.ctx)
+
 
 def do_align(seq_strings, opts: Options, backend_factory, alphabet=_alpha.AA, iters=2, return_trees=False):
     """seq_strings: name -> residue string.  -> (name -> aligned string in tree order, [newick of every tree])."""
@@ -54,7 +57,7 @@ def do_align(seq_strings, opts: Options, backend_factory, alphabet=_alpha.AA, it
     be = backend_factory(mf, opts)
 
     trees = []
-    tree = _tree.tree_nj(names, be.initial_distances(seqs, names), opts.edge_halflife)
+    tree = _tree.tree_nj(names, be.initial_distances(seqs, names), opts.edge_halflife, joins_fn=getattr(be, "nj_joins", None))
     trees.append(tree.newick())
     result = old = None
     for i in range(iters):
@@ -64,7 +67,7 @@ def do_align(seq_strings, opts: Options, backend_factory, alphabet=_alpha.AA, it
         if i > 0 and old is not None and all(np.array_equal(aligned[k], old[k]) for k in aligned):
             break
         anames = sorted(aligned)
-        tree = _tree.tree_nj(anames, be.prealigned_distances(aligned, anames), opts.edge_halflife)
+        tree = _tree.tree_nj(anames, be.prealigned_distances(aligned, anames), opts.edge_halflife, joins_fn=getattr(be, "nj_joins", None))
         trees.append(tree.newick())
         old = aligned
     result = _prog.progressive_alignment(seqs, _tree.to_progressive(tree), mf, opts, batch_align_fn=be.batch_align,

@@ -1,7 +1,8 @@
 """Host-side guide tree: BioNJ + midpoint rooting (reference TreeNJ.cpp:22-29,132-281, PhyTree.cpp:11-116,
 PhyTree.h:40-54,227-229).  north_star keeps NJ tree-building on the host; this is plain numpy glue that
 follows the reference's arithmetic order so that the branch lengths (which feed getModel at every tree
-node) agree to rounding.  Not accelerated."""
+node) agree to rounding.  The O(N^3) join loop has a GPU twin (csrc/nj_bionj.cu) that reproduces
+nj_joins_host bit for bit; tree objects, the last three taxa and midpoint rooting stay here."""
 import math
 import numpy as np
 
@@ -56,12 +57,13 @@ def support(d, edge_halflife):
     return 0.0 if math.isnan(s) else s
 
 
-def build_nj_tree(names, distances, variances, edge_halflife):
-    """buildNJTree without a topology plan (TreeNJ.cpp:132-281)."""
-    names = list(names)
-    D = np.array(distances, dtype=np.float64); V = np.array(variances, dtype=np.float64)
-    sub = [PhyTree(n) for n in names]
-    dim = len(names)
+def nj_joins_host(D, V):
+    """The join loop of buildNJTree (TreeNJ.cpp:132-235) in numpy: -> (joins, D_rest) with joins = [(i1, i2, d1, d2)] in
+    CURRENT indices (i2 is removed, later indices shift down, the new cluster takes i1).  This is the specification the
+    GPU join loop (pgm_bionj_joins) reproduces bit for bit; sums run sequentially in index order."""
+    D = np.array(D, dtype=np.float64); V = np.array(V, dtype=np.float64)
+    dim = D.shape[0]
+    joins = []
     while dim > 3:
         D = np.maximum(D, MIN_DIST); V = np.maximum(V, MIN_VAR)
         np.fill_diagonal(D, 0.0); np.fill_diagonal(V, 0.0)
@@ -76,7 +78,7 @@ def build_nj_tree(names, distances, variances, edge_halflife):
         d1 = (D[i1, i2] + (sums[i1] - sums[i2]) / (dim - 2.0)) / 2.0
         d1 = min(max(d1, MIN_DIST), D[i1, i2])
         d2 = max(D[i2, i1] - d1, MIN_DIST)
-        lam = 0.5 + (V[i2, :] - V[i1, :]).sum() / (2 * (dim - 2) * V[i1, i2]) if V[i1, i2] != 0 else float("nan")
+        lam = 0.5 + float(np.cumsum(V[i2, :] - V[i1, :])[-1]) / (2 * (dim - 2) * V[i1, i2]) if V[i1, i2] != 0 else float("nan")
         lam = 0.5 if math.isnan(lam) else min(max(0.0, lam), 1.0)
         keep = [k for k in range(dim) if k != i2]
         new_d = lam * (D[i1, keep] - d1) + (1.0 - lam) * (D[i2, keep] - d2)
@@ -85,6 +87,18 @@ def build_nj_tree(names, distances, variances, edge_halflife):
         new_d[i1] = 0.0; new_v[i1] = 0.0
         D[i1, :] = new_d; D[:, i1] = new_d
         V[i1, :] = new_v; V[:, i1] = new_v
+        joins.append((i1, i2, float(d1), float(d2)))
+        dim -= 1
+    return joins, D
+
+
+def build_nj_tree(names, distances, variances, edge_halflife, joins_fn=None):
+    """buildNJTree without a topology plan (TreeNJ.cpp:132-281).  joins_fn(D, V) -> (joins, D_rest): the O(N^3) join
+    loop, nj_joins_host by default, the GPU's (distance.bionj_joins) when a device back-end passes it."""
+    names = list(names)
+    sub = [PhyTree(n) for n in names]
+    joins, D = (joins_fn or nj_joins_host)(distances, variances)
+    for i1, i2, d1, d2 in joins:
         name1, name2 = names[i1], names[i2]
         del names[i2]
         names[i1] = name1 + "," + name2
@@ -93,7 +107,6 @@ def build_nj_tree(names, distances, variances, edge_halflife):
         t.add_child(sub[i2], d2, support(d2, edge_halflife))
         del sub[i2]
         sub[i1] = t
-        dim -= 1
     root = PhyTree("root")
     if len(names) == 2:
         d = D[0, 1] / 2
@@ -162,11 +175,11 @@ def midpoint_root(root):
     return new_root
 
 
-def tree_nj(names, dm, edge_halflife):
+def tree_nj(names, dm, edge_halflife, joins_fn=None):
     """TreeNJ<A>() after computePwDistances (TreeNJ.h:45-58): zero diagonals, BioNJ, midpoint root."""
     D = np.array(dm.distances, dtype=np.float64); V = np.array(dm.variances, dtype=np.float64)
     np.fill_diagonal(D, 0.0); np.fill_diagonal(V, 0.0)
-    return midpoint_root(build_nj_tree(names, D, V, edge_halflife))
+    return midpoint_root(build_nj_tree(names, D, V, edge_halflife, joins_fn=joins_fn))
 
 
 def to_progressive(t):

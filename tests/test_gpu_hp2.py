@@ -252,3 +252,32 @@ def test_nw_32bit_flavour_matches_16bit(dist_mod, po, monkeypatch):
     ctx.close()
     for x, y in zip(a, b):
         assert np.array_equal(x, y)
+
+
+@pytest.mark.parametrize("N,seed", [(2, 0), (3, 1), (4, 2), (5, 3), (17, 4), (200, 5), (700, 6)])
+def test_bionj_join_loop_bit_identical_to_host_specification(N, seed):
+    """N3: the GPU join loop (pgm_bionj_joins) against tree.nj_joins_host: same joins in the same order, branch lengths
+    and the remaining <= 3 x 3 matrix bit for bit; random symmetric matrices incl. values below the clamps and exact ties"""
+    from prographmsa_b200 import distance, tree
+    rng = np.random.default_rng(seed)
+    A = rng.random((N, N)) * (2.0 if seed % 2 else 0.02); D = np.round((A + A.T) / 2, 3 if N <= 17 else 12)      # rounded: exact ties
+    B = rng.random((N, N)) * 1e-3; V = (B + B.T) / 2
+    if N > 4:
+        V[1, 2] = V[2, 1] = 0.0                                                                                  # below VAR_MIN
+    np.fill_diagonal(D, 0.0); np.fill_diagonal(V, 0.0)
+    ref_j, ref_D = tree.nj_joins_host(D, V)
+    got_j, got_D = distance.bionj_joins(D, V)
+    assert [(a, b) for a, b, _, _ in got_j] == [(a, b) for a, b, _, _ in ref_j]
+    assert np.array_equal(np.array([[c, d] for _, _, c, d in got_j]).view(np.uint64), np.array([[c, d] for _, _, c, d in ref_j]).view(np.uint64))
+    assert np.array_equal(np.asarray(got_D).view(np.uint64), np.asarray(ref_D).view(np.uint64))
+
+
+def test_bionj_tree_from_gpu_joins_equals_host_tree():
+    """whole guide tree (join loop on the GPU, tree objects + midpoint root on the host) on real distances"""
+    from prographmsa_b200 import distance, tree
+    opts = Options(mldist_flag=True, nwdist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, _ = synth.simulate_family(60, 120, mf, seed=21, indel_rate=0.03)
+    names = sorted(seqs)
+    dm = distance.DistanceFactoryAlign(mf, opts).computePwDistances(seqs, names)
+    assert tree.tree_nj(names, dm, opts.edge_halflife, joins_fn=distance.bionj_joins).newick() == tree.tree_nj(names, dm, opts.edge_halflife).newick()

@@ -1,0 +1,44 @@
+#!/usr/bin/env python3
+"""BASELINE.json configs[4]: a whole doAlign (k-mer angle distances -> BioNJ -> progressive pass -> Prealigned ML
+distances -> BioNJ -> ... , -m -F -i 2) over n synthetic 500-aa sequences with every hot path on the GPU and the Python
+host glue around it; prints where the wall time goes.
+
+  python tools/run_config5.py [n_seq=5000] [iters=2]
+"""
+import sys, os, time, hashlib
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from prographmsa_b200 import pipeline, model, synth, alphabet, tree as _tree, progressive as _prog
+from prographmsa_b200.options import Options
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+opts = Options(mldist_flag=True, aafreqs_flag=True)
+mf0 = model.getDefault(Options(mldist_flag=True))
+seqs, _ = synth.simulate_family(n, 500, mf0, seed=50, forbid_first=10)
+strs = {k: "".join(alphabet.AA_LETTERS[c] for c in v) for k, v in seqs.items()}
+
+T = {}
+def timed(label, fn):
+    def wrap(*a, **kw):
+        t0 = time.perf_counter(); r = fn(*a, **kw); T[label] = T.get(label, 0.0) + time.perf_counter() - t0; return r
+    return wrap
+
+class Backend(pipeline.GpuBackend):
+    pass
+for name, label in (("initial_distances", "k-mer angle distances (GPU)"), ("prealigned_distances", "Prealigned ML distances (GPU)"),
+                    ("batch_align", "alignGraphs batches (GPU, incl. host packing)"), ("batch_merge", "mergeGraphs profiles (GPU)"),
+                    ("nj_joins", "BioNJ join loop (GPU)")):
+    setattr(Backend, name, timed(label, getattr(pipeline.GpuBackend, name)))
+_tree.midpoint_root = timed("midpoint rooting (host Python)", _tree.midpoint_root)
+
+t0 = time.perf_counter()
+out, trees = pipeline.do_align(strs, opts, lambda mf, o: Backend(mf, o), iters=iters, return_trees=True)
+wall = time.perf_counter() - t0
+cols = len(next(iter(out.values())))
+h = hashlib.sha256("".join("%s\n%s\n" % (k, out[k]) for k in sorted(out)).encode()).hexdigest()
+print("config 5 shape: %d seqs x 500 aa, -m -F -i %d: %.1f s wall, %d trees, %d columns, sha256 %s" % (n, iters, wall, len(trees), cols, h[:16]))
+acc = 0.0
+for k, v in sorted(T.items(), key=lambda kv: -kv[1]):
+    print("  %-48s %7.2f s" % (k, v)); acc += v
+print("  %-48s %7.2f s" % ("rest: Python host glue (graphs, merge edges, trees)", wall - acc))
