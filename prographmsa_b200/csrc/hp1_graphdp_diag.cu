@@ -159,6 +159,26 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                         m = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
                         xs = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
                         w = fmaxf(m, fmaxf(xs, ys));
+                    } else if (nx.cnt == 1 && nx.idx0 == x - 1 && (ny[r].cnt & 0x7fffffff) >= 1) {
+                        // row with several (or a non-adjacent) predecessors at a chain column: X through the left neighbour
+                        // once, Y and M folded over the row's predecessors (same candidates as the general loop below)
+                        const float ex = nx.val0;
+                        const float4 cl = left[r];
+                        xs = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
+                        const int c1 = ny[r].cnt & 0x7fffffff;
+                        for (int ky = 0; ky < c1; ++ky) {
+                            const int yp = ky ? P1I[ny[r].ptr + ky] : ny[r].idx0;
+                            const float ey = ky ? P1V[ny[r].ptr + ky] : ny[r].val0;
+                            const int dyy = y - yp;
+                            float4 cu, cd;
+                            if (dyy + 1 < RING && yp >= y0) {
+                                cu = ring[((d - dyy) & (RING - 1)) * ring_pitch + (yp - y0)];          // (yp, x)
+                                cd = ring[((d - dyy - 1) & (RING - 1)) * ring_pitch + (yp - y0)];      // (yp, x-1)
+                            } else { cu = cell(yp, x, d); cd = cell(yp, x - 1, d); }
+                            ys = fmaxf(ys, __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey));
+                            m = fmaxf(m, __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex));
+                        }
+                        w = fmaxf(m, fmaxf(xs, ys));
                     } else {
                         const int c1 = ny[r].cnt & 0x7fffffff, c2 = nx.cnt & 0x7fffffff;
                         for (int ky = 0; ky < c1; ++ky) {
@@ -222,13 +242,15 @@ static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_
 
 // Long graphs: bands of GF_BAND_ROWS rows, one CTA each.  All CTAs of a launch must be resident at once (they wait on each
 // other's flags), so a launch holds at most one CTA per SM; the jobs' progress flags are zeroed by the caller.
-int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms) {
+int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows) {
     if (n_jobs == 0) return 0;
-    const int threads = GF_BAND_ROWS;
-    const int ring_pitch = GF_BAND_ROWS;
+    const int threads = band_rows;
+    const int ring_pitch = band_rows;
     const size_t smem = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * threads * sizeof(float4);
     PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<false, 1, GF_RING, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int per = std::max(1, n_sms / max_bands);               // jobs per launch
+    int per_sm = 1;
+    PGM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_fill_diag_kernel<false, 1, GF_RING, true, true>, threads, smem));
+    const int per = std::max(1, (n_sms * std::max(1, per_sm)) / max_bands);     // jobs per launch: every CTA resident
     for (int j = 0; j < n_jobs; j += per) {
         const int nj = std::min(per, n_jobs - j);
         graph_fill_diag_kernel<false, 1, GF_RING, true, true><<<nj * max_bands, threads, smem, st>>>(d_jobs, d_order + j, ring_pitch, max_bands);

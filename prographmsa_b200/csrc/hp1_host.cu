@@ -20,7 +20,7 @@ pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
 int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
 int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
-int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms);
+int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
 void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
@@ -83,7 +83,7 @@ struct JobLayout {                // byte offsets into the upload arena / scratc
     size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2, colinfo, blkstart;
     size_t S, MXYW, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev, progress;     // scratch
     size_t map1, map2, result;                           // output
-    int np1, np2, cap, pitch, nb, layout, bands;
+    int np1, np2, cap, pitch, nb, layout, bands, band_rows;
 };
 
 } // namespace
@@ -104,7 +104,7 @@ struct pgm_graph_batch {
     // Fill schedule.  The fill kernel's block size and shared memory -- hence CTAs per SM -- are set by the LARGEST job
     // of a launch, so each sub-batch is swept as a few launches of similar graph-2 length (largest first), on
     // separate streams so that a class with few jobs does not leave the GPU idle.
-    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands; };
+    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands, band_rows; };
     std::vector<int> order;                 // job indices relative to their sub-batch, grouped by FillLaunch
     std::vector<FillLaunch> fills;
     size_t scratch_bytes_used = 0;
@@ -136,6 +136,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     int force_layout = -1, diag_min_generic = 8;                  // PGM_FILL_LAYOUT=block|diag forces one kernel (tests, profiling)
     if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : -1);
     if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
+    int split_rows = 0, split_min_generic = 24;
+    if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
+    if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
     int small_batch = 3 * 148;                                    // fewer jobs than three per SM: latency-bound (measured crossover 300..440 jobs of 400 x 400)
     if (const char* e = getenv("PGM_FILL_SMALL_BATCH")) small_batch = atoi(e);
     for (int k = 0; k < n_jobs; ++k) {
@@ -169,7 +172,16 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         // on chain graphs (measured, 400 x 400 nodes alone on an SM: 0.31 ms against 0.49 ms).
         L.layout = (generic > diag_min_generic || nblk > GF_MAX_NB || n_jobs < small_batch) ? GF_LAYOUT_DIAG : GF_LAYOUT_BLOCK;
         if (force_layout >= 0 && !(force_layout == GF_LAYOUT_BLOCK && nblk > GF_MAX_NB)) L.layout = force_layout;
-        L.bands = (L.layout == GF_LAYOUT_DIAG && a.N >= GF_BAND_MIN_N1) ? (a.N - 1 + GF_BAND_ROWS - 1) / GF_BAND_ROWS : 1;
+        // Bands: graphs too long for one CTA.  Short bands for the large branchy graphs (three SMs sharing one job's rows) are
+        // wired and tested (PGM_FILL_SPLIT_ROWS) but off: measured 1.73 -> 2.8 ms on the 500-row jobs of the bench batch,
+        // the first row of a band pays an L2 round trip per anti-diagonal
+        L.band_rows = 0;
+        if (L.layout == GF_LAYOUT_DIAG) {
+            if (a.N >= GF_BAND_MIN_N1) L.band_rows = GF_BAND_ROWS;
+            else if (split_rows > 0 && generic > split_min_generic && a.N - 1 >= 2 * split_rows) L.band_rows = split_rows;
+        }
+        L.bands = L.band_rows ? (a.N - 1 + L.band_rows - 1) / L.band_rows : 1;
+        if (L.bands == 1) L.band_rows = 0;
         L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 8);
         auto take = [&](size_t& off, size_t bytes) { size_t r = off; off = align_up(off + bytes, 128); return r; };
         L.sites1 = take(in_off, sizeof(float) * n * a.N);
@@ -224,7 +236,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         const pgm_graph* gs[2] = {&g1[k], &g2[k]};
         const JobLayout& L = b->lay[k];
         GraphJobDev& J = b->jobs[k];
-        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.nb = L.nb; J.layout = L.layout; J.bands = L.bands; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
+        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.nb = L.nb; J.layout = L.layout; J.bands = L.bands; J.band_rows = L.band_rows; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
         dynprog_scores(g1[k], g2[k], models[k], *opts, J.sc);
         const float rinit = J.sc[8], rext = J.sc[9];
         float* s1 = (float*)(hin + L.sites1); float* s2 = (float*)(hin + L.sites2);
@@ -319,7 +331,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         b->order.resize(n_jobs);
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
         auto class_of = [&](const GraphJobDev& J) {
-            if (J.bands > 1) return 200;                                       // banded anti-diagonal sweep: its own launches
+            if (J.bands > 1) return J.band_rows == GF_BAND_ROWS ? 201 : 200;  // banded anti-diagonal sweeps: their own launches
             if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
             const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
         };
@@ -337,7 +349,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             size_t p = 0;
             while (p < idx.size()) {
                 const int q = class_of(b->jobs[sbr.first + idx[p]]);
-                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, b->jobs[sbr.first + idx[p]].layout, 0, 0, 0, 0, 0, 1};
+                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, b->jobs[sbr.first + idx[p]].layout, 0, 0, 0, 0, 0, 1, b->jobs[sbr.first + idx[p]].band_rows};
                 while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]]) == q) {
                     const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
                     f.max_nb = std::max(f.max_nb, J.nb); f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2);
@@ -408,7 +420,7 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
                         PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * Jq.bands, sq));
                     }
                     int n_sms = 148; cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, pgm_ctx_device(c));
-                    rc = launch_graph_fill_banded(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_bands, n_sms);
+                    rc = launch_graph_fill_banded(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_bands, n_sms, fl[q]->band_rows);
                     continue;
                 }
                 rc = fl[q]->layout == GF_LAYOUT_DIAG

@@ -142,7 +142,8 @@ struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred
 
 struct GraphJobDev {        // one alignGraphs job, all pointers into the batch's device arena
     int N1, N2;
-    int bands;                  // > 1: graph 1 is swept in bands of GF_BAND_ROWS rows by the banded anti-diagonal kernel
+    int bands;                  // > 1: graph 1 is swept in bands of band_rows rows (one CTA each) by the banded anti-diagonal kernel
+    int band_rows;
     int* progress;              // bands flags (scratch, zeroed before every sweep): anti-diagonals completed per band
     int layout;                 // cell layout of MXYW = which fill kernel sweeps the job: GF_LAYOUT_BLOCK or GF_LAYOUT_DIAG
     int nb;                     // column blocks per row (columns 0 .. N2-2 cut into blocks of <= GF_K; a non-chain node starts a block)
