@@ -48,13 +48,13 @@ static cudaEvent_t get_event(pgm_ctx* c) {
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 struct ScopedKernelTimer {
-    pgm_ctx* c; TimedSection s;
-    ScopedKernelTimer(pgm_ctx* ctx, int kind) : c(ctx) {
+    pgm_ctx* c; TimedSection s; cudaStream_t st;
+    ScopedKernelTimer(pgm_ctx* ctx, int kind, cudaStream_t on = nullptr) : c(ctx), st(on ? on : ctx->stream) {
         s.kind = kind;
-        if (c->timing_on) { s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, c->stream); }
+        if (c->timing_on) { s.a = get_event(c); s.b = get_event(c); cudaEventRecord(s.a, st); }
     }
     ~ScopedKernelTimer() {
-        if (c->timing_on) { cudaEventRecord(s.b, c->stream); c->sections.push_back(s); }
+        if (c->timing_on) { cudaEventRecord(s.b, st); c->sections.push_back(s); }
     }
 };
 static void resolve_timing(pgm_ctx* c) {
@@ -580,6 +580,7 @@ uint64_t pgm_ctx_scratch(pgm_ctx* c) { return c->scratch_bytes; }
 pgm_timing* pgm_ctx_timing(pgm_ctx* c) { return &c->timing; }
 void pgm_ctx_reset_timing(pgm_ctx* c) { reset_timing(c); }
 void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok) { *tok = new ScopedKernelTimer(c, kind); }
+void pgm_ctx_time_begin_on(pgm_ctx* c, int kind, cudaStream_t st, void** tok) { *tok = new ScopedKernelTimer(c, kind, st); }
 void pgm_ctx_time_end(pgm_ctx* c, void* tok) { (void)c; delete (ScopedKernelTimer*)tok; }
 
 // ---- buffer pool (HP-1 arenas) ----------------------------------------------------------------------

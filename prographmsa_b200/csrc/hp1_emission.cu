@@ -29,8 +29,8 @@ __device__ __forceinline__ float ls_log2_add(float x, float add) {
 
 // T = M^T g2, u, v.  grid = (ceil(maxN/128), n_jobs)
 __global__ void __launch_bounds__(128)
-emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs) {
-    const GraphJobDev& J = jobs[blockIdx.y];
+emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
+    const GraphJobDev& J = jobs[order ? order[blockIdx.y] : blockIdx.y];
     extern __shared__ float sm[];            // Mf (n*n) + pif (n)
     float* sM = sm; float* sPi = sm + n * n;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) sM[i] = J.Mf[i];
@@ -54,8 +54,8 @@ emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs) {
 
 // grid = (tiles_x, tiles_y, n_jobs), block = (32, 8)
 __global__ void __launch_bounds__(256)
-emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs) {
-    const GraphJobDev& J = jobs[blockIdx.z];
+emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
+    const GraphJobDev& J = jobs[order ? order[blockIdx.z] : blockIdx.z];
     const int N1 = J.N1, N2 = J.N2;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     if (x0 >= N2 || y0 >= N1) return;
@@ -91,23 +91,23 @@ emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs) {
     }
 }
 
-int launch_emission_prep(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int maxN) {
+int launch_emission_prep(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int maxN) {
     dim3 grid((maxN + 127) / 128, n_jobs);
-    emission_prep_kernel<<<grid, 128, sizeof(float) * (n * n + n), st>>>(n, d_jobs);
+    emission_prep_kernel<<<grid, 128, sizeof(float) * (n * n + n), st>>>(n, d_jobs, d_order);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_emission_exact(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int max_N1, int max_N2) {
+int launch_emission_exact(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2) {
     if (n_jobs == 0) return 0;
     {
-        int rc = launch_emission_prep(st, n, n_jobs, d_jobs, max_N1 > max_N2 ? max_N1 : max_N2);
+        int rc = launch_emission_prep(st, n, n_jobs, d_jobs, d_order, max_N1 > max_N2 ? max_N1 : max_N2);
         if (rc) return rc;
     }
     {
         dim3 grid((max_N2 + 31) / 32, (max_N1 + 31) / 32, n_jobs);
         const size_t smem = sizeof(float) * n * 64;
-        emission_exact_kernel<<<grid, dim3(32, 8), smem, st>>>(n, d_jobs);
+        emission_exact_kernel<<<grid, dim3(32, 8), smem, st>>>(n, d_jobs, d_order);
         PGM_CUDA(cudaGetLastError());
     }
     return 0;

@@ -331,11 +331,10 @@ struct Tracer {
 // finds with two ballots how far the run extends, and up to 32 path steps are emitted at once instead of
 // one dependent load chain per step.
 __global__ void __launch_bounds__(32)
-graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs) {
-    const int job = blockIdx.x;
+graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
     const int lane = threadIdx.x;
-    if (job >= n_jobs) return;
-    const GraphJobDev& J = jobs[job];
+    if ((int)blockIdx.x >= n_jobs) return;
+    const GraphJobDev& J = jobs[order ? order[blockIdx.x] : blockIdx.x];
     const int N1 = J.N1, N2 = J.N2, pitch = J.pitch, nb = J.nb;
     const float gap_init = J.sc[0], gap_extend = J.sc[1], end_match = J.sc[3], end_gap = J.sc[4], end_skip = J.sc[5];
     const float4* __restrict__ C = J.MXYW;
@@ -535,9 +534,9 @@ int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, co
     return 0;
 }
 
-int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs) {
+int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order) {
     if (n_jobs == 0) return 0;
-    graph_trace_kernel<<<n_jobs, 32, 0, st>>>(n_jobs, d_jobs);
+    graph_trace_kernel<<<n_jobs, 32, 0, st>>>(n_jobs, d_jobs, d_order);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -15,6 +15,7 @@ cudaStream_t pgm_ctx_stream(pgm_ctx* c);
 int pgm_ctx_device(pgm_ctx* c);
 uint64_t pgm_ctx_scratch(pgm_ctx* c);
 void pgm_ctx_time_begin(pgm_ctx* c, int kind, void** tok);
+void pgm_ctx_time_begin_on(pgm_ctx* c, int kind, cudaStream_t st, void** tok);
 void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
@@ -371,76 +372,100 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     return 0;
 }
 
+// Schedule of one sub-batch.  Every size class of the fill schedule is an independent pipeline emission -> fill ->
+// traceback on its own stream, so the few long sweeps near the root start at once and overlap the bulk's emission and
+// traceback instead of every phase waiting for the slowest job of the previous one.  PGM_GRAPH_PIPELINE=0 runs the three
+// phases one after the other over the whole sub-batch (what bench.py uses for the per-kernel breakdown).
 int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
     if (!c || !b) { pgm_set_error("NULL argument"); return PGM_ERR_ARG; }
     PGM_CUDA(cudaSetDevice(pgm_ctx_device(c)));
     cudaStream_t st = pgm_ctx_stream(c);
     pgm_ctx_reset_timing(c);
+    const char* env = getenv("PGM_GRAPH_PIPELINE");
+    const bool pipelined = !(env && atoi(env) == 0);
     const GraphJobDev* dj = b->d_jobs.as<GraphJobDev>();
     const int* d_order_all = (const int*)(b->d_jobs.as<char>() + sizeof(GraphJobDev) * b->n_jobs);
+    int n_sms = 148; cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, pgm_ctx_device(c));
     for (size_t si = 0; si < b->sub.size(); ++si) {
         const auto& sb = b->sub[si];
         const int nj = sb.second - sb.first;
-        int mx1 = 0, mx2 = 0, mxd = 0, mxn = 0, mxp = 0, mxnp = 0;
-        for (int k = sb.first; k < sb.second; ++k) {
-            mx1 = std::max(mx1, b->jobs[k].N1); mx2 = std::max(mx2, b->jobs[k].N2);
-            mxd = std::max(mxd, std::min(b->jobs[k].N1, b->jobs[k].N2));
-            mxn = std::max(mxn, b->jobs[k].N1 + b->jobs[k].N2); mxp = std::max(mxp, b->jobs[k].pitch);
-            mxnp = std::max(mxnp, b->jobs[k].np1 + b->jobs[k].np2);
-        }
-        int rc; void* tok;
-        pgm_ctx_time_begin(c, 3, &tok);
-        if (b->emission_mode == PGM_EMISSION_TENSOR) rc = launch_emission_tensor(st, b->n_states, nj, dj + sb.first, b->jobs.data() + sb.first);
-        else rc = launch_emission_exact(st, b->n_states, nj, dj + sb.first, mx1, mx2);
-        pgm_ctx_time_end(c, tok);
-        if (rc) return rc;
-        pgm_ctx_time_begin(c, 4, &tok);
-        (void)mxd; (void)mxn; (void)mxp; (void)mxnp;
-        {   // one launch per size class; the first on the main stream, the others forked onto side streams and joined
-            std::vector<const pgm_graph_batch::FillLaunch*> fl;
-            for (auto& f : b->fills) if (f.sub == (int)si) fl.push_back(&f);
-            rc = 0;
-            SideStreams& ss = side_streams(pgm_ctx_device(c));
-            const size_t n_side = fl.size() > 1 ? std::min<size_t>(fl.size() - 1, 15) : 0;   // every class on its own stream: a long sweep must not queue behind another
-            if (n_side) {
-                if (!ss.fork) PGM_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
-                while (ss.streams.size() < n_side) {
-                    cudaStream_t s2; PGM_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking)); ss.streams.push_back(s2);
-                    cudaEvent_t e2; PGM_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); ss.join.push_back(e2);
+        int mx1 = 0, mx2 = 0;
+        for (int k = sb.first; k < sb.second; ++k) { mx1 = std::max(mx1, b->jobs[k].N1); mx2 = std::max(mx2, b->jobs[k].N2); }
+        std::vector<const pgm_graph_batch::FillLaunch*> fl;
+        for (auto& f : b->fills) if (f.sub == (int)si) fl.push_back(&f);
+        int rc = 0; void* tok;
+        auto emit = [&](cudaStream_t sq, int count, const int* ord, int m1, int m2) {
+            return b->emission_mode == PGM_EMISSION_TENSOR ? launch_emission_tensor(sq, b->n_states, count, dj + sb.first, ord, m1, m2)
+                                                           : launch_emission_exact(sq, b->n_states, count, dj + sb.first, ord, m1, m2);
+        };
+        auto fill = [&](cudaStream_t sq, const pgm_graph_batch::FillLaunch* f) -> int {
+            const int* ord = d_order_all + sb.first + f->offset;
+            if (f->max_bands > 1) {
+                for (int jq = 0; jq < f->count; ++jq) {             // zero the bands' progress flags
+                    const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + f->offset + jq]];
+                    PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * Jq.bands, sq));
                 }
-                PGM_CUDA(cudaEventRecord(ss.fork, st));
-                for (size_t q = 0; q < n_side; ++q) PGM_CUDA(cudaStreamWaitEvent(ss.streams[q], ss.fork, 0));
+                return launch_graph_fill_banded(sq, f->count, dj + sb.first, ord, f->max_bands, n_sms, f->band_rows);
             }
-            for (size_t q = 0; q < fl.size() && !rc; ++q) {
-                cudaStream_t sq = (q == 0 || !n_side) ? st : ss.streams[(q - 1) % n_side];
-                const int* ord = d_order_all + sb.first + fl[q]->offset;
-                if (fl[q]->max_bands > 1) {
-                    for (int jq = 0; jq < fl[q]->count; ++jq) {         // zero the bands' progress flags
-                        const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + fl[q]->offset + jq]];
-                        PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * Jq.bands, sq));
-                    }
-                    int n_sms = 148; cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, pgm_ctx_device(c));
-                    rc = launch_graph_fill_banded(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_bands, n_sms, fl[q]->band_rows);
-                    continue;
-                }
-                rc = fl[q]->layout == GF_LAYOUT_DIAG
-                         ? launch_graph_fill_diag(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_n1, fl[q]->max_n2, fl[q]->max_np)
-                         : launch_graph_fill(sq, fl[q]->count, dj + sb.first, ord, fl[q]->max_nb, fl[q]->max_n2, fl[q]->max_np2);
+            return f->layout == GF_LAYOUT_DIAG ? launch_graph_fill_diag(sq, f->count, dj + sb.first, ord, f->max_n1, f->max_n2, f->max_np)
+                                               : launch_graph_fill(sq, f->count, dj + sb.first, ord, f->max_nb, f->max_n2, f->max_np2);
+        };
+        // side streams: the first class stays on the main stream, the others fork from it and are joined at the end
+        SideStreams& ss = side_streams(pgm_ctx_device(c));
+        const size_t n_side = fl.size() > 1 ? std::min<size_t>(fl.size(), 16) : 0;
+        auto fork = [&]() -> int {
+            if (!n_side) return 0;
+            if (!ss.fork) PGM_CUDA(cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming));
+            while (ss.streams.size() < n_side) {
+                // classes are ordered longest sweep first: earlier side streams get the higher priority, so the long sweeps' CTAs
+                // are placed before the bulk's whenever an SM frees up
+                int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+                const int prio = std::min(lo, hi + (int)ss.streams.size());
+                cudaStream_t s2; PGM_CUDA(cudaStreamCreateWithPriority(&s2, cudaStreamNonBlocking, prio)); ss.streams.push_back(s2);
+                cudaEvent_t e2; PGM_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); ss.join.push_back(e2);
             }
+            PGM_CUDA(cudaEventRecord(ss.fork, st));
+            for (size_t q = 0; q < n_side; ++q) PGM_CUDA(cudaStreamWaitEvent(ss.streams[q], ss.fork, 0));
+            return 0;
+        };
+        auto join = [&]() -> int {
             for (size_t q = 0; q < n_side; ++q) {
                 PGM_CUDA(cudaEventRecord(ss.join[q], ss.streams[q]));
                 PGM_CUDA(cudaStreamWaitEvent(st, ss.join[q], 0));
             }
-            // the timing sections count one launch each; the emission section holds two kernels, the fill section one per class
-            pgm_ctx_timing(c)->emission_launches += 1;
-            pgm_ctx_timing(c)->graph_fill_launches += (uint32_t)(fl.size() ? fl.size() - 1 : 0);
+            return 0;
+        };
+        auto stream_of = [&](size_t q) { return !n_side ? st : ss.streams[q % n_side]; };
+        if (pipelined) {
+            if ((rc = fork())) return rc;
+            for (size_t q = 0; q < fl.size() && !rc; ++q) {
+                cudaStream_t sq = stream_of(q);
+                const int* ord = d_order_all + sb.first + fl[q]->offset;
+                pgm_ctx_time_begin_on(c, 3, sq, &tok); rc = emit(sq, fl[q]->count, ord, fl[q]->max_n1, fl[q]->max_n2); pgm_ctx_time_end(c, tok);
+                if (rc) break;
+                pgm_ctx_time_begin_on(c, 4, sq, &tok); rc = fill(sq, fl[q]); pgm_ctx_time_end(c, tok);
+                if (rc) break;
+                pgm_ctx_time_begin_on(c, 5, sq, &tok); rc = launch_graph_trace(sq, fl[q]->count, dj + sb.first, ord); pgm_ctx_time_end(c, tok);
+            }
+            if (rc) return rc;
+            if ((rc = join())) return rc;
+        } else {
+            pgm_ctx_time_begin(c, 3, &tok);
+            rc = emit(st, nj, nullptr, mx1, mx2);
+            pgm_ctx_time_end(c, tok);
+            if (rc) return rc;
+            pgm_ctx_time_begin(c, 4, &tok);
+            if (!(rc = fork())) {
+                for (size_t q = 0; q < fl.size() && !rc; ++q) rc = fill(stream_of(q), fl[q]);
+                if (!rc) rc = join();
+            }
+            pgm_ctx_time_end(c, tok);
+            if (rc) return rc;
+            pgm_ctx_time_begin(c, 5, &tok);
+            rc = launch_graph_trace(st, nj, dj + sb.first, nullptr);
+            pgm_ctx_time_end(c, tok);
+            if (rc) return rc;
         }
-        pgm_ctx_time_end(c, tok);
-        if (rc) return rc;
-        pgm_ctx_time_begin(c, 5, &tok);
-        rc = launch_graph_trace(st, nj, dj + sb.first);
-        pgm_ctx_time_end(c, tok);
-        if (rc) return rc;
     }
     pgm_timing* t = pgm_ctx_timing(c);
     t->graph_cell_updates += b->total_updates;
@@ -508,8 +533,8 @@ int pgm_emission_scores(pgm_ctx* c, int n, const pgm_graph* g1, const pgm_graph*
     cudaStream_t st = pgm_ctx_stream(c);
     b->jobs[0].sc[2] = match_init;
     cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(GraphJobDev), cudaMemcpyHostToDevice, st);
-    if (emission_mode == PGM_EMISSION_TENSOR) rc = launch_emission_tensor(st, n, 1, b->d_jobs.as<GraphJobDev>(), b->jobs.data());
-    else rc = launch_emission_exact(st, n, 1, b->d_jobs.as<GraphJobDev>(), g1->N, g2->N);
+    if (emission_mode == PGM_EMISSION_TENSOR) rc = launch_emission_tensor(st, n, 1, b->d_jobs.as<GraphJobDev>(), nullptr, g1->N, g2->N);
+    else rc = launch_emission_exact(st, n, 1, b->d_jobs.as<GraphJobDev>(), nullptr, g1->N, g2->N);
     if (!rc) {
         const GraphJobDev& J = b->jobs[0];
         std::vector<float> sk((size_t)J.N1 * J.ldS);

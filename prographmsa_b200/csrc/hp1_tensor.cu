@@ -95,8 +95,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 //   block (tile, job): tiles [0, tiles_y) are A tiles (graph 1 rows), the rest B tiles (graph 2 columns)
 template <int KP>
 __global__ void __launch_bounds__(ET_M)
-emission_images_kernel(int n, int tiles_y, int tiles_x, const GraphJobDev* __restrict__ jobs) {
-    const GraphJobDev& J = jobs[blockIdx.y];
+emission_images_kernel(int n, int tiles_y, int tiles_x, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
+    const GraphJobDev& J = jobs[order ? order[blockIdx.y] : blockIdx.y];
     extern __shared__ float sm[];                     // Mf (n*n) + pif (n)
     float* sM = sm; float* sPi = sm + n * n;
     for (int i = threadIdx.x; i < n * n; i += blockDim.x) sM[i] = J.Mf[i];
@@ -145,8 +145,8 @@ emission_images_kernel(int n, int tiles_y, int tiles_x, const GraphJobDev* __res
 #define ETP_THREADS 192
 template <int KP, int BST>
 __global__ void __launch_bounds__(ETP_THREADS)
-emission_tensor_kernel(int tiles_y, const GraphJobDev* __restrict__ jobs) {
-    const GraphJobDev& J = jobs[blockIdx.y];
+emission_tensor_kernel(int tiles_y, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
+    const GraphJobDev& J = jobs[order ? order[blockIdx.y] : blockIdx.y];
     const int N1 = J.N1, N2 = J.N2;
     const int y0 = blockIdx.x * ET_M;
     if (y0 >= N1) return;
@@ -272,29 +272,28 @@ emission_tensor_kernel(int tiles_y, const GraphJobDev* __restrict__ jobs) {
 }
 
 template <int KP, int BST>
-static int launch_t(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, int tiles_x, int tiles_y) {
+static int launch_t(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int tiles_x, int tiles_y) {
     {
         dim3 grid(tiles_y + tiles_x, n_jobs);
-        emission_images_kernel<KP><<<grid, ET_M, sizeof(float) * (n * n + n), st>>>(n, tiles_y, tiles_x, d_jobs);
+        emission_images_kernel<KP><<<grid, ET_M, sizeof(float) * (n * n + n), st>>>(n, tiles_y, tiles_x, d_jobs, d_order);
         PGM_CUDA(cudaGetLastError());
     }
     const size_t smem = (size_t)(1 + BST) * ET_M * KP * 4;
     PGM_CUDA(cudaFuncSetAttribute(emission_tensor_kernel<KP, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid(tiles_y, n_jobs);
-    emission_tensor_kernel<KP, BST><<<grid, ETP_THREADS, smem, st>>>(tiles_y, d_jobs);
+    emission_tensor_kernel<KP, BST><<<grid, ETP_THREADS, smem, st>>>(tiles_y, d_jobs, d_order);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
 
-int launch_emission_tensor(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, const GraphJobDev* h_jobs) {
+// d_order: optional list of the n_jobs job indices (relative to d_jobs) this launch covers; mx1 / mx2: their largest graphs
+int launch_emission_tensor(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int mx1, int mx2) {
     if (n_jobs == 0) return 0;
-    int mx1 = 0, mx2 = 0;
-    for (int k = 0; k < n_jobs; ++k) { mx1 = mx1 > h_jobs[k].N1 ? mx1 : h_jobs[k].N1; mx2 = mx2 > h_jobs[k].N2 ? mx2 : h_jobs[k].N2; }
     const int tiles_y = (mx1 + ET_M - 1) / ET_M, tiles_x = (mx2 + ET_N - 1) / ET_N;
     const int kp = (3 * n + 7) & ~7;
-    if (kp <= 16) return launch_t<16, 2>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
-    if (kp <= 64) return launch_t<64, 2>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
-    if (kp <= 184) return launch_t<184, 1>(st, n, n_jobs, d_jobs, tiles_x, tiles_y);
+    if (kp <= 16) return launch_t<16, 2>(st, n, n_jobs, d_jobs, d_order, tiles_x, tiles_y);
+    if (kp <= 64) return launch_t<64, 2>(st, n, n_jobs, d_jobs, d_order, tiles_x, tiles_y);
+    if (kp <= 184) return launch_t<184, 1>(st, n, n_jobs, d_jobs, d_order, tiles_x, tiles_y);
     pgm_set_error("tensor emission supports n_states <= 61");
     return PGM_ERR_ARG;
 }

@@ -191,6 +191,6 @@ __device__ __forceinline__ float dot_gemv_order(const float* __restrict__ g, con
 }
 #endif
 
-int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, int max_N1, int max_N2);
-int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const GraphJobDev* h_jobs);
-int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs);
+int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2);
+int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2);
+int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
