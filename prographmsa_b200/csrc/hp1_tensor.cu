@@ -109,31 +109,44 @@ emission_images_kernel(int n, int tiles_y, int tiles_x, const GraphJobDev* __res
     if (tile * ET_M >= N) return;
     const int node = tile * ET_M + r;
     char* img = (char*)(isA ? J.Aimg : J.Bimg) + (size_t)tile * ET_M * KP * 4;
-    float vals[64];                                   // n <= 61
-    if (node < N) {
-        const float* g = (isA ? J.sites1 : J.sites2) + (size_t)n * node;
-        if (isA) {
-            for (int a = 0; a < n; ++a) vals[a] = g[a];
-            J.u[node] = dot_gemv_order(g, sPi, n);
-        } else {
-            for (int a = 0; a < n; ++a) {             // T(a,x) = sum_b M(b,a) g2(b,x)
-                float s = 0.f;
-                for (int b = 0; b < n; ++b) s = __fadd_rn(s, __fmul_rn(sM[b * n + a], g[b]));
-                vals[a] = s;
+    // The node's profile column sits in registers (NMAX = KP / 3 >= n is a compile-time bound, loops are unrolled and
+    // guarded by n), so T = M^T g runs as n independent sequential-k chains the scheduler can interleave.
+    constexpr int NMAX = KP / 3;
+    float g[NMAX];
+    const float* gp = (isA ? J.sites1 : J.sites2) + (size_t)n * node;
+#pragma unroll
+    for (int a = 0; a < NMAX; ++a) g[a] = (node < N && a < n) ? gp[a] : 0.f;
+    if (node < N) {                                   // g^T pi in Eigen's gemv order (see dot_gemv_order in internal.h)
+        float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+        const int n4 = n & ~3;
+#pragma unroll
+        for (int k = 0; k + 3 < NMAX; k += 4)
+            if (k < n4) {
+                l0 = __fadd_rn(l0, __fmul_rn(g[k], sPi[k])); l1 = __fadd_rn(l1, __fmul_rn(g[k + 1], sPi[k + 1]));
+                l2 = __fadd_rn(l2, __fmul_rn(g[k + 2], sPi[k + 2])); l3 = __fadd_rn(l3, __fmul_rn(g[k + 3], sPi[k + 3]));
             }
-            J.v[node] = dot_gemv_order(g, sPi, n);
-        }
-    } else {
-        for (int a = 0; a < n; ++a) vals[a] = 0.f;
+        float sd = __fadd_rn(__fadd_rn(l0, l2), __fadd_rn(l1, l3));
+#pragma unroll
+        for (int k = 0; k < NMAX; ++k) if (k >= n4 && k < n) sd = __fadd_rn(sd, __fmul_rn(g[k], sPi[k]));
+        if (isA) J.u[node] = sd; else J.v[node] = sd;
     }
-    for (int a = 0; a < n; ++a) {
-        const float v = vals[a];
-        const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
-        const float lo = __fsub_rn(v, hi);
-        // A' = [hi | hi | lo],  B' = [hi ; lo ; hi]
-        *(float*)(img + op_offset(r, a, ET_M)) = hi;
-        *(float*)(img + op_offset(r, n + a, ET_M)) = isA ? hi : lo;
-        *(float*)(img + op_offset(r, 2 * n + a, ET_M)) = isA ? lo : hi;
+#pragma unroll
+    for (int a = 0; a < NMAX; ++a) {
+        if (a < n) {
+            float v = g[a];
+            if (!isA) {                               // T(a,x) = sum_b M(b,a) g2(b,x), sequentially in b
+                float sacc = 0.f;
+#pragma unroll
+                for (int bb = 0; bb < NMAX; ++bb) if (bb < n) sacc = __fadd_rn(sacc, __fmul_rn(sM[bb * n + a], g[bb]));
+                v = sacc;
+            }
+            const float hi = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            const float lo = __fsub_rn(v, hi);
+            // A' = [hi | hi | lo],  B' = [hi ; lo ; hi]
+            *(float*)(img + op_offset(r, a, ET_M)) = hi;
+            *(float*)(img + op_offset(r, n + a, ET_M)) = isA ? hi : lo;
+            *(float*)(img + op_offset(r, 2 * n + a, ET_M)) = isA ? lo : hi;
+        }
     }
     for (int k = 3 * n; k < KP; ++k) *(float*)(img + op_offset(r, k, ET_M)) = 0.f;
 }
