@@ -35,6 +35,9 @@ struct pgm_ctx {
     std::vector<NwTask> h_tasks, h_ftasks; std::vector<int8_t> h_tab8;
     DevBuf d_off, d_codes, d_descs, d_tasks, d_ftasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
            d_counts, d_scores, d_misc, d_rows, d_seqlen;
+    DevBuf d_tb2, d_list2;                          // second traceback / list set: chunk k+1's forward overlaps chunk k's walk + ML
+    cudaStream_t stream2 = nullptr;                 // walk + ML of the chunk pipeline
+    cudaEvent_t ev_fwd[2] = {nullptr, nullptr}, ev_wm[2] = {nullptr, nullptr};
     HostPinned h_stage;
     // buffer pool for HP-1 batches: cudaMalloc / cudaMallocHost of GB-sized arenas per call would dominate e2e
     std::vector<DevBuf> pool_dev; std::vector<HostPinned> pool_host;
@@ -110,7 +113,9 @@ void pgm_destroy(pgm_ctx* c) {
     resolve_timing(c);
     for (DevBuf* b : {&c->d_model, &c->d_off, &c->d_ftasks, &c->d_codes, &c->d_descs, &c->d_tasks, &c->d_tab, &c->d_tb, &c->d_colbuf, &c->d_list,
                       &c->d_list_len, &c->d_gaps, &c->d_dist, &c->d_var, &c->d_counts, &c->d_scores, &c->d_misc, &c->d_rows,
-                      &c->d_seqlen}) b->release();
+                      &c->d_seqlen, &c->d_tb2, &c->d_list2}) b->release();
+    if (c->stream2) cudaStreamDestroy(c->stream2);
+    for (int k = 0; k < 2; ++k) { if (c->ev_fwd[k]) cudaEventDestroy(c->ev_fwd[k]); if (c->ev_wm[k]) cudaEventDestroy(c->ev_wm[k]); }
     c->h_stage.release();
     for (auto& b : c->pool_dev) b.release();
     for (auto& b : c->pool_host) b.release();
@@ -240,7 +245,25 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     const int u16_bias = 16 * (std::abs(go) + std::abs(ge)) + 64;
     const bool u16_table_ok = (4 * smin + 3 + 2 * u16_h >= 0) && go <= 0 && ge <= 0 && !c->force_nw32;
     // tasks = up to 32 consecutive pairs of one row; chunks = runs of tasks that fit the traceback budget
-    const uint64_t tb_budget_words = std::max<uint64_t>(c->scratch_bytes / 4, 1u << 20);
+    // Chunks can also be the unit of a forward | walk + ML pipeline (two traceback sets, two streams; PGM_NW_PIPELINE=<chunks>).
+    // It is wired, bit-identical and OFF by default: on the 500 x 400 matrix 2 / 4 / 8 chunks took 8.2 / 8.9 / 9.9 ms against
+    // 7.5 ms in one chunk -- the walk's warps take issue slots from the issue-bound forward kernel and its random reads
+    // queue behind the forward kernel's traceback stream (walk 0.7 -> 2.8-3.9 ms when overlapped).
+    uint64_t tb_budget_words = std::max<uint64_t>(c->scratch_bytes / 4, 1u << 20);
+    bool pipeline_chunks = false;
+    {
+        double est_cells = 0;                                            // pairs * (mean length + 1)^2
+        const double mean_len = N > 0 ? (double)offsets[N] / N : 0.0;
+        est_cells = (double)np * (mean_len + 1.0) * (mean_len + 1.0);
+        const double est_tb_bytes = est_cells * 0.36;                    // packed traceback, 16-bit flavour: ~0.34 B per cell
+        const char* e = getenv("PGM_NW_PIPELINE");
+        const int want = (e && atoi(e) > 1) ? atoi(e) : 1;
+        if (want >= 2) {
+            pipeline_chunks = true;
+            const uint64_t per = (uint64_t)(est_tb_bytes / want / 4.0) + (1u << 20);
+            tb_budget_words = std::max<uint64_t>(std::min<uint64_t>(per, c->scratch_bytes / 8), 1u << 20);   // two sets share the budget
+        }
+    }
     std::vector<NwTask>& tasks = c->h_tasks;
     std::vector<size_t> chunk_end;                      // task index where each chunk ends
     std::vector<uint64_t> chunk_tb, chunk_list, chunk_cells;
@@ -347,34 +370,60 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
 
     if ((rc = c->d_tb.reserve(max_tb * 4))) return rc;
     if ((rc = c->d_list.reserve(max_list * 2))) return rc;
+    pipeline_chunks = pipeline_chunks && chunk_end.size() >= 2;
+    if (pipeline_chunks) {
+        if ((rc = c->d_tb2.reserve(max_tb * 4))) return rc;
+        if ((rc = c->d_list2.reserve(max_list * 2))) return rc;
+        if (!c->stream2) {
+            PGM_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+            for (int k = 0; k < 2; ++k) {
+                PGM_CUDA(cudaEventCreateWithFlags(&c->ev_fwd[k], cudaEventDisableTiming));
+                PGM_CUDA(cudaEventCreateWithFlags(&c->ev_wm[k], cudaEventDisableTiming));
+            }
+        }
+    }
     if ((rc = c->d_colbuf.reserve(max_bands > 1 ? max_tasks * 8 * 2 * colstride * 4 : 256))) return rc;
     PGM_CUDA(cudaMemcpyAsync(c->d_tasks.p, tasks.data(), tasks.size() * sizeof(NwTask), cudaMemcpyHostToDevice, c->stream));
     size_t t0 = 0;
     for (size_t k = 0; k < chunk_end.size(); ++k) {
         const int ntasks = (int)(chunk_end[k] - t0);
         const NwTask* dt = c->d_tasks.as<NwTask>() + t0;
+        const int set = pipeline_chunks ? (int)(k & 1) : 0;
+        uint32_t* tb = (set ? c->d_tb2 : c->d_tb).as<uint32_t>();
+        uint16_t* list = (set ? c->d_list2 : c->d_list).as<uint16_t>();
+        cudaStream_t s_wm = pipeline_chunks ? c->stream2 : c->stream;
+        if (pipeline_chunks && k >= 2) PGM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_wm[set], 0));   // the set's previous walk + ML are done
         {
             ScopedKernelTimer t(c, K_NW_FWD);
             rc = launch_nw_forward(c->stream, ntasks, n, max_bands, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tab.as<int8_t>(),
-                                   go, ge, c->d_tb.as<uint32_t>(), c->d_colbuf.as<int32_t>(), colstride, d_scores, u16_h, u16_bias,
+                                   go, ge, tb, c->d_colbuf.as<int32_t>(), colstride, d_scores, u16_h, u16_bias,
                                    u16_max_rows);
             if (rc) return rc;
         }
+        if (pipeline_chunks) {
+            PGM_CUDA(cudaEventRecord(c->ev_fwd[set], c->stream));
+            PGM_CUDA(cudaStreamWaitEvent(s_wm, c->ev_fwd[set], 0));
+        }
         {
-            ScopedKernelTimer t(c, K_NW_WALK);
-            rc = launch_nw_walk(c->stream, ntasks, n, d_codes, c->d_off.as<uint32_t>(), dt, c->d_tb.as<uint32_t>(),
-                                c->d_list.as<uint16_t>(), c->d_list_len.as<uint32_t>(), d_gaps, d_err, walk_lanes);
+            ScopedKernelTimer t(c, K_NW_WALK, s_wm);
+            rc = launch_nw_walk(s_wm, ntasks, n, d_codes, c->d_off.as<uint32_t>(), dt, tb,
+                                list, c->d_list_len.as<uint32_t>(), d_gaps, d_err, walk_lanes);
             if (rc) return rc;
         }
         {
-            ScopedKernelTimer t(c, K_ML);
-            rc = launch_ml_from_lists(c->stream, ml, ntasks, c->d_off.as<uint32_t>(), dt, c->d_list.as<uint16_t>(),
+            ScopedKernelTimer t(c, K_ML, s_wm);
+            rc = launch_ml_from_lists(s_wm, ml, ntasks, c->d_off.as<uint32_t>(), dt, list,
                                       c->d_list_len.as<uint32_t>(), d_gaps, d_dist, d_var, d_counts, d_evals, (int)task_pairs);
             if (rc) return rc;
         }
+        if (pipeline_chunks) PGM_CUDA(cudaEventRecord(c->ev_wm[set], s_wm));
         c->timing.nw_cells += chunk_cells[k];
         c->timing.tb_bytes += chunk_tb[k] * 4;
         t0 = chunk_end[k];
+    }
+    if (pipeline_chunks) {                                               // join: the main stream continues after the last walk + ML
+        PGM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_wm[0], 0));
+        PGM_CUDA(cudaStreamWaitEvent(c->stream, c->ev_wm[1], 0));
     }
     // error flag + evaluation counter come back with the sync of whoever consumes the results
     struct { int err; int pad[3]; unsigned long long evals; } h;
