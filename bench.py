@@ -295,6 +295,54 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
     return out
 
 
+def other_kernels_bench(ctx, torch, lib, prm, acc, steps, pk, seqs, names):
+    """SURVEY.md section 8d's remaining rooflines (N = 1 only): the ML kernel against the FP64 FMA rate measured in this
+    run, and the Prealigned front-end (MSA column scan) against HBM."""
+    from prographmsa_b200 import _lib
+    out = {}
+    tf = C.c_double(0.0)
+    _lib.check(lib.pgm_probe_fp64(ctx.handle, C.byref(tf)))
+    n = 20
+    evals = acc["ml_evaluations"] / steps
+    ml_ms = acc["ml_ms"] / steps
+    alg_flop = evals * (6.0 * n ** 3 + 10.0 * n ** 2)                   # dense-algorithm flops per likelihood evaluation (section 8d)
+    out["ml_kernel"] = dict(bound="fp64", kernel="ml_kernel", evaluations_per_step=evals, launch_ms=ml_ms,
+                            achieved=alg_flop / ml_ms / 1e9, peak=tf.value, unit="TFLOP/s (FP64)", frac=alg_flop / ml_ms / 1e9 / tf.value,
+                            peak_source="pgm_probe_fp64: 8 independent DFMA chains per thread, measured in this run",
+                            note="algorithmic flops = (6 n^3 + 10 n^2) per Newton evaluation; the kernel itself runs nnz * 3n FMA per evaluation "
+                                 "(sparse counts) and is shared-memory-bound (DESIGN.md section 4)")
+    # Prealigned: a pseudo-alignment of the bench family (gap columns inserted at random), all pairs, device-resident
+    rng = np.random.default_rng(3)
+    L_aln = int(max(len(seqs[k]) for k in names) * 1.6) & ~15
+    rows = np.full((len(names), L_aln), 255, dtype=np.uint8)
+    for r, k in enumerate(names):
+        pos = np.sort(rng.choice(L_aln, size=len(seqs[k]), replace=False))
+        rows[r, pos] = seqs[k]
+    N = len(names); P = N * (N - 1) // 2
+    d_rows = torch.from_numpy(rows).cuda()
+    d_out = torch.zeros(2, P, dtype=torch.float64, device="cuda")
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    def step():
+        _lib.check(lib.pgm_prealigned_ml_pair_range_dev(ctx.handle, C.byref(prm), vp(d_rows), N, L_aln, C.c_int64(0), C.c_int64(P),
+                                                        vp(d_out[0]), vp(d_out[1]), None, None))
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record(); torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    alg = 2.0 * L_aln * P                                                # bytes if both rows of every pair are read once
+    out["prealigned"] = dict(bound="hbm", kernel="ml_kernel<FRONT_ROWS> (column scan + Newton)", workload="%d rows x %d columns, %d pairs" % (N, L_aln, P),
+                             ms_per_matrix=ms, pairs_per_s=P / ms * 1e3, achieved=alg / ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
+                             frac=alg / ms / 1e6 / pk["hbm_gbs"],
+                             note="algorithmic bytes = 2 L_aln per pair (section 8d, rows re-read per pair); the rows (%.1f MB) stay in L2, so this "
+                                  "is a fraction of HBM peak reached out of L2, and the time includes the Newton iterations" % (rows.nbytes / 1e6))
+    return out
+
+
 def run_ours(args):
     import torch
     from prographmsa_b200 import _lib, alphabet, distance, sharding
@@ -437,6 +485,10 @@ def run_ours(args):
         )
         if world == 1:
             line["cpu_baseline"] = cpu_baseline(opts, mf, seqs, names)
+            try:
+                line["other_kernels"] = other_kernels_bench(ctx, torch, lib, prm, acc, args.steps, pk, seqs, names)
+            except Exception as e:
+                line["other_kernels"] = dict(error=repr(e))
             try:
                 line["graph_dp"] = graph_dp_bench(ctx, torch, max(3, args.steps // 2), 3, pk)
             except Exception as e:                                            # never lose the headline line

@@ -229,6 +229,10 @@ int pgm_bionj_joins(pgm_ctx* ctx, int N, const double* D, const double* V,
                     int32_t* join_i1, int32_t* join_i2, double* join_d1, double* join_d2 /* N-3 each */,
                     double* D_rest /* min(N,3)^2 */, int* rest_dim);
 
+/* Measurement helper (bench.py): FP64 FMA throughput of the device in TFLOP/s, measured in place -- the roofline
+ * of the ML-distance kernel.                                                               */
+int pgm_probe_fp64(pgm_ctx* ctx, double* tflops);
+
 /* ---- native HOST glue around the graph DP (csrc/host_graph.cpp; no GPU work, callable without a device) -------
  * What the reference does in C++ between two alignGraphs calls, on the same CSR arrays as pgm_graph:
  * CleanedGraph (CleanedGraph.h:38-146), the node plan of mergeGraphs (GraphAlign.h:569-620) and its edge

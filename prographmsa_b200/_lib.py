@@ -67,7 +67,7 @@ SYMBOLS = [
     "pgm_ml_distances", "pgm_angle_all_pairs",
     "pgm_align_graphs_batch", "pgm_graph_batch_create", "pgm_graph_batch_run", "pgm_graph_batch_fetch",
     "pgm_graph_batch_destroy", "pgm_dynprog_scores", "pgm_emission_scores",
-    "pgm_host_clean_graph", "pgm_host_merge_plan", "pgm_host_merge_edges", "pgm_bionj_joins",
+    "pgm_host_clean_graph", "pgm_host_merge_plan", "pgm_host_merge_edges", "pgm_bionj_joins", "pgm_probe_fp64",
 ]
 
 
