@@ -187,7 +187,7 @@ def run_reference_arm(args):
                     config=dict(workload=WORKLOAD), impl="reference",
                     cpu_baseline=dict(value=val, unit=UNIT, cores=1, kind="port", sample="oracle port, first 24 sequences"),
                     e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-        print(json.dumps(line)); return
+        emit(line); return
     for _ in range(args.warmup):
         _run_ref_instances(seqs, names, groups())
     tot_wall = tot_cells = 0.0
@@ -203,7 +203,7 @@ def run_reference_arm(args):
                 dtype="int32+f64", data="synthetic", config=dict(workload=WORKLOAD, sample=sample), impl="reference",
                 cpu_baseline=dict(value=val, unit=UNIT, cores=inst, kind="reference", sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -493,13 +493,31 @@ def run_ours(args):
                 line["graph_dp"] = graph_dp_bench(ctx, torch, max(3, args.steps // 2), 3, pk)
             except Exception as e:                                            # never lose the headline line
                 line["graph_dp"] = dict(error=repr(e))
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line, on the real stdout"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    # Libraries (NCCL's version banner, torch.distributed warnings) write to file descriptor 1; the driver wants exactly one
+    # JSON line there.  Everything else is sent to stderr for the lifetime of the process.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
