@@ -62,11 +62,3 @@ os.environ.pop("PGM_FILL_LAYOUT", None)
 for th in (2, 4, 6, 8, 12, 16, 30):
     os.environ["PGM_FILL_DIAG_MIN"] = str(th)
     run(idx, "all, diag if > %d non-chain" % th)
-sys.exit(0)
-run([i for i in idx if info[i][0] == 0 and info[i][1] == 0], "pure chain x chain")
-run([i for i in idx if 0 < max(info[i][0], info[i][1]) <= 8], "1..8 non-chain nodes")
-run([i for i in idx if 8 < max(info[i][0], info[i][1]) <= 30], "9..30 non-chain nodes")
-run([i for i in idx if max(info[i][0], info[i][1]) > 30], ">30 non-chain nodes")
-big = sorted(idx, key=lambda i: -info[i][2] * info[i][3])[:4]
-for i in big:
-    run([i], "single job N1 %d N2 %d nc %d/%d" % (info[i][2], info[i][3], info[i][0], info[i][1]))
