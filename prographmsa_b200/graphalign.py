@@ -74,12 +74,14 @@ class GraphBatch:
         if rc == -4:
             raise RuntimeError("backtracking failed")
         _lib.check(rc)
+        buf64 = buf.astype(np.int64)                                         # one widening pass; the per-job mappings are views
         res = []
         for k in range(self.n_jobs):
-            ln = out[k].length; o = int(offs[k])
-            res.append(dict(score=float(out[k].score), n_tr_indels=int(out[k].n_tr_indels),
-                            mapping1=buf[0, o:o + ln].astype(np.int64), mapping2=buf[1, o:o + ln].astype(np.int64),
-                            cell_updates=int(out[k].cell_updates)))
+            a = out[k]
+            ln = a.length; o = int(offs[k])
+            res.append(dict(score=float(a.score), n_tr_indels=int(a.n_tr_indels),
+                            mapping1=buf64[0, o:o + ln], mapping2=buf64[1, o:o + ln],
+                            cell_updates=int(a.cell_updates)))
         return res
 
     def close(self):
