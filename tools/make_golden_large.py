@@ -10,6 +10,7 @@ import hashlib, json, os, subprocess, sys, tempfile, time
 
 ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 from prographmsa_b200 import alphabet, model, synth
 from prographmsa_b200.options import Options
 
