@@ -75,19 +75,14 @@ def do_align(seq_strings, opts: Options, backend_factory, alphabet=_alpha.AA, it
 
     out = {}
     for k in tree.leaf_order():
-        row = result.aligned[k]
+        row = np.asarray(result.aligned[k])
         orig = seq_strings[k]
-        text, j = [], 0
-        if any_stripped:                                            # re-insert the start residue column (main.cpp:455-463)
-            if stripped[k]:
-                text.append(orig[0]); j = 1
-            else:
-                text.append("-")
-        for c in row:
-            if c == GAP:
-                text.append("-")
-            else:
-                text.append(orig[j]); j += 1
-        assert j == len(orig)
-        out[k] = "".join(text)
+        j = 1 if (any_stripped and stripped[k]) else 0               # re-insert the start residue column (main.cpp:455-463)
+        body = np.full(len(row), ord("-"), dtype=np.uint8)
+        keep = row != GAP
+        residues = np.frombuffer(orig[j:].encode("ascii"), dtype=np.uint8)
+        assert int(keep.sum()) == len(residues)
+        body[keep] = residues
+        head = (orig[0] if stripped[k] else "-") if any_stripped else ""
+        out[k] = head + body.tobytes().decode("ascii")
     return (out, trees) if return_trees else out

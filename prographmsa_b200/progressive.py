@@ -92,15 +92,17 @@ def _leaf(name, sequences, repeats, n):
 
 
 def _extend_rows(size, mapping, rows):
-    out = {}
+    """extend_alignment (ProgressiveAlignment.h:245-264): every row of the child alignment is scattered to the columns of
+    the merged graph its nodes were mapped to; one 2-D scatter for all rows of the child."""
+    if not rows:
+        return {}
     sel = np.asarray(mapping[1:size - 1])
-    for name, orig in rows.items():
-        ext = np.full(size - 2, GAP, dtype=np.uint8)
-        ok = sel != NOGAP
-        assert np.array_equal(sel[ok] - 1, np.arange(ok.sum()))
-        ext[ok] = orig
-        out[name] = ext
-    return out
+    ok = sel != NOGAP
+    assert np.array_equal(sel[ok] - 1, np.arange(ok.sum()))
+    names = list(rows)
+    ext = np.full((len(names), size - 2), GAP, dtype=np.uint8)
+    ext[:, ok] = np.stack([rows[k] for k in names])
+    return {k: ext[i] for i, k in enumerate(names)}
 
 
 def _extend_tr(size, mapping, trs):

@@ -126,20 +126,24 @@ def build_nj_tree(names, distances, variances, edge_halflife, joins_fn=None):
 
 
 def _max_dist_pair(root):
+    """the two most distant leaves (PhyTree.cpp:60-80): every pair of leaves is met once at its lowest common ancestor, in
+    the order of the reference's double loop, and a strictly larger sum replaces the current best -- evaluated per node as one
+    outer sum with a first-maximum argmax, which visits the pairs in that same order."""
     best = {"max": None, "dist": -math.inf}
 
     def rec(t):
         if t.is_leaf():
-            return [0.0], [t]
+            return np.zeros(1), [t]
         d1, l1 = rec(t.children[0]); d2, l2 = rec(t.children[1])
-        d1 = [x + t.children[0].length for x in d1]
-        d2 = [x + t.children[1].length for x in d2]
-        for i in range(len(d1)):
-            for j in range(len(d2)):
-                if d1[i] + d2[j] > best["dist"]:
-                    best["dist"] = d1[i] + d2[j]
-                    best["max"] = l1[i] if d1[i] > d2[j] else l2[j]
-        return d1 + d2, l1 + l2
+        d1 = d1 + t.children[0].length
+        d2 = d2 + t.children[1].length
+        S = d1[:, None] + d2[None, :]
+        flat = int(np.argmax(S))
+        i, j = divmod(flat, len(d2))
+        if S[i, j] > best["dist"]:
+            best["dist"] = float(S[i, j])
+            best["max"] = l1[i] if d1[i] > d2[j] else l2[j]
+        return np.concatenate([d1, d2]), l1 + l2
     rec(root)
     return best["dist"], best["max"]
 
