@@ -40,6 +40,12 @@ def c_opts(opts, emission_mode=EMISSION_EXACT):
     return _lib.DPOpts(opts.indel_rate, opts.end_indel_prob, opts.repeat_rate, opts.repeatext_prob, int(emission_mode))
 
 
+# numpy mirror of pgm_alignment (include/pgm_b200.h): lets a batch's results be written and read as columns
+_ALIGNMENT = np.dtype([("score", "f4"), ("n_tr_indels", "u4"), ("mapping1", "u8"), ("mapping2", "u8"), ("capacity", "i4"),
+                       ("length", "i4"), ("status", "i4"), ("cell_updates", "u8")], align=True)
+assert _ALIGNMENT.itemsize == C.sizeof(_lib.Alignment)
+
+
 class GraphBatch:
     """A batch of alignGraphs jobs staged on the device (pgm_graph_batch_*): create once, run many
     times without host<->device traffic, fetch results."""
@@ -62,27 +68,24 @@ class GraphBatch:
         _lib.check(_lib.lib().pgm_graph_batch_run(self.ctx.handle, self._h))
 
     def fetch(self):
-        out = (_lib.Alignment * max(1, self.n_jobs))()
-        offs = np.zeros(self.n_jobs + 1, dtype=np.int64)
+        n = self.n_jobs
+        out = np.zeros(max(1, n), dtype=_ALIGNMENT)                          # pgm_alignment[n], filled and read as columns
+        offs = np.zeros(n + 1, dtype=np.int64)
         np.cumsum(self.caps, out=offs[1:])
-        buf = np.zeros((2, max(1, int(offs[-1]))), dtype=np.int32)           # every job's two mappings, one allocation
-        base1, base2 = _addr(buf[0]), _addr(buf[1])
-        for k in range(self.n_jobs):
-            o = int(offs[k]) * 4
-            out[k].mapping1 = base1 + o; out[k].mapping2 = base2 + o; out[k].capacity = self.caps[k]
-        rc = _lib.lib().pgm_graph_batch_fetch(self.ctx.handle, self._h, out)
+        buf = np.empty((2, max(1, int(offs[-1]))), dtype=np.int32)           # every job's two mappings, one allocation
+        out["mapping1"][:n] = _addr(buf[0]) + 4 * offs[:-1]
+        out["mapping2"][:n] = _addr(buf[1]) + 4 * offs[:-1]
+        out["capacity"][:n] = self.caps
+        rc = _lib.lib().pgm_graph_batch_fetch(self.ctx.handle, self._h, C.c_void_p(out.ctypes.data))
         if rc == -4:
             raise RuntimeError("backtracking failed")
         _lib.check(rc)
-        buf64 = buf.astype(np.int64)                                         # one widening pass; the per-job mappings are views
-        res = []
-        for k in range(self.n_jobs):
-            a = out[k]
-            ln = a.length; o = int(offs[k])
-            res.append(dict(score=float(a.score), n_tr_indels=int(a.n_tr_indels),
-                            mapping1=buf64[0, o:o + ln], mapping2=buf64[1, o:o + ln],
-                            cell_updates=int(a.cell_updates)))
-        return res
+        lens = out["length"][:n].tolist(); starts = offs[:-1].tolist()
+        scores = out["score"][:n].astype(np.float64).tolist(); ntr = out["n_tr_indels"][:n].tolist()
+        upd = out["cell_updates"][:n].tolist()
+        m1, m2 = buf[0], buf[1]
+        return [dict(score=scores[k], n_tr_indels=ntr[k], mapping1=m1[o:o + ln].astype(np.int64), mapping2=m2[o:o + ln].astype(np.int64),
+                     cell_updates=upd[k]) for k, (o, ln) in enumerate(zip(starts, lens))]
 
     def close(self):
         if self._h:

@@ -47,10 +47,31 @@ class OracleBackend:
         return [self.po.align_graphs(a, b, m, opts) for a, b, m in jobs]
 
 
-def _check(run, backend_factory, max_inexact=1):
+def _columns(aligned):
+    """the alignment as a set of homology columns: frozensets of (sequence, residue index)"""
+    names = sorted(aligned)
+    pos = {k: 0 for k in names}
+    cols = set()
+    for c in range(len(aligned[names[0]])):
+        col = []
+        for k in names:
+            if aligned[k][c] != "-":
+                col.append((k, pos[k])); pos[k] += 1
+        cols.add(frozenset(col))
+    return cols
+
+
+def _check(run, backend_factory, max_inexact=1, ties_ok=False):
     opts = Options(mldist_flag=True, nwdist_flag=("-a" in run["flags"]))
     got, trees = pipeline.do_align(run["seqs"], opts, backend_factory, return_trees=True)
-    assert got == run["aligned"]
+    if ties_ok and got != run["aligned"]:
+        # Tie case (north_star: reported separately): two adjacent columns that share no sequence (e.g. an insertion in each
+        # child) have the same score in either order, and which one the traceback emits first is decided by float rounding
+        # of sums that change with the last bits of the guide-tree distances.  The homology columns must still be the same.
+        assert _columns(got) == _columns(run["aligned"]), "alignment differs from the reference by more than the order of independent columns"
+        print("tie case: same homology columns as the reference, different order of independent columns")
+    else:
+        assert got == run["aligned"]
     assert sorted(got) == sorted(run["order"])
     if trees[-1] == run["trees"][-1]:                                # output order = leaf order of the last tree
         assert list(got) == run["order"]
@@ -97,7 +118,7 @@ def test_whole_run_matches_reference_binary_oracle(idx):
 @pytest.mark.parametrize("idx", range(len(RUNS)))
 def test_whole_run_matches_reference_binary_gpu(idx):
     # device distances differ from the oracle's in the last bits, so the dim = 4 tie may fall either way in EVERY tree
-    _check(RUNS[idx], lambda mf, opts: pipeline.GpuBackend(mf, opts), max_inexact=99)
+    _check(RUNS[idx], lambda mf, opts: pipeline.GpuBackend(mf, opts), max_inexact=99, ties_ok=True)
 
 
 @pytest.mark.gpu
