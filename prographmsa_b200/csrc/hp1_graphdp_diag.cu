@@ -30,7 +30,9 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 // co-resident.  Every dependency of a cell lies on a strictly earlier global anti-diagonal, so band b may sweep
 // diagonal d once every earlier band has finished its cells on diagonals < d: each band publishes the number of
 // diagonals it has completed (fence + flag, every 4 diagonals) and waits on the earlier bands' flags (every 8).
-// Cells of other bands are read from HBM/L2 (the {M,X,Y,W} array itself is the exchange buffer).
+// Cells of other bands are read from HBM/L2 (the {M,X,Y,W} array itself is the exchange buffer); the row just above the
+// band, which the band's first row needs on every diagonal, is staged 8 diagonals at a time into shared memory right after
+// the flag check (it is complete by then), so that row runs the chain fast path like any other.
 template <bool STAGE, int RPT, int RING, bool SPF, bool BANDED>
 __global__ void __launch_bounds__(1024)
 graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch, int max_bands) {
@@ -46,6 +48,7 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     const int T = (int)blockDim.x, tid = (int)threadIdx.x;
 
     extern __shared__ __align__(16) unsigned char gsm[];
+    __shared__ float4 prevrow[16];                                                  // BANDED: cell (y0-1, dd-y0+1) at [dd & 15]
     float4* ring = (float4*)gsm;                                                    // [RING][ring_pitch], indexed by y
     float4* sring = (float4*)(gsm + (size_t)RING * ring_pitch * sizeof(float4));    // SPF: [4][RPT*T], private slots per (thread,row)
     NodeInfo* s2 = (NodeInfo*)(sring + (SPF ? 4 * RPT * T : 0));
@@ -75,7 +78,7 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     for (int r = 0; r < RPT; ++r) {
         const int y = y0 + tid + r * T;
         ny[r] = (y <= N1 - 2) ? J.ni1[y] : NodeInfo{0, 0, 0, 0.f};
-        ysimple[r] = (ny[r].cnt == 1 && ny[r].idx0 == y - 1) && !(BANDED && band > 0 && y == y0);   // row y0-1 is another band's
+        ysimple[r] = (ny[r].cnt == 1 && ny[r].idx0 == y - 1);
         left[r] = make_float4(NINF, NINF, NINF, NINF);
     }
     const int band_rows = T * RPT;
@@ -104,6 +107,14 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                     while (*(volatile int*)(J.progress + bq) < need) __nanosleep(64);
                 }
                 __threadfence();
+            }
+            __syncthreads();
+            // row y0-1 on the global diagonals [d, d+7] (the first time also d-2, d-1): what the band's first row reads as its
+            // upper and diagonal neighbours during the next 8 diagonals
+            const int lo = (d == dmin) ? d - 2 : d;
+            if (tid < 10 && lo + tid <= d + 7) {
+                const int dd = lo + tid, xx = dd - (y0 - 1);
+                if (xx >= 0 && xx <= N2 - 2) prevrow[dd & 15] = __ldcg(C + (size_t)dd * pitch + ((y0 - 1) - max(0, dd - (N2 - 1))));
             }
             __syncthreads();
         }
@@ -152,8 +163,9 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                     if (ysimple[r] && nx.cnt == 1 && nx.idx0 == x - 1) {
                         // fast path (chain nodes, the overwhelming majority): one adjacent regular predecessor each
                         const float ey = ny[r].val0, ex = nx.val0;
-                        const float4 cu = row1[y - y0 - 1];                          // (y-1, x)
-                        const float4 cd = row2[y - y0 - 1];                          // (y-1, x-1)
+                        const bool edge = BANDED && band > 0 && y == y0;             // row y-1 belongs to the previous band
+                        const float4 cu = edge ? prevrow[(d - 1) & 15] : row1[y - y0 - 1];   // (y-1, x)
+                        const float4 cd = edge ? prevrow[(d - 2) & 15] : row2[y - y0 - 1];   // (y-1, x-1)
                         const float4 cl = left[r];                                   // (y, x-1): this thread, last diagonal
                         ys = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
                         m = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);

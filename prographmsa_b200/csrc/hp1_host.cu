@@ -137,6 +137,10 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     int force_layout = -1, diag_min_generic = 8;                  // PGM_FILL_LAYOUT=block|diag forces one kernel (tests, profiling)
     if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : -1);
     if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
+    int band_min_n1 = GF_BAND_MIN_N1;
+    if (const char* e = getenv("PGM_FILL_BAND_MIN_N1")) band_min_n1 = std::max(66, atoi(e));
+    int long_band_rows = GF_BAND_ROWS;
+    if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 64 && v <= 1024) long_band_rows = v; }
     int split_rows = 0, split_min_generic = 24;
     if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
     if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
@@ -178,7 +182,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         // the first row of a band pays an L2 round trip per anti-diagonal
         L.band_rows = 0;
         if (L.layout == GF_LAYOUT_DIAG) {
-            if (a.N >= GF_BAND_MIN_N1) L.band_rows = GF_BAND_ROWS;
+            if (a.N >= band_min_n1) L.band_rows = long_band_rows;
             else if (split_rows > 0 && generic > split_min_generic && a.N - 1 >= 2 * split_rows) L.band_rows = split_rows;
         }
         L.bands = L.band_rows ? (a.N - 1 + L.band_rows - 1) / L.band_rows : 1;
@@ -332,7 +336,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         b->order.resize(n_jobs);
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
         auto class_of = [&](const GraphJobDev& J) {
-            if (J.bands > 1) return J.band_rows == GF_BAND_ROWS ? 201 : 200;  // banded anti-diagonal sweeps: their own launches
+            if (J.bands > 1) return 200 + J.band_rows / 32;                   // banded anti-diagonal sweeps: their own launches, one per band height
             if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
             const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
         };

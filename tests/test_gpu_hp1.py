@@ -68,9 +68,9 @@ def test_leaf_pair_alignment_identical(ga, po, L, t, seed):
 
 @pytest.mark.parametrize("L", [1100, 1500, 2300, 3300, 4200])
 def test_long_graphs_identical(ga, po, L):
-    """graph 1 beyond 1024 rows: several rows per thread; beyond ~1400 rows the anti-diagonal kernel switches to its
-    4-diagonal ring and reads S directly (BASELINE config 3 has 1500-nt sequences); from 3074 nodes on the rows are swept
-    in bands of 1024 by co-resident CTAs that hand over through HBM (the root of a 5000-sequence tree has > 6000 nodes)"""
+    """graph 1 beyond 1024 rows (BASELINE config 3 has 1500-nt sequences, the root of a 5000-sequence tree > 6000 nodes): the
+    rows are swept in bands of 512 by co-resident CTAs that hand over through HBM; PGM_FILL_BAND_MIN_N1 raises the threshold,
+    which brings back the single-CTA flavours with several rows per thread"""
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
     a, b = synth.random_pair(L, 0.4, mf, seed=L)

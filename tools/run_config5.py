@@ -24,12 +24,27 @@ def timed(label, fn):
         t0 = time.perf_counter(); r = fn(*a, **kw); T[label] = T.get(label, 0.0) + time.perf_counter() - t0; return r
     return wrap
 
+from prographmsa_b200 import _lib
+CTX = _lib.default_context()
+CTX.enable_timing(True)
+GPU = dict(emission_ms=0.0, graph_fill_ms=0.0, graph_trace_ms=0.0, batches=0, jobs=0, cells=0)
+
+
 class Backend(pipeline.GpuBackend):
-    pass
+    def __init__(self, mf, o):
+        super().__init__(mf, o, ctx=CTX)
+
+    def batch_align(self, jobs, o):
+        r = super().batch_align(jobs, o)
+        t = CTX.timing()                                            # device time of this level's kernels (per size-class pipeline, summed)
+        for k in ("emission_ms", "graph_fill_ms", "graph_trace_ms"):
+            GPU[k] += t[k]
+        GPU["batches"] += 1; GPU["jobs"] += len(jobs); GPU["cells"] += t["graph_cells"]
+        return r
 for name, label in (("initial_distances", "k-mer angle distances (GPU)"), ("prealigned_distances", "Prealigned ML distances (GPU)"),
                     ("batch_align", "alignGraphs batches (GPU, incl. host packing)"), ("batch_merge", "mergeGraphs profiles (GPU)"),
                     ("nj_joins", "BioNJ join loop (GPU)")):
-    setattr(Backend, name, timed(label, getattr(pipeline.GpuBackend, name)))
+    setattr(Backend, name, timed(label, getattr(Backend, name)))
 _tree.midpoint_root = timed("midpoint rooting (host Python)", _tree.midpoint_root)
 
 t0 = time.perf_counter()
@@ -42,3 +57,5 @@ acc = 0.0
 for k, v in sorted(T.items(), key=lambda kv: -kv[1]):
     print("  %-48s %7.2f s" % (k, v)); acc += v
 print("  %-48s %7.2f s" % ("rest: Python host glue (graphs, merge edges, trees)", wall - acc))
+print("  device time inside the %d alignGraphs batches (%d jobs, %.3g cells; sums over the size-class pipelines of every level): "
+      "emission %.0f ms, fill %.0f ms, traceback %.0f ms" % (GPU["batches"], GPU["jobs"], GPU["cells"], GPU["emission_ms"], GPU["graph_fill_ms"], GPU["graph_trace_ms"]))
