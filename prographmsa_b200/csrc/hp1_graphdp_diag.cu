@@ -254,21 +254,30 @@ static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_
 
 // Long graphs: bands of GF_BAND_ROWS rows, one CTA each.  All CTAs of a launch must be resident at once (they wait on each
 // other's flags), so a launch holds at most one CTA per SM; the jobs' progress flags are zeroed by the caller.
-int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows) {
-    if (n_jobs == 0) return 0;
-    const int threads = band_rows;
-    const int ring_pitch = band_rows;
-    const size_t smem = (size_t)GF_RING * ring_pitch * sizeof(float4) + (size_t)4 * threads * sizeof(float4);
-    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<false, 1, GF_RING, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+template <bool STAGE>
+static int launch_banded_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows, size_t smem) {
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, 1, GF_RING, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;
-    PGM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_fill_diag_kernel<false, 1, GF_RING, true, true>, threads, smem));
+    PGM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, graph_fill_diag_kernel<STAGE, 1, GF_RING, true, true>, band_rows, smem));
     const int per = std::max(1, (n_sms * std::max(1, per_sm)) / max_bands);     // jobs per launch: every CTA resident
     for (int j = 0; j < n_jobs; j += per) {
         const int nj = std::min(per, n_jobs - j);
-        graph_fill_diag_kernel<false, 1, GF_RING, true, true><<<nj * max_bands, threads, smem, st>>>(d_jobs, d_order + j, ring_pitch, max_bands);
+        graph_fill_diag_kernel<STAGE, 1, GF_RING, true, true><<<nj * max_bands, band_rows, smem, st>>>(d_jobs, d_order + j, band_rows, max_bands);
         PGM_CUDA(cudaGetLastError());
     }
     return 0;
+}
+
+// Long graphs: bands of band_rows rows, one CTA each.  All CTAs of a launch must be resident at once (they wait on each
+// other's flags), so a launch holds at most as many CTAs as fit the GPU; the jobs' progress flags are zeroed by the caller.
+// Graph 2's node infos and both predecessor lists are staged in shared memory when they fit next to the ring.
+int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows,
+                             int max_n2, int max_np) {
+    if (n_jobs == 0) return 0;
+    const size_t ring = (size_t)GF_RING * band_rows * sizeof(float4) + (size_t)4 * band_rows * sizeof(float4);
+    const size_t info = (size_t)max_n2 * sizeof(NodeInfo) + (size_t)max_np * 8 + 64;
+    if (ring + info <= 200 * 1024) return launch_banded_t<true>(st, n_jobs, d_jobs, d_order, max_bands, n_sms, band_rows, ring + info);
+    return launch_banded_t<false>(st, n_jobs, d_jobs, d_order, max_bands, n_sms, band_rows, ring);
 }
 
 // max_n1 / max_n2: largest graph-1 / graph-2 node counts in this launch

@@ -21,7 +21,8 @@ pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
 int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
 int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
-int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows);
+int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows,
+                             int max_n2, int max_np);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
 void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
@@ -409,7 +410,7 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
                     const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + f->offset + jq]];
                     PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * Jq.bands, sq));
                 }
-                return launch_graph_fill_banded(sq, f->count, dj + sb.first, ord, f->max_bands, n_sms, f->band_rows);
+                return launch_graph_fill_banded(sq, f->count, dj + sb.first, ord, f->max_bands, n_sms, f->band_rows, f->max_n2, f->max_np);
             }
             return f->layout == GF_LAYOUT_DIAG ? launch_graph_fill_diag(sq, f->count, dj + sb.first, ord, f->max_n1, f->max_n2, f->max_np)
                                                : launch_graph_fill(sq, f->count, dj + sb.first, ord, f->max_nb, f->max_n2, f->max_np2);

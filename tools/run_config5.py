@@ -40,6 +40,10 @@ class Backend(pipeline.GpuBackend):
         for k in ("emission_ms", "graph_fill_ms", "graph_trace_ms"):
             GPU[k] += t[k]
         GPU["batches"] += 1; GPU["jobs"] += len(jobs); GPU["cells"] += t["graph_cells"]
+        if os.environ.get("RUN5_LEVELS"):
+            print("    level batch %3d: %5d jobs, largest graphs %5d x %5d nodes, %.3g cells: emission %6.2f fill %7.2f traceback %6.2f ms" % (
+                GPU["batches"], len(jobs), max(a.N for a, _, _ in jobs), max(b.N for _, b, _ in jobs), t["graph_cells"],
+                t["emission_ms"], t["graph_fill_ms"], t["graph_trace_ms"]))
         return r
 for name, label in (("initial_distances", "k-mer angle distances (GPU)"), ("prealigned_distances", "Prealigned ML distances (GPU)"),
                     ("batch_align", "alignGraphs batches (GPU, incl. host packing)"), ("batch_merge", "mergeGraphs profiles (GPU)"),
