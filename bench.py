@@ -152,7 +152,7 @@ def _port_sample(opts, mf, seqs, names, k):
 def cpu_baseline(opts, mf, seqs, names):
     from oracle import pyoracle as po
     if po.ref_binary():
-        k = 72                                       # 2,556 pairs ~ 4.1e8 cells: ~10 s on one core
+        k = 144                                      # 10,296 pairs ~ 1.7e9 cells: ~10 s on one core of the GPU box
         wall, cells, pairs = _run_ref_instances(seqs, names, [names[:k]])
         return dict(value=cells / wall / 1e9, unit=UNIT, cores=1, kind="reference",
                     sample="oracle/_ref/ProGraphMSA_64 -a -m -i 0 -T on the first %d of the %d sequences (%d pairs, %.3g cells, %.1f s wall, "
