@@ -44,21 +44,24 @@ def test_progressive_pass_matches_reference_binary_at_scale(n):
     assert _digest(aligned) == rec["sha256"]
 
 
-def test_whole_run_5000_sequences_matches_reference_binary():
-    """BASELINE.json configs[4] end to end, without guide-tree iteration (-m -F -i 0): k-mer angle distances, the BioNJ join
-    loop, every alignGraphs and mergeGraphs node on the GPU; the final alignment equals the reference binary's (SHA-256),
-    which needs 47 minutes for it."""
+@pytest.mark.parametrize("idx", [0, 1])
+def test_whole_run_matches_reference_binary_at_scale(idx):
+    """BASELINE.json configs[4]'s pipeline end to end on the GPU back-ends -- k-mer angle distances, the BioNJ join loop, every
+    alignGraphs and mergeGraphs node, and for -i 2 the Prealigned ML distance matrices of both guide-tree iterations -- against
+    whole runs of the reference binary (SHA-256 of the final alignment): 1000 sequences with -i 2 (the binary: 157 s) and 5000
+    sequences with -i 0 (the binary: 47 minutes)."""
     from prographmsa_b200 import pipeline
-    rec = golden("large.json")["whole_runs"][0]
+    rec = golden("large.json")["whole_runs"][idx]
+    iters = int(rec["flags"][rec["flags"].index("-i") + 1])
     opts = Options(mldist_flag=True, aafreqs_flag=True)
     mf0 = model.getDefault(Options(mldist_flag=True))
     seqs, _ = synth.simulate_family(rec["n"], rec["L"], mf0, seed=rec["seed"], forbid_first=10)
     strs = {k: "".join(alphabet.AA_LETTERS[c] for c in v) for k, v in seqs.items()}
     t0 = time.perf_counter()
-    out = pipeline.do_align(strs, opts, lambda mf, o: pipeline.GpuBackend(mf, o), iters=0)
+    out = pipeline.do_align(strs, opts, lambda mf, o: pipeline.GpuBackend(mf, o), iters=iters)
     wall = time.perf_counter() - t0
     cols = len(next(iter(out.values())))
     h = hashlib.sha256("".join("%s\n%s\n" % (k, out[k]) for k in sorted(out)).encode()).hexdigest()
-    print("whole run, 5000 x 500 aa, -m -F -i 0: %d columns in %.1f s (reference binary: %.0f s)" % (cols, wall, rec["reference_wall_s"]), file=sys.stderr)
+    print("whole run, %d x %d aa, -m -F -i %d: %d columns in %.1f s (reference binary: %.0f s)" % (rec["n"], rec["L"], iters, cols, wall, rec["reference_wall_s"]), file=sys.stderr)
     assert cols == rec["columns"]
     assert h == rec["sha256"]
