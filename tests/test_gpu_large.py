@@ -44,7 +44,7 @@ def test_progressive_pass_matches_reference_binary_at_scale(n):
     assert _digest(aligned) == rec["sha256"]
 
 
-@pytest.mark.parametrize("idx", [0, 1])
+@pytest.mark.parametrize("idx", range(len(golden("large.json")["whole_runs"])))
 def test_whole_run_matches_reference_binary_at_scale(idx):
     """BASELINE.json configs[4]'s pipeline end to end on the GPU back-ends -- k-mer angle distances, the BioNJ join loop, every
     alignGraphs and mergeGraphs node, and for -i 2 the Prealigned ML distance matrices of both guide-tree iterations -- against
@@ -53,7 +53,7 @@ def test_whole_run_matches_reference_binary_at_scale(idx):
     from prographmsa_b200 import pipeline
     rec = golden("large.json")["whole_runs"][idx]
     iters = int(rec["flags"][rec["flags"].index("-i") + 1])
-    opts = Options(mldist_flag=True, aafreqs_flag=True)
+    opts = Options(mldist_flag=True, aafreqs_flag="-F" in rec["flags"], nwdist_flag="-a" in rec["flags"])
     mf0 = model.getDefault(Options(mldist_flag=True))
     seqs, _ = synth.simulate_family(rec["n"], rec["L"], mf0, seed=rec["seed"], forbid_first=10)
     strs = {k: "".join(alphabet.AA_LETTERS[c] for c in v) for k, v in seqs.items()}
@@ -62,6 +62,6 @@ def test_whole_run_matches_reference_binary_at_scale(idx):
     wall = time.perf_counter() - t0
     cols = len(next(iter(out.values())))
     h = hashlib.sha256("".join("%s\n%s\n" % (k, out[k]) for k in sorted(out)).encode()).hexdigest()
-    print("whole run, %d x %d aa, -m -F -i %d: %d columns in %.1f s (reference binary: %.0f s)" % (rec["n"], rec["L"], iters, cols, wall, rec["reference_wall_s"]), file=sys.stderr)
+    print("whole run, %d x %d aa, %s: %d columns in %.1f s (reference binary: %.0f s)" % (rec["n"], rec["L"], " ".join(rec["flags"]), cols, wall, rec["reference_wall_s"]), file=sys.stderr)
     assert cols == rec["columns"]
     assert h == rec["sha256"]

@@ -13,7 +13,8 @@ from prographmsa_b200.options import Options
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-opts = Options(mldist_flag=True, aafreqs_flag=True)
+nw = len(sys.argv) > 3 and sys.argv[3] == "nw"                      # third argument "nw": -a -m (NW + ML initial distances) instead of -m -F
+opts = Options(mldist_flag=True, aafreqs_flag=not nw, nwdist_flag=nw)
 mf0 = model.getDefault(Options(mldist_flag=True))
 seqs, _ = synth.simulate_family(n, 500, mf0, seed=50, forbid_first=10)
 strs = {k: "".join(alphabet.AA_LETTERS[c] for c in v) for k, v in seqs.items()}
@@ -45,7 +46,7 @@ class Backend(pipeline.GpuBackend):
                 GPU["batches"], len(jobs), max(a.N for a, _, _ in jobs), max(b.N for _, b, _ in jobs), t["graph_cells"],
                 t["emission_ms"], t["graph_fill_ms"], t["graph_trace_ms"]))
         return r
-for name, label in (("initial_distances", "k-mer angle distances (GPU)"), ("prealigned_distances", "Prealigned ML distances (GPU)"),
+for name, label in (("initial_distances", "initial distances: k-mer angle or NW + ML (GPU)"), ("prealigned_distances", "Prealigned ML distances (GPU)"),
                     ("batch_align", "alignGraphs batches (GPU, incl. host packing)"), ("batch_merge", "mergeGraphs profiles (GPU)"),
                     ("nj_joins", "BioNJ join loop (GPU)")):
     setattr(Backend, name, timed(label, getattr(Backend, name)))
@@ -56,7 +57,7 @@ out, trees = pipeline.do_align(strs, opts, lambda mf, o: Backend(mf, o), iters=i
 wall = time.perf_counter() - t0
 cols = len(next(iter(out.values())))
 h = hashlib.sha256("".join("%s\n%s\n" % (k, out[k]) for k in sorted(out)).encode()).hexdigest()
-print("config 5 shape: %d seqs x 500 aa, -m -F -i %d: %.1f s wall, %d trees, %d columns, sha256 %s" % (n, iters, wall, len(trees), cols, h[:16]))
+print("config 5 shape: %d seqs x 500 aa, " + ("-a -m" if nw else "-m -F") + " -i %d: %.1f s wall, %d trees, %d columns, sha256 %s" % (n, iters, wall, len(trees), cols, h[:16]))
 acc = 0.0
 for k, v in sorted(T.items(), key=lambda kv: -kv[1]):
     print("  %-48s %7.2f s" % (k, v)); acc += v
