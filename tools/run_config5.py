@@ -57,7 +57,7 @@ out, trees = pipeline.do_align(strs, opts, lambda mf, o: Backend(mf, o), iters=i
 wall = time.perf_counter() - t0
 cols = len(next(iter(out.values())))
 h = hashlib.sha256("".join("%s\n%s\n" % (k, out[k]) for k in sorted(out)).encode()).hexdigest()
-print("config 5 shape: %d seqs x 500 aa, " + ("-a -m" if nw else "-m -F") + " -i %d: %.1f s wall, %d trees, %d columns, sha256 %s" % (n, iters, wall, len(trees), cols, h[:16]))
+print(("config 5 shape: %d seqs x 500 aa, " + ("-a -m" if nw else "-m -F") + " -i %d: %.1f s wall, %d trees, %d columns, sha256 %s") % (n, iters, wall, len(trees), cols, h[:16]))
 acc = 0.0
 for k, v in sorted(T.items(), key=lambda kv: -kv[1]):
     print("  %-48s %7.2f s" % (k, v)); acc += v
