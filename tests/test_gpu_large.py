@@ -53,7 +53,7 @@ def test_whole_run_matches_reference_binary_at_scale(idx):
     from prographmsa_b200 import pipeline
     rec = golden("large.json")["whole_runs"][idx]
     iters = int(rec["flags"][rec["flags"].index("-i") + 1])
-    opts = Options(mldist_flag=True, aafreqs_flag="-F" in rec["flags"], nwdist_flag="-a" in rec["flags"])
+    opts = Options(mldist_flag=True, aafreqs_flag="-F" in rec["flags"], nwdist_flag="-a" in rec["flags"], darwin_flag="-w" in rec["flags"])
     mf0 = model.getDefault(Options(mldist_flag=True))
     seqs, _ = synth.simulate_family(rec["n"], rec["L"], mf0, seed=rec["seed"], forbid_first=10)
     strs = {k: "".join(alphabet.AA_LETTERS[c] for c in v) for k, v in seqs.items()}

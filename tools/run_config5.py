@@ -13,8 +13,9 @@ from prographmsa_b200.options import Options
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 5000
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2
-nw = len(sys.argv) > 3 and sys.argv[3] == "nw"                      # third argument "nw": -a -m (NW + ML initial distances) instead of -m -F
-opts = Options(mldist_flag=True, aafreqs_flag=not nw, nwdist_flag=nw)
+mode = sys.argv[3] if len(sys.argv) > 3 else ""                     # "nw": -a -m (NW + ML initial distances); "w": -m -w (Gonnet); default -m -F
+nw = mode == "nw"
+opts = Options(mldist_flag=True, aafreqs_flag=(mode == ""), nwdist_flag=nw, darwin_flag=(mode == "w"))
 mf0 = model.getDefault(Options(mldist_flag=True))
 seqs, _ = synth.simulate_family(n, 500, mf0, seed=50, forbid_first=10)
 strs = {k: "".join(alphabet.AA_LETTERS[c] for c in v) for k, v in seqs.items()}
@@ -57,7 +58,7 @@ out, trees = pipeline.do_align(strs, opts, lambda mf, o: Backend(mf, o), iters=i
 wall = time.perf_counter() - t0
 cols = len(next(iter(out.values())))
 h = hashlib.sha256("".join("%s\n%s\n" % (k, out[k]) for k in sorted(out)).encode()).hexdigest()
-print(("config 5 shape: %d seqs x 500 aa, " + ("-a -m" if nw else "-m -F") + " -i %d: %.1f s wall, %d trees, %d columns, sha256 %s") % (n, iters, wall, len(trees), cols, h[:16]))
+print(("config 5 shape: %d seqs x 500 aa, " + {"nw": "-a -m", "w": "-m -w"}.get(mode, "-m -F") + " -i %d: %.1f s wall, %d trees, %d columns, sha256 %s") % (n, iters, wall, len(trees), cols, h[:16]))
 acc = 0.0
 for k, v in sorted(T.items(), key=lambda kv: -kv[1]):
     print("  %-48s %7.2f s" % (k, v)); acc += v
