@@ -199,3 +199,32 @@ def test_native_host_glue_with_repeat_edges():
         for x, y in zip(_graph_arrays(r_nat.graph), _graph_arrays(r_py.graph)):
             assert np.array_equal(x, y)
         assert r_nat.n_tr_indels == r_py.n_tr_indels
+
+
+def test_first_maximum_rule_reproduces_the_reference_traceback():
+    """groundwork for direction-word tracebacks: on the oracle's dumped matrices, following the first
+    candidate that attains the maximum gives the same path as the reference's closest-|delta| search"""
+    import importlib.util
+    import numpy as np
+    from prographmsa_b200 import model, synth, progressive
+    from prographmsa_b200.options import Options
+    from oracle import pyoracle as po
+    spec = importlib.util.spec_from_file_location("check_first_max", os.path.join(os.path.dirname(__file__), "..", "tools", "check_first_max_traceback.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(14, 70, mf, seed=3, indel_rate=0.06)
+    checked = []
+
+    def batch(jobs, o):
+        out = []
+        for g1, g2, m in jobs:
+            r = po.align_graphs(g1, g2, m, o, dump=True)
+            with np.errstate(invalid="ignore", over="ignore"):
+                p = mod.first_max_trace(g1, g2, r, po.dynprog_scores(g1, g2, m, o))
+            assert p == list(zip(r["mapping1"].tolist()[::-1], r["mapping2"].tolist()[::-1]))
+            checked.append(len(p))
+            out.append(r)
+        return out
+    progressive.progressive_alignment(seqs, progressive.from_synth(root), mf, opts, batch_align_fn=batch)
+    assert len(checked) == 13
