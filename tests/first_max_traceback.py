@@ -5,7 +5,7 @@ Because the fill computed that value as the maximum of the very same float expre
 first candidate that attains the maximum", which the fill could record in a few bits.  This script re-traces the oracle's
 dumped matrices with the first-maximum rule (CPU only, pure Python) and compares with the oracle's own traceback.
 
-  python tools/check_first_max_traceback.py [n_seq=40] [length=120] [seed=33]
+  python tests/first_max_traceback.py [n_seq=40] [length=120] [seed=33]      (test infrastructure: it drives the oracle)
 """
 import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))

@@ -209,7 +209,7 @@ def test_first_maximum_rule_reproduces_the_reference_traceback():
     from prographmsa_b200 import model, synth, progressive
     from prographmsa_b200.options import Options
     from oracle import pyoracle as po
-    spec = importlib.util.spec_from_file_location("check_first_max", os.path.join(os.path.dirname(__file__), "..", "tools", "check_first_max_traceback.py"))
+    spec = importlib.util.spec_from_file_location("check_first_max", os.path.join(os.path.dirname(__file__), "first_max_traceback.py"))
     mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
