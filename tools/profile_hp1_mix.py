@@ -16,9 +16,6 @@ ctx = _lib.default_context()
 jobs = []
 def batch(js, o):
     jobs.extend(js)
-    if os.environ.get("PROFILE_ORACLE_PASS"):                      # no GPU launches before the profiled batch (ncu -c 1)
-        from oracle import pyoracle as po
-        return [po.align_graphs(a, b, m, o) for a, b, m in js]
     return graphalign.alignGraphsBatch(js, o, ctx=ctx)
 progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
 
