@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""HP-2 on the shapes of BASELINE configs 3 (DNA 1000 x 1500 nt) and 4 (codon 300 x 300): time, properties, oracle spot-check."""
+"""HP-2 on the shapes of BASELINE configs 3 (DNA 1000 x 1500 nt) and 4 (codon 300 x 300): time, properties, oracle spot-check.
+Test infrastructure (it calls the oracle as the checker), not collected by pytest:  python tests/measure_other_configs.py [dna|codon|both]"""
 import sys, time
 import numpy as np
 sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))

@@ -28,13 +28,3 @@ print("jobs %d L %d: emission %.3f ms fill %.3f ms trace %.3f ms -> fill %.1f GC
     n_jobs, L, t["emission_ms"], t["graph_fill_ms"], t["graph_trace_ms"], upd / t["graph_fill_ms"] / 1e6))
 res = gb.fetch()
 print("score checksum", sum(r["score"] for r in res))
-if len(sys.argv) > 4:
-    from oracle import pyoracle as po
-    bad = 0
-    for k in range(0, n_jobs, max(1, n_jobs // 40)):
-        ref = po.align_graphs(jobs[k][0], jobs[k][1], m, opts)
-        ok = abs(ref["score"] - res[k]["score"]) <= 1e-5 * abs(ref["score"]) and np.array_equal(ref["mapping1"], res[k]["mapping1"])
-        if not ok:
-            bad += 1
-            print("MISMATCH job", k, ref["score"], res[k]["score"], len(ref["mapping1"]), len(res[k]["mapping1"]))
-    print("checked vs oracle, mismatches:", bad)
