@@ -50,6 +50,17 @@ def peaks():
     return dict(hbm_gbs=6650.0, sm_max_mhz=1965.0, source="fallback (B200_PROFILING.md)")
 
 
+def workload_config(seqs, names):
+    """`config` of the JSON line: the same dict in both arms (ours and --impl reference), so the driver compares like with like"""
+    L = np.array([len(seqs[k]) for k in names], dtype=np.int64)
+    cells = 0
+    for i in range(len(L)):
+        cells += int(((L[i] + 1) * (L[i + 1:] + 1)).sum())
+    return dict(workload=WORKLOAD, n_seq=len(L), pairs=len(L) * (len(L) - 1) // 2, nw_cells=cells,
+                l2="GPU arm: 256 MiB flush write between timed steps, and the per-step working set (7 GB of packed traceback) >> 126 MB L2; "
+                   "CPU arm: not applicable")
+
+
 def make_family():
     from prographmsa_b200 import model, synth
     from prographmsa_b200.options import Options
@@ -184,7 +195,7 @@ def run_reference_arm(args):
         val = cells / wall / 1e9
         line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=1, warmup=0, ms_per_step=wall * 1e3,
                     higher_is_better=True, scaling="strong", vs_baseline=None, dtype="int32+f64", data="synthetic",
-                    config=dict(workload=WORKLOAD), impl="reference",
+                    config=workload_config(seqs, names), impl="reference",
                     cpu_baseline=dict(value=val, unit=UNIT, cores=1, kind="port", sample="oracle port, first 24 sequences"),
                     e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         emit(line); return
@@ -200,7 +211,7 @@ def run_reference_arm(args):
               "subsample of the family (%d pairs per step in total)" % (inst, per, tot_pairs // max(1, args.steps)))
     line = dict(metric=METRIC, value=val, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=tot_wall / args.steps * 1e3, higher_is_better=True, scaling="strong", vs_baseline=None,
-                dtype="int32+f64", data="synthetic", config=dict(workload=WORKLOAD, sample=sample), impl="reference",
+                dtype="int32+f64", data="synthetic", config=workload_config(seqs, names), impl="reference",
                 cpu_baseline=dict(value=val, unit=UNIT, cores=inst, kind="reference", sample=sample),
                 e2e=dict(value=val, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
@@ -271,8 +282,9 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 graphalign.alignGraphsBatch(jobs, opts, mode, ctx)
             e2e_ms = (time.perf_counter() - t0) / max(1, steps // 2) * 1e3
             fill_ms = tm["graph_fill_ms"] / steps
-            # algorithmic HBM bytes of the fill kernel: 4 B S read + 16 B {M,X,Y,W} write per cell
-            alg_bytes = 20.0 * cells
+            # algorithmic HBM bytes of the fill kernels: 4 B S read + 1 B packed traceback per cell.
+            # What the kernels move: 4 B S + 2 B direction word per cell, plus the few kept rows / columns of the value store
+            alg_bytes = 5.0 * cells
             out[mode_name] = dict(
                 value=upd / ms / 1e6, unit="GCUPS", ms_per_step=ms, jobs=len(jobs), cell_updates=upd, cells=cells,
                 schedule="per size class: emission -> fill -> traceback on its own stream (pgm_graph_batch_run); ms_per_step_phased = "
@@ -284,9 +296,10 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 roofline=dict(bound="hbm", kernel="graph_fill_kernel + graph_fill_diag_kernel (concurrent launches, one fill section)",
                               achieved=alg_bytes / fill_ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
                               frac=alg_bytes / fill_ms / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
-                              note="algorithmic bytes = 20 B/cell (4 B S read + 16 B MXYW write). The blocked kernel sweeps the chain-dominated jobs "
-                                   "(~45 % of HBM peak on leaf batches); the fill section ends when the few large branchy graphs near the root finish, "
-                                   "each one latency-bound sweep of ~1000 anti-diagonals (profiles/r1_s3_hp1_fill.txt)"),
+                              moved_bytes_per_cell=6.0,
+                              note="algorithmic bytes = 5 B/cell (SURVEY 8d: 4 B S read + 1 B packed traceback); the kernels move 6 B/cell (2-byte direction "
+                                   "words) plus the kept rows / columns of the value store. The fill section ends when the few large branchy graphs near "
+                                   "the root finish, each one latency-bound sweep (profiles/)"),
                 score_checksum=float(sum(r["score"] for r in res)))
         finally:
             gb.close()
@@ -468,8 +481,9 @@ def run_ours(args):
         line = dict(
             metric=METRIC, value=cells_total / ms / 1e6, unit=UNIT, n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
             ms_per_step=ms, higher_is_better=True, scaling="strong", vs_baseline=None, dtype="int32+f64", data="synthetic",
-            config=dict(workload=WORKLOAD, pairs=P, nw_cells=cells_total, sharding="pair range / rank, NCCL all-gather of (dist,var)" if world > 1 else "single GPU",
-                        l2="256 MiB flush write between timed steps; per-step working set (%.1f GB packed traceback) >> 126 MB L2" % (tb_rank * world / 1e9)),
+            config=workload_config(seqs, names),
+            sharding="pair range / rank, NCCL all-gather of (dist,var)" if world > 1 else "single GPU",
+            traceback_gb_per_step=tb_rank * world / 1e9,
             seconds_per_matrix=ms / 1e3,
             e2e=dict(value=cells_total / e2e / 1e6, unit=UNIT, ms_per_step=e2e, h2d_bytes_per_step=int(codes.nbytes),
                      d2h_bytes_per_step=int(world * 2 * per * 8), cabi_host_call_ms_rank0=cabi_host_ms),

@@ -41,7 +41,7 @@ template <class ALPHABET>
 std::vector<AlignmentResult<ALPHABET> > alignGraphsGpuBatch(const std::vector<const Graph<ALPHABET>*>& g1,
                                                             const std::vector<const Graph<ALPHABET>*>& g2,
                                                             const std::vector<Model<ALPHABET> >& models,
-                                                            int emission_mode = PGM_EMISSION_TENSOR) {
+                                                            int emission_mode = PGM_EMISSION_EXACT) {
     const int n = ALPHABET::DIM, jobs = (int)g1.size();
     std::vector<pgm_graph> a(jobs), b(jobs);
     std::vector<pgm_dp_model> m(jobs);

@@ -4,7 +4,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgm_b200.so")
+LIB_PATH = os.environ.get("PGM_LIB_PATH") or os.path.join(_HERE, "libpgm_b200.so")   # PGM_LIB_PATH: A/B runs of two builds (tools/)
 _lib = None
 
 

@@ -595,6 +595,9 @@ int pgm_ml_distances(pgm_ctx* c, const pgm_ml_params* prm, int64_t np, const int
     if (np == 0) return 0;
     MlDev ml; int rc = prepare_model(c, prm, ml); if (rc) return rc;
     const size_t nn = (size_t)prm->n_states * prm->n_states;
+    if (!counts || !gaps || !seqlen || !dist || !var) { pgm_set_error("NULL argument"); return PGM_ERR_ARG; }
+    for (size_t q = 0; q < (size_t)np * nn; ++q)                  // the kernel packs (index << 20 | count) into one word
+        if (counts[q] < 0 || counts[q] >= (1 << 20)) { pgm_set_error("counts[%zu] = %d is outside [0, 2^20)", q, counts[q]); return PGM_ERR_ARG; }
     if ((rc = c->d_counts.reserve(np * nn * 4))) return rc;
     if ((rc = c->d_gaps.reserve(np * 4))) return rc;
     if ((rc = c->d_seqlen.reserve(np * 8))) return rc;

@@ -37,7 +37,7 @@ emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __r
     for (int i = threadIdx.x; i < n; i += blockDim.x) sPi[i] = J.pif[i];
     __syncthreads();
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k < J.N2) {
+    if (k < J.N2e) {
         const float* g = J.sites2 + (size_t)n * k;
         for (int a = 0; a < n; ++a) {                       // T(a,x) = sum_b M(b,a) g2(b,x)
             float s = 0.f;
@@ -46,7 +46,7 @@ emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __r
         }
         J.v[k] = dot_gemv_order(g, sPi, n);
     }
-    if (k < J.N1) {
+    if (k < J.N1e) {
         const float* g = J.sites1 + (size_t)n * k;
         J.u[k] = dot_gemv_order(g, sPi, n);
     }
@@ -56,7 +56,7 @@ emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __r
 __global__ void __launch_bounds__(256)
 emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
     const GraphJobDev& J = jobs[order ? order[blockIdx.z] : blockIdx.z];
-    const int N1 = J.N1, N2 = J.N2;
+    const int N1 = J.N1e, N2 = J.N2e;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     if (x0 >= N2 || y0 >= N1) return;
     extern __shared__ __align__(16) float sm[];
@@ -99,15 +99,15 @@ int launch_emission_prep(cudaStream_t st, int n, int n_jobs, const GraphJobDev* 
 }
 
 int launch_emission_exact(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2) {
-    if (n_jobs == 0) return 0;
-    {
-        int rc = launch_emission_prep(st, n, n_jobs, d_jobs, d_order, max_N1 > max_N2 ? max_N1 : max_N2);
+    for (int j0 = 0; j0 < n_jobs; j0 += 65535) {                   // gridDim.y / .z hold at most 65535 jobs
+        const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+        const GraphJobDev* dj = d_order ? d_jobs : d_jobs + j0;
+        const int* ord = d_order ? d_order + j0 : nullptr;
+        int rc = launch_emission_prep(st, n, nj, dj, ord, max_N1 > max_N2 ? max_N1 : max_N2);
         if (rc) return rc;
-    }
-    {
-        dim3 grid((max_N2 + 31) / 32, (max_N1 + 31) / 32, n_jobs);
+        dim3 grid((max_N2 + 31) / 32, (max_N1 + 31) / 32, nj);
         const size_t smem = sizeof(float) * n * 64;
-        emission_exact_kernel<<<grid, dim3(32, 8), smem, st>>>(n, d_jobs, d_order);
+        emission_exact_kernel<<<grid, dim3(32, 8), smem, st>>>(n, dj, ord);
         PGM_CUDA(cudaGetLastError());
     }
     return 0;

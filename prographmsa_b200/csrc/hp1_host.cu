@@ -19,9 +19,9 @@ void pgm_ctx_time_begin_on(pgm_ctx* c, int kind, cudaStream_t st, void** tok);
 void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
-int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
-int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
-int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows,
+int launch_graph_fill(cudaStream_t st, int dbits, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
+int launch_graph_fill_diag(cudaStream_t st, int dbits, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
+int launch_graph_fill_banded(cudaStream_t st, int dbits, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int band_rows,
                              int max_n2, int max_np);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
@@ -83,10 +83,92 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct JobLayout {                // byte offsets into the upload arena / scratch arena / output arena
     size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2, colinfo, blkstart;
-    size_t S, MXYW, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev, progress;     // scratch
+    size_t S, D, Vrow, Vcol, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev, progress;     // scratch
     size_t map1, map2, result;                           // output
     int np1, np2, cap, pitch, nb, layout, bands, band_rows;
+    int dbits, ldVr, ldVc, nkr, nkc;
+    int C, nstrips, N1e, N2e, coded1, coded2;
+    size_t scol, sstart, colstrip;
+    double uniform1, uniform2;
+    std::vector<int> keep1, keep2;                       // per node: index of its row / column in the value store, or -1
+    std::vector<uint8_t> cls1, cls2;                     // class-coded graphs: site class per node
 };
+
+// Keep sets: which rows of graph 1 / columns of graph 2 the fill writes to the value store as {M,X,Y,W}.  A fill kernel
+// finds a predecessor cell in its shared-memory ring only when it was produced recently: the blocked kernel's ring holds a
+// cell (yp, xp) for the cell (y, x) while (y - yp) + (blk(x) - blk(xp)) < R (R >= 4 sweep steps), the anti-diagonal kernel
+// while (y - yp) + (x - xp) < RING.  So a source row reached by an edge spanning >= t_row positions, or a source column
+// reached by one spanning >= t_col, is kept, with t_row + t_col - 2 < ring depth: every ring miss then hits a kept row or
+// column.  Also kept: row 0 and column 0 (the traceback's closest-|delta| rule on the boundary needs their values), the
+// predecessors of graph 1's end node (end-node match), and every row an edge into a LATER band starts from.
+void mark_far_sources(const pgm_graph& g, const int* pos, int thr, int band_rows, std::vector<int>& keep) {
+    for (int to = 1; to <= g.N - 2; ++to) {
+        const int pt = pos ? pos[to] : to;
+        auto visit = [&](int from) {
+            const int pf = pos ? pos[from] : from;
+            if (pt - pf >= thr || (band_rows > 0 && from / band_rows != to / band_rows)) keep[from] = 1;
+        };
+        for (int e = g.e_rowptr[to]; e < g.e_rowptr[to + 1]; ++e) visit(g.e_col[e]);
+        if (g.r_rowptr) for (int e = g.r_rowptr[to]; e < g.r_rowptr[to + 1]; ++e) visit(g.r_col[e]);
+    }
+}
+int number_kept(std::vector<int>& keep) {                // flags -> indices
+    int n = 0;
+    for (int& k : keep) k = k ? n++ : -1;
+    return n;
+}
+int max_preds(const pgm_graph& g) {
+    int m = 0;
+    for (int node = 0; node < g.N; ++node)
+        m = std::max(m, g.e_rowptr[node + 1] - g.e_rowptr[node] + (g.r_rowptr ? g.r_rowptr[node + 1] - g.r_rowptr[node] : 0));
+    return m;
+}
+
+// ---- job analysis (parallel over jobs): everything that decides sizes ------------------------------------------------------
+struct BatchEnv {                 // environment switches, read once per create (tests, A-B runs, profiling)
+    int force_layout = -1, diag_min_generic = 8, band_min_n1 = GF_BAND_MIN_N1, long_band_rows = GF_BAND_ROWS;
+    int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, force_dbits = 0, strip = 1, coding = 1;
+    BatchEnv() {
+        if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
+        if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
+        if (const char* e = getenv("PGM_FILL_BAND_MIN_N1")) band_min_n1 = std::max(66, atoi(e));
+        if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 64 && v <= 1024) long_band_rows = v; }
+        if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
+        if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
+        if (const char* e = getenv("PGM_FILL_SMALL_BATCH")) small_batch = atoi(e);      // fewer jobs than three per SM: latency-bound (measured crossover 300..440 jobs of 400 x 400)
+        if (const char* e = getenv("PGM_DIR_BITS")) force_dbits = atoi(e);              // 7: 32-bit direction words for every job
+        if (const char* e = getenv("PGM_FILL_STRIP")) strip = atoi(e);                  // 0: never the strip kernel
+        if (const char* e = getenv("PGM_SITE_CLASSES")) coding = atoi(e);               // 0: never class-code leaf graphs
+    }
+};
+
+inline bool non_chain_node(const pgm_graph& g, int x) {
+    const int nreg = g.e_rowptr[x + 1] - g.e_rowptr[x];
+    const int nrep = g.r_rowptr ? g.r_rowptr[x + 1] - g.r_rowptr[x] : 0;
+    return !(nreg == 1 && nrep == 0 && g.e_col[g.e_rowptr[x]] == x - 1);
+}
+
+// Site classes (see GraphJobDev::coded1): class a < n = one-hot column of state a (exactly 1.0), class n = uniform column
+// (every entry equal to the graph's one uniform value, SequenceGraph.h:50-53).  -> false when some interior column is neither.
+bool site_classes(const pgm_graph& g, int n, std::vector<uint8_t>& cls, double& uniform) {
+    cls.assign(g.N, 0);
+    uniform = 0.0;
+    for (int node = 1; node <= g.N - 2; ++node) {
+        const double* s = g.sites + (size_t)n * node;
+        int hot = -1, nz = 0;
+        for (int a = 0; a < n; ++a) if (s[a] != 0.0) { ++nz; hot = a; }
+        if (nz == 1 && s[hot] == 1.0) { cls[node] = (uint8_t)hot; continue; }
+        if (nz == n) {
+            bool same = true;
+            for (int a = 1; a < n; ++a) same &= (s[a] == s[0]);
+            if (same && (uniform == 0.0 || uniform == s[0])) { uniform = s[0]; cls[node] = (uint8_t)n; continue; }
+        }
+        return false;
+    }
+    return true;
+}
+
+thread_local bool t_full_emission = false;   // pgm_emission_scores: the caller wants the whole S matrix, so no class coding
 
 } // namespace
 
@@ -106,13 +188,26 @@ struct pgm_graph_batch {
     // Fill schedule.  The fill kernel's block size and shared memory -- hence CTAs per SM -- are set by the LARGEST job
     // of a launch, so each sub-batch is swept as a few launches of similar graph-2 length (largest first), on
     // separate streams so that a class with few jobs does not leave the GPU idle.
-    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands, band_rows; };
+    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands, band_rows, dbits, C, max_n1e, max_n2e; };
     std::vector<int> order;                 // job indices relative to their sub-batch, grouped by FillLaunch
     std::vector<FillLaunch> fills;
     size_t scratch_bytes_used = 0;
     int max_N1 = 0, max_N2 = 0;
     uint64_t total_updates = 0, total_cells = 0;
 };
+
+namespace {
+template <class F> void parallel_jobs(int n_jobs, F&& fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    const int nthreads = (int)std::max(1u, std::min<unsigned>(std::min<unsigned>(hw ? hw : 1u, 16u), (unsigned)(n_jobs / 8 + 1)));
+    if (nthreads <= 1) { for (int k = 0; k < n_jobs; ++k) fn(k); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nthreads; ++t)
+        pool.emplace_back([&] { for (int k = next.fetch_add(1); k < n_jobs; k = next.fetch_add(1)) fn(k); });
+    for (auto& th : pool) th.join();
+}
+} // namespace
 
 extern "C" {
 
@@ -126,31 +221,23 @@ int pgm_dynprog_scores(int n_states, const pgm_graph* g1, const pgm_graph* g2, c
 
 int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, const pgm_graph* g2,
                            const pgm_dp_model* models, const pgm_dp_opts* opts, pgm_graph_batch** out) {
-    if (!c || !out || n_jobs < 0 || (n_jobs > 0 && (!g1 || !g2 || !models || !opts))) { pgm_set_error("bad arguments"); return PGM_ERR_ARG; }
+    if (!c || !out || !opts || n_jobs < 0 || (n_jobs > 0 && (!g1 || !g2 || !models))) { pgm_set_error("bad arguments"); return PGM_ERR_ARG; }
     if (n < 2 || n > 64) { pgm_set_error("n_states %d out of range", n); return PGM_ERR_ARG; }
     PGM_CUDA(cudaSetDevice(pgm_ctx_device(c)));
     cudaStream_t st = pgm_ctx_stream(c);
+    for (int k = 0; k < n_jobs; ++k) {
+        if (g1[k].N < 2 || g2[k].N < 2) { pgm_set_error("job %d: graphs need at least start and end nodes", k); return PGM_ERR_ARG; }
+        if (g1[k].N > 60000 || g2[k].N > 60000) { pgm_set_error("job %d: graphs of more than 60000 nodes are not supported (%d x %d)", k, g1[k].N, g2[k].N); return PGM_ERR_ARG; }
+    }
     pgm_graph_batch* b = new pgm_graph_batch();
     b->n_states = n; b->n_jobs = n_jobs; b->emission_mode = opts->emission_mode;
     b->lay.resize(n_jobs); b->jobs.resize(n_jobs); b->cell_updates.resize(n_jobs);
-    size_t in_off = 0, out_off = 0;
+    const BatchEnv env;
     std::vector<size_t> scratch_need(n_jobs);
-    int force_layout = -1, diag_min_generic = 8;                  // PGM_FILL_LAYOUT=block|diag forces one kernel (tests, profiling)
-    if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : -1);
-    if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
-    int band_min_n1 = GF_BAND_MIN_N1;
-    if (const char* e = getenv("PGM_FILL_BAND_MIN_N1")) band_min_n1 = std::max(66, atoi(e));
-    int long_band_rows = GF_BAND_ROWS;
-    if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 64 && v <= 1024) long_band_rows = v; }
-    int split_rows = 0, split_min_generic = 24;
-    if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
-    if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
-    int small_batch = 3 * 148;                                    // fewer jobs than three per SM: latency-bound (measured crossover 300..440 jobs of 400 x 400)
-    if (const char* e = getenv("PGM_FILL_SMALL_BATCH")) small_batch = atoi(e);
-    for (int k = 0; k < n_jobs; ++k) {
+    std::vector<int> too_many(n_jobs, 0);
+    // ---- pass A (parallel): per-job analysis -> layout decisions and byte sizes --------------------------------------------
+    parallel_jobs(n_jobs, [&](int k) {
         const pgm_graph &a = g1[k], &bb = g2[k];
-        if (a.N < 2 || bb.N < 2) { delete b; pgm_set_error("job %d: graphs need at least start and end nodes", k); return PGM_ERR_ARG; }
-        if (a.N > 60000 || bb.N > 60000) { delete b; pgm_set_error("job %d: graphs of more than 60000 nodes are not supported (%d x %d)", k, a.N, bb.N); return PGM_ERR_ARG; }
         JobLayout& L = b->lay[k];
         L.np1 = a.e_rowptr[a.N] + (a.r_rowptr ? a.r_rowptr[a.N] : 0);
         L.np2 = bb.e_rowptr[bb.N] + (bb.r_rowptr ? bb.r_rowptr[bb.N] : 0);
@@ -158,40 +245,105 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         // column blocks of graph 2 (columns 0 .. N2-2) for the blocked fill kernel: a block never leaves its aligned group
         // of GF_K columns, and a column whose node is not a chain node (exactly one predecessor, the regular edge from
         // x-1) starts a block, so that inside a block every column's only predecessor is its left neighbour
-        auto non_chain = [](const pgm_graph& g, int x) {
-            const int nreg = g.e_rowptr[x + 1] - g.e_rowptr[x];
-            const int nrep = g.r_rowptr ? g.r_rowptr[x + 1] - g.r_rowptr[x] : 0;
-            return !(nreg == 1 && nrep == 0 && g.e_col[g.e_rowptr[x]] == x - 1);
-        };
-        int nblk = 0, generic = 0;
+        int nblk = 0, generic1 = 0, generic2 = 0;
+        std::vector<int> blk(bb.N, 0);                              // column -> block (same rule as pack_job's colinfo)
         for (int x = 0; x <= bb.N - 2; ++x) {
-            const bool nc = x >= 1 && non_chain(bb, x);
-            generic += nc;
+            const bool nc = x >= 1 && non_chain_node(bb, x);
+            generic2 += nc;
             if ((x & (GF_K - 1)) == 0 || nc) ++nblk;
+            blk[x] = nblk - 1;
         }
-        for (int y = 1; y <= a.N - 2; ++y) generic += non_chain(a, y);
+        blk[bb.N - 1] = nblk;
+        for (int y = 1; y <= a.N - 2; ++y) generic1 += non_chain_node(a, y);
+        const int generic = generic1 + generic2;
         L.nb = nblk;
-        // Which fill kernel: the blocked sweep is ~2x faster on chain-dominated graphs (the bulk of a guide tree's cells); the
-        // anti-diagonal sweep pays almost nothing for multi-predecessor nodes and has the shorter critical path on the few
-        // large, branchy graphs near the root.  It also takes the graphs whose graph 2 is too long for the blocked kernel.
-        // A batch too small to fill the GPU is latency-bound per job, and there the anti-diagonal sweep is the shorter one even
-        // on chain graphs (measured, 400 x 400 nodes alone on an SM: 0.31 ms against 0.49 ms).
-        L.layout = (generic > diag_min_generic || nblk > GF_MAX_NB || n_jobs < small_batch) ? GF_LAYOUT_DIAG : GF_LAYOUT_BLOCK;
-        if (force_layout >= 0 && !(force_layout == GF_LAYOUT_BLOCK && nblk > GF_MAX_NB)) L.layout = force_layout;
+        {
+            const int mp = std::max(max_preds(a), max_preds(bb));
+            if (mp > GF_MAX_PREDS) { too_many[k] = mp; return; }
+            L.dbits = (mp <= 8 && env.force_dbits != 7) ? 3 : 7;
+        }
+        // Which fill kernel.  Strip kernel (register-resident, warp per job): graphs whose nodes are all chain nodes (every
+        // leaf x leaf job and the profile graphs that have no indel yet) with graph 2 short enough for 32 strips.  Otherwise: the
+        // blocked sweep is ~2x faster on chain-dominated graphs; the anti-diagonal sweep pays almost nothing for
+        // multi-predecessor nodes and has the shorter critical path on the few large, branchy graphs near the root.  It also
+        // takes the graphs whose graph 2 is too long for the blocked kernel.  A batch too small to fill the GPU is latency-bound
+        // per job, and there the anti-diagonal sweep is the shorter one even on chain graphs.
+        const int cols = bb.N - 1;                                 // DP columns 0 .. N2-2
+        int C = (cols + 31) / 32;
+        static const int strip_cs[] = {4, 8, 11, 13, 16, 20, 24};
+        int Cpick = 0;
+        for (int q : strip_cs) if (q >= C) { Cpick = q; break; }
+        const bool strip_ok = env.strip && generic == 0 && Cpick > 0 && a.N >= 3 && bb.N >= 3;
+        L.layout = (generic > env.diag_min_generic || nblk > GF_MAX_NB || n_jobs < env.small_batch) ? GF_LAYOUT_DIAG : GF_LAYOUT_BLOCK;
+        if (strip_ok) L.layout = GF_LAYOUT_STRIP;
+        if (env.force_layout >= 0 && !(env.force_layout == GF_LAYOUT_BLOCK && nblk > GF_MAX_NB) && !(env.force_layout == GF_LAYOUT_STRIP && !strip_ok)) L.layout = env.force_layout;
+        L.C = L.layout == GF_LAYOUT_STRIP ? Cpick : 0;
+        L.nstrips = L.layout == GF_LAYOUT_STRIP ? (cols + Cpick - 1) / Cpick : 0;
         // Bands: graphs too long for one CTA.  Short bands for the large branchy graphs (three SMs sharing one job's rows) are
         // wired and tested (PGM_FILL_SPLIT_ROWS) but off: measured 1.73 -> 2.8 ms on the 500-row jobs of the bench batch,
         // the first row of a band pays an L2 round trip per anti-diagonal
         L.band_rows = 0;
         if (L.layout == GF_LAYOUT_DIAG) {
-            if (a.N >= band_min_n1) L.band_rows = long_band_rows;
-            else if (split_rows > 0 && generic > split_min_generic && a.N - 1 >= 2 * split_rows) L.band_rows = split_rows;
+            if (a.N >= env.band_min_n1) L.band_rows = env.long_band_rows;
+            else if (env.split_rows > 0 && generic > env.split_min_generic && a.N - 1 >= 2 * env.split_rows) L.band_rows = env.split_rows;
         }
         L.bands = L.band_rows ? (a.N - 1 + L.band_rows - 1) / L.band_rows : 1;
         if (L.bands == 1) L.band_rows = 0;
-        L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 8);
+        L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 2);
+        {   // keep sets (see mark_far_sources): thresholds from the ring depth the job's kernel is guaranteed to have
+            L.keep1.assign(a.N, 0); L.keep2.assign(bb.N, 0);
+            L.keep1[0] = 1; L.keep2[0] = 1;
+            for (int e = a.e_rowptr[a.N - 1]; e < a.e_rowptr[a.N]; ++e) L.keep1[a.e_col[e]] = 1;
+            if (a.r_rowptr) for (int e = a.r_rowptr[a.N - 1]; e < a.r_rowptr[a.N]; ++e) L.keep1[a.r_col[e]] = 1;
+            if (L.layout == GF_LAYOUT_BLOCK) {                      // 4-step ring: rows <= 2 back and blocks <= 1 back always hit
+                mark_far_sources(a, nullptr, 3, 0, L.keep1);
+                mark_far_sources(bb, blk.data(), 2, 0, L.keep2);
+            } else if (L.layout == GF_LAYOUT_DIAG) {                // 8-diagonal ring (4 for long unbanded graphs)
+                const int thr = (L.bands == 1 && a.N - 1 > GF_DIAG_REGULAR_ROWS) ? 2 : 4;
+                mark_far_sources(a, nullptr, thr, L.band_rows, L.keep1);
+                mark_far_sources(bb, nullptr, thr, 0, L.keep2);
+            }                                                       // strip: chain nodes only, nothing is far
+            if (L.bands > 1) for (int q = 1; q < L.bands; ++q) L.keep1[q * L.band_rows - 1] = 1;   // the row above each band
+        }
+        L.nkr = number_kept(L.keep1); L.nkc = number_kept(L.keep2);
+        L.ldVr = (int)align_up((size_t)bb.N, 8) + 8; L.ldVc = (int)align_up((size_t)a.N, 4);
+        // class-coded emission inputs (strip jobs only: the other kernels stream full rows of S)
+        L.coded1 = L.coded2 = 0;
+        if (L.layout == GF_LAYOUT_STRIP && env.coding && !t_full_emission && n + 3 < 120) {
+            double u1 = 0, u2 = 0;
+            if (a.N > n + 3 && site_classes(a, n, L.cls1, u1)) { L.coded1 = 1; L.uniform1 = u1; }
+            if (bb.N > n + 3 && site_classes(bb, n, L.cls2, u2)) { L.coded2 = 1; L.uniform2 = u2; }
+        }
+        L.N1e = L.coded1 ? n + 3 : a.N; L.N2e = L.coded2 ? n + 3 : bb.N;      // pseudo-nodes: 0 (start), 1 .. n+1 (classes 0 .. n), n+2 (end)
+        const size_t d_words = L.layout == GF_LAYOUT_DIAG ? ((size_t)a.N + bb.N - 1) * L.pitch
+                             : L.layout == GF_LAYOUT_BLOCK ? ((size_t)(a.N - 1) + L.nb - 1) * GF_K * L.pitch : 0;
+        const size_t d_bytes = L.layout == GF_LAYOUT_STRIP ? ((size_t)(a.N - 1) + L.nstrips) * L.nstrips * strip_words(L.C) * 4
+                                                           : d_words * (L.dbits == 3 ? 2 : 4);
         auto take = [&](size_t& off, size_t bytes) { size_t r = off; off = align_up(off + bytes, 128); return r; };
-        L.sites1 = take(in_off, sizeof(float) * n * a.N);
-        L.sites2 = take(in_off, sizeof(float) * n * bb.N);
+        size_t so = 0;
+        L.S = take(so, (size_t)L.N1e * (((size_t)L.N2e + 3) & ~(size_t)3) * 4 + 128);
+        L.D = take(so, d_bytes + 64);
+        L.Vrow = take(so, (size_t)L.nkr * L.ldVr * 16 + 16); L.Vcol = take(so, (size_t)L.nkc * L.ldVc * 16 + 16);
+        L.Tbuf = take(so, sizeof(float) * n * L.N2e); L.u = take(so, 4 * L.N1e); L.v = take(so, 4 * L.N2e);
+        if (opts->emission_mode == PGM_EMISSION_TENSOR) {
+            const size_t kp = (size_t)((3 * n + 7) & ~7);
+            L.Aimg = take(so, (size_t)((L.N1e + 127) / 128) * 128 * kp * 4);
+            L.Bimg = take(so, (size_t)((L.N2e + 127) / 128) * 128 * kp * 4);
+        } else { L.Aimg = L.Bimg = 0; }
+        L.alt_score = take(so, 4 * std::max(a.N, bb.N)); L.alt_prev = take(so, 4 * std::max(a.N, bb.N));
+        L.progress = take(so, 4 * ((size_t)L.bands + 1));
+        scratch_need[k] = so;
+    });
+    for (int k = 0; k < n_jobs; ++k)
+        if (too_many[k]) { pgm_graph_batch_destroy(c, b); pgm_set_error("job %d: a node has %d predecessors (more than %d are not supported)", k, too_many[k], GF_MAX_PREDS); return PGM_ERR_ARG; }
+    // ---- pass B (serial): arena offsets -------------------------------------------------------------------------------------
+    size_t in_off = 0, out_off = 0;
+    for (int k = 0; k < n_jobs; ++k) {
+        const pgm_graph &a = g1[k], &bb = g2[k];
+        JobLayout& L = b->lay[k];
+        auto take = [&](size_t& off, size_t bytes) { size_t r = off; off = align_up(off + bytes, 128); return r; };
+        L.sites1 = take(in_off, sizeof(float) * n * L.N1e);
+        L.sites2 = take(in_off, sizeof(float) * n * L.N2e);
         L.Mf = take(in_off, sizeof(float) * n * n);
         L.pif = take(in_off, sizeof(float) * n);
         L.p1_ptr = take(in_off, 4 * (a.N + 1)); L.p1_idx = take(in_off, 4 * L.np1); L.p1_val = take(in_off, 4 * L.np1);
@@ -200,20 +352,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.p2_alt = take(in_off, 4 * L.np2); L.p2_rep = take(in_off, L.np2);
         L.ni1 = take(in_off, sizeof(NodeInfo) * a.N); L.ni2 = take(in_off, sizeof(NodeInfo) * bb.N);
         L.colinfo = take(in_off, 2 * (size_t)bb.N); L.blkstart = take(in_off, 2 * ((size_t)L.nb + 1));
-        L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 16);
-        const size_t mxyw_cells = L.layout == GF_LAYOUT_DIAG ? ((size_t)a.N + bb.N - 1) * L.pitch
-                                                             : ((size_t)(a.N - 1) + L.nb - 1) * GF_K * L.pitch;
-        size_t so = 0;
-        L.S = take(so, (size_t)a.N * (((size_t)bb.N + 3) & ~(size_t)3) * 4 + 64); L.MXYW = take(so, mxyw_cells * 16);
-        L.Tbuf = take(so, sizeof(float) * n * bb.N); L.u = take(so, 4 * a.N); L.v = take(so, 4 * bb.N);
-        if (opts->emission_mode == PGM_EMISSION_TENSOR) {
-            const size_t kp = (size_t)((3 * n + 7) & ~7);
-            L.Aimg = take(so, (size_t)((a.N + 127) / 128) * 128 * kp * 4);
-            L.Bimg = take(so, (size_t)((bb.N + 127) / 128) * 128 * kp * 4);
-        } else { L.Aimg = L.Bimg = 0; }
-        L.alt_score = take(so, 4 * std::max(a.N, bb.N)); L.alt_prev = take(so, 4 * std::max(a.N, bb.N));
-        L.progress = take(so, 4 * (size_t)L.bands);
-        scratch_need[k] = so;
+        L.scol = take(in_off, 2 * (size_t)bb.N);
+        L.sstart = take(in_off, 4 * ((size_t)L.nstrips + 1)); L.colstrip = take(in_off, L.nstrips ? 4 * (size_t)bb.N : 0);
+        L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 32);
         b->max_N1 = std::max(b->max_N1, a.N); b->max_N2 = std::max(b->max_N2, bb.N);
     }
     // sub-batches by scratch budget (each job's scratch offsets are relative to its sub-batch)
@@ -236,18 +377,30 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     b->out_bytes = out_off;
     char* hin = b->h_in.as<char>();
     char* din = b->d_in.as<char>(); char* dsc = b->d_scratch.as<char>(); char* dout = b->d_out.as<char>();
-    // Packing a job (double -> float sites, predecessor lists, node infos, DynProgScores) touches only that job's slices of
-    // the arenas, so the jobs are packed by a few host threads.
+    // ---- pass C (parallel): pack.  Packing a job (double -> float sites, predecessor lists, node infos, DynProgScores) touches
+    // only that job's slices of the arenas ----
     auto pack_job = [&](int k) {
         const pgm_graph* gs[2] = {&g1[k], &g2[k]};
         const JobLayout& L = b->lay[k];
         GraphJobDev& J = b->jobs[k];
-        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.nb = L.nb; J.layout = L.layout; J.bands = L.bands; J.band_rows = L.band_rows; J.cap = L.cap; J.ldS = (g2[k].N + 3) & ~3;
+        memset(&J, 0, sizeof(J));
+        J.N1 = g1[k].N; J.N2 = g2[k].N; J.pitch = L.pitch; J.nb = L.nb; J.layout = L.layout; J.bands = L.bands; J.band_rows = L.band_rows; J.cap = L.cap;
+        J.N1e = L.N1e; J.N2e = L.N2e; J.coded1 = L.coded1; J.coded2 = L.coded2; J.nstrips = L.nstrips; J.C = L.C;
+        J.ldS = (L.N2e + 3) & ~3;
         dynprog_scores(g1[k], g2[k], models[k], *opts, J.sc);
         const float rinit = J.sc[8], rext = J.sc[9];
-        float* s1 = (float*)(hin + L.sites1); float* s2 = (float*)(hin + L.sites2);
-        for (size_t i = 0; i < (size_t)n * g1[k].N; ++i) s1[i] = (float)g1[k].sites[i];
-        for (size_t i = 0; i < (size_t)n * g2[k].N; ++i) s2[i] = (float)g2[k].sites[i];
+        for (int w = 0; w < 2; ++w) {                               // emission inputs: the graph's columns, or its n + 1 class columns
+            const pgm_graph& g = *gs[w];
+            float* s = (float*)(hin + (w == 0 ? L.sites1 : L.sites2));
+            if (w == 0 ? L.coded1 : L.coded2) {
+                const float uf = (float)(w == 0 ? L.uniform1 : L.uniform2);
+                memset(s, 0, sizeof(float) * n * (n + 3));
+                for (int a = 0; a < n; ++a) s[(size_t)n * (1 + a) + a] = 1.0f;          // pseudo-node 1 + a: one-hot state a
+                for (int a = 0; a < n; ++a) s[(size_t)n * (1 + n) + a] = uf;            // pseudo-node 1 + n: the uniform column
+            } else {
+                for (size_t i = 0; i < (size_t)n * g.N; ++i) s[i] = (float)g.sites[i];
+            }
+        }
         float* Mf = (float*)(hin + L.Mf); float* pif = (float*)(hin + L.pif);
         for (int i = 0; i < n * n; ++i) Mf[i] = (float)models[k].M[i];
         for (int i = 0; i < n; ++i) pif[i] = (float)models[k].pi[i];
@@ -283,24 +436,35 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             }
             ptr[g.N] = q;
             NodeInfo* ni = (NodeInfo*)(hin + (w == 0 ? L.ni1 : L.ni2));
+            const bool coded = w == 0 ? L.coded1 : L.coded2;
+            const std::vector<uint8_t>& cls = w == 0 ? L.cls1 : L.cls2;
             for (int node = 0; node < g.N; ++node) {
                 const int cnt = ptr[node + 1] - ptr[node];
+                const int kept = (w == 0 ? L.keep1 : L.keep2)[node];                         // value-store row / column, or -1
+                const int sclass = coded ? 1 + (int)cls[node] : 0;                           // S row / column of a class-coded node (pseudo-node index)
                 ni[node].ptr = ptr[node];
-                ni[node].cnt = cnt | ((cnt && rep[ptr[node]]) ? (int)0x80000000 : 0);     // sign bit: first pred is a repeat edge
+                ni[node].cnt = cnt | ((kept + 1) << 8) | (sclass << 24) | ((cnt && rep[ptr[node]]) ? (int)0x80000000 : 0);   // NI_CNT / NI_KEEP / NI_CLASS / first pred is a repeat edge
                 ni[node].idx0 = cnt ? idx[ptr[node]] : 0; ni[node].val0 = cnt ? val[ptr[node]] : 0.f;
             }
         }
-        {   // column blocks of graph 2, from the node infos just built (same rule as the sizing pass above)
+        {   // column blocks of graph 2, from the node infos just built (same rule as the analysis pass)
             const NodeInfo* ni = (const NodeInfo*)(hin + L.ni2);
             uint16_t* ci = (uint16_t*)(hin + L.colinfo); uint16_t* bs = (uint16_t*)(hin + L.blkstart);
+            uint16_t* sc = (uint16_t*)(hin + L.scol);
             int blk = -1;
             for (int x = 0; x <= g2[k].N - 2; ++x) {
-                const bool chain = x == 0 || (ni[x].cnt == 1 && ni[x].idx0 == x - 1);
+                const bool chain = x == 0 || NI_CHAIN(ni[x], x);
                 if ((x & (GF_K - 1)) == 0 || !chain) { ++blk; bs[blk] = (uint16_t)x; }
                 ci[x] = (uint16_t)((blk << GF_LOGK) | (x & (GF_K - 1)));
             }
             bs[blk + 1] = (uint16_t)(g2[k].N - 1);
             ci[g2[k].N - 1] = 0;
+            for (int x = 0; x < g2[k].N; ++x) sc[x] = (uint16_t)(L.coded2 ? NI_CLASS(ni[x].cnt) : x);
+        }
+        if (L.nstrips) {                                            // strips of the strip kernel: C columns each
+            int* ss = (int*)(hin + L.sstart); uint32_t* cs = (uint32_t*)(hin + L.colstrip);
+            for (int j = 0; j <= L.nstrips; ++j) ss[j] = std::min(j * L.C, g2[k].N - 1);
+            for (int x = 0; x < g2[k].N; ++x) cs[x] = (uint32_t)((x / L.C) * 32 + x % L.C);
         }
         b->cell_updates[k] = deg_sum[0] * deg_sum[1];
         char* sb = dsc + scratch_base[k];
@@ -312,34 +476,28 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.p2_rep = (const uint8_t*)(din + L.p2_rep); J.p2_alt = (const float*)(din + L.p2_alt);
         J.ni1 = (const NodeInfo*)(din + L.ni1); J.ni2 = (const NodeInfo*)(din + L.ni2);
         J.colinfo = (const uint16_t*)(din + L.colinfo); J.blkstart = (const uint16_t*)(din + L.blkstart);
+        J.scol = (const uint16_t*)(din + L.scol);
+        J.sstart = (const int*)(din + L.sstart); J.colstrip = (const uint32_t*)(din + L.colstrip);
         J.np1 = L.np1; J.np2 = L.np2;
-        J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.Tbuf = (float*)(sb + L.Tbuf);
+        J.S = (float*)(sb + L.S); J.D = (void*)(sb + L.D); J.dbits = L.dbits; J.Tbuf = (float*)(sb + L.Tbuf);
+        J.Vrow = (float4*)(sb + L.Vrow); J.Vcol = (float4*)(sb + L.Vcol); J.ldVr = L.ldVr; J.ldVc = L.ldVc;
         J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
         J.Aimg = (float*)(sb + L.Aimg); J.Bimg = (float*)(sb + L.Bimg);
         J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev); J.progress = (int*)(sb + L.progress);
         J.map1 = (int*)(dout + L.map1); J.map2 = (int*)(dout + L.map2); J.result = (int*)(dout + L.result);
     };
-    {
-        unsigned hw = std::thread::hardware_concurrency();
-        const int nthreads = (int)std::max(1u, std::min<unsigned>(std::min<unsigned>(hw ? hw : 1u, 16u), (unsigned)(n_jobs / 8 + 1)));
-        if (nthreads <= 1) { for (int k = 0; k < n_jobs; ++k) pack_job(k); }
-        else {
-            std::atomic<int> next(0);
-            std::vector<std::thread> pool;
-            for (int t = 0; t < nthreads; ++t)
-                pool.emplace_back([&] { for (int k = next.fetch_add(1); k < n_jobs; k = next.fetch_add(1)) pack_job(k); });
-            for (auto& th : pool) th.join();
-        }
-        for (int k = 0; k < n_jobs; ++k) { b->total_updates += b->cell_updates[k]; b->total_cells += (uint64_t)b->jobs[k].N1 * b->jobs[k].N2; }
-    }
+    parallel_jobs(n_jobs, pack_job);
+    for (int k = 0; k < n_jobs; ++k) { b->total_updates += b->cell_updates[k]; b->total_cells += (uint64_t)b->jobs[k].N1 * b->jobs[k].N2; }
     {   // fill schedule: per kernel flavour, block-size classes (blocked: column blocks per row rounded up to warps;
-        // diagonal: graph-1 rows); longest sweeps first
+        // diagonal: graph-1 rows; strip: columns per strip); longest sweeps first
         b->order.resize(n_jobs);
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
-        auto class_of = [&](const GraphJobDev& J) {
-            if (J.bands > 1) return 200 + J.band_rows / 32;                   // banded anti-diagonal sweeps: their own launches, one per band height
-            if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
-            const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
+        auto class_of = [&](const GraphJobDev& J) {                          // + 1000: 32-bit direction words (their own kernel instantiation)
+            if (J.layout == GF_LAYOUT_STRIP) return 300 + J.C;
+            const int wide = J.dbits == 3 ? 0 : 1000;
+            if (J.bands > 1) return wide + 200 + J.band_rows / 32;            // banded anti-diagonal sweeps: their own launches, one per band height
+            if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return wide + 100 + q; }
+            const int w = (J.nb + 31) / 32; return wide + (w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16)));
         };
         for (size_t si = 0; si < b->sub.size(); ++si) {
             const auto& sbr = b->sub[si];
@@ -347,20 +505,25 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             for (int k = sbr.first; k < sbr.second; ++k) idx.push_back(k - sbr.first);
             std::stable_sort(idx.begin(), idx.end(), [&](int a, int bq) {
                 const GraphJobDev &A = b->jobs[sbr.first + a], &B = b->jobs[sbr.first + bq];
-                const int ca = class_of(A), cb = class_of(B);
+                const int ca = class_of(A) % 1000, cb = class_of(B) % 1000, wa = class_of(A) / 1000, wb = class_of(B) / 1000;
+                const bool sa = A.layout == GF_LAYOUT_STRIP, sbq = B.layout == GF_LAYOUT_STRIP;
+                if (sa != sbq) return sbq;                                   // strip launches last: the short ones
                 if (ca != cb) return ca > cb;
+                if (wa != wb) return wa > wb;
                 return A.N1 + A.N2 > B.N1 + B.N2;
             });
             std::copy(idx.begin(), idx.end(), b->order.begin() + sbr.first);
             size_t p = 0;
             while (p < idx.size()) {
-                const int q = class_of(b->jobs[sbr.first + idx[p]]);
-                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, b->jobs[sbr.first + idx[p]].layout, 0, 0, 0, 0, 0, 1, b->jobs[sbr.first + idx[p]].band_rows};
+                const GraphJobDev& J0 = b->jobs[sbr.first + idx[p]];
+                const int q = class_of(J0);
+                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, J0.layout, 0, 0, 0, 0, 0, 1, J0.band_rows, J0.dbits, J0.C, 0, 0};
                 while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]]) == q) {
                     const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
                     f.max_nb = std::max(f.max_nb, J.nb); f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2);
                     f.max_np2 = std::max(f.max_np2, J.np2); f.max_np = std::max(f.max_np, J.np1 + J.np2);
                     f.max_bands = std::max(f.max_bands, J.bands);
+                    f.max_n1e = std::max(f.max_n1e, J.N1e); f.max_n2e = std::max(f.max_n2e, J.N2e);
                     ++f.count; ++p;
                 }
                 b->fills.push_back(f);
@@ -368,10 +531,15 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         }
     }
     if (n_jobs) {
-        PGM_CUDA(cudaMemcpyAsync(b->d_in.p, b->h_in.p, in_off, cudaMemcpyHostToDevice, st));
-        PGM_CUDA(cudaMemcpyAsync(b->d_jobs.as<char>() + sizeof(GraphJobDev) * n_jobs, b->order.data(), sizeof(int) * n_jobs, cudaMemcpyHostToDevice, st));
-        PGM_CUDA(cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(GraphJobDev) * n_jobs, cudaMemcpyHostToDevice, st));
-        PGM_CUDA(cudaStreamSynchronize(st));
+        cudaError_t e = cudaMemcpyAsync(b->d_in.p, b->h_in.p, in_off, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_jobs.as<char>() + sizeof(GraphJobDev) * n_jobs, b->order.data(), sizeof(int) * n_jobs, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(GraphJobDev) * n_jobs, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            pgm_set_error("CUDA error %s while uploading the graph batch: %s", cudaGetErrorName(e), cudaGetErrorString(e));
+            pgm_graph_batch_destroy(c, b);
+            return PGM_ERR_CUDA;
+        }
     }
     *out = b;
     return 0;
@@ -390,30 +558,43 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
     const bool pipelined = !(env && atoi(env) == 0);
     const GraphJobDev* dj = b->d_jobs.as<GraphJobDev>();
     const int* d_order_all = (const int*)(b->d_jobs.as<char>() + sizeof(GraphJobDev) * b->n_jobs);
-    int n_sms = 148; cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, pgm_ctx_device(c));
+    // status words (emission failure flag, end-node pick) start from zero on every run
+    if (b->out_bytes) PGM_CUDA(cudaMemsetAsync(b->d_out.p, 0, b->out_bytes, st));
     for (size_t si = 0; si < b->sub.size(); ++si) {
         const auto& sb = b->sub[si];
         const int nj = sb.second - sb.first;
         int mx1 = 0, mx2 = 0;
-        for (int k = sb.first; k < sb.second; ++k) { mx1 = std::max(mx1, b->jobs[k].N1); mx2 = std::max(mx2, b->jobs[k].N2); }
+        for (int k = sb.first; k < sb.second; ++k) { mx1 = std::max(mx1, b->jobs[k].N1e); mx2 = std::max(mx2, b->jobs[k].N2e); }
         std::vector<const pgm_graph_batch::FillLaunch*> fl;
         for (auto& f : b->fills) if (f.sub == (int)si) fl.push_back(&f);
         int rc = 0; void* tok;
-        auto emit = [&](cudaStream_t sq, int count, const int* ord, int m1, int m2) {
-            return b->emission_mode == PGM_EMISSION_TENSOR ? launch_emission_tensor(sq, b->n_states, count, dj + sb.first, ord, m1, m2)
-                                                           : launch_emission_exact(sq, b->n_states, count, dj + sb.first, ord, m1, m2);
+        auto emit = [&](cudaStream_t sq, int count, const int* ord, int m1, int m2) -> int {
+            const int rc_e = b->emission_mode == PGM_EMISSION_TENSOR ? launch_emission_tensor(sq, b->n_states, count, dj + sb.first, ord, m1, m2)
+                                                                     : launch_emission_exact(sq, b->n_states, count, dj + sb.first, ord, m1, m2);
+            if (rc_e) return rc_e;
+            // fault injection for the tests: PGM_INJECT_EMISSION_FAIL=<job> marks that job's emission as failed, exactly as
+            // the tensor kernel does when a bounded mbarrier wait times out (result[4]); the job must then fail, not align
+            if (const char* e = getenv("PGM_INJECT_EMISSION_FAIL")) {
+                const int kf = atoi(e);
+                if (kf >= sb.first && kf < sb.second) {
+                    static const int err = PGM_ERR_CUDA;
+                    PGM_CUDA(cudaMemcpyAsync(b->jobs[kf].result + 4, &err, sizeof(int), cudaMemcpyHostToDevice, sq));
+                }
+            }
+            return 0;
         };
         auto fill = [&](cudaStream_t sq, const pgm_graph_batch::FillLaunch* f) -> int {
             const int* ord = d_order_all + sb.first + f->offset;
+            if (f->layout == GF_LAYOUT_STRIP) return launch_graph_fill_strip(sq, f->C, f->count, dj + sb.first, ord);
             if (f->max_bands > 1) {
-                for (int jq = 0; jq < f->count; ++jq) {             // zero the bands' progress flags
+                for (int jq = 0; jq < f->count; ++jq) {             // zero the bands' progress flags and the band ticket
                     const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + f->offset + jq]];
-                    PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * Jq.bands, sq));
+                    PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * (Jq.bands + 1), sq));
                 }
-                return launch_graph_fill_banded(sq, f->count, dj + sb.first, ord, f->max_bands, n_sms, f->band_rows, f->max_n2, f->max_np);
+                return launch_graph_fill_banded(sq, f->dbits, f->count, dj + sb.first, ord, f->max_bands, f->band_rows, f->max_n2, f->max_np);
             }
-            return f->layout == GF_LAYOUT_DIAG ? launch_graph_fill_diag(sq, f->count, dj + sb.first, ord, f->max_n1, f->max_n2, f->max_np)
-                                               : launch_graph_fill(sq, f->count, dj + sb.first, ord, f->max_nb, f->max_n2, f->max_np2);
+            return f->layout == GF_LAYOUT_DIAG ? launch_graph_fill_diag(sq, f->dbits, f->count, dj + sb.first, ord, f->max_n1, f->max_n2, f->max_np)
+                                               : launch_graph_fill(sq, f->dbits, f->count, dj + sb.first, ord, f->max_nb, f->max_n2, f->max_np2);
         };
         // side streams: the first class stays on the main stream, the others fork from it and are joined at the end
         SideStreams& ss = side_streams(pgm_ctx_device(c));
@@ -446,7 +627,7 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             for (size_t q = 0; q < fl.size() && !rc; ++q) {
                 cudaStream_t sq = stream_of(q);
                 const int* ord = d_order_all + sb.first + fl[q]->offset;
-                pgm_ctx_time_begin_on(c, 3, sq, &tok); rc = emit(sq, fl[q]->count, ord, fl[q]->max_n1, fl[q]->max_n2); pgm_ctx_time_end(c, tok);
+                pgm_ctx_time_begin_on(c, 3, sq, &tok); rc = emit(sq, fl[q]->count, ord, fl[q]->max_n1e, fl[q]->max_n2e); pgm_ctx_time_end(c, tok);
                 if (rc) break;
                 pgm_ctx_time_begin_on(c, 4, sq, &tok); rc = fill(sq, fl[q]); pgm_ctx_time_end(c, tok);
                 if (rc) break;
@@ -502,7 +683,8 @@ int pgm_graph_batch_fetch(pgm_ctx* c, pgm_graph_batch* b, pgm_alignment* out) {
             }
         } else if (worst == 0) {
             worst = A.status;
-            pgm_set_error(A.status == PGM_ERR_BACKTRACK ? "job %d: backtracking failed" : "job %d: mapping capacity too small", k);
+            pgm_set_error(A.status == PGM_ERR_BACKTRACK ? "job %d: backtracking failed"
+                          : (A.status == PGM_ERR_CAPACITY ? "job %d: mapping capacity too small" : "job %d: the emission kernel failed (tensor pipeline timeout)"), k);
         }
     }
     return worst;
@@ -533,7 +715,9 @@ int pgm_emission_scores(pgm_ctx* c, int n, const pgm_graph* g1, const pgm_graph*
     pgm_dp_opts o{}; o.indel_rate = 0.0093359375; o.end_indel_prob = 0.12; o.repeat_rate = 0.1; o.repeatext_prob = 0.3;
     o.emission_mode = emission_mode;
     pgm_graph_batch* b = nullptr;
+    t_full_emission = true;
     int rc = pgm_graph_batch_create(c, n, 1, g1, g2, model, &o, &b);
+    t_full_emission = false;
     if (rc) return rc;
     cudaStream_t st = pgm_ctx_stream(c);
     b->jobs[0].sc[2] = match_init;

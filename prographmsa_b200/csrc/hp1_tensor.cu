@@ -105,7 +105,7 @@ emission_images_kernel(int n, int tiles_y, int tiles_x, const GraphJobDev* __res
     const int t = blockIdx.x, r = threadIdx.x;
     const bool isA = t < tiles_y;
     const int tile = isA ? t : t - tiles_y;
-    const int N = isA ? J.N1 : J.N2;
+    const int N = isA ? J.N1e : J.N2e;
     if (tile * ET_M >= N) return;
     const int node = tile * ET_M + r;
     char* img = (char*)(isA ? J.Aimg : J.Bimg) + (size_t)tile * ET_M * KP * 4;
@@ -160,7 +160,7 @@ template <int KP, int BST>
 __global__ void __launch_bounds__(ETP_THREADS)
 emission_tensor_kernel(int tiles_y, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
     const GraphJobDev& J = jobs[order ? order[blockIdx.y] : blockIdx.y];
-    const int N1 = J.N1, N2 = J.N2;
+    const int N1 = J.N1e, N2 = J.N2e;
     const int y0 = blockIdx.x * ET_M;
     if (y0 >= N1) return;
     const int ntx = (N2 + ET_N - 1) / ET_N;
@@ -281,21 +281,26 @@ emission_tensor_kernel(int tiles_y, const GraphJobDev* __restrict__ jobs, const 
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
     __syncthreads();
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(2 * ET_N));
-    if (tid == 0 && s_fail) J.result[0] = PGM_ERR_CUDA;           // surfaces as a failed job, never as a hang
+    if (tid == 0 && s_fail) J.result[4] = PGM_ERR_CUDA;           // emission status: the traceback kernel turns it into the job's status (a failed job, never a hang)
 }
 
 template <int KP, int BST>
 static int launch_t(cudaStream_t st, int n, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int tiles_x, int tiles_y) {
-    {
-        dim3 grid(tiles_y + tiles_x, n_jobs);
-        emission_images_kernel<KP><<<grid, ET_M, sizeof(float) * (n * n + n), st>>>(n, tiles_y, tiles_x, d_jobs, d_order);
-        PGM_CUDA(cudaGetLastError());
-    }
     const size_t smem = (size_t)(1 + BST) * ET_M * KP * 4;
     PGM_CUDA(cudaFuncSetAttribute(emission_tensor_kernel<KP, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(tiles_y, n_jobs);
-    emission_tensor_kernel<KP, BST><<<grid, ETP_THREADS, smem, st>>>(tiles_y, d_jobs, d_order);
-    PGM_CUDA(cudaGetLastError());
+    for (int j0 = 0; j0 < n_jobs; j0 += 65535) {                   // gridDim.y holds at most 65535 jobs
+        const int nj = n_jobs - j0 < 65535 ? n_jobs - j0 : 65535;
+        const GraphJobDev* dj = d_order ? d_jobs : d_jobs + j0;
+        const int* ord = d_order ? d_order + j0 : nullptr;
+        {
+            dim3 grid(tiles_y + tiles_x, nj);
+            emission_images_kernel<KP><<<grid, ET_M, sizeof(float) * (n * n + n), st>>>(n, tiles_y, tiles_x, dj, ord);
+            PGM_CUDA(cudaGetLastError());
+        }
+        dim3 grid(tiles_y, nj);
+        emission_tensor_kernel<KP, BST><<<grid, ETP_THREADS, smem, st>>>(tiles_y, dj, ord);
+        PGM_CUDA(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -58,8 +58,9 @@ angle_gram_kernel(const uint16_t* __restrict__ counts, const double* __restrict_
         __syncthreads();
 #pragma unroll 8
         for (int k = 0; k < 64; ++k) {
-            const int a0 = A[ty][k], a1 = A[ty + 16][k], b0 = B[tx][k], b1 = B[tx + 16][k];
-            acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[1][0] += a1 * b0; acc[1][1] += a1 * b1;
+            // counts reach 65534 (sequences up to 65535 long): the product needs 32 unsigned bits, the sum 64
+            const uint32_t a0 = A[ty][k], a1 = A[ty + 16][k], b0 = B[tx][k], b1 = B[tx + 16][k];
+            acc[0][0] += (long long)(a0 * b0); acc[0][1] += (long long)(a0 * b1); acc[1][0] += (long long)(a1 * b0); acc[1][1] += (long long)(a1 * b1);
         }
         __syncthreads();
     }

@@ -17,6 +17,7 @@
 // Newton state redundantly (xor-shuffle reductions give every lane identical bits), so the loop has
 // no divergence.  FP64 on CUDA cores; agreement with the reference is ~1e-13 relative on P(t).
 #include "internal.h"
+#include <mutex>
 
 enum { FRONT_LIST = 0, FRONT_ROWS = 1, FRONT_COUNTS = 2 };
 
@@ -284,17 +285,24 @@ static int launch_ml_t(cudaStream_t st, const MlDev& ml, const MlFront& fr, long
     const size_t smem = sizeof(double) * ((ATAB ? (size_t)nn * (n + 1) : 2 * (size_t)nn) + ((n + 1) & ~1) + (size_t)WARPS * n * 4) +
                         sizeof(uint32_t) * (size_t)WARPS * nn;
     // attribute / occupancy queries are driver calls: do them once per (instantiation, shared-memory size), not per launch
-    static size_t cached_smem = 0; static int cached_sms = 148, cached_per_sm = 1;
-    if (cached_smem != smem) {
-        PGM_CUDA(cudaFuncSetAttribute(ml_kernel<FRONT, ATAB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cached_per_sm, ml_kernel<FRONT, ATAB, WARPS>, WARPS * 32, smem);
-        if (cached_per_sm < 1) cached_per_sm = 1;
-        cached_smem = smem;
+    // (function attributes are per device: one cache slot per device, guarded for concurrent contexts)
+    struct Cache { size_t smem = 0; int sms = 148, per_sm = 1; };
+    static Cache cache[64]; static std::mutex cache_mu;
+    int dev = 0;
+    PGM_CUDA(cudaGetDevice(&dev));
+    int sms, per_sm;
+    {
+        std::lock_guard<std::mutex> lk(cache_mu);
+        Cache& cc = cache[dev & 63];
+        if (cc.smem != smem) {
+            PGM_CUDA(cudaFuncSetAttribute(ml_kernel<FRONT, ATAB, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaDeviceGetAttribute(&cc.sms, cudaDevAttrMultiProcessorCount, dev);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&cc.per_sm, ml_kernel<FRONT, ATAB, WARPS>, WARPS * 32, smem);
+            if (cc.per_sm < 1) cc.per_sm = 1;
+            cc.smem = smem;
+        }
+        sms = cc.sms; per_sm = cc.per_sm;
     }
-    const int sms = cached_sms, per_sm = cached_per_sm;
     long long want = (n_pairs + WARPS - 1) / WARPS;
     long long grid = (long long)sms * per_sm;
     if (grid > want) grid = want;

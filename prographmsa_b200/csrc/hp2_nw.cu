@@ -36,6 +36,7 @@
 //
 // Integer arithmetic only: bit-exact against the oracle.
 #include "internal.h"
+#include <mutex>
 
 #define NW_WARPS 8
 #define NW_THREADS (NW_WARPS * 32)
@@ -413,8 +414,16 @@ int launch_nw_forward(cudaStream_t st, int n_tasks, int n_states, int max_bands,
     const size_t prof16 = u16_max_rows > 0 ? (size_t)n1 * NW_TWIN_ROW_BYTES + (size_t)NW_WARPS * (512 + rs_stride) * 4 : 0;
     const size_t smem = ((n1 * n1 + 15) & ~15) + (prof32 > prof16 ? prof32 : prof16);
     if (smem > 227 * 1024) { pgm_set_error("NW profile needs %zu B shared memory (> 227 KB)", smem); return PGM_ERR_ARG; }
-    static size_t attr_smem = 0;                               // the attribute call is a driver round trip: only when the size grows
-    if (smem > attr_smem) { PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_smem = smem; }
+    {   // the attribute call is a driver round trip: only when the size grows; attributes are per device
+        static size_t attr_smem[64] = {0}; static std::mutex attr_mu;
+        int dev = 0;
+        PGM_CUDA(cudaGetDevice(&dev));
+        std::lock_guard<std::mutex> lk(attr_mu);
+        if (smem > attr_smem[dev & 63]) {
+            PGM_CUDA(cudaFuncSetAttribute(nw_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem[dev & 63] = smem;
+        }
+    }
     nw_forward_kernel<<<n_tasks, NW_THREADS, smem, st>>>(d_codes, d_off, d_tasks, d_tab, n1, go, ge, d_tb,
                                                         d_colbuf, colbuf_stride, d_scores, 1, 4, -1, u16_h, u16_bias, rs_stride);
     PGM_CUDA(cudaGetLastError());

@@ -130,13 +130,23 @@ int launch_angle(cudaStream_t st, int n, int K, int dims, int N, const uint8_t* 
                  uint16_t* d_counts, double* d_norm2, int ml_flag, double* d_dist, double* d_var);
 
 // ---- HP-1 (hp1_*.cu) ------------------------------------------------------------------------------
-struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred list start, count (sign bit = first pred is a repeat edge), first entry inline
+struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred list start, packed count word, first entry inline
+// NodeInfo::cnt packs: bits 0..7 number of predecessors, bits 8..23 (index + 1) of the node's row / column in the value store
+// (0 = its cells are not kept as values), bit 31 = the first predecessor is a repeat edge
+#define NI_CNT(c) ((c) & 0xff)
+#define NI_KEEP(c) ((int)(((unsigned)(c) >> 8) & 0xffffu) - 1)
+#define NI_CLASS(c) ((int)(((unsigned)(c) >> 24) & 0x7fu))          // bits 24..30: site class of the node (class-coded graphs, see GraphJobDev::coded1)
+#define NI_CHAIN(ni, node) ((((ni).cnt & 0x800000ff) == 1) && (ni).idx0 == (node) - 1)   // exactly one predecessor: the regular edge from node-1
+#define GF_MAX_PREDS 128     // predecessors per node the 32-bit direction words can index (16-bit words: 8)
 
 #define GF_BAND_ROWS 512      // rows per band (= threads per CTA) of the banded anti-diagonal kernel
 #define GF_BAND_MIN_N1 1026    // graph 1 from this many nodes on is swept in bands (measured on the 5000-sequence run: 1026 / 512
                               // gives 2.35 s of fill time against 2.79 s for 3074 / 1024)
+#define GF_DIAG_REGULAR_ROWS 1024   // anti-diagonal kernel: up to this many rows one row per thread and the 8-diagonal ring
 #define GF_LAYOUT_BLOCK 0
 #define GF_LAYOUT_DIAG 1
+#define GF_LAYOUT_STRIP 2    // hp1_strip.cu: warp per job, a lane owns a strip of <= C columns in registers, 4 direction bits per cell
+#define GF_STRIP_MAX_C 24    // most columns per strip (register arrays)
 #define GF_K 8               // columns a fill-kernel thread sweeps per step (one block of a row)
 #define GF_LOGK 3
 #define GF_MAX_NB 512        // most column blocks per row the fill kernel's shared memory holds (graph 2 up to ~4000 nodes)
@@ -145,15 +155,25 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     int N1, N2;
     int bands;                  // > 1: graph 1 is swept in bands of band_rows rows (one CTA each) by the banded anti-diagonal kernel
     int band_rows;
-    int* progress;              // bands flags (scratch, zeroed before every sweep): anti-diagonals completed per band
-    int layout;                 // cell layout of MXYW = which fill kernel sweeps the job: GF_LAYOUT_BLOCK or GF_LAYOUT_DIAG
+    int* progress;              // bands + 1 ints (scratch, zeroed before every sweep): anti-diagonals completed per band, then the band ticket
+    int layout;                 // cell layout of D = which fill kernel sweeps the job: GF_LAYOUT_BLOCK or GF_LAYOUT_DIAG
     int nb;                     // column blocks per row (columns 0 .. N2-2 cut into blocks of <= GF_K; a non-chain node starts a block)
-    int pitch;                  // block-skewed layout (hp1_graphdp.cu): cell (y,x) at (((y + blk(x))*GF_K + off(x))*pitch + y%nb;
+    int pitch;                  // block-skewed layout (hp1_graphdp.cu): cell (y,x) at ((y + blk(x))*pitch + y%nb)*GF_K + off(x);
                                 // diagonal layout (hp1_graphdp_diag.cu): (y+x)*pitch + y - max(0, y+x-(N2-1))
     const uint16_t* colinfo;    // N2 entries: (blk(x) << GF_LOGK) | off(x)
     const uint16_t* blkstart;   // nb + 1 entries: first column of each block, blkstart[nb] = N2 - 1
-    const float* sites1;        // n * N1 (float cast of Graph::sites), column-major
-    const float* sites2;        // n * N2
+    // Emission inputs.  A graph whose every interior profile column is one-hot or uniform (a leaf: SequenceGraph.h:44-54)
+    // is CLASS-CODED: the emission runs on its n + 1 distinct columns only (N1e / N2e = n + 3 pseudo-nodes) and the fill
+    // reads S(class(y), class(x)) -- bit-identical, because S(y,x) depends on the two profile columns only.  Only jobs
+    // swept by the strip kernel are coded (the other fill kernels stream full rows of S).
+    int N1e, N2e;               // nodes the emission kernels see (= N1, N2 unless coded)
+    int coded1, coded2;         // graph 1 / graph 2 class-coded: S row of node y = NI_CLASS(ni1[y].cnt), S column of node x = scol[x]
+    const uint16_t* scol;       // N2 entries: S column of graph-2 node x (x itself unless coded2)
+    const float* sites1;        // n * N1e (float cast of Graph::sites), column-major
+    const float* sites2;        // n * N2e
+    // strip layout (hp1_strip.cu): strip j = columns [sstart[j], sstart[j+1]) of graph 2, at most C of them; colstrip[x] = strip * 32 + slot
+    int nstrips, C;
+    const int* sstart; const uint32_t* colstrip;
     const float* Mf;            // n*n row-major float cast of Model::M
     const float* pif;           // n
     // unified predecessor lists (regular edges ascending, then repeat edges ascending; Graph.h:196,241-247)
@@ -166,14 +186,24 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     float sc[10];               // DynProgScores
     float* S;                   // row-major by graph-1 node: S(y,x) at y*ldS + x (a DP thread streams its own row)
     int ldS;                    // N2 rounded up to a multiple of 4
-    float4* MXYW;               // block-skewed {M,X,Y,W}, (N1-1 + nb-1) * GF_K * pitch cells
+    // Packed traceback: one direction word per cell (hp1_dir.cuh), 16 bit when no node has more than 8 predecessors, else
+    // 32 bit.  The DP values themselves live only in the fill kernels' shared-memory rings, except for the rows of graph 1
+    // and columns of graph 2 that some far predecessor edge (or the end-node match, a band boundary, the traceback of the
+    // boundary row / column) reads back: those are kept as {M,X,Y,W} in the value store.
+    void* D;                    // direction words, (N1-1 + nb-1) * pitch * GF_K (blocked) or (N1+N2-1) * pitch (diagonal) entries;
+                                // strip layout: 4-bit cells, strip j of row y at uint32 words ((y + j) * nstrips + j) * W32 (hp1_strip.cu)
+    int dbits;                  // 3: uint16_t words, 7: uint32_t words (bits per predecessor index)
+    int ldVr, ldVc;             // pitches of the value store
+    float4* Vrow;               // kept row r (NI_KEEP of its graph-1 node), column x at r*ldVr + x
+    float4* Vcol;               // kept column c (NI_KEEP of its graph-2 node), row y at c*ldVc + y
     float* Tbuf;                // n * N2 scratch: T = M^T g2
     float* Aimg; float* Bimg;   // tensor flavour: per-128-row-tile UMMA operand images (ceil(N/128) * 128 * KP floats)
     float* u; float* v;         // g1^T pi (N1), pi^T g2 (N2)
     int* map1; int* map2;       // output mappings (capacity cap), written reversed then flipped
     int cap;
     float* alt_score; int* alt_prev;   // markAlternativePath scratch, max(N1,N2) each
-    int* result;                // [0]=status [1]=length [2]=n_tr_indels ; score at ((float*)result)[3]
+    int* result;                // [0]=status [1]=length [2]=n_tr_indels, score at ((float*)result)[3], [4]=emission status,
+                                // [5]=end-node pick: state (0 M, 1 X, 2 Y, 3 end_skip) | ky << 8 | kx << 16 (set by the fill)
 };
 
 #ifdef __CUDACC__
@@ -195,3 +225,5 @@ __device__ __forceinline__ float dot_gemv_order(const float* __restrict__ g, con
 int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2);
 int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2);
 int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
+int launch_graph_fill_strip(cudaStream_t st, int C, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
+__host__ __device__ __forceinline__ int strip_words(int C) { return C <= 8 ? 1 : (C <= 16 ? 2 : 4); }   // uint32 words of direction nibbles per strip and row

@@ -220,3 +220,151 @@ def test_large_batch_is_deterministic_and_correct(ga, po):
     assert [r["score"] for r in r1] == [r["score"] for r in r2]
     for k in range(0, 600, 37):
         _same_alignment(r1[k], po.align_graphs(jobs[k][0], jobs[k][1], m, opts))
+
+
+# ---- packed traceback: every fill flavour / direction-word width must give the oracle's path -------------------
+FLAVOURS = {
+    "default": {},
+    "block": {"PGM_FILL_LAYOUT": "block"},
+    "diag": {"PGM_FILL_LAYOUT": "diag"},
+    "block32": {"PGM_FILL_LAYOUT": "block", "PGM_DIR_BITS": "7"},
+    "diag32": {"PGM_FILL_LAYOUT": "diag", "PGM_DIR_BITS": "7"},
+    "banded": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_BAND_MIN_N1": "66", "PGM_FILL_BAND_ROWS": "64"},
+    "nostrip": {"PGM_FILL_STRIP": "0"},
+    "strip_full_s": {"PGM_SITE_CLASSES": "0"},
+}
+
+
+@pytest.fixture(params=sorted(FLAVOURS))
+def flavour(request, monkeypatch):
+    for k, v in FLAVOURS[request.param].items():
+        monkeypatch.setenv(k, v)
+    return request.param
+
+
+def test_every_fill_flavour_identical_to_oracle(ga, po, flavour):
+    """a 40-sequence progressive pass with many indels (skip edges, multi-predecessor nodes, far predecessors that
+    are read back from the value store) under every fill kernel and both direction-word widths"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(40, 150, mf, seed=51, indel_rate=0.08)
+    tree = progressive.from_synth(root)
+    n = [0]
+
+    def batch(jobs, o):
+        out = ga.alignGraphsBatch(jobs, o)
+        for (g1, g2, m), r in zip(jobs, out):
+            _same_alignment(r, po.align_graphs(g1, g2, m, o))
+            n[0] += 1
+        return out
+    progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
+    assert n[0] == 39
+
+
+@pytest.mark.parametrize("E", [0.12, 0.01, 0.5, 0.99, -1.0])
+def test_boundary_row_and_column_follow_the_reference_rule(ga, po, flavour, E):
+    """paths that run along row 0 / column 0 (one sequence is a suffix, a prefix or an infix of the other): there the
+    reference's traceback recomputes the candidates with gap_init although the fill used start_gap
+    (GraphAlign.h:212-234 against :378-398), which the packed traceback reproduces from the kept boundary values"""
+    opts = Options(mldist_flag=True, end_indel_prob=E)
+    mf = model.getDefault(opts)
+    rng = np.random.default_rng(7)
+    a = rng.integers(0, 20, 90).astype(np.uint8)
+    m = mf.getModel(0.2, 0.2)
+    cases = [(a, a[35:]), (a[35:], a), (a, a[:40]), (a[:40], a), (a, a[20:70]), (a[20:70], a),
+             (a, rng.integers(0, 20, 30).astype(np.uint8)), (a[:3], a[50:])]
+    jobs = [(sequence_graph(p, 20), sequence_graph(q, 20), m) for p, q in cases]
+    for (g1, g2, mm), r in zip(jobs, ga.alignGraphsBatch(jobs, opts)):
+        _same_alignment(r, po.align_graphs(g1, g2, mm, opts))
+
+
+def _branchy_graph(rng, N, extra_preds, n=20):
+    """a chain of N nodes in which some nodes get `extra_preds` more predecessors at random distances (ascending costs)"""
+    from prographmsa_b200.graph import Graph
+    sites = np.zeros((N, n))
+    sites[np.arange(1, N - 1), rng.integers(0, n, N - 2)] = 1.0
+    edges = {(i, i - 1): 0.0 for i in range(1, N)}
+    for to in rng.choice(np.arange(2, N), size=max(1, N // 6), replace=False):
+        for frm in rng.choice(np.arange(0, to - 1), size=min(extra_preds, to - 1), replace=False):
+            edges[(int(to), int(frm))] = float(rng.uniform(0.5, 6.0))
+    return Graph(sites, edges)
+
+
+@pytest.mark.parametrize("extra", [3, 7, 20])
+def test_many_predecessors(ga, po, flavour, extra):
+    """nodes with up to 21 predecessors at arbitrary distances: more than 8 needs the 32-bit direction words, and most
+    predecessors are far (value store)"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    rng = np.random.default_rng(100 + extra)
+    m = mf.getModel(0.3, 0.3)
+    jobs = [(_branchy_graph(rng, 70 + 13 * k, extra), _branchy_graph(rng, 90 - 7 * k, extra), m) for k in range(4)]
+    for (g1, g2, mm), r in zip(jobs, ga.alignGraphsBatch(jobs, opts)):
+        _same_alignment(r, po.align_graphs(g1, g2, mm, opts))
+
+
+def test_too_many_predecessors_is_an_error(ga):
+    from prographmsa_b200._lib import PgmError
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    rng = np.random.default_rng(5)
+    g = _branchy_graph(rng, 200, 140)
+    with pytest.raises(PgmError):
+        ga.alignGraphs(g, _branchy_graph(rng, 50, 2), mf.getModel(0.3, 0.3), opts)
+
+
+def test_failed_emission_fails_the_job(ga, monkeypatch):
+    """a tensor-emission failure (bounded mbarrier wait timed out) must surface as a failed job, not as an
+    alignment of a partly written S.  The failure is injected into the emission status word of job 1."""
+    from prographmsa_b200._lib import PgmError
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    m = mf.getModel(0.5, 0.5)
+    jobs = []
+    for k in range(3):
+        a, b = synth.random_pair(60, 0.5, mf, seed=70 + k)
+        jobs.append((sequence_graph(a, 20), sequence_graph(b, 20), m))
+    for mode in (ga.EMISSION_EXACT, ga.EMISSION_TENSOR):
+        assert len(ga.alignGraphsBatch(jobs, opts, emission_mode=mode)) == 3
+        monkeypatch.setenv("PGM_INJECT_EMISSION_FAIL", "1")
+        with pytest.raises(PgmError):
+            ga.alignGraphsBatch(jobs, opts, emission_mode=mode)
+        monkeypatch.delenv("PGM_INJECT_EMISSION_FAIL")
+
+
+@pytest.mark.parametrize("L1,L2", [(3, 3), (1, 40), (40, 1), (13, 14), (130, 417), (417, 130), (400, 400), (760, 300), (300, 767), (2000, 700)])
+def test_strip_kernel_leaf_pairs(ga, po, flavour, L1, L2):
+    """chain x chain jobs go to the strip kernel (every strip width, partial last strips, graphs shorter than a strip);
+    unknown residues make uniform profile columns (their own site class)"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    rng = np.random.default_rng(L1 * 1000 + L2)
+    a = rng.integers(0, 20, L1).astype(np.uint8)
+    b = rng.integers(0, 20, L2).astype(np.uint8)
+    k = min(L1, L2)
+    b[:k // 2] = a[:k // 2]                                     # some homology
+    if L1 > 5:
+        a[rng.integers(0, L1, max(1, L1 // 20))] = 20           # unknown residues
+    if L2 > 5:
+        b[rng.integers(0, L2, max(1, L2 // 25))] = 21
+    g1, g2 = sequence_graph(a, 20), sequence_graph(b, 20)
+    m = mf.getModel(0.4, 0.4)
+    _same_alignment(ga.alignGraphs(g1, g2, m, opts), po.align_graphs(g1, g2, m, opts))
+
+
+def test_strip_kernel_profile_chain_graphs(ga, po, flavour):
+    """chain graphs whose columns are real profiles (not class-coded): S is read as a full matrix by the strip kernel"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    m = mf.getModel(0.5, 0.5)
+    jobs = []
+    for k in range(6):
+        a, b = synth.random_pair(150 + 37 * k, 0.5, mf, seed=300 + k)
+        g1, g2 = sequence_graph(a, 20), sequence_graph(b, 20)
+        if k % 3 != 1:
+            g1.sites[1:-1] = g1.sites[1:-1] @ m.P.T
+        if k % 3 != 2:
+            g2.sites[1:-1] = g2.sites[1:-1] @ m.P.T
+        jobs.append((g1, g2, m))
+    for (g1, g2, mm), r in zip(jobs, ga.alignGraphsBatch(jobs, opts)):
+        _same_alignment(r, po.align_graphs(g1, g2, mm, opts))

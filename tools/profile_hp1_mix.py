@@ -1,7 +1,11 @@
 #!/usr/bin/env python3
-"""Fill-kernel timing of the bench's progressive-pass jobs, split by how many non-chain columns graph 2 has."""
+"""Kernel timing of the bench's progressive-pass jobs, split by how many non-chain nodes the graphs have.
+
+  python tools/profile_hp1_mix.py [n_seq=256] [replicas=4] [only]      (PGM_LIB_PATH=<other build> for A/B runs)
+Phases run one after the other (PGM_GRAPH_PIPELINE=0), so fill_ms is the wall time of the fill section."""
 import sys, os
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+os.environ["PGM_GRAPH_PIPELINE"] = "0"
 import numpy as np
 from prographmsa_b200 import model, synth, graphalign, progressive, _lib
 from prographmsa_b200.options import Options
@@ -28,16 +32,20 @@ def nonchain(g):
     return n
 info = [(nonchain(a), nonchain(b), a.N, b.N) for a, b, m in jobs]
 ctx.enable_timing(True)
-def run(sel, label):
+def run(sel, label, mode=0):
     js = [jobs[i] for i in sel] * rep
     if not js:
         return
-    gb = graphalign.GraphBatch(js, opts, 0, ctx)
-    for _ in range(3):
+    gb = graphalign.GraphBatch(js, opts, mode, ctx)
+    acc = dict(emission_ms=0.0, graph_fill_ms=0.0, graph_trace_ms=0.0)
+    for it in range(5):
         gb.run(); ctx.sync()
-    t = ctx.timing()
+        if it >= 2:
+            t = ctx.timing()
+            for k in acc: acc[k] += t[k] / 3
     cells = sum(info[i][2] * info[i][3] for i in sel) * rep
-    print("%-34s jobs %4d cells %.3g: fill %.3f ms (%.1f GCUPS) trace %.3f ms" % (label, len(js), cells, t["graph_fill_ms"], cells / t["graph_fill_ms"] / 1e6, t["graph_trace_ms"]))
+    print("%-34s jobs %4d cells %.3g: emission %.3f fill %.3f ms (%.1f GCUPS) trace %.3f ms" % (
+        label, len(js), cells, acc["emission_ms"], acc["graph_fill_ms"], cells / acc["graph_fill_ms"] / 1e6, acc["graph_trace_ms"]))
     gb.close()
 idx = list(range(len(jobs)))
 only = sys.argv[3] if len(sys.argv) > 3 else None
@@ -45,17 +53,26 @@ if only == "few":
     run([i for i in idx if 0 < max(info[i][0], info[i][1]) <= 8], "1..8 non-chain nodes"); sys.exit(0)
 if only == "big":
     run(sorted(idx, key=lambda i: -info[i][2] * info[i][3])[:1], "largest job"); sys.exit(0)
-for lay in (None,):
+if only == "chain":
+    run([i for i in idx if info[i][0] == 0 and info[i][1] == 0], "pure chain x chain"); sys.exit(0)
+if only == "branchy":
+    run([i for i in idx if info[i][0] + info[i][1] > 40], ">40 non-chain nodes"); sys.exit(0)
+for lay in (None, "block", "diag"):
     if lay: os.environ["PGM_FILL_LAYOUT"] = lay
     print("--- PGM_FILL_LAYOUT =", lay)
     run(idx, "all")
+    run(idx, "all (tensor emission)", 1)
     run([i for i in idx if info[i][0] == 0 and info[i][1] == 0], "pure chain x chain")
     run([i for i in idx if 0 < info[i][0] + info[i][1] <= 4], "1..4 non-chain nodes")
     run([i for i in idx if 4 < info[i][0] + info[i][1] <= 8], "5..8 non-chain nodes")
     run([i for i in idx if 8 < info[i][0] + info[i][1] <= 16], "9..16 non-chain nodes")
     run([i for i in idx if 16 < info[i][0] + info[i][1] <= 40], "17..40 non-chain nodes")
     run([i for i in idx if info[i][0] + info[i][1] > 40], ">40 non-chain nodes")
+    big = sorted(idx, key=lambda i: -info[i][2] * info[i][3])[:1]
+    print("largest job: %d x %d nodes, %d + %d non-chain" % (info[big[0]][2], info[big[0]][3], info[big[0]][0], info[big[0]][1]))
+    os.environ["PGM_FILL_SMALL_BATCH"] = "0"
+    rep_save = rep; rep = 1
+    run(big, "largest job alone")
+    rep = rep_save
+    os.environ.pop("PGM_FILL_SMALL_BATCH")
 os.environ.pop("PGM_FILL_LAYOUT", None)
-for th in (2, 4, 6, 8, 12, 16, 30):
-    os.environ["PGM_FILL_DIAG_MIN"] = str(th)
-    run(idx, "all, diag if > %d non-chain" % th)
