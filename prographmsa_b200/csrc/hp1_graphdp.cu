@@ -358,7 +358,13 @@ __device__ __forceinline__ void graph_trace_job(const GraphJobDev& J, const int 
             const int j = (int)(cs >> 5), k = (int)(cs & 31u), g = k >> 3, gsz = min(8, sC - 8 * g);
             const uint32_t word = ((const uint32_t*)J.D)[((size_t)(yy + j) * sN + j) * sW + g];
             const uint32_t nib = (word >> (4 * (gsz - 1 - (k & 7)))) & 15u;
-            return ((nib & 1u) ? ((nib & 2u) ? 1u : 2u) : 0u) | (nib & 12u);
+            uint32_t idx = 0u;                           // predecessor-index fields: only cells in non-chain rows / columns have any
+            if (J.sgen) {
+                const int r1 = J.ncidx1[yy];
+                if (r1 >= 0) idx = ((const uint32_t*)J.RowIdx)[(size_t)r1 * J.ldRI + xx];
+                else { const int r2 = J.ncidx2[xx]; if (r2 >= 0) idx = ((const uint32_t*)J.ColIdx)[(size_t)r2 * J.ldCI + yy]; }
+            }
+            return ((nib & 1u) ? ((nib & 2u) ? 1u : 2u) : 0u) | (nib & 12u) | (idx & ~15u);
         }
         return D[cix(yy, xx)];
     };

@@ -31,8 +31,8 @@
 // keeps every row an edge into a later band starts from); the row just above the band, which the band's first row needs on
 // every diagonal, is staged 8 diagonals at a time into shared memory right after the flag check (it is complete by then),
 // so that row runs the chain fast path like any other.
-template <int B, bool STAGE, int RPT, int RING, bool SPF, bool BANDED>
-__global__ void __launch_bounds__(1024)
+template <int B, bool STAGE, int RPT, int RING, bool SPF, bool BANDED, int MAXT>
+__global__ void __launch_bounds__(MAXT)
 graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch, int max_bands) {
     typedef typename DirWord<B>::T DW;
     const GraphJobDev& J = jobs[order[BANDED ? blockIdx.x / max_bands : blockIdx.x]];
@@ -239,8 +239,14 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
 
 template <int B, bool STAGE, int RPT, int RING, bool SPF>
 static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int threads, int ring_pitch, size_t smem) {
-    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<B, STAGE, RPT, RING, SPF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_fill_diag_kernel<B, STAGE, RPT, RING, SPF, false><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch, 1);
+    // up to 512 threads the kernel may use 128 registers (the first-maximum bookkeeping of the packed traceback needs them)
+    if (threads <= 512) {
+        PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<B, STAGE, RPT, RING, SPF, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        graph_fill_diag_kernel<B, STAGE, RPT, RING, SPF, false, 512><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch, 1);
+    } else {
+        PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<B, STAGE, RPT, RING, SPF, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        graph_fill_diag_kernel<B, STAGE, RPT, RING, SPF, false, 1024><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch, 1);
+    }
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -249,8 +255,13 @@ static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_
 // progress flags and tickets are zeroed by the caller.
 template <int B, bool STAGE>
 static int launch_banded_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int band_rows, size_t smem) {
-    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<B, STAGE, 1, GF_RING, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_fill_diag_kernel<B, STAGE, 1, GF_RING, true, true><<<n_jobs * max_bands, band_rows, smem, st>>>(d_jobs, d_order, band_rows, max_bands);
+    if (band_rows <= 512) {
+        PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<B, STAGE, 1, GF_RING, true, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        graph_fill_diag_kernel<B, STAGE, 1, GF_RING, true, true, 512><<<n_jobs * max_bands, band_rows, smem, st>>>(d_jobs, d_order, band_rows, max_bands);
+    } else {
+        PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<B, STAGE, 1, GF_RING, true, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        graph_fill_diag_kernel<B, STAGE, 1, GF_RING, true, true, 1024><<<n_jobs * max_bands, band_rows, smem, st>>>(d_jobs, d_order, band_rows, max_bands);
+    }
     PGM_CUDA(cudaGetLastError());
     return 0;
 }

@@ -88,7 +88,9 @@ struct JobLayout {                // byte offsets into the upload arena / scratc
     int np1, np2, cap, pitch, nb, layout, bands, band_rows;
     int dbits, ldVr, ldVc, nkr, nkc;
     int C, nstrips, N1e, N2e, coded1, coded2;
-    size_t scol, sstart, colstrip;
+    int sgen, nsrc, ring_rows, hist_rows, swarps, nstrips_gen, nnc1, nnc2, ldRI, ldCI;
+    size_t scol, sstart, colstrip, specmask, srcmask, colsrc_off, ncidx1_off, ncidx2_off, rinfo_off, RowIdx, ColIdx;
+    std::vector<int16_t> colsrc; std::vector<int> ncidx1, ncidx2;
     double uniform1, uniform2;
     std::vector<int> keep1, keep2;                       // per node: index of its row / column in the value store, or -1
     std::vector<uint8_t> cls1, cls2;                     // class-coded graphs: site class per node
@@ -127,7 +129,7 @@ int max_preds(const pgm_graph& g) {
 // ---- job analysis (parallel over jobs): everything that decides sizes ------------------------------------------------------
 struct BatchEnv {                 // environment switches, read once per create (tests, A-B runs, profiling)
     int force_layout = -1, diag_min_generic = 8, band_min_n1 = GF_BAND_MIN_N1, long_band_rows = GF_BAND_ROWS;
-    int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, force_dbits = 0, strip = 1, coding = 1;
+    int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, force_dbits = 0, strip = 2, coding = 1, strip_c = 0, hist_kb = 0, dbg = 0;
     BatchEnv() {
         if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
         if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
@@ -137,7 +139,10 @@ struct BatchEnv {                 // environment switches, read once per create 
         if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
         if (const char* e = getenv("PGM_FILL_SMALL_BATCH")) small_batch = atoi(e);      // fewer jobs than three per SM: latency-bound (measured crossover 300..440 jobs of 400 x 400)
         if (const char* e = getenv("PGM_DIR_BITS")) force_dbits = atoi(e);              // 7: 32-bit direction words for every job
-        if (const char* e = getenv("PGM_FILL_STRIP")) strip = atoi(e);                  // 0: never the strip kernel
+        if (const char* e = getenv("PGM_FILL_STRIP")) strip = atoi(e);                  // 0: never a strip kernel, 1: chain graphs only, 2: also graphs with non-chain nodes
+        if (const char* e = getenv("PGM_STRIP_HIST_KB")) hist_kb = atoi(e);             // shared-memory budget of the (Y,W) history ring
+        if (const char* e = getenv("PGM_STRIP_DEBUG")) dbg = atoi(e);
+        if (const char* e = getenv("PGM_STRIP_C")) strip_c = atoi(e);                   // force the general strip kernel's strip width
         if (const char* e = getenv("PGM_SITE_CLASSES")) coding = atoi(e);               // 0: never class-code leaf graphs
     }
 };
@@ -188,7 +193,7 @@ struct pgm_graph_batch {
     // Fill schedule.  The fill kernel's block size and shared memory -- hence CTAs per SM -- are set by the LARGEST job
     // of a launch, so each sub-batch is swept as a few launches of similar graph-2 length (largest first), on
     // separate streams so that a class with few jobs does not leave the GPU idle.
-    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands, band_rows, dbits, C, max_n1e, max_n2e; };
+    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands, band_rows, dbits, C, max_n1e, max_n2e, sgen, swarps; size_t ring_bytes; };
     std::vector<int> order;                 // job indices relative to their sub-batch, grouped by FillLaunch
     std::vector<FillLaunch> fills;
     size_t scratch_bytes_used = 0;
@@ -269,16 +274,65 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         // takes the graphs whose graph 2 is too long for the blocked kernel.  A batch too small to fill the GPU is latency-bound
         // per job, and there the anti-diagonal sweep is the shorter one even on chain graphs.
         const int cols = bb.N - 1;                                 // DP columns 0 .. N2-2
-        int C = (cols + 31) / 32;
-        static const int strip_cs[] = {4, 8, 11, 13, 16, 20, 24};
         int Cpick = 0;
-        for (int q : strip_cs) if (q >= C) { Cpick = q; break; }
-        const bool strip_ok = env.strip && generic == 0 && Cpick > 0 && a.N >= 3 && bb.N >= 3;
+        bool strip_ok = false;
+        L.sgen = 0; L.nsrc = 0; L.ring_rows = 0; L.swarps = 1;
+        if (env.strip && env.strip != 3 && generic == 0 && a.N >= 3 && bb.N >= 3) {  // chain x chain: warp per job (PGM_FILL_STRIP=3: the general kernel for everything)
+            static const int strip_cs[] = {4, 8, 11, 13, 16, 20, 24};
+            for (int q : strip_cs) if (q * 32 >= cols) { Cpick = q; break; }
+            strip_ok = Cpick > 0;
+        }
+        if (!strip_ok && env.strip >= 2 && a.N >= 3 && bb.N >= 3 && L.dbits != 0) {
+            // general strip kernel: W warps per job.  Strip width: wide strips (one warp per job) for a batch that fills the GPU,
+            // narrow strips (more lanes, shorter steps) when the batch is small and the job's own latency is what counts
+            static const int gen_cs[] = {2, 4, 8, 13, 16};
+            // strips of the general kernel: a strip starts at column 0, at every non-chain column (so that the special
+            // handling sits in slot 0 only) and when the current strip is full
+            auto count_strips = [&](int q) {
+                int nsq = 0, len = 0;
+                for (int x = 0; x < cols; ++x) {
+                    if (x == 0 || len == q || non_chain_node(bb, x)) { ++nsq; len = 0; }
+                    ++len;
+                }
+                return nsq;
+            };
+            double best = 0; int best_ns = 0;
+            for (int q : gen_cs) {
+                if (env.strip_c && q != env.strip_c) continue;
+                const int ns_q = count_strips(q), w_q = (ns_q + 31) / 32;
+                if (w_q > SG_MAX_WARPS) continue;
+                if (q > 8 && Cpick && !env.strip_c) continue;       // wide strips (255 registers, one job per SM) only when the narrow ones do not fit
+                // cost model (cycles): steps x (fixed + per-slot); a full GPU prefers the fewest warp-steps, a small batch the shortest sweep
+                const double sweep = (double)(a.N - 1 + ns_q) * (500.0 + 70.0 * q);
+                const double cost = n_jobs >= 16 * 148 ? sweep * w_q : sweep;
+                if (!Cpick || cost < best) { Cpick = q; best = cost; best_ns = ns_q; }
+            }
+            if (Cpick) {
+                L.colsrc.assign(bb.N, -1);
+                int nsrc = 0;
+                for (int x = 1; x <= bb.N - 2; ++x) {
+                    auto visit = [&](int xp) { if (xp != x - 1 && L.colsrc[xp] < 0) L.colsrc[xp] = (int16_t)nsrc++; };
+                    for (int e = bb.e_rowptr[x]; e < bb.e_rowptr[x + 1]; ++e) visit(bb.e_col[e]);
+                    if (bb.r_rowptr) for (int e = bb.r_rowptr[x]; e < bb.r_rowptr[x + 1]; ++e) visit(bb.r_col[e]);
+                }
+                int rr = 64; while (rr < best_ns + 2) rr *= 2;
+                // history ring: (Y,W) of the last hist_rows rows of every column, for the rows with non-adjacent predecessors
+                int hr = 32;                                        // fewer jobs than SMs: the whole shared memory of an SM is the job's
+                size_t hist_budget = (n_jobs < 148 ? 128 : 24) * 1024;
+                if (env.hist_kb > 0) hist_budget = (size_t)env.hist_kb * 1024;      // PGM_STRIP_HIST_KB (tests)
+                while (hr > 4 && (size_t)hr * (size_t)(Cpick + 1) * ((best_ns + 31) & ~31) * 8 > hist_budget) hr /= 2;
+                const size_t smem = (size_t)nsrc * rr * 8 + (size_t)hr * (size_t)(Cpick + 1) * ((best_ns + 31) & ~31) * 8;
+                if (nsrc <= SG_MAX_SRC && smem <= 200 * 1024) {
+                    strip_ok = true; L.sgen = 1; L.nsrc = nsrc; L.ring_rows = rr; L.hist_rows = hr; L.swarps = (best_ns + 31) / 32; L.nstrips_gen = best_ns;
+                }
+            }
+        }
         L.layout = (generic > env.diag_min_generic || nblk > GF_MAX_NB || n_jobs < env.small_batch) ? GF_LAYOUT_DIAG : GF_LAYOUT_BLOCK;
         if (strip_ok) L.layout = GF_LAYOUT_STRIP;
         if (env.force_layout >= 0 && !(env.force_layout == GF_LAYOUT_BLOCK && nblk > GF_MAX_NB) && !(env.force_layout == GF_LAYOUT_STRIP && !strip_ok)) L.layout = env.force_layout;
+        if (L.layout != GF_LAYOUT_STRIP) L.sgen = 0;
         L.C = L.layout == GF_LAYOUT_STRIP ? Cpick : 0;
-        L.nstrips = L.layout == GF_LAYOUT_STRIP ? (cols + Cpick - 1) / Cpick : 0;
+        L.nstrips = L.layout == GF_LAYOUT_STRIP ? (L.sgen ? L.nstrips_gen : (cols + Cpick - 1) / Cpick) : 0;
         // Bands: graphs too long for one CTA.  Short bands for the large branchy graphs (three SMs sharing one job's rows) are
         // wired and tested (PGM_FILL_SPLIT_ROWS) but off: measured 1.73 -> 2.8 ms on the 500-row jobs of the bench batch,
         // the first row of a band pays an L2 round trip per anti-diagonal
@@ -302,11 +356,21 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 const int thr = (L.bands == 1 && a.N - 1 > GF_DIAG_REGULAR_ROWS) ? 2 : 4;
                 mark_far_sources(a, nullptr, thr, L.band_rows, L.keep1);
                 mark_far_sources(bb, nullptr, thr, 0, L.keep2);
-            }                                                       // strip: chain nodes only, nothing is far
+            } else if (L.sgen) {                                    // general strip kernel: every source of a non-adjacent edge
+                mark_far_sources(a, nullptr, 2, 0, L.keep1);
+                mark_far_sources(bb, nullptr, 2, 0, L.keep2);
+            }                                                       // chain strip kernel: nothing is far
             if (L.bands > 1) for (int q = 1; q < L.bands; ++q) L.keep1[q * L.band_rows - 1] = 1;   // the row above each band
         }
         L.nkr = number_kept(L.keep1); L.nkc = number_kept(L.keep2);
-        L.ldVr = (int)align_up((size_t)bb.N, 8) + 8; L.ldVc = (int)align_up((size_t)a.N, 4);
+        L.ldVr = (int)align_up((size_t)bb.N, 8) + 32; L.ldVc = (int)align_up((size_t)a.N, 4);
+        L.nnc1 = L.nnc2 = 0;
+        if (L.sgen) {
+            L.ncidx1.assign(a.N, -1); L.ncidx2.assign(bb.N, -1);
+            for (int y = 1; y <= a.N - 2; ++y) if (non_chain_node(a, y)) L.ncidx1[y] = L.nnc1++;
+            for (int x = 1; x <= bb.N - 2; ++x) if (non_chain_node(bb, x)) L.ncidx2[x] = L.nnc2++;
+        }
+        L.ldRI = (int)align_up((size_t)bb.N, 8); L.ldCI = (int)align_up((size_t)a.N, 8);
         // class-coded emission inputs (strip jobs only: the other kernels stream full rows of S)
         L.coded1 = L.coded2 = 0;
         if (L.layout == GF_LAYOUT_STRIP && env.coding && !t_full_emission && n + 3 < 120) {
@@ -324,6 +388,8 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.S = take(so, (size_t)L.N1e * (((size_t)L.N2e + 3) & ~(size_t)3) * 4 + 128);
         L.D = take(so, d_bytes + 64);
         L.Vrow = take(so, (size_t)L.nkr * L.ldVr * 16 + 16); L.Vcol = take(so, (size_t)L.nkc * L.ldVc * 16 + 16);
+        if (L.sgen) L.dbits = 7;                                    // the side arrays hold 32-bit index words
+        L.RowIdx = take(so, (size_t)L.nnc1 * L.ldRI * 4 + 16); L.ColIdx = take(so, (size_t)L.nnc2 * L.ldCI * 4 + 16);
         L.Tbuf = take(so, sizeof(float) * n * L.N2e); L.u = take(so, 4 * L.N1e); L.v = take(so, 4 * L.N2e);
         if (opts->emission_mode == PGM_EMISSION_TENSOR) {
             const size_t kp = (size_t)((3 * n + 7) & ~7);
@@ -354,6 +420,10 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.colinfo = take(in_off, 2 * (size_t)bb.N); L.blkstart = take(in_off, 2 * ((size_t)L.nb + 1));
         L.scol = take(in_off, 2 * (size_t)bb.N);
         L.sstart = take(in_off, 4 * ((size_t)L.nstrips + 1)); L.colstrip = take(in_off, L.nstrips ? 4 * (size_t)bb.N : 0);
+        L.specmask = take(in_off, L.sgen ? 4 * (size_t)L.nstrips : 0); L.srcmask = take(in_off, L.sgen ? 4 * (size_t)L.nstrips : 0);
+        L.colsrc_off = take(in_off, L.sgen ? 2 * (size_t)bb.N : 0);
+        L.ncidx1_off = take(in_off, L.sgen ? 4 * (size_t)a.N : 0); L.ncidx2_off = take(in_off, L.sgen ? 4 * (size_t)bb.N : 0);
+        L.rinfo_off = take(in_off, L.sgen ? sizeof(RowInfo) * (size_t)a.N : 0);
         L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 32);
         b->max_N1 = std::max(b->max_N1, a.N); b->max_N2 = std::max(b->max_N2, bb.N);
     }
@@ -461,11 +531,53 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             ci[g2[k].N - 1] = 0;
             for (int x = 0; x < g2[k].N; ++x) sc[x] = (uint16_t)(L.coded2 ? NI_CLASS(ni[x].cnt) : x);
         }
-        if (L.nstrips) {                                            // strips of the strip kernel: C columns each
+        if (L.nstrips) {                                            // strips of the strip kernels
             int* ss = (int*)(hin + L.sstart); uint32_t* cs = (uint32_t*)(hin + L.colstrip);
-            for (int j = 0; j <= L.nstrips; ++j) ss[j] = std::min(j * L.C, g2[k].N - 1);
-            for (int x = 0; x < g2[k].N; ++x) cs[x] = (uint32_t)((x / L.C) * 32 + x % L.C);
+            const int cols = g2[k].N - 1;
+            if (!L.sgen) {                                          // chain kernel: C columns each
+                for (int j = 0; j <= L.nstrips; ++j) ss[j] = std::min(j * L.C, cols);
+                for (int x = 0; x < g2[k].N; ++x) cs[x] = (uint32_t)((x / L.C) * 32 + x % L.C);
+            } else {                                                // general kernel: a non-chain column starts a strip
+                int j = -1, len = 0;
+                for (int x = 0; x < cols; ++x) {
+                    if (x == 0 || len == L.C || L.ncidx2[x] >= 0) { ++j; ss[j] = x; len = 0; }
+                    cs[x] = (uint32_t)(j * 32 + len);
+                    ++len;
+                }
+                ss[j + 1] = cols; cs[cols] = 0;
+            }
         }
+        if (L.sgen) {
+            uint32_t* sm = (uint32_t*)(hin + L.specmask); uint32_t* rm = (uint32_t*)(hin + L.srcmask);
+            const int* ss = (const int*)(hin + L.sstart);
+            for (int j = 0; j < L.nstrips; ++j) {
+                uint32_t a_ = 0, b_ = 0;
+                for (int x = ss[j]; x < ss[j + 1]; ++x) {
+                    if (L.ncidx2[x] >= 0) a_ |= 1u << (x - ss[j]);
+                    if (L.colsrc[x] >= 0) b_ |= 1u << (x - ss[j]);
+                }
+                sm[j] = a_; rm[j] = b_;
+            }
+            memcpy(hin + L.colsrc_off, L.colsrc.data(), 2 * (size_t)g2[k].N);
+            memcpy(hin + L.ncidx1_off, L.ncidx1.data(), 4 * (size_t)g1[k].N);
+            memcpy(hin + L.ncidx2_off, L.ncidx2.data(), 4 * (size_t)g2[k].N);
+            const NodeInfo* ni = (const NodeInfo*)(hin + L.ni1);
+            const int* pidx = (const int*)(hin + L.p1_idx); const float* pval = (const float*)(hin + L.p1_val);
+            RowInfo* ri = (RowInfo*)(hin + L.rinfo_off);
+            for (int y = 0; y < g1[k].N; ++y) {
+                const int cnt = NI_CNT(ni[y].cnt);
+                RowInfo r; r.cnt = ni[y].cnt; r.idx0 = ni[y].idx0; r.val0 = ni[y].val0; r.ptr = ni[y].ptr; r.ncidx = L.ncidx1[y];
+                r.idx1 = cnt > 1 ? pidx[ni[y].ptr + 1] : 0; r.val1 = cnt > 1 ? pval[ni[y].ptr + 1] : 0.f;
+                const int k0 = cnt > 0 ? L.keep1[r.idx0] + 1 : 0, k1 = cnt > 1 ? L.keep1[r.idx1] + 1 : 0;
+                r.kq01 = k0 | (k1 << 16);
+                ri[y] = r;
+            }
+        }
+        J.dbg = env.dbg; J.sgen = L.sgen; J.nsrc = L.nsrc; J.ring_rows = L.ring_rows; J.hist_rows = L.hist_rows; J.ldRI = L.ldRI; J.ldCI = L.ldCI;
+        J.specmask = (const uint32_t*)(din + L.specmask); J.srcmask = (const uint32_t*)(din + L.srcmask);
+        J.colsrc = (const int16_t*)(din + L.colsrc_off); J.ncidx1 = (const int*)(din + L.ncidx1_off); J.ncidx2 = (const int*)(din + L.ncidx2_off);
+        J.rinfo = (const RowInfo*)(din + L.rinfo_off);
+        J.RowIdx = (void*)(dsc + scratch_base[k] + L.RowIdx); J.ColIdx = (void*)(dsc + scratch_base[k] + L.ColIdx);
         b->cell_updates[k] = deg_sum[0] * deg_sum[1];
         char* sb = dsc + scratch_base[k];
         J.sites1 = (const float*)(din + L.sites1); J.sites2 = (const float*)(din + L.sites2);
@@ -493,7 +605,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         b->order.resize(n_jobs);
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
         auto class_of = [&](const GraphJobDev& J) {                          // + 1000: 32-bit direction words (their own kernel instantiation)
-            if (J.layout == GF_LAYOUT_STRIP) return 300 + J.C;
+            if (J.layout == GF_LAYOUT_STRIP) return J.sgen ? 400 + J.C + 32 * ((J.nstrips + 31) / 32) : 300 + J.C;
             const int wide = J.dbits == 3 ? 0 : 1000;
             if (J.bands > 1) return wide + 200 + J.band_rows / 32;            // banded anti-diagonal sweeps: their own launches, one per band height
             if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return wide + 100 + q; }
@@ -506,7 +618,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             std::stable_sort(idx.begin(), idx.end(), [&](int a, int bq) {
                 const GraphJobDev &A = b->jobs[sbr.first + a], &B = b->jobs[sbr.first + bq];
                 const int ca = class_of(A) % 1000, cb = class_of(B) % 1000, wa = class_of(A) / 1000, wb = class_of(B) / 1000;
-                const bool sa = A.layout == GF_LAYOUT_STRIP, sbq = B.layout == GF_LAYOUT_STRIP;
+                const bool sa = A.layout == GF_LAYOUT_STRIP && !A.sgen, sbq = B.layout == GF_LAYOUT_STRIP && !B.sgen;
                 if (sa != sbq) return sbq;                                   // strip launches last: the short ones
                 if (ca != cb) return ca > cb;
                 if (wa != wb) return wa > wb;
@@ -517,13 +629,14 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             while (p < idx.size()) {
                 const GraphJobDev& J0 = b->jobs[sbr.first + idx[p]];
                 const int q = class_of(J0);
-                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, J0.layout, 0, 0, 0, 0, 0, 1, J0.band_rows, J0.dbits, J0.C, 0, 0};
+                pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, J0.layout, 0, 0, 0, 0, 0, 1, J0.band_rows, J0.dbits, J0.C, 0, 0, J0.sgen, (J0.nstrips + 31) / 32, 0};
                 while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]]) == q) {
                     const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
                     f.max_nb = std::max(f.max_nb, J.nb); f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2);
                     f.max_np2 = std::max(f.max_np2, J.np2); f.max_np = std::max(f.max_np, J.np1 + J.np2);
                     f.max_bands = std::max(f.max_bands, J.bands);
                     f.max_n1e = std::max(f.max_n1e, J.N1e); f.max_n2e = std::max(f.max_n2e, J.N2e);
+                    f.ring_bytes = std::max(f.ring_bytes, (size_t)J.nsrc * J.ring_rows * 8 + (size_t)J.hist_rows * (size_t)(J.C + 1) * ((J.nstrips + 31) & ~31) * 8);
                     ++f.count; ++p;
                 }
                 b->fills.push_back(f);
@@ -585,7 +698,9 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
         };
         auto fill = [&](cudaStream_t sq, const pgm_graph_batch::FillLaunch* f) -> int {
             const int* ord = d_order_all + sb.first + f->offset;
-            if (f->layout == GF_LAYOUT_STRIP) return launch_graph_fill_strip(sq, f->C, f->count, dj + sb.first, ord);
+            if (f->layout == GF_LAYOUT_STRIP)
+                return f->sgen ? launch_graph_fill_strip_gen(sq, f->C, f->dbits, f->swarps, f->ring_bytes, f->count, dj + sb.first, ord)
+                               : launch_graph_fill_strip(sq, f->C, f->count, dj + sb.first, ord);
             if (f->max_bands > 1) {
                 for (int jq = 0; jq < f->count; ++jq) {             // zero the bands' progress flags and the band ticket
                     const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + f->offset + jq]];

@@ -137,6 +137,9 @@ struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred
 #define NI_KEEP(c) ((int)(((unsigned)(c) >> 8) & 0xffffu) - 1)
 #define NI_CLASS(c) ((int)(((unsigned)(c) >> 24) & 0x7fu))          // bits 24..30: site class of the node (class-coded graphs, see GraphJobDev::coded1)
 #define NI_CHAIN(ni, node) ((((ni).cnt & 0x800000ff) == 1) && (ni).idx0 == (node) - 1)   // exactly one predecessor: the regular edge from node-1
+// general strip kernel: everything a row needs in one 32-byte record, fetched two rows ahead (no dependent loads in a step)
+struct RowInfo { int cnt; int idx0; float val0; int idx1; float val1; int kq01; int ncidx; int ptr; };   // cnt as NodeInfo::cnt; the first two
+                             // predecessors inline; kq01 = (value-store row of idx0 + 1) | (... of idx1 + 1) << 16; ncidx = row of RowIdx or -1
 #define GF_MAX_PREDS 128     // predecessors per node the 32-bit direction words can index (16-bit words: 8)
 
 #define GF_BAND_ROWS 512      // rows per band (= threads per CTA) of the banded anti-diagonal kernel
@@ -174,6 +177,17 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     // strip layout (hp1_strip.cu): strip j = columns [sstart[j], sstart[j+1]) of graph 2, at most C of them; colstrip[x] = strip * 32 + slot
     int nstrips, C;
     const int* sstart; const uint32_t* colstrip;
+    // general strip kernel (graphs with non-chain nodes): per strip the slots whose column is not a chain node (specmask) and
+    // the slots whose column is the SOURCE of a non-adjacent column edge (srcmask; its (X,W) go to a shared-memory ring,
+    // slot colsrc[x]); direction-word index fields of the cells in non-chain rows / columns (ncidx = row in RowIdx / ColIdx)
+    int sgen;                   // 1: swept by graph_fill_strip_gen_kernel
+    int dbg;                    // PGM_STRIP_DEBUG bits (experiments): 1 = never the fused fast path, 2 = fence after the step barrier
+    int nsrc, ring_rows;        // source columns, rows per ring (power of two > nstrips + 1)
+    int hist_rows;              // rows of the (Y,W) history ring (power of two >= 2)
+    const uint32_t* specmask; const uint32_t* srcmask; const int16_t* colsrc;
+    const int* ncidx1; const int* ncidx2;
+    const RowInfo* rinfo;       // N1 records (general strip kernel)
+    void* RowIdx; void* ColIdx; int ldRI, ldCI;
     const float* Mf;            // n*n row-major float cast of Model::M
     const float* pif;           // n
     // unified predecessor lists (regular edges ascending, then repeat edges ascending; Graph.h:196,241-247)
@@ -226,4 +240,7 @@ int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const Graph
 int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2);
 int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
 int launch_graph_fill_strip(cudaStream_t st, int C, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
+int launch_graph_fill_strip_gen(cudaStream_t st, int C, int dbits, int warps, size_t smem, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
+#define SG_MAX_WARPS 8       // warps per job of the general strip kernel (256 strips)
+#define SG_MAX_SRC 256       // source columns of non-adjacent column edges per job (shared-memory rings)
 __host__ __device__ __forceinline__ int strip_words(int C) { return C <= 8 ? 1 : (C <= 16 ? 2 : 4); }   // uint32 words of direction nibbles per strip and row

@@ -67,7 +67,8 @@ class GraphBatch:
     def run(self):
         _lib.check(_lib.lib().pgm_graph_batch_run(self.ctx.handle, self._h))
 
-    def fetch(self):
+    def fetch(self, statuses=None):
+        """statuses: optional list that receives every job's status instead of raising on the first failed job (tools)"""
         n = self.n_jobs
         out = np.zeros(max(1, n), dtype=_ALIGNMENT)                          # pgm_alignment[n], filled and read as columns
         offs = np.zeros(n + 1, dtype=np.int64)
@@ -77,6 +78,9 @@ class GraphBatch:
         out["mapping2"][:n] = _addr(buf[1]) + 4 * offs[:-1]
         out["capacity"][:n] = self.caps
         rc = _lib.lib().pgm_graph_batch_fetch(self.ctx.handle, self._h, C.c_void_p(out.ctypes.data))
+        if statuses is not None:
+            statuses.extend(out["status"][:n].tolist())
+            rc = 0
         if rc == -4:
             raise RuntimeError("backtracking failed")
         _lib.check(rc)

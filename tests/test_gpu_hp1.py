@@ -231,6 +231,11 @@ FLAVOURS = {
     "diag32": {"PGM_FILL_LAYOUT": "diag", "PGM_DIR_BITS": "7"},
     "banded": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_BAND_MIN_N1": "66", "PGM_FILL_BAND_ROWS": "64"},
     "nostrip": {"PGM_FILL_STRIP": "0"},
+    "strip_chain_only": {"PGM_FILL_STRIP": "1"},
+    "strip_c4": {"PGM_STRIP_C": "4"},
+    "strip_c8": {"PGM_STRIP_C": "8"},
+    "strip_c16": {"PGM_STRIP_C": "16"},
+    "strip32": {"PGM_DIR_BITS": "7"},
     "strip_full_s": {"PGM_SITE_CLASSES": "0"},
 }
 
@@ -368,3 +373,25 @@ def test_strip_kernel_profile_chain_graphs(ga, po, flavour):
         jobs.append((g1, g2, m))
     for (g1, g2, mm), r in zip(jobs, ga.alignGraphsBatch(jobs, opts)):
         _same_alignment(r, po.align_graphs(g1, g2, mm, opts))
+
+
+def test_more_jobs_than_sms_multi_warp_strips(ga, po):
+    """every job of a pass, replicated to more jobs than the GPU has SMs: CTAs of the general strip kernel then start on an SM
+    whose shared memory still holds the previous CTA's data (regression: the warp hand-over slot of row -1 must be -inf,
+    not whatever was left there)"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, root = synth.simulate_family(48, 300, mf, seed=61, indel_rate=0.03)
+    tree = progressive.from_synth(root)
+    jobs, refs = [], []
+
+    def batch(js, o):
+        out = [po.align_graphs(g1, g2, m, o) for g1, g2, m in js]
+        jobs.extend(js); refs.extend(out)
+        return out
+    progressive.progressive_alignment(seqs, tree, mf, opts, batch_align_fn=batch)
+    rep = 8
+    for _ in range(2):
+        got = ga.alignGraphsBatch(jobs * rep, opts)
+        for k, r in enumerate(got):
+            _same_alignment(r, refs[k % len(jobs)])
