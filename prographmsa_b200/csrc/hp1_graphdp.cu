@@ -1,4 +1,4 @@
-// hp1_graphdp.cu -- K5 (blocked wavefront fill + end-node match) and K6 (traceback walk).
+// hp1_graphdp.cu -- K5 (anti-diagonal wavefront fill + end-node match) and K6 (traceback walk).
 //
 // Replaces alignGraphs (reference GraphAlign.h:201-534):
 //   boundary column/row   :212-234      fill over predecessor pairs :238-260
@@ -10,25 +10,29 @@
 //   M,X,Y,W <- running max over all predecessor pairs (yp,xp) of (y,x)
 //
 // Design: every dependency of a cell lies on a strictly earlier anti-diagonal (predecessors have
-// smaller node indices in both graphs), so one CTA sweeps one job with a barrier between the steps; a
-// batch of independent jobs (all ready guide-tree nodes) fills the GPU.  The DP values never leave the
-// SM: they live in a shared-memory ring of the last few sweep steps.  What is written to HBM is the
-// packed traceback, one direction word (2 bytes) per cell (hp1_dir.cuh), and the {M,X,Y,W} of the few
-// rows / columns that are read back later (value store: far predecessor edges, end-node match, the
-// boundary row and column for the traceback).  The traceback chases the direction words and is
-// bit-identical to the reference's closest-|delta| search on the dense matrices.
-#include "hp1_dir.cuh"
+// smaller node indices in both graphs), so one CTA sweeps the anti-diagonals of one job with a
+// barrier between them; a batch of independent jobs (all ready guide-tree nodes) fills the GPU.
+// {M,X,Y,W} of a cell is one float4 in a skewed layout (diagonal-major), so a diagonal is one
+// coalesced 16 B-per-thread store and the common predecessor (y-1, x-1 / y, x-1 / y-1, x) reads
+// are coalesced too.  Arbitrary predecessors (skip edges after indels, tandem-repeat edges) are read
+// from the same arrays, so no graph shape needs a fallback.
+//
+// The traceback re-runs the reference's "closest |delta|" search verbatim on the stored matrices
+// (one thread per job): first-wins ties in predecessor order, M > Y > X when landing on W,
+// alternative-path marking for repeat edges.  With identical S it is bit-identical to the oracle.
+#include "internal.h"
+#include <math_constants.h>
 #include <algorithm>
 #include <cstdlib>
 
-// Direction words live in a BLOCK-SKEWED layout.  The columns of graph 2 are cut (on the host, hp1_host.cu) into nb
-// blocks: a block is a run of columns inside one aligned group of GF_K columns [8g, 8g+8), and every column whose node is
-// not a chain node (several predecessors, or one that is not x-1) STARTS a block.  A column keeps its slot x % GF_K;
-// colinfo[x] = (block << GF_LOGK) | slot.  Block b of row y is produced at sweep step st = y + b by thread y % nb, which
-// stores the group's 8 words as one 16-byte vector at ((st * pitch + y % nb) * GF_K): a warp's store is one contiguous run.
+// Cell (y,x) of the {M,X,Y,W} matrices lives in a BLOCK-SKEWED layout.  The columns of graph 2 are cut (on the host,
+// hp1_host.cu) into nb blocks: a block is a run of columns inside one aligned group of GF_K columns [8g, 8g+8), and every
+// column whose node is not a chain node (several predecessors, or one that is not x-1) STARTS a block.  A column keeps its
+// slot x % GF_K; colinfo[x] = (block << GF_LOGK) | slot.  Block b of row y is produced at sweep step st = y + b by thread
+// y % nb, and the cell sits at ((st * GF_K + slot) * pitch + y % nb): a warp's store of one slot is a contiguous run.
 __device__ __forceinline__ size_t cidx(int y, int x, const uint16_t* __restrict__ colinfo, int nb, int pitch) {
     const int ci = colinfo[x];
-    return ((size_t)(y + (ci >> GF_LOGK)) * pitch + (y % nb)) * GF_K + (ci & (GF_K - 1));
+    return ((size_t)(y + (ci >> GF_LOGK)) * GF_K + (ci & (GF_K - 1))) * pitch + (y % nb);
 }
 
 // either layout, for the traceback
@@ -43,8 +47,8 @@ struct CellIndex {
 #define GF_SPF 6             // S is pulled into L2 this many steps before the step that loads it into registers
 #define GF_SMEM_PER_SLOT(R) ((R) * GF_K * 12 + GF_K * 4 + 2 + 1)   // shared-memory bytes per thread slot; R = ring depth in sweep steps (power of two >= 4)
 
-__device__ __forceinline__ void st_global_u4(void* p, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-    asm volatile("st.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+__device__ __forceinline__ void st_global_f4(float4* p, const float4& v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
 // K5: blocked wavefront.  The rows of a job are dealt round-robin to nb threads (nb = column blocks per row):
@@ -53,30 +57,26 @@ __device__ __forceinline__ void st_global_u4(void* p, uint32_t a, uint32_t b, ui
 // is never idle between its first and its last block.  One barrier per step; ~(N1 + N2/GF_K) steps per job instead of
 // N1 + N2 anti-diagonals, and the per-step overhead is shared by the block's cells.
 //   phase 1 (independent across the slots): for every predecessor yp of row y fetch the window (Y,W)(yp, block b) and
-//            W(yp, x0-1) -- from the shared-memory ring when it was produced < R steps ago, else from the value store --
-//            and fold it into ys[k] and the diagonal term m[k];
+//            W(yp, x0-1) -- from the shared-memory ring when it was produced < R steps ago, else from HBM/L2 -- and
+//            fold it into ys[k] and the diagonal term m[k];
 //   phase 1b (only a block whose first column is not a chain node): that column's M and X terms over all predecessor
-//            pairs; all its column predecessors lie in earlier blocks, i.e. in the ring or in the value store;
-//   phase 2 (sequential in x): the X recurrence through the left neighbour in registers, W, the direction word.
-// All eight slots of the group are always computed and their words stored; the slots outside the block ([lo, hi)) are
-// never read: a block starts inside a group only at a non-chain column, whose terms come from phase 1b and not from its
-// left neighbour or the window's previous slot.
-// max() is exact, so accumulating the candidates in this order gives the reference's running maxima bit for bit; strict
-// '>' updates in the reference's candidate order record the FIRST maximum, which is what its traceback picks.
+//            pairs; all its column predecessors lie in earlier blocks, i.e. in the ring or in HBM/L2;
+//   phase 2 (sequential in x): the X recurrence through the left neighbour in registers.
+// All eight slots of the group are always computed; the slots outside the block ([lo, hi)) are simply not stored and
+// nothing valid ever reads them: a block starts inside a group only at a non-chain column, whose terms come from phase 1b
+// and not from its left neighbour or the window's previous slot.
+// max() is exact, so accumulating the candidates in this order gives the reference's running maxima bit for bit.
 // The ring keeps {Y,W} and X of the last R steps (M is never read back by the sweep).  S (row-major) is loaded one
 // step ahead into registers as the aligned 32-byte group (thread-per-row means every lane touches its own line, so the
 // L1 tag stage is the scarce resource: two 16-byte requests per lane and step), and pulled into L2 a few steps earlier.
-template <int B, int MAXT, int MINB>
+template <int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB)
 graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int Tp, int R, int ci_cap, int np_cap) {
-    typedef typename DirWord<B>::T DW;
-    constexpr uint32_t YF = DIR_YOPEN | (dir_mask<B>() << (4 + 2 * B));        // the Y fields of a direction word
-    constexpr uint32_t MF = (dir_mask<B>() << 4) | (dir_mask<B>() << (4 + B)); // the M fields
     const GraphJobDev* Jp = jobs + order[blockIdx.x];
     const int N1 = Jp->N1, N2 = Jp->N2, pitch = Jp->pitch, nb = Jp->nb, ldS = Jp->ldS;
     const float gap_init = Jp->sc[0], gap_extend = Jp->sc[1], start_gap = Jp->sc[6], start_init = Jp->sc[7];
     const float NINF = -CUDART_INF_F;
-    DW* const D = (DW*)Jp->D;
+    float4* const C = Jp->MXYW;
     const float* const S = Jp->S;
     const NodeInfo* const ni1 = Jp->ni1;
     const NodeInfo* const ni2 = Jp->ni2;
@@ -91,7 +91,7 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
     float* exs = ringX + (size_t)R * K * Tp;                       // [Tp * K]: first-predecessor edge value of graph-2 node x
     unsigned short* bst = (unsigned short*)(exs + (size_t)Tp * K); // [Tp + 2]: first column of block b (bst[nb] = N2 - 1)
     unsigned short* cis = bst + Tp + 2;                            // [ci_cap]: colinfo staged (launches whose jobs have many non-chain nodes)
-    unsigned char* gfl = (unsigned char*)(cis + ci_cap);           // [Tp]: bit 0: block's first column is not a chain node, bit 1: block has a kept column
+    unsigned char* gfl = (unsigned char*)(cis + ci_cap);           // [Tp]: block's first column is not a chain node
     const uint16_t* colinfo = Jp->colinfo;
     const int* p2i = Jp->p2_idx; const float* p2v = Jp->p2_val;
     const NodeInfo* gni = ni2;                                     // node infos / predecessor lists read by phase 1b
@@ -113,29 +113,28 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
         const int ncol = (N2 - 1 + K - 1) & ~(K - 1);
         for (int x = t; x < ncol; x += (int)blockDim.x) exs[x] = (x >= 1 && x <= N2 - 2) ? __ldg(&ni2[x].val0) : 0.f;
         for (int b = t; b < nb; b += (int)blockDim.x) {
-            const int x = bs[b], xe = bs[b + 1];
-            unsigned char g = 0;
-            if (x >= 1) { const int cnt = __ldg(&ni2[x].cnt), i0 = __ldg(&ni2[x].idx0); g = ((cnt & 0x800000ff) == 1 && i0 == x - 1) ? 0 : 1; }
-            for (int xx = x; xx < xe; ++xx) if (NI_KEEP(__ldg(&ni2[xx].cnt)) >= 0) g |= 2;
-            gfl[b] = g;
+            const int x = bs[b];
+            bool g = false;
+            if (x >= 1) { const int cnt = __ldg(&ni2[x].cnt), i0 = __ldg(&ni2[x].idx0); g = !(cnt == 1 && i0 == x - 1); }
+            gfl[b] = g ? 1 : 0;
         }
     }
     __syncthreads();
 
     const bool lane_on = t < nb;
     int y = t, b = 0;
-    // any earlier cell (yy, xx) as {X, Y, W}: ring when produced < R steps ago, else the value store (written by this CTA >= R barriers ago)
+    // any earlier cell (yy, xx) as {X, Y, W}: ring when produced < R steps ago, else HBM/L2 (written by this CTA >= R barriers ago)
     auto cell_at = [&](int yy, int xx, int s) -> float3 {
         const int ci = colinfo[xx];
         const int st = yy + (ci >> GF_LOGK), kk = ci & (K - 1);
+        int tp = t - (y - yy);                                     // yy % nb without the division when yy is a recent row
+        if (tp < 0) { tp += nb; if (tp < 0) tp = yy % nb; }
         if (s - st < R) {
-            int tp = t - (y - yy);                                 // yy % nb without the division when yy is a recent row
-            if (tp < 0) { tp += nb; if (tp < 0) tp = yy % nb; }
             const int o = ((st & Rm) * K + kk) * Tp + tp;
             const float2 yw = ringYW[o];
             return make_float3(ringX[o], yw.x, yw.y);
         }
-        const float4 c = dir_far_cell(*Jp, NI_KEEP(__ldg(&ni1[yy].cnt)), NI_KEEP(gni[xx].cnt), yy, xx);
+        const float4 c = __ldcg(C + ((size_t)st * K + kk) * pitch + tp);
         return make_float3(c.y, c.z, c.w);
     };
 
@@ -146,7 +145,7 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
     }
     // ---- S stream: position p of this thread = (row t + (p / nb) * nb, block p % nb).  The aligned group of S for
     // position p+1 is loaded while position p is computed; reads past the row's end stay inside the S allocation (rows
-    // are contiguous, 64 bytes of slack at the end) and feed only slots that are never read back ----
+    // are contiguous, 64 bytes of slack at the end) and feed only slots that are never stored ----
     float4 sna = make_float4(0.f, 0.f, 0.f, 0.f), snb = sna;
     if (lane_on && y >= 1 && y <= N1 - 2) {
         const float4* sp = (const float4*)(S + (size_t)y * ldS);
@@ -157,9 +156,9 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
     for (int d = 0; d <= GF_SPF; ++d) if (++bF == nb) { bF = 0; yF += nb; }
     float leftX = NINF, leftW = NINF;
     const int n_steps = (N1 - 1) + nb - 1;
-    DW* dcur = D + (size_t)t * K;                                  // this thread's 8 words of sweep step s
-    const size_t dstep = (size_t)K * pitch;
-    for (int s = 0; s < n_steps; ++s, dcur += dstep) {
+    float4* gcur = C + t;                                          // this thread's slot of sweep step s
+    const size_t gstep = (size_t)K * pitch;
+    for (int s = 0; s < n_steps; ++s, gcur += gstep) {
         if (lane_on && s >= t && y <= N1 - 2) {
             const int x0 = bst[b], x1 = bst[b + 1];                // this block: columns x0 .. x1-1, slots lo .. hi-1
             const int lo = x0 & (K - 1), hi = lo + (x1 - x0), g8 = x0 - lo;
@@ -186,15 +185,14 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
                 const float4 e0 = *(const float4*)(exs + g8), e1 = *(const float4*)(exs + g8 + 4);
                 ex[0] = e0.x; ex[1] = e0.y; ex[2] = e0.z; ex[3] = e0.w; ex[4] = e1.x; ex[5] = e1.y; ex[6] = e1.z; ex[7] = e1.w;
             }
-            const unsigned gflag = gfl[b];
-            const bool gen0 = (gflag & 1u) != 0;
-            float ys[K], m[K]; uint32_t dr[K];                     // dr: the direction word's Y and M fields so far
+            const bool gen0 = gfl[b] != 0;
+            float ys[K], m[K];
 #pragma unroll
-            for (int k = 0; k < K; ++k) { ys[k] = NINF; m[k] = NINF; dr[k] = 0u; }
+            for (int k = 0; k < K; ++k) { ys[k] = NINF; m[k] = NINF; }
             // ---- phase 1: row predecessors ----
-            const int c1 = NI_CNT(ny.cnt);
+            const int c1 = ny.cnt & 0x7fffffff;
             const float gi0 = (b == 0) ? start_gap : gap_init;
-            auto fold_pred = [&](const uint32_t ky, int yp, float ey, const bool first) {
+            auto fold_pred = [&](int yp, float ey) {
                 const int dy = y - yp;
                 float2 win[K]; float wprev = NINF;                 // wprev = W(yp, x0-1), used only when the block starts a group
                 if (dy + 1 < R) {
@@ -204,97 +202,88 @@ graph_fill_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ 
 #pragma unroll
                     for (int k = 0; k < K; ++k) win[k] = r0[k * Tp];
                     if (b > 0) wprev = ringYW[(((s - dy - 1) & Rm) * K + (K - 1)) * Tp + tp].y;
-                } else {                                           // far row predecessor: a kept row of the value store
-                    const int kr = NI_KEEP(__ldg(&ni1[yp].cnt));
-                    const float4* base = Jp->Vrow + (size_t)(kr < 0 ? 0 : kr) * Jp->ldVr + g8;
+                } else {
+                    const int tp = yp % nb;
+                    const float4* base = C + ((size_t)(yp + b) * K) * pitch + tp;
 #pragma unroll
-                    for (int k = 0; k < K; ++k) { const float4 c = __ldcg(base + k); win[k] = kr < 0 ? make_float2(CUDART_NAN_F, CUDART_NAN_F) : make_float2(c.z, c.w); }
-                    if (b > 0) wprev = kr < 0 ? CUDART_NAN_F : __ldcg(base - 1).w;
+                    for (int k = 0; k < K; ++k) { const float4 c = __ldcg(base + (size_t)k * pitch); win[k] = make_float2(c.z, c.w); }
+                    if (b > 0) wprev = __ldcg(C + ((size_t)(yp + b - 1) * K + (K - 1)) * pitch + tp).w;
                 }
 #pragma unroll
                 for (int k = 0; k < K; ++k) {
                     const float gi = (k == 0) ? gi0 : gap_init;
-                    const float cE = __fsub_rn(__fadd_rn(win[k].x, gap_extend), ey), cO = __fsub_rn(__fadd_rn(win[k].y, gi), ey);
+                    ys[k] = fmaxf(ys[k], __fsub_rn(fmaxf(__fadd_rn(win[k].x, gap_extend), __fadd_rn(win[k].y, gi)), ey));
                     const float wd = (k == 0) ? wprev : win[k - 1].y;
-                    const float v = __fsub_rn(__fsub_rn(__fadd_rn(wd, sv[k]), ey), ex[k]);
-                    if (first) {
-                        ys[k] = fmaxf(cE, cO); dr[k] = (cO > cE) ? DIR_YOPEN : 0u;
-                        m[k] = v;
-                    } else {
-                        if (cE > ys[k]) { ys[k] = cE; dr[k] = (dr[k] & ~YF) | (ky << (4 + 2 * B)); }
-                        if (cO > ys[k]) { ys[k] = cO; dr[k] = (dr[k] & ~YF) | (ky << (4 + 2 * B)) | DIR_YOPEN; }
-                        if (v > m[k]) { m[k] = v; dr[k] = (dr[k] & ~MF) | (ky << 4); }
-                    }
+                    m[k] = fmaxf(m[k], __fsub_rn(__fsub_rn(__fadd_rn(wd, sv[k]), ey), ex[k]));
                 }
             };
-            if (c1 > 0) fold_pred(0u, ny.idx0, ny.val0, true);      // the first predecessor is inline in the node info
-            for (int i = 1; i < c1; ++i) fold_pred((uint32_t)i, __ldg(p1i + ny.ptr + i), __ldg(p1v + ny.ptr + i), false);
+            if (c1 > 0) fold_pred(ny.idx0, ny.val0);                // the first predecessor is inline in the node info
+            for (int i = 1; i < c1; ++i) fold_pred(__ldg(p1i + ny.ptr + i), __ldg(p1v + ny.ptr + i));
             const float gix = (y == 0) ? start_gap : gap_init;
             // ---- phase 1b: a first column that is not a chain node (all its predecessors are in earlier blocks) ----
-            float xsg = NINF, mg = NINF; uint32_t dg = 0u;          // dg: the X and M fields of that column's direction word
+            float xsg = NINF, mg = NINF;
             if (gen0) {
                 const int4 v = *(const int4*)(gni + x0);
-                const int c2 = NI_CNT(v.y);
+                const int c2 = v.y & 0x7fffffff;
                 const float s0 = __ldg(S + (size_t)y * ldS + x0);  // == sv[lo]; y >= 1 whenever it matters (c1 == 0 for row 0)
-                if (c1 > 0 || y == 0)
-                    for (int j = 0; j < c2; ++j) {
-                        const int xp = j ? p2i[v.x + j] : v.z;
-                        const float exj = j ? p2v[v.x + j] : __int_as_float(v.w);
-                        const float3 cl = cell_at(y, xp, s);
-                        const float cE = __fsub_rn(__fadd_rn(cl.x, gap_extend), exj), cO = __fsub_rn(__fadd_rn(cl.z, gix), exj);
-                        if (cE > xsg) { xsg = cE; dg = (dg & MF) | ((uint32_t)j << (4 + 3 * B)); }
-                        if (cO > xsg) { xsg = cO; dg = (dg & MF) | ((uint32_t)j << (4 + 3 * B)) | DIR_XOPEN; }
-                    }
-                for (int i = 0; i < c1; ++i) {                      // pairs in the reference's nested order: rows outer, columns inner
-                    const int yp = i ? __ldg(p1i + ny.ptr + i) : ny.idx0;
-                    const float ey = i ? __ldg(p1v + ny.ptr + i) : ny.val0;
-                    for (int j = 0; j < c2; ++j) {
-                        const int xp = j ? p2i[v.x + j] : v.z;
-                        const float exj = j ? p2v[v.x + j] : __int_as_float(v.w);
+                for (int j = 0; j < c2; ++j) {
+                    const int xp = j ? p2i[v.x + j] : v.z;
+                    const float exj = j ? p2v[v.x + j] : __int_as_float(v.w);
+                    const float3 cl = cell_at(y, xp, s);
+                    xsg = fmaxf(xsg, __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.z, gix)), exj));
+                    for (int i = 0; i < c1; ++i) {
+                        const int yp = i ? __ldg(p1i + ny.ptr + i) : ny.idx0;
+                        const float ey = i ? __ldg(p1v + ny.ptr + i) : ny.val0;
                         const float cw = cell_at(yp, xp, s).z;
-                        const float vm = __fsub_rn(__fsub_rn(__fadd_rn(cw, s0), ey), exj);
-                        if (vm > mg) { mg = vm; dg = (dg & ~MF) | ((uint32_t)i << 4) | ((uint32_t)j << (4 + B)); }
+                        mg = fmaxf(mg, __fsub_rn(__fsub_rn(__fadd_rn(cw, s0), ey), exj));
                     }
                 }
             }
             const int gslot = gen0 ? lo : -1;
-            const int krow = NI_KEEP(ny.cnt);
-            const bool keep_any = krow >= 0 || (gflag & 2u) != 0;
             // ---- phase 2: along the row ----
             const int ro = ((s & Rm) * K) * Tp + t;
-            uint32_t dw[K];
+            float4* gk = gcur;
 #pragma unroll
             for (int k = 0; k < K; ++k) {
                 float mk = m[k];
-                uint32_t dk = dr[k];
-                const float cE = __fsub_rn(__fadd_rn(leftX, gap_extend), ex[k]), cO = __fsub_rn(__fadd_rn(leftW, gix), ex[k]);
-                float xs = fmaxf(cE, cO);
-                if (cO > cE) dk |= DIR_XOPEN;
-                if (k == gslot) { mk = mg; xs = xsg; dk = (dr[k] & YF) | dg; }
+                float xs = __fsub_rn(fmaxf(__fadd_rn(leftX, gap_extend), __fadd_rn(leftW, gix)), ex[k]);
+                if (k == gslot) { mk = mg; xs = xsg; }
                 if (k == 0 && b == 0) { mk = NINF; xs = NINF; }     // column 0: Y only (GraphAlign.h:212-222)
                 float wv = fmaxf(mk, fmaxf(xs, ys[k]));
                 if (k == 0 && b == 0 && y == 0) wv = start_init;
                 leftX = xs; leftW = wv;
-                dw[k] = dk | dir_wstate(mk, xs, ys[k], wv);
                 if (k >= lo && k < hi) {
                     ringYW[ro + k * Tp] = make_float2(ys[k], wv); ringX[ro + k * Tp] = xs;
-                    if (keep_any) {                                 // value store: kept row and / or kept column
-                        const float4 out = make_float4(mk, xs, ys[k], wv);
-                        if (krow >= 0) Jp->Vrow[(size_t)krow * Jp->ldVr + g8 + k] = out;
-                        if (gflag & 2u) { const int kc = NI_KEEP(gni[g8 + k].cnt); if (kc >= 0) Jp->Vcol[(size_t)kc * Jp->ldVc + y] = out; }
-                    }
+                    st_global_f4(gk, make_float4(mk, xs, ys[k], wv));
                 }
+                gk += pitch;
             }
-            if (B == 3) st_global_u4(dcur, dw[0] | (dw[1] << 16), dw[2] | (dw[3] << 16), dw[4] | (dw[5] << 16), dw[6] | (dw[7] << 16));
-            else { st_global_u4(dcur, dw[0], dw[1], dw[2], dw[3]); st_global_u4(dcur + 4, dw[4], dw[5], dw[6], dw[7]); }
             // ---- advance ----
             b = bn;
             if (yn != y) { y = yn; ny = nyn; }
         }
         __syncthreads();
     }
-    // end-node match (GraphAlign.h:262-280) and the traceback's first pick
-    if (t == 0) dir_end_match(*Jp);
+    // end-node match (GraphAlign.h:262-280)
+    if (t == 0) {
+        const GraphJobDev& J = *Jp;
+        const float end_match = J.sc[3], end_gap = J.sc[4], end_skip = J.sc[5];
+        float Wend = NINF;
+        for (int ky = J.p1_ptr[N1 - 1]; ky < J.p1_ptr[N1]; ++ky)
+            for (int kx = J.p2_ptr[N2 - 1]; kx < J.p2_ptr[N2]; ++kx) {
+                const int yp = J.p1_idx[ky], xp = J.p2_idx[kx];
+                const float ey = J.p1_val[ky], ex = J.p2_val[kx];
+                if (xp == 0 && yp == 0) {
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(end_skip, ey), ex), Wend);
+                } else {
+                    const float4 c = __ldcg(C + cidx(yp, xp, colinfo, nb, pitch));
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.y, end_gap), ey), ex), Wend);
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.z, end_gap), ey), ex), Wend);
+                    Wend = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(c.x, end_match), ey), ex), Wend);
+                }
+            }
+        ((float*)J.result)[3] = Wend;
+    }
 }
 
 // ---- traceback ------------------------------------------------------------------------------------------
@@ -336,91 +325,87 @@ struct Tracer {
     }
 };
 
-// One WARP per job chases the direction words from the end node to the start node.  All 32 lanes run the walk
-// redundantly (identical values, so the duplicate stores are benign and every load is a broadcast); the lanes earn
-// their keep on DIAGONAL RUNS: in state M at chain nodes the next cell is forced to be (y-1, x-1), so lane k fetches the
-// word of (y-k, x-k) and its nodes, the warp finds with two ballots how far the run extends, and up to 32 path steps are
-// emitted at once instead of one dependent load per step.
-// The boundary row and column follow the reference's closest-|delta| search on the kept values (hp1_dir.cuh).
-template <int B>
-__device__ __forceinline__ void graph_trace_job(const GraphJobDev& J, const int lane) {
-    typedef typename DirWord<B>::T DW;
-    const int N1 = J.N1, N2 = J.N2;
-    const float gap_init = J.sc[0], gap_extend = J.sc[1];
-    const DW* __restrict__ D = (const DW*)J.D;
-    const CellIndex cix{J.colinfo, J.nb, J.pitch, N2, J.layout};
-    const bool strip = J.layout == GF_LAYOUT_STRIP;
-    const int sC = J.C, sW = strip_words(J.C), sN = J.nstrips;
-    // the direction word of cell (yy, xx) in the canonical format of hp1_dir.cuh, whatever layout the fill wrote
-    auto dword = [&](int yy, int xx) -> uint32_t {
-        if (strip) {                                     // 4-bit cells (hp1_strip.cu): mlose, xbeats, yopen, xopen
-            const uint32_t cs = J.colstrip[xx];
-            const int j = (int)(cs >> 5), k = (int)(cs & 31u), g = k >> 3, gsz = min(8, sC - 8 * g);
-            const uint32_t word = ((const uint32_t*)J.D)[((size_t)(yy + j) * sN + j) * sW + g];
-            const uint32_t nib = (word >> (4 * (gsz - 1 - (k & 7)))) & 15u;
-            uint32_t idx = 0u;                           // predecessor-index fields: only cells in non-chain rows / columns have any
-            if (J.sgen) {
-                const int r1 = J.ncidx1[yy];
-                if (r1 >= 0) idx = ((const uint32_t*)J.RowIdx)[(size_t)r1 * J.ldRI + xx];
-                else { const int r2 = J.ncidx2[xx]; if (r2 >= 0) idx = ((const uint32_t*)J.ColIdx)[(size_t)r2 * J.ldCI + yy]; }
-            }
-            return ((nib & 1u) ? ((nib & 2u) ? 1u : 2u) : 0u) | (nib & 12u) | (idx & ~15u);
-        }
-        return D[cix(yy, xx)];
-    };
+// One WARP per job.  All 32 lanes run the walk redundantly (identical values, so the duplicate stores are
+// benign and every load is a broadcast); the lanes earn their keep on DIAGONAL RUNS: in state M at chain
+// nodes the next cell is forced to be (y-1, x-1), so lane k fetches cell (y-k, x-k) and its nodes, the warp
+// finds with two ballots how far the run extends, and up to 32 path steps are emitted at once instead of
+// one dependent load chain per step.
+__global__ void __launch_bounds__(32)
+graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
+    const int lane = threadIdx.x;
+    if ((int)blockIdx.x >= n_jobs) return;
+    const GraphJobDev& J = jobs[order ? order[blockIdx.x] : blockIdx.x];
+    if (J.layout == GF_LAYOUT_STRIP) return;             // the packed traceback (hp1_trace.cu) walks the strip kernels' jobs
+    if (J.result[4] != 0) {                              // a failed emission (tensor flavour: bounded mbarrier wait timed out) fails the job
+        if (lane == 0) { J.result[0] = J.result[4]; J.result[1] = 0; J.result[2] = 0; }
+        return;
+    }
+    const int N1 = J.N1, N2 = J.N2, pitch = J.pitch, nb = J.nb;
+    const float gap_init = J.sc[0], gap_extend = J.sc[1], end_match = J.sc[3], end_gap = J.sc[4], end_skip = J.sc[5];
+    const float4* __restrict__ C = J.MXYW;
+    const CellIndex cix{J.colinfo, nb, pitch, N2, J.layout};
+    const float Wend = ((const float*)J.result)[3];
     const float FINF = CUDART_INF_F;
     Tracer T(J);
-    int status = J.result[4];            // a failed emission (tensor flavour: bounded mbarrier wait timed out) fails the job
+    int status = 0;
     unsigned n_tr = 0;
-    if (status != 0) { J.result[0] = status; J.result[1] = 0; J.result[2] = 0; return; }
-    // predecessor k of a node: the first one is inline in its NodeInfo (one 16-byte load)
-    auto pred1 = [&](const NodeInfo& ni, int k, int& idx, bool& rep) {
-        if (k == 0) { idx = ni.idx0; rep = ni.cnt < 0; }
-        else { idx = J.p1_idx[ni.ptr + k]; rep = J.p1_rep[ni.ptr + k] != 0; }
-    };
-    auto pred2 = [&](const NodeInfo& ni, int k, int& idx, bool& rep) {
-        if (k == 0) { idx = ni.idx0; rep = ni.cnt < 0; }
-        else { idx = J.p2_idx[ni.ptr + k]; rep = J.p2_rep[ni.ptr + k] != 0; }
-    };
     int state = 0;                       // 0 = M, 1 = X, 2 = Y
+    float cur = -FINF;
     int y = N1 - 1, x = N2 - 1;
     T.push(N1 - 1, N2 - 1);
     bool trx = false, try_ = false;
-    {   // the fill's end-node match recorded the reference's first pick
-        const int pick = J.result[5];
-        const int ky = (pick >> 8) & 0xff, kx = (pick >> 16) & 0xff, st = pick & 3;
-        const int p1 = J.p1_ptr[N1 - 1], p2 = J.p2_ptr[N2 - 1];
-        if (J.p1_ptr[N1] - p1 <= ky || J.p2_ptr[N2] - p2 <= kx || !(((const float*)J.result)[3] > -FINF)) status = PGM_ERR_BACKTRACK;
-        else {
-            y = J.p1_idx[p1 + ky]; x = J.p2_idx[p2 + kx];
-            try_ = J.p1_rep[p1 + ky] != 0; trx = J.p2_rep[p2 + kx] != 0;
-            state = (st == 3) ? 0 : st;
+    float best = FINF;
+    for (int ky = J.p1_ptr[N1 - 1]; ky < J.p1_ptr[N1]; ++ky)
+        for (int kx = J.p2_ptr[N2 - 1]; kx < J.p2_ptr[N2]; ++kx) {
+            const int yp = J.p1_idx[ky], xp = J.p2_idx[kx];
+            const float ey = J.p1_val[ky], ex = J.p2_val[kx];
+            const bool ry = J.p1_rep[ky] != 0, rx = J.p2_rep[kx] != 0;
+            const float4 c = C[cix(yp, xp)];
+            float q = fabsf(__fsub_rn(Wend, __fsub_rn(__fsub_rn(__fadd_rn(c.x, end_match), ey), ex)));
+            if (best > q) { best = q; trx = rx; try_ = ry; cur = c.x; state = 0; y = yp; x = xp; }
+            q = fabsf(__fsub_rn(Wend, __fsub_rn(__fsub_rn(__fadd_rn(c.z, end_gap), ey), ex)));
+            if (best > q) { best = q; trx = rx; try_ = ry; cur = c.z; state = 2; y = yp; x = xp; }
+            q = fabsf(__fsub_rn(Wend, __fsub_rn(__fsub_rn(__fadd_rn(c.y, end_gap), ey), ex)));
+            if (best > q) { best = q; trx = rx; try_ = ry; cur = c.y; state = 1; y = yp; x = xp; }
+            if (xp == 0 && yp == 0) {
+                q = fabsf(__fsub_rn(Wend, __fsub_rn(__fsub_rn(end_skip, ey), ex)));
+                if (best > q) { best = q; trx = rx; try_ = ry; y = yp; x = xp; }
+            }
         }
+    n_tr += (trx ? 1u : 0u) + (try_ ? 1u : 0u);
+    if (try_) T.alt_path(y, N1 - 1, 0);
+    if (trx) T.alt_path(x, N2 - 1, 1);
+    if (x != 0 || y != 0) {
+        if (state == 0) T.push(y, x); else if (state == 1) T.push(-1, x); else T.push(y, -1);
     }
-    if (status == 0) {
-        n_tr += (trx ? 1u : 0u) + (try_ ? 1u : 0u);
-        if (try_) T.alt_path(y, N1 - 1, 0);
-        if (trx) T.alt_path(x, N2 - 1, 1);
-        if (x != 0 || y != 0) {
-            if (state == 0) T.push(y, x); else if (state == 1) T.push(-1, x); else T.push(y, -1);
-        }
-    }
+    float nscore = FINF; int nstate = 0, nx = -1, ny = -1;
     long guard = 0;
     const long guard_max = 4L * (N1 + N2) + 16;
+    // predecessor k of a node: the first one is inline in its NodeInfo (one 16-byte load)
+    auto pred1 = [&](const NodeInfo& ni, int k, int& idx, float& val, bool& rep) {
+        if (k == 0) { idx = ni.idx0; val = ni.val0; rep = ni.cnt < 0; }
+        else { idx = J.p1_idx[ni.ptr + k]; val = J.p1_val[ni.ptr + k]; rep = J.p1_rep[ni.ptr + k] != 0; }
+    };
+    auto pred2 = [&](const NodeInfo& ni, int k, int& idx, float& val, bool& rep) {
+        if (k == 0) { idx = ni.idx0; val = ni.val0; rep = ni.cnt < 0; }
+        else { idx = J.p2_idx[ni.ptr + k]; val = J.p2_val[ni.ptr + k]; rep = J.p2_rep[ni.ptr + k] != 0; }
+    };
     const int PF = 8;                                   // prefetch distance (steps) along the diagonal
-    const int kr0 = NI_KEEP(J.ni1[0].cnt), kc0 = NI_KEEP(J.ni2[0].cnt);   // row 0 / column 0 of the value store
-    while (status == 0 && (x != 0 || y != 0)) {
+    while (x != 0 || y != 0) {
         if (++guard > guard_max) { status = PGM_ERR_BACKTRACK; break; }
-        if (state == 0 && y > 0 && x > 0) {
+        if (state == 0 && isfinite(cur)) {
             // ---- diagonal run: lane -> k = lane+1, position (y-k, x-k), reached from (y-k+1, x-k+1) ----
             const int k = lane + 1, yk = y - k, xk = x - k;
-            bool tr = false, stM = false; int st = 3;
+            bool tr = false, stM = false; int st = 3; float4 c = make_float4(0.f, 0.f, 0.f, 0.f);
             if (yk >= 0 && xk >= 0) {
                 const NodeInfo a1 = J.ni1[yk + 1], a2 = J.ni2[xk + 1];          // the nodes whose predecessor is followed
-                tr = NI_CHAIN(a1, yk + 1) && NI_CHAIN(a2, xk + 1);
+                const float sv = J.S[(size_t)(yk + 1) * J.ldS + (xk + 1)];
+                c = C[cix(yk, xk)];
+                tr = a1.cnt == 1 && a1.idx0 == yk && a2.cnt == 1 && a2.idx0 == xk && isfinite(a1.val0) && isfinite(a2.val0) &&
+                     isfinite(sv) && isfinite(c.w);
                 if (yk == 0 && xk == 0) st = 4;                                 // start node: the walk ends here
-                else st = (int)(dword(yk, xk) & 3u);
-                stM = (st == 0) && yk > 0 && xk > 0;                            // a boundary cell ends the run (closest-|delta| rule there)
+                else if (c.w == c.x) st = 0; else if (c.w == c.z) st = 2; else if (c.w == c.y) st = 1;
+                stM = (st == 0);
             }
             const unsigned mtr = __ballot_sync(0xffffffffu, tr), mM = __ballot_sync(0xffffffffu, stM);
             const unsigned cond = mtr & ((mM << 1) | 1u);                        // step k needs state M at k-1
@@ -436,8 +421,11 @@ __device__ __forceinline__ void graph_trace_job(const GraphJobDev& J, const int 
                     }
                 }
                 T.len += (stR == 4) ? R - 1 : R;
+                const float cx = __shfl_sync(0xffffffffu, c.x, R - 1), cy = __shfl_sync(0xffffffffu, c.y, R - 1),
+                            cz = __shfl_sync(0xffffffffu, c.z, R - 1);
                 y -= R; x -= R;
-                if (stR != 4) state = stR;
+                if (stR != 4) { state = stR; cur = (stR == 0) ? cx : (stR == 1 ? cy : cz); }
+                trx = false; try_ = false; nx = x; ny = y; nstate = state; nscore = cur;
                 guard += R;
                 continue;
             }
@@ -445,75 +433,67 @@ __device__ __forceinline__ void graph_trace_job(const GraphJobDev& J, const int 
         {   // the path is mostly diagonal: pull the lines it will touch PF steps from now into L2
             const int py = y - PF, px = x - PF;
             if (py > 0 && px > 0) {
-                if (!strip) asm volatile("prefetch.global.L2 [%0];" ::"l"(D + cix(py, px)));
+                const size_t o = cix(py, px);
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(C + o));
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(J.S + (size_t)py * J.ldS + px));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(J.ni1 + py));
                 asm volatile("prefetch.global.L2 [%0];" ::"l"(J.ni2 + px));
             }
         }
-        int ny = -1, nx = -1, nstate = state;
+        best = FINF;
         bool landed_w = false;
-        trx = false; try_ = false;
         if (state == 2) {
             const NodeInfo ni = J.ni1[y];
-            const int cnt = NI_CNT(ni.cnt);
-            if (x == 0) {
-                // boundary column: the reference's closest-|delta| search with gap_init on the kept values (GraphAlign.h:378-398)
-                const float cur = dir_far_cell(J, -1, kc0, y, 0).z;
-                float best = FINF;
-                for (int ky = 0; ky < cnt; ++ky) {
-                    int yp; bool ry; pred1(ni, ky, yp, ry);
-                    const float ey = ky ? J.p1_val[ni.ptr + ky] : ni.val0;
-                    const float4 c = dir_far_cell(J, -1, kc0, yp, 0);
-                    float q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.z, gap_extend), ey)));
-                    if (best > q) { best = q; try_ = ry; nx = 0; ny = yp; nstate = 2; landed_w = false; }
-                    q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.w, gap_init), ey)));
-                    if (best > q) { best = q; try_ = ry; nx = 0; ny = yp; landed_w = true; }
-                }
-            } else {
-                const uint32_t w = dword(y, x);
-                const int ky = (int)dir_kyy<B>(w);
-                if (ky < cnt) { int yp; bool ry; pred1(ni, ky, yp, ry); ny = yp; nx = x; try_ = ry; landed_w = (w & DIR_YOPEN) != 0; nstate = 2; }
+            const int cnt = ni.cnt & 0x7fffffff;
+            for (int ky = 0; ky < cnt; ++ky) {
+                int yp; float ey; bool ry; pred1(ni, ky, yp, ey, ry);
+                const float4 c = C[cix(yp, x)];
+                float q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.z, gap_extend), ey)));
+                if (best > q) { best = q; trx = false; try_ = ry; nx = x; ny = yp; nscore = c.z; nstate = 2; landed_w = false; }
+                q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.w, gap_init), ey)));
+                if (best > q) { best = q; trx = false; try_ = ry; nx = x; ny = yp; landed_w = true; }
             }
         } else if (state == 1) {
             const NodeInfo ni = J.ni2[x];
-            const int cnt = NI_CNT(ni.cnt);
-            if (y == 0) {
-                const float cur = dir_far_cell(J, kr0, -1, 0, x).y;
-                float best = FINF;
-                for (int kx = 0; kx < cnt; ++kx) {
-                    int xp; bool rx; pred2(ni, kx, xp, rx);
-                    const float ex = kx ? J.p2_val[ni.ptr + kx] : ni.val0;
-                    const float4 c = dir_far_cell(J, kr0, -1, 0, xp);
-                    float q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.y, gap_extend), ex)));
-                    if (best > q) { best = q; trx = rx; nx = xp; ny = 0; nstate = 1; landed_w = false; }
-                    q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.w, gap_init), ex)));
-                    if (best > q) { best = q; trx = rx; nx = xp; ny = 0; landed_w = true; }
-                }
-            } else {
-                const uint32_t w = dword(y, x);
-                const int kx = (int)dir_kxx<B>(w);
-                if (kx < cnt) { int xp; bool rx; pred2(ni, kx, xp, rx); nx = xp; ny = y; trx = rx; landed_w = (w & DIR_XOPEN) != 0; nstate = 1; }
+            const int cnt = ni.cnt & 0x7fffffff;
+            for (int kx = 0; kx < cnt; ++kx) {
+                int xp; float ex; bool rx; pred2(ni, kx, xp, ex, rx);
+                const float4 c = C[cix(y, xp)];
+                float q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.y, gap_extend), ex)));
+                if (best > q) { best = q; trx = rx; try_ = false; nx = xp; ny = y; nscore = c.y; nstate = 1; landed_w = false; }
+                q = fabsf(__fsub_rn(cur, __fsub_rn(__fadd_rn(c.w, gap_init), ex)));
+                if (best > q) { best = q; trx = rx; try_ = false; nx = xp; ny = y; landed_w = true; }
             }
-        } else if (y > 0 && x > 0) {
+        } else {
             const NodeInfo n1 = J.ni1[y], n2 = J.ni2[x];
-            const uint32_t w = dword(y, x);
-            const int ky = (int)dir_kym<B>(w), kx = (int)dir_kxm<B>(w);
-            if (ky < NI_CNT(n1.cnt) && kx < NI_CNT(n2.cnt)) {
-                int yp, xp; bool ry, rx; pred1(n1, ky, yp, ry); pred2(n2, kx, xp, rx);
-                ny = yp; nx = xp; try_ = ry; trx = rx; landed_w = true;
+            const float s = J.S[(size_t)y * J.ldS + x];
+            const int c1 = n1.cnt & 0x7fffffff, c2 = n2.cnt & 0x7fffffff;
+            for (int ky = 0; ky < c1; ++ky) {
+                int yp; float ey; bool ry; pred1(n1, ky, yp, ey, ry);
+                for (int kx = 0; kx < c2; ++kx) {
+                    int xp; float ex; bool rx; pred2(n2, kx, xp, ex, rx);
+                    const float4 c = C[cix(yp, xp)];
+                    const float q = fabsf(__fsub_rn(cur, __fsub_rn(__fsub_rn(__fadd_rn(c.w, s), ey), ex)));
+                    if (best > q) { best = q; trx = rx; try_ = ry; ny = yp; nx = xp; landed_w = true; }
+                }
             }
         }
-        // state M on the boundary has no predecessor pair (the reference's search would find none either): failure
-        if (ny < 0) { status = PGM_ERR_BACKTRACK; break; }
-        // Landing on W resolves the state by equality, M then Y then X (GraphAlign.h:399-411): the cell's wstate.
+        // Landing on W resolves the state by equality, M then Y then X (GraphAlign.h:399-411).  The
+        // reference resolves at every improving candidate; only the last improvement survives, so
+        // resolving once for the winner is equivalent -- except for its error(), which would fire on
+        // any improving candidate whose W matches none of M/Y/X.  W is the max of exactly those, so
+        // that cannot happen for a finite W; a non-finite W is reported as a backtracking failure.
         if (landed_w && (nx != 0 || ny != 0)) {
-            nstate = (int)(dword(ny, nx) & 3u);
-            if (nstate == 3) { status = PGM_ERR_BACKTRACK; break; }
+            const float4 c = C[cix(ny, nx)];
+            if (c.w == c.x) { nscore = c.x; nstate = 0; }
+            else if (c.w == c.z) { nscore = c.z; nstate = 2; }
+            else if (c.w == c.y) { nscore = c.y; nstate = 1; }
+            else { status = PGM_ERR_BACKTRACK; break; }
         }
         n_tr += (trx ? 1u : 0u) + (try_ ? 1u : 0u);
         if (try_) T.alt_path(ny, y, 0);
         if (trx) T.alt_path(nx, x, 1);
-        x = nx; y = ny; state = nstate;
+        x = nx; y = ny; state = nstate; cur = nscore;
         if (x != 0 || y != 0) {
             if (state == 0) T.push(y, x); else if (state == 1) T.push(-1, x); else T.push(y, -1);
         }
@@ -523,24 +503,16 @@ __device__ __forceinline__ void graph_trace_job(const GraphJobDev& J, const int 
     J.result[0] = status; J.result[1] = T.len; J.result[2] = (int)n_tr;
 }
 
-__global__ void __launch_bounds__(32)
-graph_trace_kernel(int n_jobs, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
-    if ((int)blockIdx.x >= n_jobs) return;
-    const GraphJobDev& J = jobs[order ? order[blockIdx.x] : blockIdx.x];
-    if (J.dbits == 3) graph_trace_job<3>(J, (int)threadIdx.x); else graph_trace_job<7>(J, (int)threadIdx.x);
-}
-
 // max_nb: most column blocks per row (= threads that work) among this launch's jobs.  d_order: the n_jobs job indices
 // the launch sweeps (the host groups jobs of similar graph-2 length, because block size and shared memory -- hence CTAs
 // per SM -- are set by the launch's largest job)
-template <int B>
-static int launch_graph_fill_b(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2) {
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2) {
+    if (n_jobs == 0) return 0;
     const int Tp = std::max(32, (max_nb + 31) & ~31);
     if (Tp > GF_MAX_NB) { pgm_set_error("graph 2 has more than %d nodes; the wavefront kernel's shared-memory ring does not hold it", GF_MAX_NB * GF_K); return PGM_ERR_ARG; }
     // Ring depth.  Launches of small blocks hold mostly chain graphs and want as many resident jobs per SM as possible:
     // 4 steps.  Larger blocks mean graphs with many non-chain nodes (every one starts a block), whose predecessors reach
-    // further back: 8 steps (7 rows) and the column table in shared memory, as long as it fits.  (The host's keep sets
-    // assume only the 4-step ring, so either depth is safe.)
+    // further back: 8 steps (7 rows) and the column table in shared memory, as long as it fits.
     int R = 4, ci_cap = 0, np_cap = 0;
     size_t stage = 0;
     if (Tp > 64) {
@@ -555,22 +527,16 @@ static int launch_graph_fill_b(cudaStream_t st, int n_jobs, const GraphJobDev* d
     // small blocks: cap the registers so that 8 CTAs of 64 threads (or 16 of 32) fit an SM; the sweep is latency-bound per
     // job, so resident jobs per SM is what fills the issue slots
     if (Tp <= 64) {
-        graph_fill_kernel<B, 64, 8><<<n_jobs, Tp, smem, st>>>(d_jobs, d_order, Tp, R, ci_cap, np_cap);
+        graph_fill_kernel<64, 8><<<n_jobs, Tp, smem, st>>>(d_jobs, d_order, Tp, R, ci_cap, np_cap);
     } else if (Tp <= 128) {
-        if (smem > 48 * 1024) PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<B, 128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        graph_fill_kernel<B, 128, 4><<<n_jobs, Tp, smem, st>>>(d_jobs, d_order, Tp, R, ci_cap, np_cap);
+        if (smem > 48 * 1024) PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<128, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        graph_fill_kernel<128, 4><<<n_jobs, Tp, smem, st>>>(d_jobs, d_order, Tp, R, ci_cap, np_cap);
     } else {
-        PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<B, GF_MAX_NB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
-        graph_fill_kernel<B, GF_MAX_NB, 1><<<n_jobs, Tp, smem, st>>>(d_jobs, d_order, Tp, R, ci_cap, np_cap);
+        PGM_CUDA(cudaFuncSetAttribute(graph_fill_kernel<GF_MAX_NB, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(227 * 1024)));
+        graph_fill_kernel<GF_MAX_NB, 1><<<n_jobs, Tp, smem, st>>>(d_jobs, d_order, Tp, R, ci_cap, np_cap);
     }
     PGM_CUDA(cudaGetLastError());
     return 0;
-}
-
-int launch_graph_fill(cudaStream_t st, int dbits, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2) {
-    if (n_jobs == 0) return 0;
-    return dbits == 3 ? launch_graph_fill_b<3>(st, n_jobs, d_jobs, d_order, max_nb, max_n2, max_np2)
-                      : launch_graph_fill_b<7>(st, n_jobs, d_jobs, d_order, max_nb, max_n2, max_np2);
 }
 
 int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order) {

@@ -19,9 +19,9 @@ void pgm_ctx_time_begin_on(pgm_ctx* c, int kind, cudaStream_t st, void** tok);
 void pgm_ctx_time_end(pgm_ctx* c, void* tok);
 pgm_timing* pgm_ctx_timing(pgm_ctx* c);
 void pgm_ctx_reset_timing(pgm_ctx* c);
-int launch_graph_fill(cudaStream_t st, int dbits, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
-int launch_graph_fill_diag(cudaStream_t st, int dbits, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
-int launch_graph_fill_banded(cudaStream_t st, int dbits, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int band_rows,
+int launch_graph_fill(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_nb, int max_n2, int max_np2);
+int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1, int max_n2, int max_np);
+int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows,
                              int max_n2, int max_np);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
@@ -83,7 +83,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct JobLayout {                // byte offsets into the upload arena / scratch arena / output arena
     size_t sites1, sites2, Mf, pif, p1_ptr, p1_idx, p1_val, p1_rep, p1_alt, p2_ptr, p2_idx, p2_val, p2_rep, p2_alt, ni1, ni2, colinfo, blkstart;
-    size_t S, D, Vrow, Vcol, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev, progress;     // scratch
+    size_t S, MXYW, D, Vrow, Vcol, Tbuf, Aimg, Bimg, u, v, alt_score, alt_prev, progress;     // scratch
     size_t map1, map2, result;                           // output
     int np1, np2, cap, pitch, nb, layout, bands, band_rows;
     int dbits, ldVr, ldVc, nkr, nkc;
@@ -129,7 +129,7 @@ int max_preds(const pgm_graph& g) {
 // ---- job analysis (parallel over jobs): everything that decides sizes ------------------------------------------------------
 struct BatchEnv {                 // environment switches, read once per create (tests, A-B runs, profiling)
     int force_layout = -1, diag_min_generic = 8, band_min_n1 = GF_BAND_MIN_N1, long_band_rows = GF_BAND_ROWS;
-    int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, force_dbits = 0, strip = 2, coding = 1, strip_c = 0, hist_kb = 0, dbg = 0;
+    int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, strip = 2, coding = 1, strip_c = 0, hist_kb = 0, dbg = 0, strip_max_generic = 16;
     BatchEnv() {
         if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
         if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
@@ -138,10 +138,10 @@ struct BatchEnv {                 // environment switches, read once per create 
         if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
         if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
         if (const char* e = getenv("PGM_FILL_SMALL_BATCH")) small_batch = atoi(e);      // fewer jobs than three per SM: latency-bound (measured crossover 300..440 jobs of 400 x 400)
-        if (const char* e = getenv("PGM_DIR_BITS")) force_dbits = atoi(e);              // 7: 32-bit direction words for every job
         if (const char* e = getenv("PGM_FILL_STRIP")) strip = atoi(e);                  // 0: never a strip kernel, 1: chain graphs only, 2: also graphs with non-chain nodes
         if (const char* e = getenv("PGM_STRIP_HIST_KB")) hist_kb = atoi(e);             // shared-memory budget of the (Y,W) history ring
         if (const char* e = getenv("PGM_STRIP_DEBUG")) dbg = atoi(e);
+        if (const char* e = getenv("PGM_STRIP_MAX_GENERIC")) strip_max_generic = atoi(e); // most non-chain nodes of a job the general strip kernel takes
         if (const char* e = getenv("PGM_STRIP_C")) strip_c = atoi(e);                   // force the general strip kernel's strip width
         if (const char* e = getenv("PGM_SITE_CLASSES")) coding = atoi(e);               // 0: never class-code leaf graphs
     }
@@ -239,7 +239,6 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
     b->lay.resize(n_jobs); b->jobs.resize(n_jobs); b->cell_updates.resize(n_jobs);
     const BatchEnv env;
     std::vector<size_t> scratch_need(n_jobs);
-    std::vector<int> too_many(n_jobs, 0);
     // ---- pass A (parallel): per-job analysis -> layout decisions and byte sizes --------------------------------------------
     parallel_jobs(n_jobs, [&](int k) {
         const pgm_graph &a = g1[k], &bb = g2[k];
@@ -262,11 +261,8 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         for (int y = 1; y <= a.N - 2; ++y) generic1 += non_chain_node(a, y);
         const int generic = generic1 + generic2;
         L.nb = nblk;
-        {
-            const int mp = std::max(max_preds(a), max_preds(bb));
-            if (mp > GF_MAX_PREDS) { too_many[k] = mp; return; }
-            L.dbits = (mp <= 8 && env.force_dbits != 7) ? 3 : 7;
-        }
+        const int mp = std::max(max_preds(a), max_preds(bb));      // the packed traceback's index fields hold GF_MAX_PREDS predecessors
+        L.dbits = 7;
         // Which fill kernel.  Strip kernel (register-resident, warp per job): graphs whose nodes are all chain nodes (every
         // leaf x leaf job and the profile graphs that have no indel yet) with graph 2 short enough for 32 strips.  Otherwise: the
         // blocked sweep is ~2x faster on chain-dominated graphs; the anti-diagonal sweep pays almost nothing for
@@ -282,7 +278,10 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             for (int q : strip_cs) if (q * 32 >= cols) { Cpick = q; break; }
             strip_ok = Cpick > 0;
         }
-        if (!strip_ok && env.strip >= 2 && a.N >= 3 && bb.N >= 3 && L.dbits != 0) {
+        // General strip kernel: measured at parity with the dense kernels on jobs with a few non-chain nodes (and its emission
+        // is cheaper when one side is a leaf); on branchy graphs the anti-diagonal kernel's per-cell parallelism wins
+        // (profiles/): up to strip_max_generic non-chain nodes by default.
+        if (!strip_ok && env.strip >= 2 && a.N >= 3 && bb.N >= 3 && mp <= GF_MAX_PREDS && (generic <= env.strip_max_generic || env.strip == 3 || env.force_layout == GF_LAYOUT_STRIP)) {
             // general strip kernel: W warps per job.  Strip width: wide strips (one warp per job) for a batch that fills the GPU,
             // narrow strips (more lanes, shorter steps) when the batch is small and the job's own latency is what counts
             static const int gen_cs[] = {2, 4, 8, 13, 16};
@@ -299,12 +298,13 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             double best = 0; int best_ns = 0;
             for (int q : gen_cs) {
                 if (env.strip_c && q != env.strip_c) continue;
+                if (q == 2 && !env.strip_c) continue;               // 8 warps per 400-column job: only on request
                 const int ns_q = count_strips(q), w_q = (ns_q + 31) / 32;
                 if (w_q > SG_MAX_WARPS) continue;
                 if (q > 8 && Cpick && !env.strip_c) continue;       // wide strips (255 registers, one job per SM) only when the narrow ones do not fit
                 // cost model (cycles): steps x (fixed + per-slot); a full GPU prefers the fewest warp-steps, a small batch the shortest sweep
                 const double sweep = (double)(a.N - 1 + ns_q) * (500.0 + 70.0 * q);
-                const double cost = n_jobs >= 16 * 148 ? sweep * w_q : sweep;
+                const double cost = n_jobs >= 4 * 148 ? sweep * w_q : sweep;
                 if (!Cpick || cost < best) { Cpick = q; best = cost; best_ns = ns_q; }
             }
             if (Cpick) {
@@ -343,24 +343,18 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         }
         L.bands = L.band_rows ? (a.N - 1 + L.band_rows - 1) / L.band_rows : 1;
         if (L.bands == 1) L.band_rows = 0;
-        L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 2);
-        {   // keep sets (see mark_far_sources): thresholds from the ring depth the job's kernel is guaranteed to have
+        L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 8);
+        {   // keep sets of the strip kernels (see mark_far_sources); the dense kernels keep everything
             L.keep1.assign(a.N, 0); L.keep2.assign(bb.N, 0);
-            L.keep1[0] = 1; L.keep2[0] = 1;
-            for (int e = a.e_rowptr[a.N - 1]; e < a.e_rowptr[a.N]; ++e) L.keep1[a.e_col[e]] = 1;
-            if (a.r_rowptr) for (int e = a.r_rowptr[a.N - 1]; e < a.r_rowptr[a.N]; ++e) L.keep1[a.r_col[e]] = 1;
-            if (L.layout == GF_LAYOUT_BLOCK) {                      // 4-step ring: rows <= 2 back and blocks <= 1 back always hit
-                mark_far_sources(a, nullptr, 3, 0, L.keep1);
-                mark_far_sources(bb, blk.data(), 2, 0, L.keep2);
-            } else if (L.layout == GF_LAYOUT_DIAG) {                // 8-diagonal ring (4 for long unbanded graphs)
-                const int thr = (L.bands == 1 && a.N - 1 > GF_DIAG_REGULAR_ROWS) ? 2 : 4;
-                mark_far_sources(a, nullptr, thr, L.band_rows, L.keep1);
-                mark_far_sources(bb, nullptr, thr, 0, L.keep2);
-            } else if (L.sgen) {                                    // general strip kernel: every source of a non-adjacent edge
-                mark_far_sources(a, nullptr, 2, 0, L.keep1);
-                mark_far_sources(bb, nullptr, 2, 0, L.keep2);
-            }                                                       // chain strip kernel: nothing is far
-            if (L.bands > 1) for (int q = 1; q < L.bands; ++q) L.keep1[q * L.band_rows - 1] = 1;   // the row above each band
+            if (L.layout == GF_LAYOUT_STRIP) {
+                L.keep1[0] = 1; L.keep2[0] = 1;
+                for (int e = a.e_rowptr[a.N - 1]; e < a.e_rowptr[a.N]; ++e) L.keep1[a.e_col[e]] = 1;
+                if (a.r_rowptr) for (int e = a.r_rowptr[a.N - 1]; e < a.r_rowptr[a.N]; ++e) L.keep1[a.r_col[e]] = 1;
+                if (L.sgen) {                                       // general strip kernel: every source of a non-adjacent edge
+                    mark_far_sources(a, nullptr, 2, 0, L.keep1);
+                    mark_far_sources(bb, nullptr, 2, 0, L.keep2);
+                }                                                   // chain strip kernel: nothing is far
+            }
         }
         L.nkr = number_kept(L.keep1); L.nkc = number_kept(L.keep2);
         L.ldVr = (int)align_up((size_t)bb.N, 8) + 32; L.ldVc = (int)align_up((size_t)a.N, 4);
@@ -379,13 +373,13 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             if (bb.N > n + 3 && site_classes(bb, n, L.cls2, u2)) { L.coded2 = 1; L.uniform2 = u2; }
         }
         L.N1e = L.coded1 ? n + 3 : a.N; L.N2e = L.coded2 ? n + 3 : bb.N;      // pseudo-nodes: 0 (start), 1 .. n+1 (classes 0 .. n), n+2 (end)
-        const size_t d_words = L.layout == GF_LAYOUT_DIAG ? ((size_t)a.N + bb.N - 1) * L.pitch
-                             : L.layout == GF_LAYOUT_BLOCK ? ((size_t)(a.N - 1) + L.nb - 1) * GF_K * L.pitch : 0;
-        const size_t d_bytes = L.layout == GF_LAYOUT_STRIP ? ((size_t)(a.N - 1) + L.nstrips) * L.nstrips * strip_words(L.C) * 4
-                                                           : d_words * (L.dbits == 3 ? 2 : 4);
+        const size_t mxyw_cells = L.layout == GF_LAYOUT_DIAG ? ((size_t)a.N + bb.N - 1) * L.pitch
+                                : L.layout == GF_LAYOUT_BLOCK ? ((size_t)(a.N - 1) + L.nb - 1) * GF_K * L.pitch : 0;
+        const size_t d_bytes = L.layout == GF_LAYOUT_STRIP ? ((size_t)(a.N - 1) + L.nstrips) * L.nstrips * strip_words(L.C) * 4 : 0;
         auto take = [&](size_t& off, size_t bytes) { size_t r = off; off = align_up(off + bytes, 128); return r; };
         size_t so = 0;
         L.S = take(so, (size_t)L.N1e * (((size_t)L.N2e + 3) & ~(size_t)3) * 4 + 128);
+        L.MXYW = take(so, mxyw_cells * 16);
         L.D = take(so, d_bytes + 64);
         L.Vrow = take(so, (size_t)L.nkr * L.ldVr * 16 + 16); L.Vcol = take(so, (size_t)L.nkc * L.ldVc * 16 + 16);
         if (L.sgen) L.dbits = 7;                                    // the side arrays hold 32-bit index words
@@ -400,8 +394,6 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.progress = take(so, 4 * ((size_t)L.bands + 1));
         scratch_need[k] = so;
     });
-    for (int k = 0; k < n_jobs; ++k)
-        if (too_many[k]) { pgm_graph_batch_destroy(c, b); pgm_set_error("job %d: a node has %d predecessors (more than %d are not supported)", k, too_many[k], GF_MAX_PREDS); return PGM_ERR_ARG; }
     // ---- pass B (serial): arena offsets -------------------------------------------------------------------------------------
     size_t in_off = 0, out_off = 0;
     for (int k = 0; k < n_jobs; ++k) {
@@ -591,7 +583,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.scol = (const uint16_t*)(din + L.scol);
         J.sstart = (const int*)(din + L.sstart); J.colstrip = (const uint32_t*)(din + L.colstrip);
         J.np1 = L.np1; J.np2 = L.np2;
-        J.S = (float*)(sb + L.S); J.D = (void*)(sb + L.D); J.dbits = L.dbits; J.Tbuf = (float*)(sb + L.Tbuf);
+        J.S = (float*)(sb + L.S); J.MXYW = (float4*)(sb + L.MXYW); J.D = (void*)(sb + L.D); J.dbits = L.dbits; J.Tbuf = (float*)(sb + L.Tbuf);
         J.Vrow = (float4*)(sb + L.Vrow); J.Vcol = (float4*)(sb + L.Vcol); J.ldVr = L.ldVr; J.ldVc = L.ldVc;
         J.u = (float*)(sb + L.u); J.v = (float*)(sb + L.v);
         J.Aimg = (float*)(sb + L.Aimg); J.Bimg = (float*)(sb + L.Bimg);
@@ -604,12 +596,11 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         // diagonal: graph-1 rows; strip: columns per strip); longest sweeps first
         b->order.resize(n_jobs);
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
-        auto class_of = [&](const GraphJobDev& J) {                          // + 1000: 32-bit direction words (their own kernel instantiation)
+        auto class_of = [&](const GraphJobDev& J) {
             if (J.layout == GF_LAYOUT_STRIP) return J.sgen ? 400 + J.C + 32 * ((J.nstrips + 31) / 32) : 300 + J.C;
-            const int wide = J.dbits == 3 ? 0 : 1000;
-            if (J.bands > 1) return wide + 200 + J.band_rows / 32;            // banded anti-diagonal sweeps: their own launches, one per band height
-            if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return wide + 100 + q; }
-            const int w = (J.nb + 31) / 32; return wide + (w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16)));
+            if (J.bands > 1) return 200 + J.band_rows / 32;                   // banded anti-diagonal sweeps: their own launches, one per band height
+            if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
+            const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
         };
         for (size_t si = 0; si < b->sub.size(); ++si) {
             const auto& sbr = b->sub[si];
@@ -706,10 +697,10 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
                     const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + f->offset + jq]];
                     PGM_CUDA(cudaMemsetAsync(Jq.progress, 0, sizeof(int) * (Jq.bands + 1), sq));
                 }
-                return launch_graph_fill_banded(sq, f->dbits, f->count, dj + sb.first, ord, f->max_bands, f->band_rows, f->max_n2, f->max_np);
+                return launch_graph_fill_banded(sq, f->count, dj + sb.first, ord, f->max_bands, 148, f->band_rows, f->max_n2, f->max_np);
             }
-            return f->layout == GF_LAYOUT_DIAG ? launch_graph_fill_diag(sq, f->dbits, f->count, dj + sb.first, ord, f->max_n1, f->max_n2, f->max_np)
-                                               : launch_graph_fill(sq, f->dbits, f->count, dj + sb.first, ord, f->max_nb, f->max_n2, f->max_np2);
+            return f->layout == GF_LAYOUT_DIAG ? launch_graph_fill_diag(sq, f->count, dj + sb.first, ord, f->max_n1, f->max_n2, f->max_np)
+                                               : launch_graph_fill(sq, f->count, dj + sb.first, ord, f->max_nb, f->max_n2, f->max_np2);
         };
         // side streams: the first class stays on the main stream, the others fork from it and are joined at the end
         SideStreams& ss = side_streams(pgm_ctx_device(c));
@@ -746,7 +737,9 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
                 if (rc) break;
                 pgm_ctx_time_begin_on(c, 4, sq, &tok); rc = fill(sq, fl[q]); pgm_ctx_time_end(c, tok);
                 if (rc) break;
-                pgm_ctx_time_begin_on(c, 5, sq, &tok); rc = launch_graph_trace(sq, fl[q]->count, dj + sb.first, ord); pgm_ctx_time_end(c, tok);
+                pgm_ctx_time_begin_on(c, 5, sq, &tok);
+                rc = fl[q]->layout == GF_LAYOUT_STRIP ? launch_graph_trace_packed(sq, fl[q]->count, dj + sb.first, ord) : launch_graph_trace(sq, fl[q]->count, dj + sb.first, ord);
+                pgm_ctx_time_end(c, tok);
             }
             if (rc) return rc;
             if ((rc = join())) return rc;
@@ -763,7 +756,8 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             pgm_ctx_time_end(c, tok);
             if (rc) return rc;
             pgm_ctx_time_begin(c, 5, &tok);
-            rc = launch_graph_trace(st, nj, dj + sb.first, nullptr);
+            rc = launch_graph_trace(st, nj, dj + sb.first, nullptr);        // each traceback kernel skips the other layouts' jobs
+            if (!rc) rc = launch_graph_trace_packed(st, nj, dj + sb.first, nullptr);
             pgm_ctx_time_end(c, tok);
             if (rc) return rc;
         }

@@ -140,7 +140,7 @@ struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred
 // general strip kernel: everything a row needs in one 32-byte record, fetched two rows ahead (no dependent loads in a step)
 struct RowInfo { int cnt; int idx0; float val0; int idx1; float val1; int kq01; int ncidx; int ptr; };   // cnt as NodeInfo::cnt; the first two
                              // predecessors inline; kq01 = (value-store row of idx0 + 1) | (... of idx1 + 1) << 16; ncidx = row of RowIdx or -1
-#define GF_MAX_PREDS 128     // predecessors per node the 32-bit direction words can index (16-bit words: 8)
+#define GF_MAX_PREDS 128     // predecessors per node the packed traceback's index fields can hold (graphs beyond it take the dense kernels)
 
 #define GF_BAND_ROWS 512      // rows per band (= threads per CTA) of the banded anti-diagonal kernel
 #define GF_BAND_MIN_N1 1026    // graph 1 from this many nodes on is swept in bands (measured on the 5000-sequence run: 1026 / 512
@@ -161,7 +161,7 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     int* progress;              // bands + 1 ints (scratch, zeroed before every sweep): anti-diagonals completed per band, then the band ticket
     int layout;                 // cell layout of D = which fill kernel sweeps the job: GF_LAYOUT_BLOCK or GF_LAYOUT_DIAG
     int nb;                     // column blocks per row (columns 0 .. N2-2 cut into blocks of <= GF_K; a non-chain node starts a block)
-    int pitch;                  // block-skewed layout (hp1_graphdp.cu): cell (y,x) at ((y + blk(x))*pitch + y%nb)*GF_K + off(x);
+    int pitch;                  // block-skewed layout (hp1_graphdp.cu): cell (y,x) at (((y + blk(x))*GF_K + off(x))*pitch + y%nb;
                                 // diagonal layout (hp1_graphdp_diag.cu): (y+x)*pitch + y - max(0, y+x-(N2-1))
     const uint16_t* colinfo;    // N2 entries: (blk(x) << GF_LOGK) | off(x)
     const uint16_t* blkstart;   // nb + 1 entries: first column of each block, blkstart[nb] = N2 - 1
@@ -200,13 +200,16 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     float sc[10];               // DynProgScores
     float* S;                   // row-major by graph-1 node: S(y,x) at y*ldS + x (a DP thread streams its own row)
     int ldS;                    // N2 rounded up to a multiple of 4
-    // Packed traceback: one direction word per cell (hp1_dir.cuh), 16 bit when no node has more than 8 predecessors, else
-    // 32 bit.  The DP values themselves live only in the fill kernels' shared-memory rings, except for the rows of graph 1
-    // and columns of graph 2 that some far predecessor edge (or the end-node match, a band boundary, the traceback of the
-    // boundary row / column) reads back: those are kept as {M,X,Y,W} in the value store.
-    void* D;                    // direction words, (N1-1 + nb-1) * pitch * GF_K (blocked) or (N1+N2-1) * pitch (diagonal) entries;
-                                // strip layout: 4-bit cells, strip j of row y at uint32 words ((y + j) * nstrips + j) * W32 (hp1_strip.cu)
-    int dbits;                  // 3: uint16_t words, 7: uint32_t words (bits per predecessor index)
+    // Blocked / anti-diagonal kernels (latency-bound: the dense matrices cost them nothing, the first-maximum bookkeeping of
+    // a packed traceback 25-70 % of their time, profiles/): {M,X,Y,W} of every cell, one float4, re-traced by the reference's
+    // closest-|delta| search.
+    float4* MXYW;               // block-skewed: (N1-1 + nb-1) * GF_K * pitch cells; diagonal: (N1+N2-1) * pitch
+    // Strip kernels: PACKED traceback, 4 direction bits per cell (hp1_dir.cuh, hp1_strip.cu).  The DP values themselves live
+    // only in registers / shared-memory rings, except for the rows of graph 1 and columns of graph 2 that a far predecessor
+    // edge, the end-node match or the traceback of the boundary row / column reads back: those are kept as {M,X,Y,W} in the
+    // value store.
+    void* D;                    // strip j of row y at uint32 words ((y + j) * nstrips + j) * W32
+    int dbits;                  // bits per predecessor index of the side arrays' words (7)
     int ldVr, ldVc;             // pitches of the value store
     float4* Vrow;               // kept row r (NI_KEEP of its graph-1 node), column x at r*ldVr + x
     float4* Vcol;               // kept column c (NI_KEEP of its graph-2 node), row y at c*ldVc + y
@@ -238,7 +241,8 @@ __device__ __forceinline__ float dot_gemv_order(const float* __restrict__ g, con
 
 int launch_emission_exact(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2);
 int launch_emission_tensor(cudaStream_t st, int n_states, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_N1, int max_N2);
-int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
+int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);          // dense matrices (hp1_graphdp.cu)
+int launch_graph_trace_packed(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);   // direction bits (hp1_trace.cu)
 int launch_graph_fill_strip(cudaStream_t st, int C, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
 int launch_graph_fill_strip_gen(cudaStream_t st, int C, int dbits, int warps, size_t smem, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
 #define SG_MAX_WARPS 8       // warps per job of the general strip kernel (256 strips)

@@ -227,15 +227,15 @@ FLAVOURS = {
     "default": {},
     "block": {"PGM_FILL_LAYOUT": "block"},
     "diag": {"PGM_FILL_LAYOUT": "diag"},
-    "block32": {"PGM_FILL_LAYOUT": "block", "PGM_DIR_BITS": "7"},
-    "diag32": {"PGM_FILL_LAYOUT": "diag", "PGM_DIR_BITS": "7"},
     "banded": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_BAND_MIN_N1": "66", "PGM_FILL_BAND_ROWS": "64"},
     "nostrip": {"PGM_FILL_STRIP": "0"},
     "strip_chain_only": {"PGM_FILL_STRIP": "1"},
     "strip_c4": {"PGM_STRIP_C": "4"},
     "strip_c8": {"PGM_STRIP_C": "8"},
     "strip_c16": {"PGM_STRIP_C": "16"},
-    "strip32": {"PGM_DIR_BITS": "7"},
+    "strip_c2": {"PGM_STRIP_C": "2"},
+    "strip_small_rings": {"PGM_STRIP_HIST_KB": "6"},
+    "strip_general_only": {"PGM_FILL_STRIP": "3"},
     "strip_full_s": {"PGM_SITE_CLASSES": "0"},
 }
 
@@ -249,7 +249,7 @@ def flavour(request, monkeypatch):
 
 def test_every_fill_flavour_identical_to_oracle(ga, po, flavour):
     """a 40-sequence progressive pass with many indels (skip edges, multi-predecessor nodes, far predecessors that
-    are read back from the value store) under every fill kernel and both direction-word widths"""
+    are read back from the value store) under every fill kernel and strip width"""
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
     seqs, root = synth.simulate_family(40, 150, mf, seed=51, indel_rate=0.08)
@@ -297,8 +297,7 @@ def _branchy_graph(rng, N, extra_preds, n=20):
 
 @pytest.mark.parametrize("extra", [3, 7, 20])
 def test_many_predecessors(ga, po, flavour, extra):
-    """nodes with up to 21 predecessors at arbitrary distances: more than 8 needs the 32-bit direction words, and most
-    predecessors are far (value store)"""
+    """nodes with up to 21 predecessors at arbitrary distances: most predecessors are far (value store, list walks)"""
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
     rng = np.random.default_rng(100 + extra)
@@ -308,14 +307,14 @@ def test_many_predecessors(ga, po, flavour, extra):
         _same_alignment(r, po.align_graphs(g1, g2, mm, opts))
 
 
-def test_too_many_predecessors_is_an_error(ga):
-    from prographmsa_b200._lib import PgmError
+def test_more_predecessors_than_the_packed_traceback_holds(ga, po):
+    """a node with 141 predecessors: beyond the index fields of the packed traceback, so the job takes the dense kernels"""
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
     rng = np.random.default_rng(5)
-    g = _branchy_graph(rng, 200, 140)
-    with pytest.raises(PgmError):
-        ga.alignGraphs(g, _branchy_graph(rng, 50, 2), mf.getModel(0.3, 0.3), opts)
+    g1, g2 = _branchy_graph(rng, 200, 140), _branchy_graph(rng, 50, 2)
+    m = mf.getModel(0.3, 0.3)
+    _same_alignment(ga.alignGraphs(g1, g2, m, opts), po.align_graphs(g1, g2, m, opts))
 
 
 def test_failed_emission_fails_the_job(ga, monkeypatch):
