@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <map>
 
 struct pgm_ctx;
 cudaStream_t pgm_ctx_stream(pgm_ctx* c);
@@ -606,14 +607,20 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             const auto& sbr = b->sub[si];
             std::vector<int> idx;
             for (int k = sbr.first; k < sbr.second; ++k) idx.push_back(k - sbr.first);
+            // classes ordered by their longest sweep (estimated, microseconds), longest first: earlier launches get the higher
+            // stream priority, so the few long latency-bound sweeps near the root start at once and are not starved of issue slots
+            auto est_us = [&](const GraphJobDev& J) -> double {
+                if (J.layout == GF_LAYOUT_STRIP) return (double)(J.N1 + J.nstrips) * (J.sgen ? 1.2 : 0.6);
+                if (J.layout == GF_LAYOUT_DIAG) return (double)(J.N1 + J.N2) * (J.bands > 1 ? 8.0 : 1.8);
+                return (double)(J.N1 + J.nb) * 1.2;
+            };
+            std::map<int, double> class_est;
+            for (int k = sbr.first; k < sbr.second; ++k) { double& e = class_est[class_of(b->jobs[k])]; e = std::max(e, est_us(b->jobs[k])); }
             std::stable_sort(idx.begin(), idx.end(), [&](int a, int bq) {
                 const GraphJobDev &A = b->jobs[sbr.first + a], &B = b->jobs[sbr.first + bq];
-                const int ca = class_of(A) % 1000, cb = class_of(B) % 1000, wa = class_of(A) / 1000, wb = class_of(B) / 1000;
-                const bool sa = A.layout == GF_LAYOUT_STRIP && !A.sgen, sbq = B.layout == GF_LAYOUT_STRIP && !B.sgen;
-                if (sa != sbq) return sbq;                                   // strip launches last: the short ones
-                if (ca != cb) return ca > cb;
-                if (wa != wb) return wa > wb;
-                return A.N1 + A.N2 > B.N1 + B.N2;
+                const int ca = class_of(A), cb = class_of(B);
+                if (ca != cb) { const double ea = class_est[ca], eb = class_est[cb]; return ea != eb ? ea > eb : ca > cb; }
+                return est_us(A) > est_us(B);
             });
             std::copy(idx.begin(), idx.end(), b->order.begin() + sbr.first);
             size_t p = 0;

@@ -23,7 +23,7 @@
 #include <type_traits>
 
 template <int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128)      // (register caps for 3 or 4 CTAs per SM were measured slower: spills)
 graph_fill_strip_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int n_jobs) {
     constexpr int W32 = C <= 8 ? 1 : (C <= 16 ? 2 : 4);
     const int lane = (int)threadIdx.x & 31;
