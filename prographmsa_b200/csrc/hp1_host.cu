@@ -25,6 +25,7 @@ int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_job
 int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows,
                              int max_n2, int max_np);
 int pgm_ctx_take_dev(pgm_ctx* c, size_t bytes, DevBuf& out);
+static inline int ru32(int v) { return (v + 31) & ~31; }
 int pgm_ctx_take_host(pgm_ctx* c, size_t bytes, HostPinned& out);
 void pgm_ctx_give_dev(pgm_ctx* c, DevBuf& b);
 void pgm_ctx_give_host(pgm_ctx* c, HostPinned& b);
@@ -90,6 +91,8 @@ struct JobLayout {                // byte offsets into the upload arena / scratc
     int dbits, ldVr, ldVc, nkr, nkc;
     int C, nstrips, N1e, N2e, coded1, coded2;
     int sgen, nsrc, ring_rows, hist_rows, swarps, nstrips_gen, nnc1, nnc2, ldRI, ldCI;
+    int wave, wv_tr, wv_chain_pad, wv_ncols, wv_nx, wv_L;       // role-sorted anti-diagonal kernel (hp1_wave.cu)
+    size_t wv_rows, wv_cols, wv_ci, wv_rowslot, wv_xi, wv_xv;
     size_t scol, sstart, colstrip, specmask, srcmask, colsrc_off, ncidx1_off, ncidx2_off, rinfo_off, RowIdx, ColIdx;
     std::vector<int16_t> colsrc; std::vector<int> ncidx1, ncidx2;
     double uniform1, uniform2;
@@ -131,6 +134,7 @@ int max_preds(const pgm_graph& g) {
 struct BatchEnv {                 // environment switches, read once per create (tests, A-B runs, profiling)
     int force_layout = -1, diag_min_generic = 8, band_min_n1 = GF_BAND_MIN_N1, long_band_rows = GF_BAND_ROWS;
     int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, strip = 2, coding = 1, strip_c = 0, hist_kb = 0, dbg = 0, strip_max_generic = 16;
+    int wave = 0, wave_L = 0, wave_ring = 0;
     BatchEnv() {
         if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
         if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
@@ -145,6 +149,9 @@ struct BatchEnv {                 // environment switches, read once per create 
         if (const char* e = getenv("PGM_STRIP_MAX_GENERIC")) strip_max_generic = atoi(e); // most non-chain nodes of a job the general strip kernel takes
         if (const char* e = getenv("PGM_STRIP_C")) strip_c = atoi(e);                   // force the general strip kernel's strip width
         if (const char* e = getenv("PGM_SITE_CLASSES")) coding = atoi(e);               // 0: never class-code leaf graphs
+        if (const char* e = getenv("PGM_FILL_WAVE")) wave = atoi(e);                    // 0: never the role-sorted anti-diagonal kernel, 1: for every anti-diagonal job it fits
+        if (const char* e = getenv("PGM_WAVE_L")) wave_L = atoi(e);                     // force the lanes per non-chain column (1, 2, 4)
+        if (const char* e = getenv("PGM_WAVE_RING")) wave_ring = atoi(e);               // force the ring depth (8, 16)
     }
 };
 
@@ -194,7 +201,8 @@ struct pgm_graph_batch {
     // Fill schedule.  The fill kernel's block size and shared memory -- hence CTAs per SM -- are set by the LARGEST job
     // of a launch, so each sub-batch is swept as a few launches of similar graph-2 length (largest first), on
     // separate streams so that a class with few jobs does not leave the GPU idle.
-    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands, band_rows, dbits, C, max_n1e, max_n2e, sgen, swarps; size_t ring_bytes; };
+    struct FillLaunch { int sub, offset, count, layout, max_nb, max_n1, max_n2, max_np2, max_np, max_bands, band_rows, dbits, C, max_n1e, max_n2e, sgen, swarps; size_t ring_bytes;
+                        int wave = 0, wL = 0, wring = 8, wthreads = 0, max_tr = 0, max_np1 = 0, max_nx = 0; };
     std::vector<int> order;                 // job indices relative to their sub-batch, grouped by FillLaunch
     std::vector<FillLaunch> fills;
     size_t scratch_bytes_used = 0;
@@ -345,6 +353,26 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.bands = L.band_rows ? (a.N - 1 + L.band_rows - 1) / L.band_rows : 1;
         if (L.bands == 1) L.band_rows = 0;
         L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 8);
+        // Role-sorted anti-diagonal kernel (hp1_wave.cu): a thread per row (chain rows and non-chain rows in separate warps) plus
+        // wv_L threads per non-chain column, all in one CTA
+        L.wave = 0; L.wv_tr = L.wv_chain_pad = L.wv_ncols = L.wv_nx = L.wv_L = 0;
+        if (env.wave && L.layout == GF_LAYOUT_DIAG && L.bands == 1 && a.N >= 3 && bb.N >= 3) {
+            const int nspec = generic1, nchain = (a.N - 1) - generic1;          // rows 0 .. N1-2; row 0 sweeps with the chain rows
+            const int tr = ru32(nchain) + ru32(nspec);
+            int lw = 0;
+            for (int q : {4, 2, 1}) if ((!env.wave_L || env.wave_L == q) && tr + ru32(generic2 * q) <= 1024) { lw = q; break; }
+            int nx = 0;
+            for (int y = 1; y <= a.N - 2; ++y)
+                if (non_chain_node(a, y)) {
+                    bool adj = false;
+                    auto visit = [&](int from) { if (from == y - 1 && !adj) adj = true; else ++nx; };
+                    for (int e = a.e_rowptr[y]; e < a.e_rowptr[y + 1]; ++e) visit(a.e_col[e]);
+                    if (a.r_rowptr) for (int e = a.r_rowptr[y]; e < a.r_rowptr[y + 1]; ++e) visit(a.r_col[e]);
+                }
+            if (lw && wave_smem_bytes(8, a.N, bb.N, tr, L.np1, nx) <= 227 * 1024) {
+                L.wave = 1; L.wv_tr = tr; L.wv_chain_pad = ru32(nchain); L.wv_ncols = generic2; L.wv_nx = nx; L.wv_L = lw;
+            }
+        }
         {   // keep sets of the strip kernels (see mark_far_sources); the dense kernels keep everything
             L.keep1.assign(a.N, 0); L.keep2.assign(bb.N, 0);
             if (L.layout == GF_LAYOUT_STRIP) {
@@ -417,6 +445,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.colsrc_off = take(in_off, L.sgen ? 2 * (size_t)bb.N : 0);
         L.ncidx1_off = take(in_off, L.sgen ? 4 * (size_t)a.N : 0); L.ncidx2_off = take(in_off, L.sgen ? 4 * (size_t)bb.N : 0);
         L.rinfo_off = take(in_off, L.sgen ? sizeof(RowInfo) * (size_t)a.N : 0);
+        L.wv_rows = take(in_off, L.wave ? sizeof(WaveRow) * (size_t)L.wv_tr : 0); L.wv_cols = take(in_off, L.wave ? sizeof(WaveCol) * (size_t)L.wv_ncols : 0);
+        L.wv_ci = take(in_off, L.wave ? sizeof(WaveCI) * (size_t)bb.N : 0); L.wv_rowslot = take(in_off, L.wave ? 2 * (size_t)a.N : 0);
+        L.wv_xi = take(in_off, L.wave ? 4 * (size_t)L.wv_nx : 0); L.wv_xv = take(in_off, L.wave ? 4 * (size_t)L.wv_nx : 0);
         L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 32);
         b->max_N1 = std::max(b->max_N1, a.N); b->max_N2 = std::max(b->max_N2, bb.N);
     }
@@ -566,6 +597,52 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 ri[y] = r;
             }
         }
+        if (L.wave) {                                               // role-sorted anti-diagonal kernel: thread records
+            const int N1 = g1[k].N, N2 = g2[k].N;
+            const NodeInfo* ni1 = (const NodeInfo*)(hin + L.ni1); const NodeInfo* ni2 = (const NodeInfo*)(hin + L.ni2);
+            const int* p1i = (const int*)(hin + L.p1_idx); const float* p1v = (const float*)(hin + L.p1_val);
+            const int* p2i = (const int*)(hin + L.p2_idx); const float* p2v = (const float*)(hin + L.p2_val);
+            WaveRow* wr = (WaveRow*)(hin + L.wv_rows); WaveCol* wc = (WaveCol*)(hin + L.wv_cols); WaveCI* ci = (WaveCI*)(hin + L.wv_ci);
+            uint16_t* slot = (uint16_t*)(hin + L.wv_rowslot); int* xi = (int*)(hin + L.wv_xi); float* xv = (float*)(hin + L.wv_xv);
+            for (int t = 0; t < L.wv_tr; ++t) wr[t] = WaveRow{-1, 0, 0.f, 0, 0.f, 0, 0.f, 0};
+            int tc = 0, ts = L.wv_chain_pad, nx = 0;
+            slot[N1 - 1] = 0;
+            for (int y = 0; y <= N1 - 2; ++y) {
+                const bool chain = y == 0 || NI_CHAIN(ni1[y], y);
+                WaveRow r{y, 0, 0.f, 0, 0.f, 0, 0.f, nx};
+                if (y >= 1 && chain) r.ey_adj = ni1[y].val0;
+                if (!chain) {
+                    r.ey_adj = FINF;                                // no edge from y-1: its candidates come out as -inf
+                    bool adj = false;
+                    const int cnt = NI_CNT(ni1[y].cnt);
+                    for (int q = 0; q < cnt; ++q) {
+                        const int yp = p1i[ni1[y].ptr + q]; const float ey = p1v[ni1[y].ptr + q];
+                        if (yp == y - 1 && !adj) { adj = true; r.ey_adj = ey; continue; }
+                        if (r.nextra == 0) { r.yp0 = yp; r.ey0 = ey; } else if (r.nextra == 1) { r.yp1 = yp; r.ey1 = ey; }
+                        xi[nx] = yp; xv[nx] = ey; ++nx; ++r.nextra;
+                    }
+                }
+                const int t = chain ? tc++ : ts++;
+                wr[t] = r; slot[y] = (uint16_t)t;
+            }
+            int nc = 0;
+            for (int x = 0; x < N2; ++x) {
+                const bool spec = x >= 1 && x <= N2 - 2 && !NI_CHAIN(ni2[x], x);
+                const bool lspec = x >= 2 && x <= N2 - 2 && !NI_CHAIN(ni2[x - 1], x - 1);
+                ci[x].ex_adj = (x >= 1 && x <= N2 - 2 && !spec) ? ni2[x].val0 : 0.f;
+                ci[x].flags = (spec ? 1 : 0) | (lspec ? 2 : 0);
+                if (spec) {
+                    const int cnt = NI_CNT(ni2[x].cnt), ptr = ni2[x].ptr;
+                    WaveCol c{x, cnt, 0, 0.f, 0, 0.f, ptr, 0};
+                    if (cnt > 0) { c.xp0 = p2i[ptr]; c.ex0 = p2v[ptr]; }
+                    if (cnt > 1) { c.xp1 = p2i[ptr + 1]; c.ex1 = p2v[ptr + 1]; }
+                    wc[nc++] = c;
+                }
+            }
+        }
+        J.wave = L.wave; J.wv_tr = L.wv_tr; J.wv_ncols = L.wv_ncols; J.wv_nx = L.wv_nx;
+        J.wv_rows = (const WaveRow*)(din + L.wv_rows); J.wv_cols = (const WaveCol*)(din + L.wv_cols); J.wv_ci = (const WaveCI*)(din + L.wv_ci);
+        J.wv_rowslot = (const uint16_t*)(din + L.wv_rowslot); J.wv_xi = (const int*)(din + L.wv_xi); J.wv_xv = (const float*)(din + L.wv_xv);
         J.dbg = env.dbg; J.sgen = L.sgen; J.nsrc = L.nsrc; J.ring_rows = L.ring_rows; J.hist_rows = L.hist_rows; J.ldRI = L.ldRI; J.ldCI = L.ldCI;
         J.specmask = (const uint32_t*)(din + L.specmask); J.srcmask = (const uint32_t*)(din + L.srcmask);
         J.colsrc = (const int16_t*)(din + L.colsrc_off); J.ncidx1 = (const int*)(din + L.ncidx1_off); J.ncidx2 = (const int*)(din + L.ncidx2_off);
@@ -599,6 +676,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
         auto class_of = [&](const GraphJobDev& J) {
             if (J.layout == GF_LAYOUT_STRIP) return J.sgen ? 400 + J.C + 32 * ((J.nstrips + 31) / 32) : 300 + J.C;
+            if (J.wave) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 500 + 16 * b->lay[&J - b->jobs.data()].wv_L + q; }
             if (J.bands > 1) return 200 + J.band_rows / 32;                   // banded anti-diagonal sweeps: their own launches, one per band height
             if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
             const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
@@ -611,6 +689,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             // stream priority, so the few long latency-bound sweeps near the root start at once and are not starved of issue slots
             auto est_us = [&](const GraphJobDev& J) -> double {
                 if (J.layout == GF_LAYOUT_STRIP) return (double)(J.N1 + J.nstrips) * (J.sgen ? 1.2 : 0.6);
+                if (J.wave) return (double)(J.N1 + J.N2) * 0.6;
                 if (J.layout == GF_LAYOUT_DIAG) return (double)(J.N1 + J.N2) * (J.bands > 1 ? 8.0 : 1.8);
                 return (double)(J.N1 + J.nb) * 1.2;
             };
@@ -628,6 +707,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 const GraphJobDev& J0 = b->jobs[sbr.first + idx[p]];
                 const int q = class_of(J0);
                 pgm_graph_batch::FillLaunch f{(int)si, (int)p, 0, J0.layout, 0, 0, 0, 0, 0, 1, J0.band_rows, J0.dbits, J0.C, 0, 0, J0.sgen, (J0.nstrips + 31) / 32, 0};
+                f.wave = J0.wave; f.wL = b->lay[sbr.first + idx[p]].wv_L;
                 while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]]) == q) {
                     const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
                     f.max_nb = std::max(f.max_nb, J.nb); f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2);
@@ -635,7 +715,18 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                     f.max_bands = std::max(f.max_bands, J.bands);
                     f.max_n1e = std::max(f.max_n1e, J.N1e); f.max_n2e = std::max(f.max_n2e, J.N2e);
                     f.ring_bytes = std::max(f.ring_bytes, (size_t)J.nsrc * J.ring_rows * 8 + (size_t)J.hist_rows * (size_t)(J.C + 1) * ((J.nstrips + 31) & ~31) * 8);
+                    if (J.wave) {
+                        f.wthreads = std::max(f.wthreads, J.wv_tr + ru32(J.wv_ncols * f.wL)); f.max_tr = std::max(f.max_tr, J.wv_tr);
+                        f.max_np1 = std::max(f.max_np1, J.np1); f.max_nx = std::max(f.max_nx, J.wv_nx);
+                    }
                     ++f.count; ++p;
+                }
+                if (f.wave) {       // ring depth: 16 anti-diagonals when that does not cost resident CTAs the launch can use
+                    const size_t s8 = wave_smem_bytes(8, f.max_n1, f.max_n2, f.max_tr, f.max_np1, f.max_nx), s16 = wave_smem_bytes(16, f.max_n1, f.max_n2, f.max_tr, f.max_np1, f.max_nx);
+                    const int by_thr = std::max(1, 2048 / std::max(f.wthreads, 32));
+                    const int c8 = std::min<int>(by_thr, (int)((227 * 1024) / (s8 + 1024))), c16 = std::min<int>(by_thr, (int)((227 * 1024) / (s16 + 1024)));
+                    f.wring = (s16 <= 227 * 1024 && (c16 >= c8 || f.count <= 148 * std::max(c16, 1))) ? 16 : 8;
+                    if (env.wave_ring == 8 || (env.wave_ring == 16 && s16 <= 227 * 1024)) f.wring = env.wave_ring;
                 }
                 b->fills.push_back(f);
             }
@@ -699,6 +790,7 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             if (f->layout == GF_LAYOUT_STRIP)
                 return f->sgen ? launch_graph_fill_strip_gen(sq, f->C, f->dbits, f->swarps, f->ring_bytes, f->count, dj + sb.first, ord)
                                : launch_graph_fill_strip(sq, f->C, f->count, dj + sb.first, ord);
+            if (f->wave) return launch_graph_fill_wave(sq, f->wL, f->wring, f->wthreads, f->count, dj + sb.first, ord, f->max_n1, f->max_n2, f->max_tr, f->max_np1, f->max_nx);
             if (f->max_bands > 1) {
                 for (int jq = 0; jq < f->count; ++jq) {             // zero the bands' progress flags and the band ticket
                     const GraphJobDev& Jq = b->jobs[sb.first + b->order[sb.first + f->offset + jq]];

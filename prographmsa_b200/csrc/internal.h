@@ -140,6 +140,11 @@ struct NodeInfo { int ptr; int cnt; int idx0; float val0; };   // per node: pred
 // general strip kernel: everything a row needs in one 32-byte record, fetched two rows ahead (no dependent loads in a step)
 struct RowInfo { int cnt; int idx0; float val0; int idx1; float val1; int kq01; int ncidx; int ptr; };   // cnt as NodeInfo::cnt; the first two
                              // predecessors inline; kq01 = (value-store row of idx0 + 1) | (... of idx1 + 1) << 16; ncidx = row of RowIdx or -1
+// role-sorted anti-diagonal kernel (hp1_wave.cu): one record per row thread / per non-chain column, one per column for the row threads
+struct WaveRow { int y; int nextra; float ey_adj; int yp0; float ey0; int yp1; float ey1; int rest; };   // y = -1: padding slot; ey_adj = +inf: no
+                             // edge from y-1; extra predecessor k (every list entry but the adjacent one) inline for k < 2, else at wv_xi/wv_xv[rest + k]
+struct WaveCol { int x; int cnt; int xp0; float ex0; int xp1; float ex1; int ptr; int pad; };            // all predecessors of the column, k >= 2 at p2_idx/p2_val[ptr + k]
+struct WaveCI { float ex_adj; int flags; };                  // flags bit 0: non-chain column (its cells belong to the column threads), bit 1: column x-1 is one
 #define GF_MAX_PREDS 128     // predecessors per node the packed traceback's index fields can hold (graphs beyond it take the dense kernels)
 
 #define GF_BAND_ROWS 512      // rows per band (= threads per CTA) of the banded anti-diagonal kernel
@@ -180,6 +185,10 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     // general strip kernel (graphs with non-chain nodes): per strip the slots whose column is not a chain node (specmask) and
     // the slots whose column is the SOURCE of a non-adjacent column edge (srcmask; its (X,W) go to a shared-memory ring,
     // slot colsrc[x]); direction-word index fields of the cells in non-chain rows / columns (ncidx = row in RowIdx / ColIdx)
+    // role-sorted anti-diagonal kernel (hp1_wave.cu; layout = GF_LAYOUT_DIAG)
+    int wave;                   // 1: swept by graph_fill_wave_kernel
+    int wv_tr, wv_ncols, wv_nx; // row-thread slots (chain rows, then non-chain rows, each padded to warps), non-chain columns, extra-predecessor entries
+    const WaveRow* wv_rows; const WaveCol* wv_cols; const WaveCI* wv_ci; const uint16_t* wv_rowslot; const int* wv_xi; const float* wv_xv;
     int sgen;                   // 1: swept by graph_fill_strip_gen_kernel
     int dbg;                    // PGM_STRIP_DEBUG bits (experiments): 1 = never the fused fast path, 2 = fence after the step barrier
     int nsrc, ring_rows;        // source columns, rows per ring (power of two > nstrips + 1)
@@ -245,6 +254,9 @@ int launch_graph_trace(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, c
 int launch_graph_trace_packed(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);   // direction bits (hp1_trace.cu)
 int launch_graph_fill_strip(cudaStream_t st, int C, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
 int launch_graph_fill_strip_gen(cudaStream_t st, int C, int dbits, int warps, size_t smem, int n_jobs, const GraphJobDev* d_jobs, const int* d_order);
+size_t wave_smem_bytes(int ring, int max_n1, int max_n2, int max_tr, int max_np1, int max_nx);
+int launch_graph_fill_wave(cudaStream_t st, int L, int ring, int threads, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1,
+                           int max_n2, int max_tr, int max_np1, int max_nx);
 #define SG_MAX_WARPS 8       // warps per job of the general strip kernel (256 strips)
 #define SG_MAX_SRC 256       // source columns of non-adjacent column edges per job (shared-memory rings)
 __host__ __device__ __forceinline__ int strip_words(int C) { return C <= 8 ? 1 : (C <= 16 ? 2 : 4); }   // uint32 words of direction nibbles per strip and row

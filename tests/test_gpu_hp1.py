@@ -237,6 +237,10 @@ FLAVOURS = {
     "strip_small_rings": {"PGM_STRIP_HIST_KB": "6"},
     "strip_general_only": {"PGM_FILL_STRIP": "3"},
     "strip_full_s": {"PGM_SITE_CLASSES": "0"},
+    "wave": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1"},
+    "wave_l1": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1", "PGM_WAVE_L": "1"},
+    "wave_l2_ring8": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1", "PGM_WAVE_L": "2", "PGM_WAVE_RING": "8"},
+    "wave_ring16": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1", "PGM_WAVE_RING": "16"},
 }
 
 

@@ -57,7 +57,8 @@ if only == "chain":
     run([i for i in idx if info[i][0] == 0 and info[i][1] == 0], "pure chain x chain"); sys.exit(0)
 if only == "branchy":
     run([i for i in idx if info[i][0] + info[i][1] > 40], ">40 non-chain nodes"); sys.exit(0)
-for lay in (None, "block", "diag"):
+lays = (None,) if only == "default" else (None, "block", "diag")
+for lay in lays:
     if lay: os.environ["PGM_FILL_LAYOUT"] = lay
     print("--- PGM_FILL_LAYOUT =", lay)
     run(idx, "all")
