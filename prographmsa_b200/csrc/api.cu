@@ -61,8 +61,14 @@ struct ScopedKernelTimer {
     }
 };
 static void resolve_timing(pgm_ctx* c) {
+    const bool timeline = getenv("PGM_TIMELINE") != nullptr && !c->sections.empty();     // profiling aid: when each timed section began and ended
     for (auto& s : c->sections) {
         float ms = 0; cudaEventElapsedTime(&ms, s.a, s.b);
+        if (timeline) {
+            float t0 = 0; cudaEventElapsedTime(&t0, c->sections.front().a, s.a);
+            static const char* names[] = {"nw_forward", "nw_walk", "ml", "emission", "fill", "trace"};
+            fprintf(stderr, "[timeline] %-10s start %8.3f ms  duration %8.3f ms\n", names[s.kind], t0, ms);
+        }
         switch (s.kind) {
             case K_NW_FWD: c->timing.nw_forward_ms += ms; c->timing.nw_forward_launches++; break;
             case K_NW_WALK: c->timing.nw_walk_ms += ms; c->timing.nw_walk_launches++; break;

@@ -92,7 +92,7 @@ struct JobLayout {                // byte offsets into the upload arena / scratc
     int C, nstrips, N1e, N2e, coded1, coded2;
     int sgen, nsrc, ring_rows, hist_rows, swarps, nstrips_gen, nnc1, nnc2, ldRI, ldCI;
     int wave, wv_tr, wv_chain_pad, wv_ncols, wv_nx, wv_L;       // role-sorted anti-diagonal kernel (hp1_wave.cu)
-    size_t wv_rows, wv_cols, wv_ci, wv_rowslot, wv_xi, wv_xv;
+    size_t wv_rows, wv_cols, wv_ci, wv_rowslot, wv_xi, wv_xv, wv_adj1;
     size_t scol, sstart, colstrip, specmask, srcmask, colsrc_off, ncidx1_off, ncidx2_off, rinfo_off, RowIdx, ColIdx;
     std::vector<int16_t> colsrc; std::vector<int> ncidx1, ncidx2;
     double uniform1, uniform2;
@@ -134,7 +134,7 @@ int max_preds(const pgm_graph& g) {
 struct BatchEnv {                 // environment switches, read once per create (tests, A-B runs, profiling)
     int force_layout = -1, diag_min_generic = 8, band_min_n1 = GF_BAND_MIN_N1, long_band_rows = GF_BAND_ROWS;
     int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, strip = 2, coding = 1, strip_c = 0, hist_kb = 0, dbg = 0, strip_max_generic = 16;
-    int wave = 0, wave_L = 0, wave_ring = 0;
+    int wave = 1, wave_L = 0, wave_ring = 0;
     BatchEnv() {
         if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
         if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
@@ -186,7 +186,7 @@ thread_local bool t_full_emission = false;   // pgm_emission_scores: the caller 
 } // namespace
 
 // side streams for concurrent fill launches: one set per device, created on first use and kept for the process
-struct SideStreams { std::vector<cudaStream_t> streams; std::vector<cudaEvent_t> join; cudaEvent_t fork = nullptr; };
+struct SideStreams { std::vector<cudaStream_t> streams; std::vector<cudaEvent_t> join, emit_done; cudaEvent_t fork = nullptr; };
 static SideStreams& side_streams(int device) { static SideStreams s[64]; return s[device & 63]; }
 
 struct pgm_graph_batch {
@@ -362,14 +362,18 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             int lw = 0;
             for (int q : {4, 2, 1}) if ((!env.wave_L || env.wave_L == q) && tr + ru32(generic2 * q) <= 1024) { lw = q; break; }
             int nx = 0;
-            for (int y = 1; y <= a.N - 2; ++y)
-                if (non_chain_node(a, y)) {
-                    bool adj = false;
-                    auto visit = [&](int from) { if (from == y - 1 && !adj) adj = true; else ++nx; };
-                    for (int e = a.e_rowptr[y]; e < a.e_rowptr[y + 1]; ++e) visit(a.e_col[e]);
-                    if (a.r_rowptr) for (int e = a.r_rowptr[y]; e < a.r_rowptr[y + 1]; ++e) visit(a.r_col[e]);
-                }
-            if (lw && wave_smem_bytes(8, a.N, bb.N, tr, L.np1, nx) <= 227 * 1024) {
+            bool dup = false;                                       // two list entries from the adjacent predecessor: not handled by the look-ahead split
+            for (int w = 0; w < 2; ++w) {
+                const pgm_graph& g = w ? bb : a;
+                for (int y = 1; y <= g.N - 2; ++y)
+                    if (non_chain_node(g, y)) {
+                        bool adj = false;
+                        auto visit = [&](int from) { if (from == y - 1) { if (adj) dup = true; adj = true; } else if (w == 0) ++nx; };
+                        for (int e = g.e_rowptr[y]; e < g.e_rowptr[y + 1]; ++e) visit(g.e_col[e]);
+                        if (g.r_rowptr) for (int e = g.r_rowptr[y]; e < g.r_rowptr[y + 1]; ++e) visit(g.r_col[e]);
+                    }
+            }
+            if (lw && !dup && wave_smem_bytes(8, a.N, bb.N, tr, L.np1, nx) <= 227 * 1024) {
                 L.wave = 1; L.wv_tr = tr; L.wv_chain_pad = ru32(nchain); L.wv_ncols = generic2; L.wv_nx = nx; L.wv_L = lw;
             }
         }
@@ -448,6 +452,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.wv_rows = take(in_off, L.wave ? sizeof(WaveRow) * (size_t)L.wv_tr : 0); L.wv_cols = take(in_off, L.wave ? sizeof(WaveCol) * (size_t)L.wv_ncols : 0);
         L.wv_ci = take(in_off, L.wave ? sizeof(WaveCI) * (size_t)bb.N : 0); L.wv_rowslot = take(in_off, L.wave ? 2 * (size_t)a.N : 0);
         L.wv_xi = take(in_off, L.wave ? 4 * (size_t)L.wv_nx : 0); L.wv_xv = take(in_off, L.wave ? 4 * (size_t)L.wv_nx : 0);
+        L.wv_adj1 = take(in_off, L.wave ? 4 * (size_t)a.N : 0);
         L.map1 = take(out_off, 4 * L.cap); L.map2 = take(out_off, 4 * L.cap); L.result = take(out_off, 32);
         b->max_N1 = std::max(b->max_N1, a.N); b->max_N2 = std::max(b->max_N2, bb.N);
     }
@@ -604,12 +609,14 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             const int* p2i = (const int*)(hin + L.p2_idx); const float* p2v = (const float*)(hin + L.p2_val);
             WaveRow* wr = (WaveRow*)(hin + L.wv_rows); WaveCol* wc = (WaveCol*)(hin + L.wv_cols); WaveCI* ci = (WaveCI*)(hin + L.wv_ci);
             uint16_t* slot = (uint16_t*)(hin + L.wv_rowslot); int* xi = (int*)(hin + L.wv_xi); float* xv = (float*)(hin + L.wv_xv);
+            float* adj1 = (float*)(hin + L.wv_adj1);
+            adj1[0] = FINF; adj1[N1 - 1] = FINF;
             for (int t = 0; t < L.wv_tr; ++t) wr[t] = WaveRow{-1, 0, 0.f, 0, 0.f, 0, 0.f, 0};
             int tc = 0, ts = L.wv_chain_pad, nx = 0;
             slot[N1 - 1] = 0;
             for (int y = 0; y <= N1 - 2; ++y) {
                 const bool chain = y == 0 || NI_CHAIN(ni1[y], y);
-                WaveRow r{y, 0, 0.f, 0, 0.f, 0, 0.f, nx};
+                WaveRow r{y, 0, FINF, 0, 0.f, 0, 0.f, nx};                  // row 0: no predecessor row, Y and M come out as -inf
                 if (y >= 1 && chain) r.ey_adj = ni1[y].val0;
                 if (!chain) {
                     r.ey_adj = FINF;                                // no edge from y-1: its candidates come out as -inf
@@ -624,6 +631,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 }
                 const int t = chain ? tc++ : ts++;
                 wr[t] = r; slot[y] = (uint16_t)t;
+                if (y >= 1) adj1[y] = r.ey_adj;
             }
             int nc = 0;
             for (int x = 0; x < N2; ++x) {
@@ -633,14 +641,16 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 ci[x].flags = (spec ? 1 : 0) | (lspec ? 2 : 0);
                 if (spec) {
                     const int cnt = NI_CNT(ni2[x].cnt), ptr = ni2[x].ptr;
-                    WaveCol c{x, cnt, 0, 0.f, 0, 0.f, ptr, 0};
+                    WaveCol c{x, cnt, 0, 0.f, 0, 0.f, ptr, FINF};
                     if (cnt > 0) { c.xp0 = p2i[ptr]; c.ex0 = p2v[ptr]; }
                     if (cnt > 1) { c.xp1 = p2i[ptr + 1]; c.ex1 = p2v[ptr + 1]; }
+                    for (int q = 0; q < cnt; ++q) if (p2i[ptr + q] == x - 1) c.ex_adj_col = p2v[ptr + q];
                     wc[nc++] = c;
                 }
             }
         }
-        J.wave = L.wave; J.wv_tr = L.wv_tr; J.wv_ncols = L.wv_ncols; J.wv_nx = L.wv_nx;
+        J.wave = L.wave; J.wv_tr = L.wv_tr; J.wv_ncols = L.wv_ncols; J.wv_nx = L.wv_nx; J.wv_chain_pad = L.wv_chain_pad;
+        J.wv_adj1 = (const float*)(din + L.wv_adj1);
         J.wv_rows = (const WaveRow*)(din + L.wv_rows); J.wv_cols = (const WaveCol*)(din + L.wv_cols); J.wv_ci = (const WaveCI*)(din + L.wv_ci);
         J.wv_rowslot = (const uint16_t*)(din + L.wv_rowslot); J.wv_xi = (const int*)(din + L.wv_xi); J.wv_xv = (const float*)(din + L.wv_xv);
         J.dbg = env.dbg; J.sgen = L.sgen; J.nsrc = L.nsrc; J.ring_rows = L.ring_rows; J.hist_rows = L.hist_rows; J.ldRI = L.ldRI; J.ldCI = L.ldCI;
@@ -689,7 +699,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             // stream priority, so the few long latency-bound sweeps near the root start at once and are not starved of issue slots
             auto est_us = [&](const GraphJobDev& J) -> double {
                 if (J.layout == GF_LAYOUT_STRIP) return (double)(J.N1 + J.nstrips) * (J.sgen ? 1.2 : 0.6);
-                if (J.wave) return (double)(J.N1 + J.N2) * 0.6;
+                if (J.wave) return (double)(J.N1 + J.N2) * 1.0;
                 if (J.layout == GF_LAYOUT_DIAG) return (double)(J.N1 + J.N2) * (J.bands > 1 ? 8.0 : 1.8);
                 return (double)(J.N1 + J.nb) * 1.2;
             };
@@ -725,7 +735,8 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                     const size_t s8 = wave_smem_bytes(8, f.max_n1, f.max_n2, f.max_tr, f.max_np1, f.max_nx), s16 = wave_smem_bytes(16, f.max_n1, f.max_n2, f.max_tr, f.max_np1, f.max_nx);
                     const int by_thr = std::max(1, 2048 / std::max(f.wthreads, 32));
                     const int c8 = std::min<int>(by_thr, (int)((227 * 1024) / (s8 + 1024))), c16 = std::min<int>(by_thr, (int)((227 * 1024) / (s16 + 1024)));
-                    f.wring = (s16 <= 227 * 1024 && (c16 >= c8 || f.count <= 148 * std::max(c16, 1))) ? 16 : 8;
+                    // (a batch with more jobs than SMs: the other classes' CTAs want to share the SM, so the smaller ring)
+                    f.wring = (s16 <= 227 * 1024 && (c16 >= c8 || (n_jobs <= 148 && f.count <= 148 * std::max(c16, 1)))) ? 16 : 8;
                     if (env.wave_ring == 8 || (env.wave_ring == 16 && s16 <= 227 * 1024)) f.wring = env.wave_ring;
                 }
                 b->fills.push_back(f);
@@ -758,6 +769,8 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
     pgm_ctx_reset_timing(c);
     const char* env = getenv("PGM_GRAPH_PIPELINE");
     const bool pipelined = !(env && atoi(env) == 0);
+    const int pipe_mode = env ? atoi(env) : 1;
+    const bool skip_trace = getenv("PGM_SKIP_TRACE") != nullptr;       // timing experiments on fill kernels whose results are wrong on purpose
     const GraphJobDev* dj = b->d_jobs.as<GraphJobDev>();
     const int* d_order_all = (const int*)(b->d_jobs.as<char>() + sizeof(GraphJobDev) * b->n_jobs);
     // status words (emission failure flag, end-node pick) start from zero on every run
@@ -827,7 +840,34 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             return 0;
         };
         auto stream_of = [&](size_t q) { return !n_side ? st : ss.streams[q % n_side]; };
-        if (pipelined) {
+        if (pipe_mode >= 2) {
+            // emissions of every class first, back to back on the main stream (throughput kernels: they get the whole GPU instead
+            // of the SMs the long sweeps leave over); then one fill -> traceback pipeline per class.  Mode 3: a class's pipeline
+            // starts as soon as ITS emission is done
+            std::vector<cudaEvent_t>& evs = ss.emit_done;
+            while (pipe_mode == 3 && evs.size() < fl.size()) { cudaEvent_t e2; PGM_CUDA(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming)); evs.push_back(e2); }
+            if (pipe_mode == 3 && (rc = fork())) return rc;               // (the side streams then wait for their own class's emission only)
+            for (size_t q = 0; q < fl.size() && !rc; ++q) {
+                const int* ord = d_order_all + sb.first + fl[q]->offset;
+                pgm_ctx_time_begin_on(c, 3, st, &tok); rc = emit(st, fl[q]->count, ord, fl[q]->max_n1e, fl[q]->max_n2e); pgm_ctx_time_end(c, tok);
+                if (!rc && pipe_mode == 3) PGM_CUDA(cudaEventRecord(evs[q], st));
+            }
+            if (rc) return rc;
+            if (pipe_mode != 3 && (rc = fork())) return rc;
+            for (size_t q = 0; q < fl.size() && !rc; ++q) {
+                cudaStream_t sq = stream_of(q);
+                const int* ord = d_order_all + sb.first + fl[q]->offset;
+                if (pipe_mode == 3 && sq != st) PGM_CUDA(cudaStreamWaitEvent(sq, evs[q], 0));
+                pgm_ctx_time_begin_on(c, 4, sq, &tok); rc = fill(sq, fl[q]); pgm_ctx_time_end(c, tok);
+                if (rc) break;
+                pgm_ctx_time_begin_on(c, 5, sq, &tok);
+                if (skip_trace) { pgm_ctx_time_end(c, tok); continue; }
+                rc = fl[q]->layout == GF_LAYOUT_STRIP ? launch_graph_trace_packed(sq, fl[q]->count, dj + sb.first, ord) : launch_graph_trace(sq, fl[q]->count, dj + sb.first, ord);
+                pgm_ctx_time_end(c, tok);
+            }
+            if (rc) return rc;
+            if ((rc = join())) return rc;
+        } else if (pipelined) {
             if ((rc = fork())) return rc;
             for (size_t q = 0; q < fl.size() && !rc; ++q) {
                 cudaStream_t sq = stream_of(q);
@@ -837,6 +877,7 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
                 pgm_ctx_time_begin_on(c, 4, sq, &tok); rc = fill(sq, fl[q]); pgm_ctx_time_end(c, tok);
                 if (rc) break;
                 pgm_ctx_time_begin_on(c, 5, sq, &tok);
+                if (skip_trace) { pgm_ctx_time_end(c, tok); continue; }
                 rc = fl[q]->layout == GF_LAYOUT_STRIP ? launch_graph_trace_packed(sq, fl[q]->count, dj + sb.first, ord) : launch_graph_trace(sq, fl[q]->count, dj + sb.first, ord);
                 pgm_ctx_time_end(c, tok);
             }
@@ -855,8 +896,8 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             pgm_ctx_time_end(c, tok);
             if (rc) return rc;
             pgm_ctx_time_begin(c, 5, &tok);
-            rc = launch_graph_trace(st, nj, dj + sb.first, nullptr);        // each traceback kernel skips the other layouts' jobs
-            if (!rc) rc = launch_graph_trace_packed(st, nj, dj + sb.first, nullptr);
+            if (!skip_trace) rc = launch_graph_trace(st, nj, dj + sb.first, nullptr);        // each traceback kernel skips the other layouts' jobs
+            if (!rc && !skip_trace) rc = launch_graph_trace_packed(st, nj, dj + sb.first, nullptr);
             pgm_ctx_time_end(c, tok);
             if (rc) return rc;
         }

@@ -143,7 +143,8 @@ struct RowInfo { int cnt; int idx0; float val0; int idx1; float val1; int kq01; 
 // role-sorted anti-diagonal kernel (hp1_wave.cu): one record per row thread / per non-chain column, one per column for the row threads
 struct WaveRow { int y; int nextra; float ey_adj; int yp0; float ey0; int yp1; float ey1; int rest; };   // y = -1: padding slot; ey_adj = +inf: no
                              // edge from y-1; extra predecessor k (every list entry but the adjacent one) inline for k < 2, else at wv_xi/wv_xv[rest + k]
-struct WaveCol { int x; int cnt; int xp0; float ex0; int xp1; float ex1; int ptr; int pad; };            // all predecessors of the column, k >= 2 at p2_idx/p2_val[ptr + k]
+struct WaveCol { int x; int cnt; int xp0; float ex0; int xp1; float ex1; int ptr; float ex_adj_col; };   // all predecessors of the column, k >= 2 at p2_idx/p2_val[ptr + k];
+                             // ex_adj_col = value of the edge x-1 -> x, +inf if there is none
 struct WaveCI { float ex_adj; int flags; };                  // flags bit 0: non-chain column (its cells belong to the column threads), bit 1: column x-1 is one
 #define GF_MAX_PREDS 128     // predecessors per node the packed traceback's index fields can hold (graphs beyond it take the dense kernels)
 
@@ -188,6 +189,8 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     // role-sorted anti-diagonal kernel (hp1_wave.cu; layout = GF_LAYOUT_DIAG)
     int wave;                   // 1: swept by graph_fill_wave_kernel
     int wv_tr, wv_ncols, wv_nx; // row-thread slots (chain rows, then non-chain rows, each padded to warps), non-chain columns, extra-predecessor entries
+    int wv_chain_pad;           // slots of the chain rows (a multiple of 32): the non-chain rows' slots start here
+    const float* wv_adj1;       // N1 entries: value of the edge y-1 -> y, +inf if there is none
     const WaveRow* wv_rows; const WaveCol* wv_cols; const WaveCI* wv_ci; const uint16_t* wv_rowslot; const int* wv_xi; const float* wv_xv;
     int sgen;                   // 1: swept by graph_fill_strip_gen_kernel
     int dbg;                    // PGM_STRIP_DEBUG bits (experiments): 1 = never the fused fast path, 2 = fence after the step barrier

@@ -226,7 +226,7 @@ def test_large_batch_is_deterministic_and_correct(ga, po):
 FLAVOURS = {
     "default": {},
     "block": {"PGM_FILL_LAYOUT": "block"},
-    "diag": {"PGM_FILL_LAYOUT": "diag"},
+    "diag": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "0"},
     "banded": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_BAND_MIN_N1": "66", "PGM_FILL_BAND_ROWS": "64"},
     "nostrip": {"PGM_FILL_STRIP": "0"},
     "strip_chain_only": {"PGM_FILL_STRIP": "1"},
@@ -240,6 +240,8 @@ FLAVOURS = {
     "wave": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1"},
     "wave_l1": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1", "PGM_WAVE_L": "1"},
     "wave_l2_ring8": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1", "PGM_WAVE_L": "2", "PGM_WAVE_RING": "8"},
+    "wave_pipeline3": {"PGM_FILL_LAYOUT": "diag", "PGM_GRAPH_PIPELINE": "3"},
+    "pipeline2": {"PGM_GRAPH_PIPELINE": "2"},
     "wave_ring16": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "1", "PGM_WAVE_RING": "16"},
 }
 

@@ -52,7 +52,12 @@ only = sys.argv[3] if len(sys.argv) > 3 else None
 if only == "few":
     run([i for i in idx if 0 < max(info[i][0], info[i][1]) <= 8], "1..8 non-chain nodes"); sys.exit(0)
 if only == "big":
-    run(sorted(idx, key=lambda i: -info[i][2] * info[i][3])[:1], "largest job"); sys.exit(0)
+    big = sorted(idx, key=lambda i: -info[i][2] * info[i][3])[:1]
+    for dbgv in os.environ.get("DBG_LIST", "0").split(","):
+        os.environ["PGM_STRIP_DEBUG"] = dbgv
+        if dbgv != "0": os.environ["PGM_SKIP_TRACE"] = "1"
+        run(big, "largest job dbg=" + dbgv)
+    sys.exit(0)
 if only == "chain":
     run([i for i in idx if info[i][0] == 0 and info[i][1] == 0], "pure chain x chain"); sys.exit(0)
 if only == "branchy":
