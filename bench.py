@@ -293,13 +293,18 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 e2e=dict(value=upd / e2e_ms / 1e6, unit="GCUPS", ms_per_step=e2e_ms),
                 kernels_ms=dict(emission=tm["emission_ms"] / steps, fill=fill_ms, trace=tm["graph_trace_ms"] / steps),
                 gpu_launches=tp["launches"],
-                roofline=dict(bound="hbm", kernel="graph_fill_kernel + graph_fill_diag_kernel (concurrent launches, one fill section)",
+                roofline=dict(bound="hbm", kernel="graph_fill_strip_kernel + graph_fill_strip_gen_kernel + graph_fill_wave_kernel (concurrent launches, one fill section)",
                               achieved=alg_bytes / fill_ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
                               frac=alg_bytes / fill_ms / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
                               moved_bytes_per_cell=6.0,
-                              note="algorithmic bytes = 5 B/cell (SURVEY 8d: 4 B S read + 1 B packed traceback); the kernels move 6 B/cell (2-byte direction "
-                                   "words) plus the kept rows / columns of the value store. The fill section ends when the few large branchy graphs near "
-                                   "the root finish, each one latency-bound sweep (profiles/)"),
+                              note="algorithmic bytes = 5 B/cell (SURVEY 8d: 4 B S read + 1 B packed traceback); the strip kernels move 4.5 B/cell (4 direction "
+                                   "bits + S, class-coded S for leaf graphs), the anti-diagonal (wave) kernel 20 B/cell on the few branchy graphs it sweeps. "
+                                   "Not the binding roof: the fill is bound by dependent-issue latency (roofline_issue; profiles/r2_*)"),
+                roofline_issue=dict(bound="sm fp32 issue", kernel="fill section (all fill kernels)", achieved=17.0 * upd / fill_ms / 1e9,
+                                    peak=148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12, unit="Tlane-op/s",
+                                    frac=17.0 * upd / fill_ms / 1e9 / (148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12),
+                                    note="algorithmic work = 17 fp32 add/max per predecessor-pair cell update (SURVEY 8d, GraphAlign.h:245-256); "
+                                         "peak = 148 SM x 128 lanes x sm_max_mhz"),
                 score_checksum=float(sum(r["score"] for r in res)))
         finally:
             gb.close()

@@ -720,6 +720,12 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 f.wave = J0.wave; f.wL = b->lay[sbr.first + idx[p]].wv_L;
                 while (p < idx.size() && class_of(b->jobs[sbr.first + idx[p]]) == q) {
                     const GraphJobDev& J = b->jobs[sbr.first + idx[p]];
+                    if (J.wave && f.count > 0) {                    // the launch's shared memory is sized by the maxima over its jobs: every job fits
+                        // on its own (checked in the analysis pass), the combination may not -- then the job starts the next launch
+                        const size_t s8 = wave_smem_bytes(8, std::max(f.max_n1, J.N1), std::max(f.max_n2, J.N2), std::max(f.max_tr, J.wv_tr),
+                                                          std::max(f.max_np1, J.np1), std::max(f.max_nx, J.wv_nx));
+                        if (s8 > 227 * 1024) break;
+                    }
                     f.max_nb = std::max(f.max_nb, J.nb); f.max_n1 = std::max(f.max_n1, J.N1); f.max_n2 = std::max(f.max_n2, J.N2);
                     f.max_np2 = std::max(f.max_np2, J.np2); f.max_np = std::max(f.max_np, J.np1 + J.np2);
                     f.max_bands = std::max(f.max_bands, J.bands);

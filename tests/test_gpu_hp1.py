@@ -400,3 +400,16 @@ def test_more_jobs_than_sms_multi_warp_strips(ga, po):
         got = ga.alignGraphsBatch(jobs * rep, opts)
         for k, r in enumerate(got):
             _same_alignment(r, refs[k % len(jobs)])
+
+
+def test_wave_kernel_large_and_mixed_shapes(ga, po):
+    """the role-sorted anti-diagonal kernel near its limits: ~1000 rows (threads), long graph 2 (shared-memory staging), many
+    non-chain columns (column threads), and a launch whose jobs fit one by one but not with the maxima of all of them"""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    rng = np.random.default_rng(77)
+    m = mf.getModel(0.3, 0.3)
+    shapes = [(1000, 120, 2, 2), (120, 1400, 2, 2), (700, 260, 3, 1), (260, 700, 1, 3), (1020, 90, 1, 1), (60, 2600, 1, 2)]
+    jobs = [(_branchy_graph(rng, a, ea), _branchy_graph(rng, b, eb), m) for a, b, ea, eb in shapes]
+    for (g1, g2, mm), r in zip(jobs, ga.alignGraphsBatch(jobs, opts)):
+        _same_alignment(r, po.align_graphs(g1, g2, mm, opts))

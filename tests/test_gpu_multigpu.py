@@ -48,3 +48,30 @@ def test_two_gpus_reproduce_single_gpu_matrix(tmp_path):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
     assert "multigpu ok" in r.stdout
+
+
+def test_two_contexts_in_one_process():
+    """two pgm_ctx in one process (on two devices when the box has them, else both on device 0): the kernels'
+    opted-in dynamic shared memory sizes are per device, so the second context must not inherit a skipped opt-in.  Both
+    contexts run the n = 20 ML kernel (> 48 KB of dynamic shared memory), the NW profile kernel and a graph DP job."""
+    import numpy as np
+    import torch
+    from prographmsa_b200 import model, synth, distance, graphalign, _lib
+    from prographmsa_b200.graph import sequence_graph
+    from prographmsa_b200.options import Options
+    opts = Options(mldist_flag=True, nwdist_flag=True)
+    mf = model.getDefault(opts)
+    seqs, _ = synth.simulate_family(24, 150, mf, seed=5, indel_rate=0.03)
+    names = sorted(seqs)
+    second = 1 if torch.cuda.device_count() >= 2 else 0
+    ctxs = [_lib.Context(0), _lib.Context(second)]
+    try:
+        mats = [distance.DistanceFactoryAlign(mf, opts, c).computePwDistances(seqs, names) for c in ctxs]
+        assert np.array_equal(mats[0].distances, mats[1].distances) and np.array_equal(mats[0].variances, mats[1].variances)
+        g1, g2 = sequence_graph(seqs[names[0]], 20), sequence_graph(seqs[names[1]], 20)
+        m = mf.getModel(0.4, 0.4)
+        res = [graphalign.alignGraphs(g1, g2, m, opts, ctx=c) for c in ctxs]
+        assert res[0]["score"] == res[1]["score"] and np.array_equal(res[0]["mapping1"], res[1]["mapping1"])
+    finally:
+        for c in ctxs:
+            c.close()
