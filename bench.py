@@ -275,12 +275,36 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
             ev, upd, cells = timed_runs(tp)
             ms = sum(a.elapsed_time(b) for a, b in ev) / steps
             res = gb.fetch()
-            # e2e: host graphs in, mappings out, per step (one untimed call first: buffer pools, side streams)
+            # e2e: host graphs in, mappings out, per step (one untimed call first: buffer pools, side streams).  Two figures: through the
+            # Python mirror of alignGraphs (alignGraphsBatch: marshals the graphs, builds result objects), and the C-ABI call alone
+            # (pgm_align_graphs_batch on prebuilt pgm_graph / pgm_alignment arrays in host memory: pack, H2D, kernels, D2H)
             graphalign.alignGraphsBatch(jobs, opts, mode, ctx)
             t0 = time.perf_counter()
             for _ in range(max(1, steps // 2)):
                 graphalign.alignGraphsBatch(jobs, opts, mode, ctx)
+            e2e_py_ms = (time.perf_counter() - t0) / max(1, steps // 2) * 1e3
+            import ctypes as C
+            from prographmsa_b200 import _lib as L_
+            keep = []
+            nj = len(jobs)
+            G1 = (L_.Graph * nj)(); G2 = (L_.Graph * nj)(); MM = (L_.DPModel * nj)()
+            for k, (g1, g2, mdl) in enumerate(jobs):
+                G1[k] = graphalign.c_graph(g1, keep); G2[k] = graphalign.c_graph(g2, keep); MM[k] = graphalign.c_model(mdl, keep)
+            caps = np.array([2 * (g1.N + g2.N) + 8 for g1, g2, _ in jobs], dtype=np.int64)
+            offs = np.concatenate([[0], np.cumsum(caps)])
+            maps = np.empty((2, int(offs[-1])), dtype=np.int32)
+            res_arr = np.zeros(nj, dtype=graphalign._ALIGNMENT)
+            res_arr["mapping1"] = maps[0].ctypes.data + 4 * offs[:-1]; res_arr["mapping2"] = maps[1].ctypes.data + 4 * offs[:-1]
+            res_arr["capacity"] = caps
+            o_ = graphalign.c_opts(opts, mode)
+            def cabi():
+                L_.check(L_.lib().pgm_align_graphs_batch(ctx.handle, jobs[0][0].n, nj, G1, G2, MM, C.byref(o_), C.c_void_p(res_arr.ctypes.data)))
+            cabi()
+            t0 = time.perf_counter()
+            for _ in range(max(1, steps // 2)):
+                cabi()
             e2e_ms = (time.perf_counter() - t0) / max(1, steps // 2) * 1e3
+            assert abs(float(res_arr["score"].astype(np.float64).sum()) - float(sum(r["score"] for r in res))) <= 1e-3 * abs(float(sum(r["score"] for r in res)))
             fill_ms = tm["graph_fill_ms"] / steps
             # algorithmic HBM bytes of the fill kernels: 4 B S read + 1 B packed traceback per cell.
             # What the kernels move: 4 B S + 2 B direction word per cell, plus the few kept rows / columns of the value store
@@ -290,7 +314,8 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 schedule="per size class: emission -> fill -> traceback on its own stream (pgm_graph_batch_run); ms_per_step_phased = "
                          "the three phases one after the other over the whole batch (PGM_GRAPH_PIPELINE=0), which is what kernels_ms splits",
                 ms_per_step_phased=ms_phased,
-                e2e=dict(value=upd / e2e_ms / 1e6, unit="GCUPS", ms_per_step=e2e_ms),
+                e2e=dict(value=upd / e2e_ms / 1e6, unit="GCUPS", ms_per_step=e2e_ms, through="pgm_align_graphs_batch (C ABI, host graphs in, mappings out)",
+                         python_mirror_ms_per_step=e2e_py_ms),
                 kernels_ms=dict(emission=tm["emission_ms"] / steps, fill=fill_ms, trace=tm["graph_trace_ms"] / steps),
                 gpu_launches=tp["launches"],
                 roofline=dict(bound="hbm", kernel="graph_fill_strip_kernel + graph_fill_strip_gen_kernel + graph_fill_wave_kernel (concurrent launches, one fill section)",
