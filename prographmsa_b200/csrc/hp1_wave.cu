@@ -44,6 +44,13 @@ __device__ __forceinline__ void sts128(uint32_t a, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// a cell older than the ring, re-read from the {M,X,Y,W} array (L2).  Out of line on purpose: inlined, the compiler computed
+// the 64-bit address in front of every ring read (12 % of the kernel's instructions, profiles/r2_wave_v3.txt) although far
+// predecessors are rare
+__device__ __noinline__ float4 wave_far_cell(const float4* __restrict__ C, int dd, int yy, int pitch, int N2) {
+    return C[(size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)))];
+}
+
 template <int RING, int L, int MAXT>
 __global__ void __launch_bounds__(MAXT, MAXT <= 512 ? 2 : 1)
 graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch, int max_tr,
@@ -89,15 +96,31 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     const int dbg = J.dbg;                                              // PGM_STRIP_DEBUG bits >= 16: timing experiments (the results are then wrong)
     // any cell (yy, xx) on an anti-diagonal dd = yy + xx < d.  The ring read is unconditional (its address is always inside the
     // ring); cells older than the ring are re-read from the {M,X,Y,W} array in L2 (rare: lanes branch only then)
-    auto cell = [&](int yy, int xx, int d, bool usable) -> float4 {
+    // A ring cell is {X, W, Y, W}: the up candidate reads (Y, W) and the left candidate (X, W) as one 8-byte word each, the
+    // diagonal candidate W alone; M is never read back.  (ncu on the first version, profiles/r2_wave_v3.txt: 62 % of the
+    // shared-memory wavefronts were bank-conflict replays and the MIO queue was the top stall -- 16-byte reads of whole cells
+    // at scattered rows, and the S reads 4-way conflicted.)
+    auto cell_yw = [&](int yy, int xx, int d, bool usable) -> float2 {  // (Y, W) of cell (yy, xx)
         const int dd = yy + xx;
-        float4 v = lds128(ringa + (uint32_t)((dd & (RING - 1)) * pitchB + (yy + 1) * 16));
-        if (usable && d - dd >= RING) v = C[(size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)))];
+        float2 v = lds64(ringa + (uint32_t)((dd & (RING - 1)) * pitchB + (yy + 1) * 16 + 8));
+        if (usable && d - dd >= RING) { const float4 c = wave_far_cell(C, dd, yy, pitch, N2); v = make_float2(c.z, c.w); }
+        return v;
+    };
+    auto cell_xw = [&](int yy, int xx, int d, bool usable) -> float2 {  // (X, W)
+        const int dd = yy + xx;
+        float2 v = lds64(ringa + (uint32_t)((dd & (RING - 1)) * pitchB + (yy + 1) * 16));
+        if (usable && d - dd >= RING) { const float4 c = wave_far_cell(C, dd, yy, pitch, N2); v = make_float2(c.y, c.w); }
+        return v;
+    };
+    auto cell_w = [&](int yy, int xx, int d, bool usable) -> float {    // W
+        const int dd = yy + xx;
+        float v = lds32(ringa + (uint32_t)((dd & (RING - 1)) * pitchB + (yy + 1) * 16 + 4));
+        if (usable && d - dd >= RING) v = wave_far_cell(C, dd, yy, pitch, N2).w;
         return v;
     };
     if (tid == 0) {                                                     // cell (0, 0); the sweep starts at anti-diagonal 1
-        const float4 c00 = make_float4(NINF, NINF, NINF, start_init);
-        ring[1] = c00; C[0] = c00;
+        ring[1] = make_float4(NINF, start_init, NINF, start_init);
+        C[0] = make_float4(NINF, NINF, NINF, start_init);
     }
     const float PINF = CUDART_INF_F;
 
@@ -118,11 +141,22 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         const float ey0 = wr.nextra > 0 ? wr.ey0 : PINF, ey1 = wr.nextra > 1 ? wr.ey1 : PINF;
         const float* __restrict__ Srow = J.S + (size_t)yc * J.ldS;
         const int ldS = J.ldS;
-        const uint32_t smine = sringa + (uint32_t)tid * 16u;
+        // S(y, x) of this thread's row sits at word (x & 15) * max_tr + tid of the S ring: the 32 lanes of a warp read 32
+        // consecutive words whatever their columns are (one wavefront), at the price of four 4-byte cp.async per group
+        const uint32_t smine = sringa + (uint32_t)tid * 4u;
+        const int sstep = max_tr * 4;                                   // bytes between consecutive columns
+        auto fetch_group = [&](int q) {                                 // columns 4q .. 4q+3 of the row, asynchronously
+            const uint32_t dst = smine + (uint32_t)(((4 * q) & 15) * sstep);
+            const float* src = Srow + 4 * q;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst), "l"(src) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + (uint32_t)sstep), "l"(src + 1) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + (uint32_t)(2 * sstep)), "l"(src + 2) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + (uint32_t)(3 * sstep)), "l"(src + 3) : "memory");
+        };
         if (y >= 1 && y <= 12) {                                        // the groups no event will fetch for the first rows (first event: d = 4)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smine), "l"(Srow) : "memory");
-            if (4 < ldS) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smine + (uint32_t)strideB), "l"(Srow + 4) : "memory");
-            if (8 < ldS) asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smine + (uint32_t)(2 * strideB)), "l"(Srow + 8) : "memory");
+            fetch_group(0);
+            if (4 < ldS) fetch_group(1);
+            if (8 < ldS) fetch_group(2);
         }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
         asm volatile("cp.async.wait_group 0;\n" ::: "memory");
@@ -130,61 +164,68 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         const uint32_t a_up = ringa + (uint32_t)yc * 16u;               // + ring row: the cell of row y-1
         const uint32_t a_me = a_up + 16u;                               // ... of row y
         size_t cidx = (size_t)pitch + (size_t)yc;                       // cell index on anti-diagonal 1 (N2 >= 3: no row offset yet)
-        int rb0 = pitchB, rb1 = 0, rb2 = (RING - 1) * pitchB;           // ring rows of anti-diagonals d, d-1, d-2 (byte offsets)
+        int rb0 = pitchB, rb1 = 0;                                      // ring rows of anti-diagonals d, d-1 (byte offsets)
+        float wdiag = NINF;                                             // W(y-1, x-1): the W this thread read as its up neighbour one step ago
+        float2 left = make_float2(NINF, y == 0 ? start_init : NINF);    // (X, W)(y, x-1): this thread's last cell
+        float w0p = NINF, w1p = NINF;                                   // W(yp_k, x): last step's look-ahead reads (the diagonal candidates' W now)
         for (int d = 1; d <= dmax; ++d) {
             const int x = d - y;
             if ((d & 3) == 0) {                                         // S prefetch event (warp-uniform): the group 9 .. 12 columns ahead
                 const int q = (x >> 2) + 3;
-                if (y >= 1 && q >= 0 && 4 * q < ldS)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(smine + (uint32_t)((q & 3) * strideB)), "l"(Srow + 4 * q) : "memory");
+                if (y >= 1 && q >= 0 && 4 * q < ldS) fetch_group(q);
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
                 asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // the group of the previous event has landed
             }
             const int xcl = min(max(x, 0), xmax);
             const float2 cc = lds64(cia + (uint32_t)xcl * 8u);          // ex of the column's adjacent edge, flags
-            const float s = lds32(smine + (uint32_t)(((xcl >> 2) & 3) * strideB + (xcl & 3) * 4));
-            const float4 cu = lds128(a_up + (uint32_t)rb1);             // (y-1, x)
-            const float4 cd = lds128(a_up + (uint32_t)rb2);             // (y-1, x-1)
-            const float4 cl = lds128(a_me + (uint32_t)rb1);             // (y, x-1); at x = 0 the slot still holds -inf
+            const float s = lds32(smine + (uint32_t)((xcl & 15) * sstep));
+            const float2 cu = lds64(a_up + (uint32_t)rb1 + 8u);         // (Y, W)(y-1, x)
             const float ex = cc.x;
             const int cflags = __float_as_int(cc.y);
+            float2 cl = left;                                           // (X, W)(y, x-1): this thread, last anti-diagonal ...
+            if (cflags & 2) cl = lds64(a_me + (uint32_t)rb1);           // ... unless that column's threads made it
             const float giy = x == 0 ? start_gap : gap_init;            // column 0: GraphAlign.h:212-222
-            float ys = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, giy)), ey);
-            float m = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
-            const float xs = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gix)), ex);
+            float ys = __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, giy)), ey);
+            float m = __fsub_rn(__fsub_rn(__fadd_rn(wdiag, s), ey), ex);
+            const float xs = __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gix)), ex);
+            wdiag = cu.y;
             if (x == 0) m = NINF;                                       // S(y, 0) is not defined
             if (spec) { m = fmaxf(m, m_pre); ys = fmaxf(ys, ys_pre); }
-            const float4 out = make_float4(m, xs, ys, fmaxf(m, fmaxf(xs, ys)));
-            if (yvalid && (unsigned)x <= (unsigned)xmax && !(cflags & 1)) {     // a non-chain column's cell belongs to its column threads
-                sts128(a_me + (uint32_t)rb0, out);
-                C[cidx] = out;
+            const float w = fmaxf(m, fmaxf(xs, ys));
+            const bool active = yvalid && (unsigned)x <= (unsigned)xmax;
+            if (active) left = make_float2(xs, w);
+            if (active && !(cflags & 1)) {                              // a non-chain column's cell belongs to its column threads
+                sts128(a_me + (uint32_t)rb0, make_float4(xs, w, ys, w));
+                C[cidx] = make_float4(m, xs, ys, w);
             }
             if (spec) {                                                 // look-ahead: the extra predecessors' candidates of cell (y, x+1)
                 const int xn = x + 1;
                 const int xnc = min(max(xn, 0), xmax);
                 const bool usable = yvalid && (unsigned)xn <= (unsigned)xmax;
                 const float2 cn = lds64(cia + (uint32_t)xnc * 8u);
-                const float sn = lds32(smine + (uint32_t)(((xnc >> 2) & 3) * strideB + (xnc & 3) * 4));
+                const float sn = lds32(smine + (uint32_t)((xnc & 15) * sstep));
                 const float gin = xn == 0 ? start_gap : gap_init;
                 const bool use0 = usable && wr.nextra > 0, use1 = usable && wr.nextra > 1;      // (an unused slot must not fetch from L2)
-                const float4 u0 = cell(yp0, xnc, d, use0), u1 = cell(yp1, xnc, d, use1);
-                const float4 v0 = cell(yp0, xnc - 1, d, use0 && xn > 0), v1 = cell(yp1, xnc - 1, d, use1 && xn > 0);
-                float yq = fmaxf(__fsub_rn(fmaxf(__fadd_rn(u0.z, gap_extend), __fadd_rn(u0.w, gin)), ey0),
-                                 __fsub_rn(fmaxf(__fadd_rn(u1.z, gap_extend), __fadd_rn(u1.w, gin)), ey1));
-                float mq = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(v0.w, sn), ey0), cn.x), __fsub_rn(__fsub_rn(__fadd_rn(v1.w, sn), ey1), cn.x));
+                // (Y, W)(yp_k, x+1) is read now; W(yp_k, x), the diagonal candidate's, is what this thread read one step ago
+                const float2 u0 = cell_yw(yp0, xnc, d, use0), u1 = cell_yw(yp1, xnc, d, use1);
+                float yq = fmaxf(__fsub_rn(fmaxf(__fadd_rn(u0.x, gap_extend), __fadd_rn(u0.y, gin)), ey0),
+                                 __fsub_rn(fmaxf(__fadd_rn(u1.x, gap_extend), __fadd_rn(u1.y, gin)), ey1));
+                float mq = fmaxf(__fsub_rn(__fsub_rn(__fadd_rn(w0p, sn), ey0), cn.x), __fsub_rn(__fsub_rn(__fadd_rn(w1p, sn), ey1), cn.x));
+                w0p = u0.y; w1p = u1.y;
                 if (wr.nextra > 2)                                      // rare: the rest of the list
                     for (int k = 2; k < wr.nextra; ++k) {
                         const int yp = lds32i(sxia + (uint32_t)(wr.rest + k) * 4u);
                         const float eyk = lds32(sxva + (uint32_t)(wr.rest + k) * 4u);
-                        const float4 u = cell(yp, xnc, d, usable), v = cell(yp, xnc - 1, d, usable && xn > 0);
-                        yq = fmaxf(yq, __fsub_rn(fmaxf(__fadd_rn(u.z, gap_extend), __fadd_rn(u.w, gin)), eyk));
-                        mq = fmaxf(mq, __fsub_rn(__fsub_rn(__fadd_rn(v.w, sn), eyk), cn.x));
+                        const float2 u = cell_yw(yp, xnc, d, usable);
+                        const float vw = cell_w(yp, xnc - 1, d, usable && xn > 0);
+                        yq = fmaxf(yq, __fsub_rn(fmaxf(__fadd_rn(u.x, gap_extend), __fadd_rn(u.y, gin)), eyk));
+                        mq = fmaxf(mq, __fsub_rn(__fsub_rn(__fadd_rn(vw, sn), eyk), cn.x));
                     }
                 if (xn <= 0) mq = NINF;
                 m_pre = mq; ys_pre = yq;
             }
             cidx += (size_t)pitch - (d >= N2 - 1 ? 1 : 0);
-            rb2 = rb1; rb1 = rb0; rb0 += pitchB; if (rb0 == ringB) rb0 = 0;
+            rb1 = rb0; rb0 += pitchB; if (rb0 == ringB) rb0 = 0;
             WAVE_SYNC();
         }
     } else {
@@ -207,20 +248,20 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         WAVE_SYNC();
         size_t cidx = (size_t)pitch + (size_t)(1 - xc);                 // index of (d - xc, xc) on anti-diagonal d = 1 (wraps while inactive)
         int rb0 = pitchB, rb1 = 0;
-        const uint32_t sbase = sringa + (uint32_t)(((xc >> 2) & 3) * strideB + (xc & 3) * 4);
+        const uint32_t sbase = sringa + (uint32_t)((xc & 15) * max_tr * 4);  // S(., xc): word (xc & 15) * max_tr + row slot
         for (int d = 1; d <= dmax; ++d) {
             const int yy = d - xc;
             {   // fold the adjacent candidates, write the cell (lane 0 of the column's lanes)
                 const int yyc = min(max(yy, 0), N1 - 2);
-                const float4 cu = lds128(ringa + (uint32_t)(rb1 + yyc * 16));          // (yy-1, xc)
-                const float4 cl = lds128(ringa + (uint32_t)(rb1 + yyc * 16 + 16));     // (yy, xc-1)
+                const float2 cu = lds64(ringa + (uint32_t)(rb1 + yyc * 16 + 8));       // (Y, W)(yy-1, xc)
+                const float2 cl = lds64(ringa + (uint32_t)(rb1 + yyc * 16 + 16));      // (X, W)(yy, xc-1)
                 const float gi = yy == 0 ? start_gap : gap_init;
-                const float ys = fmaxf(ys_pre, __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey_up));
-                const float xs = fmaxf(xs_pre, __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gi)), exl));
-                const float4 out = make_float4(m_pre, xs, ys, fmaxf(m_pre, fmaxf(xs, ys)));
+                const float ys = fmaxf(ys_pre, __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, gap_init)), ey_up));
+                const float xs = fmaxf(xs_pre, __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gi)), exl));
+                const float w = fmaxf(m_pre, fmaxf(xs, ys));
                 if (is_col && lq == 0 && (unsigned)yy <= (unsigned)(N1 - 2)) {
-                    sts128(ringa + (uint32_t)(rb0 + yyc * 16 + 16), out);
-                    C[cidx] = out;
+                    sts128(ringa + (uint32_t)(rb0 + yyc * 16 + 16), make_float4(xs, w, ys, w));
+                    C[cidx] = make_float4(m_pre, xs, ys, w);
                 }
             }
             {   // look-ahead: every candidate of (yn, xc) that is at least two anti-diagonals back
@@ -229,7 +270,7 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                 const bool usable = is_col && (unsigned)yn <= (unsigned)(N1 - 2);
                 const float4 nyv = lds128(n1a + (uint32_t)ync * 16u);          // NodeInfo: ptr, cnt, idx0, val0
                 const int ny_ptr = __float_as_int(nyv.x), c1 = NI_CNT(__float_as_int(nyv.y));
-                const float s = lds32(sbase + (uint32_t)lds16u(rowslota + (uint32_t)ync * 2u) * 16u);
+                const float s = lds32(sbase + (uint32_t)lds16u(rowslota + (uint32_t)ync * 2u) * 4u);
                 const float gi = yn == 0 ? start_gap : gap_init;
                 float m = NINF, xs = NINF, ys = NINF;
                 // one pair (row predecessor ky, column predecessor kx): its M candidate, and the Y candidate of ky / the X
@@ -242,12 +283,12 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                         eyk = ky ? lds32(p1va + (uint32_t)(ny_ptr + ky) * 4u) : nyv.w;
                     }
                     const bool has_y = usable && ky < c1, has_x = usable && kx < c2;
-                    const float4 cd = cell(yp, xp, d, has_y && has_x);  // anti-diagonal d + 1 - dy - dx <= d - 1
-                    const float4 cu = cell(yp, xc, d, has_y && yp != yn - 1);
-                    const float4 cl = cell(ync, xp, d, has_x && xp != xc - 1);
-                    const float mc = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), eyk), exk);
-                    const float yv = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), eyk);
-                    const float xv = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gi)), exk);
+                    const float cdw = cell_w(yp, xp, d, has_y && has_x);     // anti-diagonal d + 1 - dy - dx <= d - 1
+                    const float2 cu = cell_yw(yp, xc, d, has_y && yp != yn - 1);
+                    const float2 cl = cell_xw(ync, xp, d, has_x && xp != xc - 1);
+                    const float mc = __fsub_rn(__fsub_rn(__fadd_rn(cdw, s), eyk), exk);
+                    const float yv = __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, gap_init)), eyk);
+                    const float xv = __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gi)), exk);
                     m = fmaxf(m, mc);
                     ys = fmaxf(ys, yp == yn - 1 ? NINF : yv);           // the adjacent edges' candidates are folded when the cell is made
                     xs = fmaxf(xs, xp == xc - 1 ? NINF : xv);
