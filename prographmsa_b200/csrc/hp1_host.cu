@@ -313,7 +313,10 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 if (q > 8 && Cpick && !env.strip_c) continue;       // wide strips (255 registers, one job per SM) only when the narrow ones do not fit
                 // cost model (cycles): steps x (fixed + per-slot); a full GPU prefers the fewest warp-steps, a small batch the shortest sweep
                 const double sweep = (double)(a.N - 1 + ns_q) * (500.0 + 70.0 * q);
-                const double cost = n_jobs >= 4 * 148 ? sweep * w_q : sweep;
+                // (the switch to "fewest warp-steps" used to sit at 4 jobs per SM; on the 1020-job bench batch the narrow strips
+                // are still the faster ones -- C = 4 with 4 warps 1.15 ms against 1.50 ms for C = 8 with 2 warps over its 452
+                // jobs, although the latter executes 16 % fewer instructions -- so it now needs 16 jobs per SM)
+                const double cost = n_jobs >= 16 * 148 ? sweep * w_q : sweep;
                 if (!Cpick || cost < best) { Cpick = q; best = cost; best_ns = ns_q; }
             }
             if (Cpick) {
@@ -875,10 +878,22 @@ int pgm_graph_batch_run(pgm_ctx* c, pgm_graph_batch* b) {
             if ((rc = join())) return rc;
         } else if (pipelined) {
             if ((rc = fork())) return rc;
+            // The emission of the BULK classes (more jobs than SMs) goes out first: these are short throughput kernels, and launched
+            // behind the long sweeps they only get the SMs those leave over, which delays the bulk's own fill (measured on the bench
+            // batch: 2.71-2.80 ms against 2.90-2.95 ms; PGM_NO_BULK_FIRST=1 for the A/B run)
+            std::vector<char> emitted(fl.size(), 0);
+            const bool bulk_first = !getenv("PGM_NO_BULK_FIRST");
+            for (size_t q = 0; q < fl.size() && !rc && bulk_first; ++q)
+                if (fl[q]->count > 148) {
+                    cudaStream_t sq = stream_of(q);
+                    const int* ord = d_order_all + sb.first + fl[q]->offset;
+                    pgm_ctx_time_begin_on(c, 3, sq, &tok); rc = emit(sq, fl[q]->count, ord, fl[q]->max_n1e, fl[q]->max_n2e); pgm_ctx_time_end(c, tok);
+                    emitted[q] = 1;
+                }
             for (size_t q = 0; q < fl.size() && !rc; ++q) {
                 cudaStream_t sq = stream_of(q);
                 const int* ord = d_order_all + sb.first + fl[q]->offset;
-                pgm_ctx_time_begin_on(c, 3, sq, &tok); rc = emit(sq, fl[q]->count, ord, fl[q]->max_n1e, fl[q]->max_n2e); pgm_ctx_time_end(c, tok);
+                if (!emitted[q]) { pgm_ctx_time_begin_on(c, 3, sq, &tok); rc = emit(sq, fl[q]->count, ord, fl[q]->max_n1e, fl[q]->max_n2e); pgm_ctx_time_end(c, tok); }
                 if (rc) break;
                 pgm_ctx_time_begin_on(c, 4, sq, &tok); rc = fill(sq, fl[q]); pgm_ctx_time_end(c, tok);
                 if (rc) break;
