@@ -52,42 +52,54 @@ emission_prep_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __r
     }
 }
 
-// grid = (tiles_x, tiles_y, n_jobs), block = (32, 8)
+// grid = (tiles_x, tiles_y, n_jobs), block = (32, 8).  NT: the number of states as a compile-time constant (20, 4, 61; 0 = run time):
+// the tile staging divides by it, and with a run-time divisor that division was half of the kernel's instructions
+// (ncu: 4.0 warp instructions per cell against 2 * 20 multiply / add).  The T tile is padded to 33 columns so that the transposing
+// stores are conflict-free; the g1 tile is stored as one float4 per (row quad, state), read as a broadcast.
+template <int NT>
 __global__ void __launch_bounds__(256)
-emission_exact_kernel(int n, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
+emission_exact_kernel(int n_rt, const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
+    const int n = NT ? NT : n_rt;
     const GraphJobDev& J = jobs[order ? order[blockIdx.z] : blockIdx.z];
     const int N1 = J.N1e, N2 = J.N2e;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     if (x0 >= N2 || y0 >= N1) return;
     extern __shared__ __align__(16) float sm[];
-    float* g1t = sm;                       // [n][32 rows]
-    float* Tt = sm + n * 32;               // [n][32 cols]
+    float* g1q = sm;                       // [8 row quads][n][4]
+    float* Tt = sm + n * 32;               // [n][33]
     const int tid = threadIdx.y * 32 + threadIdx.x;
-    for (int i = tid; i < n * 32; i += 256) {           // sites are n contiguous floats per node: coalesced
+    const float* __restrict__ src1 = J.sites1 + (size_t)n * y0;      // the tile's 32 nodes x n states are contiguous
+    const float* __restrict__ src2 = J.Tbuf + (size_t)n * x0;
+    const int lim1 = n * min(32, N1 - y0), lim2 = n * min(32, N2 - x0);
+    for (int i = tid; i < n * 32; i += 256) {
         const int yy = i / n, a = i - yy * n;
-        g1t[a * 32 + yy] = (y0 + yy < N1) ? J.sites1[(size_t)n * (y0 + yy) + a] : 0.f;
+        g1q[((yy >> 2) * n + a) * 4 + (yy & 3)] = i < lim1 ? src1[i] : 0.f;
     }
     for (int i = tid; i < n * 32; i += 256) {
         const int xx = i / n, a = i - xx * n;
-        Tt[a * 32 + xx] = (x0 + xx < N2) ? J.Tbuf[(size_t)n * (x0 + xx) + a] : 0.f;
+        Tt[a * 33 + xx] = i < lim2 ? src2[i] : 0.f;
     }
     __syncthreads();
     const int x = x0 + threadIdx.x;
     const int yl = threadIdx.y * 4;                      // 4 consecutive rows
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const float4* __restrict__ gq = reinterpret_cast<const float4*>(g1q) + threadIdx.y * n;
+#pragma unroll 4
     for (int a = 0; a < n; ++a) {                        // sequential-k, mul then add (no FMA)
-        const float t = Tt[a * 32 + threadIdx.x];
-        const float4 g = *reinterpret_cast<const float4*>(g1t + a * 32 + yl);
+        const float t = Tt[a * 33 + threadIdx.x];
+        const float4 g = gq[a];
         s0 = __fadd_rn(s0, __fmul_rn(g.x, t)); s1 = __fadd_rn(s1, __fmul_rn(g.y, t));
         s2 = __fadd_rn(s2, __fmul_rn(g.z, t)); s3 = __fadd_rn(s3, __fmul_rn(g.w, t));
     }
     if (x >= N2) return;
     const float vx = J.v[x], add = J.sc[2];              // match_init
     const float ss[4] = {s0, s1, s2, s3};
+    float* __restrict__ S = J.S;
+    const int ldS = J.ldS;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         const int y = y0 + yl + r;
-        if (y < N1) J.S[(size_t)y * J.ldS + x] = ls_log2_add(__fdiv_rn(ss[r], __fmul_rn(J.u[y], vx)), add);
+        if (y < N1) S[(size_t)y * ldS + x] = ls_log2_add(__fdiv_rn(ss[r], __fmul_rn(J.u[y], vx)), add);
     }
 }
 
@@ -106,8 +118,11 @@ int launch_emission_exact(cudaStream_t st, int n, int n_jobs, const GraphJobDev*
         int rc = launch_emission_prep(st, n, nj, dj, ord, max_N1 > max_N2 ? max_N1 : max_N2);
         if (rc) return rc;
         dim3 grid((max_N2 + 31) / 32, (max_N1 + 31) / 32, nj);
-        const size_t smem = sizeof(float) * n * 64;
-        emission_exact_kernel<<<grid, dim3(32, 8), smem, st>>>(n, dj, ord);
+        const size_t smem = sizeof(float) * n * 65;
+        if (n == 20) emission_exact_kernel<20><<<grid, dim3(32, 8), smem, st>>>(n, dj, ord);
+        else if (n == 4) emission_exact_kernel<4><<<grid, dim3(32, 8), smem, st>>>(n, dj, ord);
+        else if (n == 61) emission_exact_kernel<61><<<grid, dim3(32, 8), smem, st>>>(n, dj, ord);
+        else emission_exact_kernel<0><<<grid, dim3(32, 8), smem, st>>>(n, dj, ord);
         PGM_CUDA(cudaGetLastError());
     }
     return 0;
