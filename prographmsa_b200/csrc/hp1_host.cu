@@ -689,7 +689,12 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         static const int dcls[] = {192, 320, 448, 544, 672, 832, 1024, 1 << 30};
         auto class_of = [&](const GraphJobDev& J) {
             if (J.layout == GF_LAYOUT_STRIP) return J.sgen ? 400 + J.C + 32 * ((J.nstrips + 31) / 32) : 300 + J.C;
-            if (J.wave) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 500 + 16 * b->lay[&J - b->jobs.data()].wv_L + q; }
+            if (J.wave) {      // by graph-1 length and by block size (a launch's block is its largest job's: a job with many non-chain
+                               // columns must not make every other job of its launch carry hundreds of idle threads through the barriers)
+                int q = 0; while (J.N1 - 1 > dcls[q]) ++q;
+                const int lw = b->lay[&J - b->jobs.data()].wv_L, thr = J.wv_tr + ru32(J.wv_ncols * lw);
+                return 500 + 64 * lw + 16 * (thr <= 512 ? 0 : (thr <= 768 ? 1 : 2)) + q;
+            }
             if (J.bands > 1) return 200 + J.band_rows / 32;                   // banded anti-diagonal sweeps: their own launches, one per band height
             if (J.layout == GF_LAYOUT_DIAG) { int q = 0; while (J.N1 - 1 > dcls[q]) ++q; return 100 + q; }
             const int w = (J.nb + 31) / 32; return w <= 4 ? w : (w <= 6 ? 6 : (w <= 8 ? 8 : 16));
