@@ -190,6 +190,19 @@ int launch_graph_fill_strip(cudaStream_t st, int C, int n_jobs, const GraphJobDe
 //     (GraphAlign.h:238-260);
 //   * the 4 direction bits of every cell go to the strip's word as in the chain kernel; the predecessor-index fields of the
 //     cells in non-chain rows / columns go to two small side arrays (RowIdx / ColIdx) that the traceback consults.
+// A float2 array in shared memory, addressed with a 32-bit shared-window address and explicit ld.shared / st.shared: through
+// generic pointers the compiler re-derived the window base (S2R SR_CgaCtaId + LEA) in front of most of the 15 access sites of
+// the step loop (39 S2R in the SASS of one instantiation)
+struct SharedF2 {
+    uint32_t a;
+    __device__ __forceinline__ float2 ld(size_t i) const {
+        float2 v; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a + (uint32_t)i * 8u)); return v;
+    }
+    __device__ __forceinline__ void st(size_t i, float2 v) const {
+        asm volatile("st.shared.v2.f32 [%0], {%1,%2};" ::"r"(a + (uint32_t)i * 8u), "f"(v.x), "f"(v.y) : "memory");
+    }
+    __device__ __forceinline__ SharedF2 at(size_t i) const { return SharedF2{a + (uint32_t)i * 8u}; }
+};
 #define SG_MAXP 4            // column predecessors of a special column held in registers (more: read from the lists)
 template <int C, int WB>     // WB: most warps per job of the launch (1, 2, 4 or SG_MAX_WARPS); the smaller ones leave room for several jobs per SM
 __global__ void __launch_bounds__(32 * WB, WB >= 8 ? 1 : 12 / WB)
@@ -207,8 +220,12 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
     const int N1 = J.N1, ns = J.nstrips, ldS = J.ldS, RRm = J.ring_rows - 1, RR = J.ring_rows, HR = J.hist_rows, HRm = J.hist_rows - 1;
     const int NSP = (ns + 31) & ~31;
     const int dbg = J.dbg;
-    float2* ring = (float2*)sg_smem;                                // [nsrc][RR]: (X, W)(y, source column) of the last RR rows
-    float2* hist = ring + (size_t)J.nsrc * RR;                      // [HR][C + 1][NSP]: (Y, W)(row, slot) per strip; slot C = (X, W) of the strip's last column
+    uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(sg_smem), hand_a = (uint32_t)__cvta_generic_to_shared(&hand[0][0]);
+    asm volatile("mov.u32 %0, %0;" : "+r"(smem_a));                 // opaque: kept in registers instead of being rematerialised at every use
+    asm volatile("mov.u32 %0, %0;" : "+r"(hand_a));
+    const SharedF2 ring{smem_a};                                    // [nsrc][RR]: (X, W)(y, source column) of the last RR rows
+    const SharedF2 hist{smem_a + (uint32_t)((size_t)J.nsrc * RR * 8)};   // [HR][C + 1][NSP]: (Y, W)(row, slot) per strip; slot C = (X, W) of the strip's last column
+    const SharedF2 handv{hand_a};                                   // hand[w][p] at w * 2 + p
     const float gap_init = J.sc[0], gap_extend = J.sc[1], start_gap = J.sc[6], start_init = J.sc[7];
     const float NINF = -CUDART_INF_F;
     const float* __restrict__ S = J.S;
@@ -284,8 +301,8 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
         else { yp = __ldg(p1_idx + ri.ptr + ky); ey = __ldg(p1_val + ri.ptr + ky); kq = NI_KEEP(__ldg(&ni1[yp].cnt)); }
     };
     // the rings start at -inf: a dummy predecessor (infinite edge) may read a row nobody has written yet, and -inf stays -inf
-    for (int i = L; i < J.nsrc * RR + HR * (C + 1) * NSP; i += (int)blockDim.x) ring[i] = make_float2(NINF, NINF);
-    if (L < 2 * SG_MAX_WARPS) hand[L >> 1][L & 1] = make_float2(NINF, NINF);   // a warp's first strip reads the hand-over before the previous warp's last strip has started: row -1 is -inf
+    for (int i = L; i < J.nsrc * RR + HR * (C + 1) * NSP; i += (int)blockDim.x) ring.st(i, make_float2(NINF, NINF));
+    if (L < 2 * SG_MAX_WARPS) handv.st(L, make_float2(NINF, NINF));   // a warp's first strip reads the hand-over before the previous warp's last strip has started: row -1 is -inf
     __syncthreads();
     int y = -L;                                                     // the row of step t is t - L
     RowInfo cur = rzero, n1 = rzero;
@@ -303,7 +320,7 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
         float gX = __shfl_up_sync(0xffffffffu, outX, 1), gW = __shfl_up_sync(0xffffffffu, outW, 1);   // (y, x0 - 1) from strip L - 1
         if (lane == 0) {
             if (WB == 1 || warp == 0) { gX = NINF; gW = NINF; }
-            else { const float2 h = hand[warp - 1][(t + 1) & 1]; gX = h.x; gW = h.y; }
+            else { const float2 h = handv.ld((warp - 1) * 2 + ((t + 1) & 1)); gX = h.x; gW = h.y; }
         }
         RowInfo n2 = rzero;
         if (lane_on) {                                              // two rows ahead: row record; one row ahead: S (consumed next step)
@@ -333,7 +350,7 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
             auto publish = [&](const int k, float mk, float xs, float ysk, float w) {
                 if ((wsrc >> k) & 1u) {
                     if ((mysrc >> k) & 1u) {
-                        ring[(size_t)(srck[k] & 0xffff) * RR + (y & RRm)] = make_float2(xs, w);
+                        ring.st((size_t)(srck[k] & 0xffff) * RR + (y & RRm), make_float2(xs, w));
                         const int kc = (srck[k] >> 16) - 1;
                         if (kc >= 0) Vcol[(size_t)kc * ldVc + y] = make_float4(mk, xs, ysk, w);
                     }
@@ -373,7 +390,7 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                 // W(yp, x0 - 1) of an earlier row: the neighbour strip's history, else the value store
                 auto w_left_of_strip = [&](int yp, int kq) -> float {
                     if (x0 == 0) return NINF;
-                    if (y - yp <= HR - 2) return hist[((size_t)(yp & HRm) * (C + 1) + C) * NSP + (L - 1)].y;
+                    if (y - yp <= HR - 2) return hist.ld(((size_t)(yp & HRm) * (C + 1) + C) * NSP + (L - 1)).y;
                     return kq < 0 ? CUDART_NAN_F : __ldcg(Vrow + (size_t)kq * ldVr + (x0 - 1)).w;
                 };
                 // ---- phase 1: row predecessors -> ys[k], m[k] (through the chain column edge x-1 -> x), index fields ----
@@ -403,12 +420,12 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                 const bool slowrow = c1 > 2 || !near0 || !near1;
                 {
                     const int r0 = (c1 > 0 && near0) ? (yp0 & HRm) : (y & HRm), r1 = (c1 > 1 && near1) ? (yp1 & HRm) : r0;
-                    const float2* h0 = hist + ((size_t)r0 * (C + 1)) * NSP + L;
-                    const float2* h1 = hist + ((size_t)r1 * (C + 1)) * NSP + L;
+                    const SharedF2 h0 = hist.at(((size_t)r0 * (C + 1)) * NSP + L);
+                    const SharedF2 h1 = hist.at(((size_t)r1 * (C + 1)) * NSP + L);
                     float2 win0[C], win1[C];
 #pragma unroll
-                    for (int k = 0; k < C; ++k) { win0[k] = h0[(size_t)k * NSP]; win1[k] = h1[(size_t)k * NSP]; }
-                    const float wp0 = (x0 == 0) ? NINF : h0[(size_t)C * NSP - 1].y, wp1 = (x0 == 0) ? NINF : h1[(size_t)C * NSP - 1].y;
+                    for (int k = 0; k < C; ++k) { win0[k] = h0.ld((size_t)k * NSP); win1[k] = h1.ld((size_t)k * NSP); }
+                    const float wp0 = (x0 == 0) ? NINF : h0.ld((size_t)C * NSP - 1).y, wp1 = (x0 == 0) ? NINF : h1.ld((size_t)C * NSP - 1).y;
                     fold(0u, ey0, true, win0, wp0);
                     fold(1u, ey1, false, win1, wp1);
                 }
@@ -420,9 +437,9 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                         row_pred(cur, ky, yp, ey, kq);
                         float2 win[C]; float wprev;
                         if (y - yp <= HR - 2) {                     // recent row: the strip's history ring
-                            const float2* hb = hist + ((size_t)(yp & HRm) * (C + 1)) * NSP + L;
+                            const SharedF2 hb = hist.at(((size_t)(yp & HRm) * (C + 1)) * NSP + L);
 #pragma unroll
-                            for (int k = 0; k < C; ++k) win[k] = hb[(size_t)k * NSP];
+                            for (int k = 0; k < C; ++k) win[k] = hb.ld((size_t)k * NSP);
                             wprev = w_left_of_strip(yp, -1);
                         } else {                                    // a kept row of the value store
                             const float4* base = Vrow + (size_t)(kq < 0 ? 0 : kq) * ldVr + x0;
@@ -445,12 +462,12 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                     // W(yp, xp) for the M pairs: the source ring, the neighbour strip's history, the value store
                     auto w_cell = [&](int yp, int kq, int xp, int src) -> float {
                         if (src < 0) return w_left_of_strip(yp, kq);
-                        if (yp == y - 1 || y - yp < RR - 1 - ns) return ring[(size_t)src * RR + (yp & RRm)].y;
+                        if (yp == y - 1 || y - yp < RR - 1 - ns) return ring.ld((size_t)src * RR + (yp & RRm)).y;
                         return kq < 0 ? CUDART_NAN_F : __ldcg(Vrow + (size_t)kq * ldVr + xp).w;
                     };
                     auto x_cand = [&](uint32_t kx, int src, float exj) {
                         float Xv = xl, Wv = wl;
-                        if (src >= 0) { const float2 q = ring[(size_t)src * RR + (y & RRm)]; Xv = q.x; Wv = q.y; }
+                        if (src >= 0) { const float2 q = ring.ld((size_t)src * RR + (y & RRm)); Xv = q.x; Wv = q.y; }
                         const float cE = __fsub_rn(__fadd_rn(Xv, gap_extend), exj), cO = __fsub_rn(__fadd_rn(Wv, gix), exj);
                         if (cE > xg) { xg = cE; dg = (dg & ~XF) | (kx << (4 + 3 * B)); }
                         if (cO > xg) { xg = cO; dg = (dg & ~XF) | (kx << (4 + 3 * B)) | DIR_XOPEN; }
@@ -519,14 +536,14 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                 }
             }
             {   // history ring: this row's (Y,W) per slot, and (X,W) of the strip's last column
-                float2* hb = hist + ((size_t)(y & HRm) * (C + 1)) * NSP + L;
+                const SharedF2 hb = hist.at(((size_t)(y & HRm) * (C + 1)) * NSP + L);
 #pragma unroll
-                for (int k = 0; k < C; ++k) hb[(size_t)k * NSP] = make_float2(Yup[k], Wup[k]);
-                hb[(size_t)C * NSP] = make_float2(xl, wl);
+                for (int k = 0; k < C; ++k) hb.st((size_t)k * NSP, make_float2(Yup[k], Wup[k]));
+                hb.st((size_t)C * NSP, make_float2(xl, wl));
             }
             if (L == 0) Vcol[(size_t)kc0 * ldVc + y] = make_float4(m0, xs0, ys0, w0);   // column 0 is always kept
             outX = xl; outW = wl;
-            if (WB > 1 && lane == 31) hand[warp][t & 1] = make_float2(xl, wl);
+            if (WB > 1 && lane == 31) handv.st(warp * 2 + (t & 1), make_float2(xl, wl));
             uint32_t* dp = D + ((size_t)t * ns + L) * W32;
             if (W32 == 1) dp[0] = rr[0];
             else if (W32 == 2) *reinterpret_cast<uint2*>(dp) = make_uint2(rr[0], rr[1]);
