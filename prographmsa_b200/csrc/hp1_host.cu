@@ -91,7 +91,7 @@ struct JobLayout {                // byte offsets into the upload arena / scratc
     int dbits, ldVr, ldVc, nkr, nkc;
     int C, nstrips, N1e, N2e, coded1, coded2;
     int sgen, nsrc, ring_rows, hist_rows, swarps, nstrips_gen, nnc1, nnc2, ldRI, ldCI;
-    int wave, wv_tr, wv_chain_pad, wv_ncols, wv_nx, wv_L;       // role-sorted anti-diagonal kernel (hp1_wave.cu)
+    int wave, wv_tr, wv_chain_pad, wv_ncols, wv_nx, wv_L, wv_tcols;       // role-sorted anti-diagonal kernel (hp1_wave.cu)
     size_t wv_rows, wv_cols, wv_ci, wv_rowslot, wv_xi, wv_xv, wv_adj1;
     size_t scol, sstart, colstrip, specmask, srcmask, colsrc_off, ncidx1_off, ncidx2_off, rinfo_off, RowIdx, ColIdx;
     std::vector<int16_t> colsrc; std::vector<int> ncidx1, ncidx2;
@@ -358,12 +358,29 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.pitch = L.layout == GF_LAYOUT_DIAG ? (int)align_up((size_t)std::min(a.N, bb.N), 32) : (int)align_up((size_t)L.nb, 8);
         // Role-sorted anti-diagonal kernel (hp1_wave.cu): a thread per row (chain rows and non-chain rows in separate warps) plus
         // wv_L threads per non-chain column, all in one CTA
-        L.wave = 0; L.wv_tr = L.wv_chain_pad = L.wv_ncols = L.wv_nx = L.wv_L = 0;
+        L.wave = 0; L.wv_tr = L.wv_chain_pad = L.wv_ncols = L.wv_nx = L.wv_L = L.wv_tcols = 0;
         if (env.wave && L.layout == GF_LAYOUT_DIAG && L.bands == 1 && a.N >= 3 && bb.N >= 3) {
             const int nspec = generic1, nchain = (a.N - 1) - generic1;          // rows 0 .. N1-2; row 0 sweeps with the chain rows
             const int tr = ru32(nchain) + ru32(nspec);
+            // column lane groups: a non-chain column is busy for N1 - 1 anti-diagonals, so a group can take column r + T once
+            // column r is done -- T = the most non-chain columns in any window of N1 - 1 consecutive columns
+            int tcols = 0;
+            {
+                std::vector<int> xs_;
+                for (int x = 1; x <= bb.N - 2; ++x) if (non_chain_node(bb, x)) xs_.push_back(x);
+                size_t lo = 0;
+                for (size_t hi = 0; hi < xs_.size(); ++hi) {
+                    while (xs_[hi] - xs_[lo] >= a.N - 1) ++lo;          // x_hi < x_lo + N1 - 1: still in flight together
+                    tcols = std::max(tcols, (int)(hi - lo + 1));
+                }
+            }
+            // Lanes per non-chain column.  Measured level by level on 1000- and 5000-sequence passes (tools/wave_vs_diag_levels.py): with
+            // 4 lanes per column and up to ~130 columns in flight the wave kernel wins (0.92 against 1.20 ms ... 1.85 against 2.17 ms); on the
+            // deep profiles further up (150-500 non-chain columns: only 1-2 lanes per column fit a CTA) the thread-per-row kernel is as fast
+            // or faster (7.5 against 12.6 ms at 688 x 1389 with 134 + 486 non-chain nodes), so those keep it.  PGM_WAVE_L forces a width.
             int lw = 0;
-            for (int q : {4, 2, 1}) if ((!env.wave_L || env.wave_L == q) && tr + ru32(generic2 * q) <= 1024) { lw = q; break; }
+            for (int q : {4, 2, 1}) if ((!env.wave_L || env.wave_L == q) && tr + ru32(tcols * q) <= 1024) { lw = q; break; }
+            if (!env.wave_L && (lw != 4 || tcols > 128)) lw = 0;
             int nx = 0;
             bool dup = false;                                       // two list entries from the adjacent predecessor: not handled by the look-ahead split
             for (int w = 0; w < 2; ++w) {
@@ -377,7 +394,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                     }
             }
             if (lw && !dup && wave_smem_bytes(8, a.N, bb.N, tr, L.np1, nx) <= 227 * 1024) {
-                L.wave = 1; L.wv_tr = tr; L.wv_chain_pad = ru32(nchain); L.wv_ncols = generic2; L.wv_nx = nx; L.wv_L = lw;
+                L.wave = 1; L.wv_tr = tr; L.wv_chain_pad = ru32(nchain); L.wv_ncols = generic2; L.wv_nx = nx; L.wv_L = lw; L.wv_tcols = tcols;
             }
         }
         {   // keep sets of the strip kernels (see mark_far_sources); the dense kernels keep everything
@@ -652,7 +669,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                 }
             }
         }
-        J.wave = L.wave; J.wv_tr = L.wv_tr; J.wv_ncols = L.wv_ncols; J.wv_nx = L.wv_nx; J.wv_chain_pad = L.wv_chain_pad;
+        J.wave = L.wave; J.wv_tr = L.wv_tr; J.wv_ncols = L.wv_ncols; J.wv_nx = L.wv_nx; J.wv_chain_pad = L.wv_chain_pad; J.wv_tcols = L.wv_tcols;
         J.wv_adj1 = (const float*)(din + L.wv_adj1);
         J.wv_rows = (const WaveRow*)(din + L.wv_rows); J.wv_cols = (const WaveCol*)(din + L.wv_cols); J.wv_ci = (const WaveCI*)(din + L.wv_ci);
         J.wv_rowslot = (const uint16_t*)(din + L.wv_rowslot); J.wv_xi = (const int*)(din + L.wv_xi); J.wv_xv = (const float*)(din + L.wv_xv);
@@ -692,7 +709,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             if (J.wave) {      // by graph-1 length and by block size (a launch's block is its largest job's: a job with many non-chain
                                // columns must not make every other job of its launch carry hundreds of idle threads through the barriers)
                 int q = 0; while (J.N1 - 1 > dcls[q]) ++q;
-                const int lw = b->lay[&J - b->jobs.data()].wv_L, thr = J.wv_tr + ru32(J.wv_ncols * lw);
+                const int lw = b->lay[&J - b->jobs.data()].wv_L, thr = J.wv_tr + ru32(J.wv_tcols * lw);
                 return 500 + 64 * lw + 16 * (thr <= 512 ? 0 : (thr <= 768 ? 1 : 2)) + q;
             }
             if (J.bands > 1) return 200 + J.band_rows / 32;                   // banded anti-diagonal sweeps: their own launches, one per band height
@@ -740,7 +757,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                     f.max_n1e = std::max(f.max_n1e, J.N1e); f.max_n2e = std::max(f.max_n2e, J.N2e);
                     f.ring_bytes = std::max(f.ring_bytes, (size_t)J.nsrc * J.ring_rows * 8 + (size_t)J.hist_rows * (size_t)(J.C + 1) * ((J.nstrips + 31) & ~31) * 8);
                     if (J.wave) {
-                        f.wthreads = std::max(f.wthreads, J.wv_tr + ru32(J.wv_ncols * f.wL)); f.max_tr = std::max(f.max_tr, J.wv_tr);
+                        f.wthreads = std::max(f.wthreads, J.wv_tr + ru32(J.wv_tcols * f.wL)); f.max_tr = std::max(f.max_tr, J.wv_tr);
                         f.max_np1 = std::max(f.max_np1, J.np1); f.max_nx = std::max(f.max_nx, J.wv_nx);
                     }
                     ++f.count; ++p;

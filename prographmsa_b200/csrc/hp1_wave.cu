@@ -230,25 +230,30 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         }
     } else {
         // ================================================ column threads =====================================================
+        // A group of L lanes sweeps the non-chain columns r, r + TCG, r + 2 TCG, ... one after the other: a column is busy for
+        // N1 - 1 consecutive anti-diagonals, and the host chose TCG so that column r + TCG starts after column r has ended (graph 2
+        // may be far longer than graph 1: at most ~N1 columns are in flight at a time, whatever N2 is)
         const int cq = tid - TR;
-        const bool is_col = cq < NSC * L;
+        const int TCG = J.wv_tcols;
+        int cr = cq / L;                                                // the column's rank among the non-chain columns
+        bool is_col = cq < TCG * L && cr < NSC;
         WaveCol wc = {0, 0, 0, 0.f, 0, 0.f, 0, 0.f};
-        if (is_col) wc = J.wv_cols[cq / L];
-        const int xc = is_col ? wc.x : 1, c2 = wc.cnt;
+        if (is_col) wc = J.wv_cols[cr];
+        int xc = is_col ? wc.x : 1, c2 = wc.cnt;
         const int lq = cq & (L - 1);
         const int kyq = L == 4 ? (lq >> 1) : 0, kxq = L >= 2 ? (lq & 1) : 0;
         constexpr int SY = L == 4 ? 2 : 1, SX = L >= 2 ? 2 : 1;
         const unsigned gmask = L == 1 ? 0u : (((1u << L) - 1u) << ((tid & 31) & ~(L - 1)));
-        const float exl = is_col ? wc.ex_adj_col : PINF;                // value of the edge x-1 -> x, +inf if there is none
+        float exl = is_col ? wc.ex_adj_col : PINF;                      // value of the edge x-1 -> x, +inf if there is none
         const int* __restrict__ P2I = J.p2_idx; const float* __restrict__ P2V = J.p2_val;
         // this lane's first column predecessor in registers; an absent one is (column 0, +inf)
-        const int xpq = kxq < c2 ? (kxq == 0 ? wc.xp0 : wc.xp1) : 0;
-        const float exq = kxq < c2 ? (kxq == 0 ? wc.ex0 : wc.ex1) : PINF;
+        int xpq = kxq < c2 ? (kxq == 0 ? wc.xp0 : wc.xp1) : 0;
+        float exq = kxq < c2 ? (kxq == 0 ? wc.ex0 : wc.ex1) : PINF;
         float m_pre = NINF, xs_pre = NINF, ys_pre = NINF, ey_up = PINF;
         WAVE_SYNC();
-        size_t cidx = (size_t)pitch + (size_t)(1 - xc);                 // index of (d - xc, xc) on anti-diagonal d = 1 (wraps while inactive)
+        size_t cidx0 = (size_t)pitch;                                   // index of row 0's cell on anti-diagonal d (as for the row threads)
         int rb0 = pitchB, rb1 = 0;
-        const uint32_t sbase = sringa + (uint32_t)((xc & 15) * max_tr * 4);  // S(., xc): word (xc & 15) * max_tr + row slot
+        uint32_t sbase = sringa + (uint32_t)((xc & 15) * max_tr * 4);   // S(., xc): word (xc & 15) * max_tr + row slot
         for (int d = 1; d <= dmax; ++d) {
             const int yy = d - xc;
             {   // fold the adjacent candidates, write the cell (lane 0 of the column's lanes)
@@ -261,11 +266,23 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                 const float w = fmaxf(m_pre, fmaxf(xs, ys));
                 if (is_col && lq == 0 && (unsigned)yy <= (unsigned)(N1 - 2)) {
                     sts128(ringa + (uint32_t)(rb0 + yyc * 16 + 16), make_float4(xs, w, ys, w));
-                    C[cidx] = make_float4(m_pre, xs, ys, w);
+                    C[cidx0 + (size_t)yyc] = make_float4(m_pre, xs, ys, w);
                 }
             }
+            if (is_col && yy >= N1 - 2) {                               // the column's last cell is made: on to column r + TCG
+                cr += TCG;
+                is_col = cr < NSC;
+                if (is_col) {
+                    wc = J.wv_cols[cr];
+                    xc = wc.x; c2 = wc.cnt; exl = wc.ex_adj_col;
+                    xpq = kxq < c2 ? (kxq == 0 ? wc.xp0 : wc.xp1) : 0;
+                    exq = kxq < c2 ? (kxq == 0 ? wc.ex0 : wc.ex1) : PINF;
+                    sbase = sringa + (uint32_t)((xc & 15) * max_tr * 4);
+                }
+                m_pre = NINF; xs_pre = NINF; ys_pre = NINF; ey_up = PINF;
+            }
             {   // look-ahead: every candidate of (yn, xc) that is at least two anti-diagonals back
-                const int yn = yy + 1;
+                const int yn = d - xc + 1;                              // (the column may have just changed)
                 const int ync = min(max(yn, 0), N1 - 2);
                 const bool usable = is_col && (unsigned)yn <= (unsigned)(N1 - 2);
                 const float4 nyv = lds128(n1a + (uint32_t)ync * 16u);          // NodeInfo: ptr, cnt, idx0, val0
@@ -314,7 +331,7 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                 m_pre = m; xs_pre = xs; ys_pre = ys;
                 ey_up = lds32(adj1a + (uint32_t)ync * 4u);
             }
-            cidx += (size_t)pitch + 1 - (d >= N2 - 1 ? 1 : 0);         // the column's cell moves one row down per anti-diagonal
+            cidx0 += (size_t)pitch - (d >= N2 - 1 ? 1 : 0);
             rb1 = rb0; rb0 += pitchB; if (rb0 == ringB) rb0 = 0;
             WAVE_SYNC();
         }

@@ -190,6 +190,7 @@ struct GraphJobDev {        // one alignGraphs job, all pointers into the batch'
     int wave;                   // 1: swept by graph_fill_wave_kernel
     int wv_tr, wv_ncols, wv_nx; // row-thread slots (chain rows, then non-chain rows, each padded to warps), non-chain columns, extra-predecessor entries
     int wv_chain_pad;           // slots of the chain rows (a multiple of 32): the non-chain rows' slots start here
+    int wv_tcols;               // lane groups of the column threads: group g sweeps the non-chain columns g, g + wv_tcols, ... in turn
     const float* wv_adj1;       // N1 entries: value of the edge y-1 -> y, +inf if there is none
     const WaveRow* wv_rows; const WaveCol* wv_cols; const WaveCI* wv_ci; const uint16_t* wv_rowslot; const int* wv_xi; const float* wv_xv;
     int sgen;                   // 1: swept by graph_fill_strip_gen_kernel
