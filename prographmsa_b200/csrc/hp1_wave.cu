@@ -3,15 +3,16 @@
 //
 // Same recurrences as hp1_graphdp_diag.cu (reference GraphAlign.h:205-280), same {M,X,Y,W} cell layout (anti-diagonal-major,
 // so the dense traceback of hp1_graphdp.cu re-traces the job unchanged).  What changed is how one anti-diagonal's work is
-// dealt.  ncu on the thread-per-row kernel (profiles/r2_diag_branchy.txt): half of all instructions ran with 1.7 of 32 lanes
+// dealt.  ncu on the thread-per-row kernel (profiles/r2_diag_branchy_before.txt): half of all instructions ran with 1.7 of 32 lanes
 // active (fast path, multi-predecessor row path and general path serialised in every warp) and 60 % of the warp samples
 // sat at the barrier waiting for those warps.  Here
 //
 //   * chain rows (one predecessor, the regular edge from y-1) own a thread each, packed into their own warps;
 //   * rows with other / more predecessors own a thread each in SEPARATE warps;
-//   * every NON-CHAIN COLUMN owns L threads (1, 2 or 4) in further warps that compute the column's cell of each
+//   * a NON-CHAIN COLUMN is swept by a group of L lanes (1, 2 or 4) in further warps that compute the column's cell of each
 //     anti-diagonal in full (row threads skip those cells); the predecessor pairs (yp, xp) are dealt over the L lanes and
-//     folded with shuffles.  max is exact, associative and idempotent, so the fold order does not change a bit;
+//     folded with shuffles.  max is exact, associative and idempotent, so the fold order does not change a bit.  A column is
+//     busy for N1 - 1 anti-diagonals; a lane group then moves on to the next column the host dealt it;
 //   * every candidate of cell (y, x) except the two that come through the ADJACENT edges -- (y-1, x) and (y, x-1), made on
 //     the previous anti-diagonal -- lies at least two anti-diagonals back.  So a thread folds all non-adjacent candidates of
 //     its NEXT cell during the current step (predecessor-list walks, ring or L2 reads, shuffles: all off the critical
@@ -20,9 +21,9 @@
 //     -inf without a branch.
 //
 // One barrier per anti-diagonal orders everything.  Cells of the last RING (8 or 16) anti-diagonals are read from a
-// shared-memory ring indexed by row; older ones (edges spanning more positions) from the {M,X,Y,W} array in L2 -- during
-// the look-ahead, where that latency is hidden.  S is streamed per row thread with cp.async, one 16-byte group every
-// fourth anti-diagonal (a warp-uniform event), 9 .. 12 columns ahead.
+// shared-memory ring indexed by row ({X,W,Y,W} per cell: the halves a candidate needs are one 8-byte read each); older
+// ones (edges spanning more positions) from the {M,X,Y,W} array in L2 -- during the look-ahead.  S is streamed per row
+// thread with cp.async, four columns every fourth anti-diagonal (a warp-uniform event), 9 .. 12 columns ahead.
 // Graphs in which a node has TWO list entries from its adjacent predecessor (a regular and a repeat edge) stay with the
 // thread-per-row kernel (hp1_host.cu checks).
 #include "internal.h"
@@ -83,7 +84,6 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     }
     __syncthreads();
     const int ringB = RING * ring_pitch * 16, pitchB = ring_pitch * 16;
-    const int strideB = max_tr * 16;
     uint32_t ringa = (uint32_t)__cvta_generic_to_shared(wsm);
     asm volatile("mov.u32 %0, %0;" : "+r"(ringa));                     // opaque: kept in a register instead of being rematerialised (S2R) at every use
     const uint32_t sringa = ringa + (uint32_t)((unsigned char*)sring - wsm);
@@ -93,7 +93,6 @@ graph_fill_wave_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     const uint32_t adj1a = ringa + (uint32_t)((unsigned char*)adj1 - wsm), rowslota = ringa + (uint32_t)((unsigned char*)rowslot - wsm);
     const int dmax = (N1 - 2) + (N2 - 2);
     const int xmax = N2 - 2;
-    const int dbg = J.dbg;                                              // PGM_STRIP_DEBUG bits >= 16: timing experiments (the results are then wrong)
     // any cell (yy, xx) on an anti-diagonal dd = yy + xx < d.  The ring read is unconditional (its address is always inside the
     // ring); cells older than the ring are re-read from the {M,X,Y,W} array in L2 (rare: lanes branch only then)
     // A ring cell is {X, W, Y, W}: the up candidate reads (Y, W) and the left candidate (X, W) as one 8-byte word each, the
