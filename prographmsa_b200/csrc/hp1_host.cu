@@ -10,6 +10,9 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <memory>
+#include <chrono>
+#include <cstdio>
 
 struct pgm_ctx;
 cudaStream_t pgm_ctx_stream(pgm_ctx* c);
@@ -243,6 +246,10 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         if (g1[k].N < 2 || g2[k].N < 2) { pgm_set_error("job %d: graphs need at least start and end nodes", k); return PGM_ERR_ARG; }
         if (g1[k].N > 60000 || g2[k].N > 60000) { pgm_set_error("job %d: graphs of more than 60000 nodes are not supported (%d x %d)", k, g1[k].N, g2[k].N); return PGM_ERR_ARG; }
     }
+    const bool host_prof = getenv("PGM_HOST_PROFILE") != nullptr;    // stderr: where the host time of this call goes
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms_since = [&](std::chrono::steady_clock::time_point t0) { return std::chrono::duration<double, std::milli>(now() - t0).count(); };
+    auto t_begin = now();
     pgm_graph_batch* b = new pgm_graph_batch();
     b->n_states = n; b->n_jobs = n_jobs; b->emission_mode = opts->emission_mode;
     b->lay.resize(n_jobs); b->jobs.resize(n_jobs); b->cell_updates.resize(n_jobs);
@@ -447,6 +454,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         L.progress = take(so, 4 * ((size_t)L.bands + 1));
         scratch_need[k] = so;
     });
+    const double ms_a = ms_since(t_begin); auto t_b = now();
     // ---- pass B (serial): arena offsets -------------------------------------------------------------------------------------
     size_t in_off = 0, out_off = 0;
     for (int k = 0; k < n_jobs; ++k) {
@@ -494,6 +502,7 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         (rc = pgm_ctx_take_dev(c, std::max<size_t>(b->scratch_bytes_used, 1), b->d_scratch)) ||
         (rc = pgm_ctx_take_dev(c, std::max<size_t>((sizeof(GraphJobDev) + sizeof(int)) * n_jobs, 1), b->d_jobs))) { pgm_graph_batch_destroy(c, b); return rc; }
     b->out_bytes = out_off;
+    const double ms_b = ms_since(t_b); auto t_c = now();
     char* hin = b->h_in.as<char>();
     char* din = b->d_in.as<char>(); char* dsc = b->d_scratch.as<char>(); char* dout = b->d_out.as<char>();
     // ---- pass C (parallel): pack.  Packing a job (double -> float sites, predecessor lists, node infos, DynProgScores) touches
@@ -698,7 +707,35 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         J.alt_score = (float*)(sb + L.alt_score); J.alt_prev = (int*)(sb + L.alt_prev); J.progress = (int*)(sb + L.progress);
         J.map1 = (int*)(dout + L.map1); J.map2 = (int*)(dout + L.map2); J.result = (int*)(dout + L.result);
     };
-    parallel_jobs(n_jobs, pack_job);
+    // The workers pack job after job (their slices of the pinned arena lie in job order); the calling thread meanwhile sends
+    // every finished prefix to the device in pieces of >= 8 MB, so that the upload overlaps the packing instead of following it
+    cudaError_t up_err = cudaSuccess;
+    {
+        unsigned hw = std::thread::hardware_concurrency();
+        const int nthreads = (int)std::max(1u, std::min<unsigned>(std::min<unsigned>(hw ? hw : 1u, 16u), (unsigned)(n_jobs / 8 + 1)));
+        if (nthreads <= 1 || in_off < ((size_t)16 << 20)) {
+            parallel_jobs(n_jobs, pack_job);
+            if (n_jobs) up_err = cudaMemcpyAsync(b->d_in.p, b->h_in.p, in_off, cudaMemcpyHostToDevice, st);
+        } else {
+            std::unique_ptr<std::atomic<unsigned char>[]> done(new std::atomic<unsigned char>[n_jobs]);
+            for (int k = 0; k < n_jobs; ++k) done[k].store(0, std::memory_order_relaxed);
+            std::atomic<int> next(0);
+            std::vector<std::thread> pool;
+            for (int t = 0; t < nthreads; ++t)
+                pool.emplace_back([&] { for (int k = next.fetch_add(1); k < n_jobs; k = next.fetch_add(1)) { pack_job(k); done[k].store(1, std::memory_order_release); } });
+            int ready = 0; size_t sent = 0;
+            while (sent < in_off && up_err == cudaSuccess) {
+                while (ready < n_jobs && done[ready].load(std::memory_order_acquire)) ++ready;
+                const size_t upto = ready == n_jobs ? in_off : b->lay[ready].sites1;     // job k's slices start at its sites1
+                if (upto > sent && (upto - sent >= ((size_t)8 << 20) || ready == n_jobs)) {
+                    up_err = cudaMemcpyAsync(din + sent, hin + sent, upto - sent, cudaMemcpyHostToDevice, st);
+                    sent = upto;
+                } else std::this_thread::yield();
+            }
+            for (auto& th : pool) th.join();
+        }
+    }
+    const double ms_c = ms_since(t_c); auto t_d = now();
     for (int k = 0; k < n_jobs; ++k) { b->total_updates += b->cell_updates[k]; b->total_cells += (uint64_t)b->jobs[k].N1 * b->jobs[k].N2; }
     {   // fill schedule: per kernel flavour, block-size classes (blocked: column blocks per row rounded up to warps;
         // diagonal: graph-1 rows; strip: columns per strip); longest sweeps first
@@ -774,8 +811,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             }
         }
     }
+    const double ms_d = ms_since(t_d); auto t_e = now();
     if (n_jobs) {
-        cudaError_t e = cudaMemcpyAsync(b->d_in.p, b->h_in.p, in_off, cudaMemcpyHostToDevice, st);
+        cudaError_t e = up_err;
         if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_jobs.as<char>() + sizeof(GraphJobDev) * n_jobs, b->order.data(), sizeof(int) * n_jobs, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaMemcpyAsync(b->d_jobs.p, b->jobs.data(), sizeof(GraphJobDev) * n_jobs, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -785,6 +823,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             return PGM_ERR_CUDA;
         }
     }
+    if (host_prof)
+        fprintf(stderr, "[host] create: analysis %.2f ms, offsets + arenas %.2f ms, pack %.2f ms, schedule %.2f ms, upload %.2f ms (%.1f MB in, %.1f MB scratch)\n",
+                ms_a, ms_b, ms_c, ms_d, ms_since(t_e), in_off / 1e6, b->scratch_bytes_used / 1e6);
     *out = b;
     return 0;
 }
@@ -956,11 +997,13 @@ int pgm_graph_batch_fetch(pgm_ctx* c, pgm_graph_batch* b, pgm_alignment* out) {
     PGM_CUDA(cudaSetDevice(pgm_ctx_device(c)));
     cudaStream_t st = pgm_ctx_stream(c);
     if (b->n_jobs == 0) return 0;
+    auto t0f = std::chrono::steady_clock::now();
     PGM_CUDA(cudaMemcpyAsync(b->h_out.p, b->d_out.p, b->out_bytes, cudaMemcpyDeviceToHost, st));
     PGM_CUDA(cudaStreamSynchronize(st));
+    const double ms_d2h = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0f).count();
     const char* ho = b->h_out.as<char>();
     int worst = 0;
-    for (int k = 0; k < b->n_jobs; ++k) {
+    parallel_jobs(b->n_jobs, [&](int k) {                        // every job writes its own pgm_alignment and mapping buffers
         const JobLayout& L = b->lay[k];
         const int* res = (const int*)(ho + L.result);
         pgm_alignment& A = out[k];
@@ -973,12 +1016,19 @@ int pgm_graph_batch_fetch(pgm_ctx* c, pgm_graph_batch* b, pgm_alignment* out) {
                 A.mapping1[i] = m1[A.length - 1 - i];
                 A.mapping2[i] = m2[A.length - 1 - i];
             }
-        } else if (worst == 0) {
+        }
+    });
+    for (int k = 0; k < b->n_jobs; ++k) {
+        const pgm_alignment& A = out[k];
+        if (A.status != 0 && worst == 0) {
             worst = A.status;
             pgm_set_error(A.status == PGM_ERR_BACKTRACK ? "job %d: backtracking failed"
                           : (A.status == PGM_ERR_CAPACITY ? "job %d: mapping capacity too small" : "job %d: the emission kernel failed (tensor pipeline timeout)"), k);
         }
     }
+    if (getenv("PGM_HOST_PROFILE"))
+        fprintf(stderr, "[host] fetch: wait + D2H %.2f ms (%.1f MB), unpack %.2f ms\n", ms_d2h, b->out_bytes / 1e6,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0f).count() - ms_d2h);
     return worst;
 }
 
