@@ -87,8 +87,8 @@ class GraphBatch:
         lens = out["length"][:n].tolist(); starts = offs[:-1].tolist()
         scores = out["score"][:n].astype(np.float64).tolist(); ntr = out["n_tr_indels"][:n].tolist()
         upd = out["cell_updates"][:n].tolist()
-        m1, m2 = buf[0], buf[1]
-        return [dict(score=scores[k], n_tr_indels=ntr[k], mapping1=m1[o:o + ln].astype(np.int64), mapping2=m2[o:o + ln].astype(np.int64),
+        m1, m2 = buf[0].astype(np.int64), buf[1].astype(np.int64)          # one widening pass; the jobs' mappings are views of it
+        return [dict(score=scores[k], n_tr_indels=ntr[k], mapping1=m1[o:o + ln], mapping2=m2[o:o + ln],
                      cell_updates=upd[k]) for k, (o, ln) in enumerate(zip(starts, lens))]
 
     def close(self):

@@ -65,12 +65,55 @@ def from_synth(node):
     return nd
 
 
+class _RowTree:
+    """The alignment rows of a subtree, unmaterialised.  The reference's extend_alignment (ProgressiveAlignment.h:245-264)
+    re-scatters EVERY row of both children at EVERY internal node -- O(rows x columns) per node, a third of a 5000-sequence
+    pass in numpy.  A node here only records where each child's columns land in its own columns; the rows are produced once,
+    at whichever node they are asked for, by composing these column maps top-down (one gather per node) and one scatter
+    per leaf.  Same rows, bit for bit: a column map is exactly the `mapping != NOGAP` selection extend_alignment uses."""
+    __slots__ = ("name", "codes", "parts", "ncols")
+
+    def __init__(self, name=None, codes=None, parts=None, ncols=0):
+        self.name, self.codes, self.parts, self.ncols = name, codes, parts, ncols
+
+    def rows(self):
+        out = {}
+        stack = [(self, None)]                       # (subtree, root column of each of its columns; None = identity)
+        while stack:
+            t, pos = stack.pop()
+            if t.parts is None:
+                if pos is None:
+                    out[t.name] = t.codes
+                else:
+                    row = np.full(self.ncols, GAP, dtype=np.uint8)
+                    row[pos] = t.codes
+                    out[t.name] = row
+                continue
+            for child, cols in t.parts:
+                stack.append((child, cols if pos is None else pos[cols]))
+        return out
+
+
 class Result:
-    __slots__ = ("aligned", "tr_homologies", "tr_source", "graph", "score", "n_tr_indels")
+    __slots__ = ("_rows", "_tree", "tr_homologies", "tr_source", "graph", "score", "n_tr_indels")
 
     def __init__(self):
-        self.aligned, self.tr_homologies, self.tr_source = {}, [], []
+        self._rows, self._tree = {}, None
+        self.tr_homologies, self.tr_source = [], []
         self.graph, self.score, self.n_tr_indels = None, 0.0, 0
+
+    @property
+    def aligned(self):
+        """name -> aligned row (uint8 codes, GAP where the sequence has no residue); materialised on first use"""
+        if self._rows is None:
+            self._rows = self._tree.rows()
+        return self._rows
+
+    def row_tree(self):
+        if self._tree is None:                        # a leaf (or a result whose rows were given explicitly)
+            (name, codes), = self._rows.items()
+            self._tree = _RowTree(name=name, codes=codes, ncols=len(codes))
+        return self._tree
 
 
 def _leaf(name, sequences, repeats, n):
@@ -91,18 +134,13 @@ def _leaf(name, sequences, repeats, n):
     return r
 
 
-def _extend_rows(size, mapping, rows):
-    """extend_alignment (ProgressiveAlignment.h:245-264): every row of the child alignment is scattered to the columns of
-    the merged graph its nodes were mapped to; one 2-D scatter for all rows of the child."""
-    if not rows:
-        return {}
+def _child_columns(size, mapping, child_cols):
+    """extend_alignment (ProgressiveAlignment.h:245-264): column j of the child alignment lands in the column of the merged
+    graph its node was mapped to -> the merged column of every child column (see _RowTree)."""
     sel = np.asarray(mapping[1:size - 1])
     ok = sel != NOGAP
-    assert np.array_equal(sel[ok] - 1, np.arange(ok.sum()))
-    names = list(rows)
-    ext = np.full((len(names), size - 2), GAP, dtype=np.uint8)
-    ext[:, ok] = np.stack([rows[k] for k in names])
-    return {k: ext[i] for i, k in enumerate(names)}
+    assert np.array_equal(sel[ok] - 1, np.arange(ok.sum())) and int(ok.sum()) == child_cols
+    return np.flatnonzero(ok)
 
 
 def _extend_tr(size, mapping, trs):
@@ -149,8 +187,9 @@ def finish_job(r1, r2, job, ali, s1, s2, opts, nodes=None):
     graph, am1, am2, _ = merge_graphs(r1.graph, r2.graph, m1, m2, job["model1"], job["model2"], s1, s2,
                                       opts.altsplice_prob, nodes=nodes)
     res.graph = graph
-    res.aligned.update(_extend_rows(graph.N, am1, r1.aligned))
-    res.aligned.update(_extend_rows(graph.N, am2, r2.aligned))
+    t1, t2 = r1.row_tree(), r2.row_tree()
+    res._rows = None
+    res._tree = _RowTree(parts=[(t1, _child_columns(graph.N, am1, t1.ncols)), (t2, _child_columns(graph.N, am2, t2.ncols))], ncols=graph.N - 2)
     res.tr_homologies = _extend_tr(graph.N, am1, r1.tr_homologies) + _extend_tr(graph.N, am2, r2.tr_homologies)
     res.tr_source = r1.tr_source + r2.tr_source
     res.graph.addRepeats(res.tr_homologies)       # replaces whatever mergeGraphs mapped through (:468)
