@@ -145,11 +145,25 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
             const uint8_t* __restrict__ r2 = fr.rows + (size_t)j * fr.L;
             const int lim = n < 20 ? n : 20;               // hard-coded 20, DistanceFactoryPrealigned.h:65
             int carry = 0;                                   // 0 = none/match, 1 = run in seq1 (A), 2 = run in seq2 (B)
-            for (int base = 0; base < fr.L; base += 32) {
+            // The scan is a chain of L2 round trips (the rows are L2-resident, one 32-column group per trip: measured 84 ns per pair
+            // at 6660 columns = ~1900 cycles per group): the residues of PF groups are loaded up front, then the groups are walked
+            // in order as before
+            constexpr int PF = 8;
+            for (int base0 = 0; base0 < fr.L; base0 += 32 * PF) {
+              int c1v[PF], c2v[PF];
+#pragma unroll
+              for (int u = 0; u < PF; ++u) {
+                  const int k = base0 + 32 * u + lane;
+                  c1v[u] = k < fr.L ? (int)r1[k] : 254; c2v[u] = k < fr.L ? (int)r2[k] : 254;
+              }
+#pragma unroll
+              for (int u = 0; u < PF; ++u) {
+                const int base = base0 + 32 * u;
+                if (base >= fr.L) break;
                 const int k = base + lane;
                 int type = 3;                                // 3 = skip (both gaps / out of range)
                 if (k < fr.L) {
-                    const int c1 = r1[k], c2 = r2[k];
+                    const int c1 = c1v[u], c2 = c2v[u];
                     const bool g1 = (c1 == 254), g2 = (c2 == 254);
                     if (!g1 && !g2) { type = 0; if (c1 < lim && c2 < lim) atomicAdd(&hist[c1 * n + c2], 1u); }
                     else if (g1 && g2) type = 3;
@@ -166,6 +180,7 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
                 const bool ev = (type == 1 && prev != 1) || (type == 2 && prev != 2);
                 gaps += __popc(__ballot_sync(0xffffffffu, ev));
                 if (ns) { const int q = 31 - __clz(ns); carry = ((mA >> q) & 1u) ? 1 : (((mB >> q) & 1u) ? 2 : 0); }
+              }
             }
             seqlen = ((double)fr.L + (double)fr.L) / 2.0;
         } else {
