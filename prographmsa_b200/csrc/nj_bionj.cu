@@ -8,8 +8,14 @@
 //   D <- max(D, 1e-4), V <- max(V, 1e-5), zero diagonals          (only the row/column written by the last join changes)
 //   sums[j] = sum_i D[i][j], sequentially in i                    (tiles staged in shared memory, one adding thread per column)
 //   Q[i][j] = 0.5 D[i][j] - (0.5 / (dim - 2)) (sums[j] + sums[i]); first minimum in column-major order
-//   d1, d2, lambda (its row difference summed sequentially), new row, then row/column i2 removed by compaction
+//   d1, d2, lambda (its row difference summed sequentially), new row, then row/column i2 removed
 // The whole loop is enqueued without a host synchronisation: the join parameters live in device memory.
+//
+// Removing a row and a column by copying the matrices (what the reference and the first version here did) is 4 of the 6
+// dim^2 passes of a join.  The matrices now stay where they are: `alive` maps the logical index of a taxon (the order the
+// reference's compacted matrices would have) to its physical row / column, a join rewrites row and column alive[i1] in place
+// and drops i2 from `alive`; every kernel walks logical indices in increasing order, so sums, ties and results are bit for bit
+// those of the compacted matrices.  When a quarter of the physical rows are dead the matrices are compacted once.
 #include "internal.h"
 #include <math_constants.h>
 #include <algorithm>
@@ -31,13 +37,13 @@ struct NjCand { double q; unsigned long long flat; };
 
 // clamp: the first join touches everything, later joins only the row / column written by the previous join
 __global__ void __launch_bounds__(256)
-nj_clamp_kernel(double* __restrict__ D, double* __restrict__ V, int dim, int P, const NjParams* __restrict__ prm, int first) {
+nj_clamp_kernel(double* __restrict__ D, double* __restrict__ V, int dim, int P, const int* __restrict__ alive, const NjParams* __restrict__ prm, int first) {
     const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int i, j;
-    if (first) { if (e >= (size_t)dim * dim) return; i = (int)(e / dim); j = (int)(e - (size_t)i * dim); }
+    int i, j;                                                       // physical
+    if (first) { if (e >= (size_t)dim * dim) return; i = (int)(e / dim); j = (int)(e - (size_t)i * dim); }     // (alive is the identity then)
     else {
         if (e >= 2 * (size_t)dim) return;
-        const int t = prm->i1, k = (int)(e >> 1);
+        const int t = alive[prm->i1], k = alive[(int)(e >> 1)];
         if (e & 1) { i = t; j = k; } else { i = k; j = t; }
     }
     const size_t o = (size_t)i * P + j;
@@ -50,14 +56,15 @@ nj_clamp_kernel(double* __restrict__ D, double* __restrict__ V, int dim, int P, 
 // the loads are wide.
 #define CS_ROWS 128
 __global__ void __launch_bounds__(256)
-nj_colsum_kernel(const double* __restrict__ D, int dim, int P, double* __restrict__ sums) {
+nj_colsum_kernel(const double* __restrict__ D, int dim, int P, const int* __restrict__ alive, double* __restrict__ sums) {
     __shared__ double tile[CS_ROWS][33];
     const int j0 = blockIdx.x * 32, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int pj = j0 + lane < dim ? alive[j0 + lane] : 0;
     double s = 0.0;
     for (int i0 = 0; i0 < dim; i0 += CS_ROWS) {
         for (int r = w; r < CS_ROWS; r += 8) {
             const int i = i0 + r, j = j0 + lane;
-            tile[r][lane] = (i < dim && j < dim) ? D[(size_t)i * P + j] : 0.0;
+            tile[r][lane] = (i < dim && j < dim) ? D[(size_t)alive[i] * P + pj] : 0.0;
         }
         __syncthreads();
         if (w == 0) {
@@ -75,14 +82,15 @@ __device__ __forceinline__ bool nj_better(double q, unsigned long long f, double
 
 // Q criterion: per-block minimum, ties to the smallest column-major index (Eigen minCoeff / numpy argmin order)
 __global__ void __launch_bounds__(ARGMIN_THREADS)
-nj_argmin_kernel(const double* __restrict__ D, int dim, int P, const double* __restrict__ sums, NjCand* __restrict__ part) {
+nj_argmin_kernel(const double* __restrict__ D, int dim, int P, const int* __restrict__ alive, const double* __restrict__ sums, NjCand* __restrict__ part) {
     const double c = 0.5 / ((double)dim - 2.0);
     double bq = CUDART_INF; unsigned long long bf = ~0ull;
     for (int i = blockIdx.x; i < dim; i += gridDim.x) {
         const double si = sums[i];
+        const double* __restrict__ row = D + (size_t)alive[i] * P;
         for (int j = threadIdx.x; j < dim; j += blockDim.x) {
             if (i == j) continue;
-            const double q = 0.5 * D[(size_t)i * P + j] - c * (sums[j] + si);
+            const double q = 0.5 * row[alive[j]] - c * (sums[j] + si);
             const unsigned long long f = (unsigned long long)j * dim + i;
             if (nj_better(q, f, bq, bf)) { bq = q; bf = f; }
         }
@@ -102,7 +110,7 @@ nj_argmin_kernel(const double* __restrict__ D, int dim, int P, const double* __r
 // one block: final argmin over the partials, then the join's scalars (TreeNJ.cpp:176-214 / tree.py)
 #define JN_CHUNK 2048
 __global__ void __launch_bounds__(ARGMIN_THREADS)
-nj_join_kernel(const double* __restrict__ D, const double* __restrict__ V, int dim, int P, const double* __restrict__ sums,
+nj_join_kernel(const double* __restrict__ D, const double* __restrict__ V, int dim, int P, const int* __restrict__ alive, const double* __restrict__ sums,
                const NjCand* __restrict__ part, int n_part, NjParams* __restrict__ prm, int join,
                int32_t* __restrict__ j1, int32_t* __restrict__ j2, double* __restrict__ jd1, double* __restrict__ jd2) {
     __shared__ double sq[ARGMIN_THREADS]; __shared__ unsigned long long sf[ARGMIN_THREADS];
@@ -125,47 +133,74 @@ nj_join_kernel(const double* __restrict__ D, const double* __restrict__ V, int d
     }
     __syncthreads();
     const int i1 = s_i1, i2 = s_i2;
+    const int a1 = alive[i1], a2 = alive[i2];                       // physical rows of the two taxa
     // sum_k (V[i2][k] - V[i1][k]) sequentially in k: the differences are staged by the whole block, added by one thread
     double s = 0.0;
     for (int k0 = 0; k0 < dim; k0 += JN_CHUNK) {
-        for (int k = threadIdx.x; k < JN_CHUNK && k0 + k < dim; k += blockDim.x)
-            diff[k] = V[(size_t)i2 * P + k0 + k] - V[(size_t)i1 * P + k0 + k];
+        for (int k = threadIdx.x; k < JN_CHUNK && k0 + k < dim; k += blockDim.x) {
+            const int pk = alive[k0 + k];
+            diff[k] = V[(size_t)a2 * P + pk] - V[(size_t)a1 * P + pk];
+        }
         __syncthreads();
         if (threadIdx.x == 0) { const int m = min(JN_CHUNK, dim - k0); for (int k = 0; k < m; ++k) s = s + diff[k]; }
         __syncthreads();
     }
     if (threadIdx.x != 0) return;
-    const double d12 = D[(size_t)i1 * P + i2];
+    const double d12 = D[(size_t)a1 * P + a2];
     double d1 = (d12 + (sums[i1] - sums[i2]) / ((double)dim - 2.0)) / 2.0;
     d1 = fmin(fmax(d1, NJ_MIN_DIST), d12);
-    const double d2 = fmax(D[(size_t)i2 * P + i1] - d1, NJ_MIN_DIST);
-    const double v12 = V[(size_t)i1 * P + i2];
+    const double d2 = fmax(D[(size_t)a2 * P + a1] - d1, NJ_MIN_DIST);
+    const double v12 = V[(size_t)a1 * P + a2];
     double lam = (v12 != 0.0) ? 0.5 + s / ((double)(2 * (dim - 2)) * v12) : CUDART_NAN;
     lam = isnan(lam) ? 0.5 : fmin(fmax(0.0, lam), 1.0);
     prm->i1 = i1; prm->i2 = i2; prm->d1 = d1; prm->d2 = d2; prm->lam = lam; prm->v12 = v12;
     j1[join] = i1; j2[join] = i2; jd1[join] = d1; jd2[join] = d2;
 }
 
-// reduced matrices: row/column i2 removed, row/column i1 replaced by the BioNJ combination
+// the join's new taxon takes row and column alive[i1], in place: the BioNJ combination of the two joined rows
 __global__ void __launch_bounds__(256)
-nj_reduce_kernel(const double* __restrict__ Ds, const double* __restrict__ Vs, double* __restrict__ Dd, double* __restrict__ Vd,
-                 int dim, int P, const NjParams* __restrict__ prm) {
+nj_update_kernel(double* __restrict__ D, double* __restrict__ V, int dim, int P, const int* __restrict__ alive, const NjParams* __restrict__ prm) {
     const int i1 = prm->i1, i2 = prm->i2;
     const double d1 = prm->d1, d2 = prm->d2, lam = prm->lam, v12 = prm->v12;
-    const int nd = dim - 1;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;            // the other taxon, logical
+    if (k >= dim || k == i1 || k == i2) return;
+    const int a1 = alive[i1], a2 = alive[i2], ks = alive[k];
+    const double d = lam * (D[(size_t)a1 * P + ks] - d1) + (1.0 - lam) * (D[(size_t)a2 * P + ks] - d2);
+    const double v = lam * V[(size_t)a1 * P + ks] + (1.0 - lam) * V[(size_t)a2 * P + ks] - lam * (1.0 - lam) * v12;
+    D[(size_t)a1 * P + ks] = d; D[(size_t)ks * P + a1] = d;
+    V[(size_t)a1 * P + ks] = v; V[(size_t)ks * P + a1] = v;
+}
+
+// taxon i2 leaves: alive[k] <- alive[k + 1] for k >= i2 (one block, ascending chunks)
+__global__ void __launch_bounds__(1024)
+nj_drop_kernel(int* __restrict__ alive, int dim, const NjParams* __restrict__ prm) {
+    const int i2 = prm->i2;
+    for (int base = i2; base < dim - 1; base += (int)blockDim.x) {
+        const int k = base + (int)threadIdx.x;
+        const int v = k < dim - 1 ? alive[k + 1] : 0;
+        __syncthreads();
+        if (k < dim - 1) alive[k] = v;
+        __syncthreads();
+    }
+}
+
+// physical compaction: the alive rows / columns copied densely into the other buffer pair, alive <- identity
+__global__ void __launch_bounds__(256)
+nj_compact_kernel(const double* __restrict__ Ds, const double* __restrict__ Vs, double* __restrict__ Dd, double* __restrict__ Vd,
+                  int dim, int P, const int* __restrict__ alive) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
-    if (c >= nd) return;
-    const int rs = r + (r >= i2), cs = c + (c >= i2);
-    double d, v;
-    if (r == i1 || c == i1) {
-        const int ks = (r == i1) ? cs : rs;                      // the other taxon, source index
-        if (r == c) { d = 0.0; v = 0.0; }
-        else {
-            d = lam * (Ds[(size_t)i1 * P + ks] - d1) + (1.0 - lam) * (Ds[(size_t)i2 * P + ks] - d2);
-            v = lam * Vs[(size_t)i1 * P + ks] + (1.0 - lam) * Vs[(size_t)i2 * P + ks] - lam * (1.0 - lam) * v12;
-        }
-    } else { d = Ds[(size_t)rs * P + cs]; v = Vs[(size_t)rs * P + cs]; }
-    Dd[(size_t)r * P + c] = d; Vd[(size_t)r * P + c] = v;
+    if (c >= dim) return;
+    const size_t src = (size_t)alive[r] * P + alive[c];
+    Dd[(size_t)r * P + c] = Ds[src]; Vd[(size_t)r * P + c] = Vs[src];
+}
+__global__ void nj_iota_kernel(int* __restrict__ alive, int n) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n) alive[k] = k;
+}
+// the remaining <= 3 x 3 distances, dense
+__global__ void nj_rest_kernel(const double* __restrict__ D, int dim, int P, const int* __restrict__ alive, double* __restrict__ out) {
+    const int k = threadIdx.x;
+    if (k < dim * dim) out[k] = D[(size_t)alive[k / dim] * P + alive[k % dim]];
 }
 
 } // namespace
@@ -182,7 +217,8 @@ extern "C" int pgm_bionj_joins(pgm_ctx* c, int N, const double* D, const double*
     const size_t mat = (size_t)N * N * sizeof(double);
     DevBuf buf;
     const size_t small = align_up_sz((size_t)N * 8, 256) + align_up_sz(sizeof(NjCand) * ARGMIN_BLOCKS, 256) + 256 +
-                         2 * align_up_sz((size_t)n_joins * 4, 256) + 2 * align_up_sz((size_t)n_joins * 8, 256);
+                         2 * align_up_sz((size_t)n_joins * 4, 256) + 2 * align_up_sz((size_t)n_joins * 8, 256) +
+                         align_up_sz((size_t)N * 4, 256) + 256;
     int rc = pgm_ctx_take_dev(c, 4 * mat + small, buf);
     if (rc) return rc;
     char* p = buf.as<char>();
@@ -194,26 +230,35 @@ extern "C" int pgm_bionj_joins(pgm_ctx* c, int N, const double* D, const double*
     int32_t* dj1 = (int32_t*)p; p += align_up_sz((size_t)n_joins * 4, 256);
     int32_t* dj2 = (int32_t*)p; p += align_up_sz((size_t)n_joins * 4, 256);
     double* dd1 = (double*)p; p += align_up_sz((size_t)n_joins * 8, 256);
-    double* dd2 = (double*)p;
+    double* dd2 = (double*)p; p += align_up_sz((size_t)n_joins * 8, 256);
+    int* alive = (int*)p; p += align_up_sz((size_t)N * 4, 256);
+    double* rest = (double*)p;
     cudaError_t e = cudaMemcpyAsync(Dm[0], D, mat, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(Vm[0], V, mat, cudaMemcpyHostToDevice, st);
-    int cur = 0, dim = N;
+    nj_iota_kernel<<<(N + 255) / 256, 256, 0, st>>>(alive, N);
+    int cur = 0, dim = N, phys = N;                                 // phys: physical rows in use (alive + dead)
     for (int join = 0; join < n_joins && e == cudaSuccess; ++join, --dim) {
+        if (dim >= 64 && 4 * dim <= 3 * phys) {                     // a quarter of the physical rows are dead: compact once
+            nj_compact_kernel<<<dim3((dim + 255) / 256, dim), 256, 0, st>>>(Dm[cur], Vm[cur], Dm[cur ^ 1], Vm[cur ^ 1], dim, N, alive);
+            nj_iota_kernel<<<(dim + 255) / 256, 256, 0, st>>>(alive, dim);
+            cur ^= 1; phys = dim;
+        }
         const size_t n_clamp = join == 0 ? (size_t)dim * dim : 2 * (size_t)dim;
-        nj_clamp_kernel<<<(unsigned)((n_clamp + 255) / 256), 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, prm, join == 0);
-        nj_colsum_kernel<<<(dim + 31) / 32, 256, 0, st>>>(Dm[cur], dim, N, sums);
+        nj_clamp_kernel<<<(unsigned)((n_clamp + 255) / 256), 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, prm, join == 0);
+        nj_colsum_kernel<<<(dim + 31) / 32, 256, 0, st>>>(Dm[cur], dim, N, alive, sums);
         const int nblk = std::min(ARGMIN_BLOCKS, dim);
-        nj_argmin_kernel<<<nblk, ARGMIN_THREADS, 0, st>>>(Dm[cur], dim, N, sums, part);
-        nj_join_kernel<<<1, ARGMIN_THREADS, 0, st>>>(Dm[cur], Vm[cur], dim, N, sums, part, nblk, prm, join, dj1, dj2, dd1, dd2);
-        nj_reduce_kernel<<<dim3((dim - 1 + 255) / 256, dim - 1), 256, 0, st>>>(Dm[cur], Vm[cur], Dm[cur ^ 1], Vm[cur ^ 1], dim, N, prm);
-        cur ^= 1;
+        nj_argmin_kernel<<<nblk, ARGMIN_THREADS, 0, st>>>(Dm[cur], dim, N, alive, sums, part);
+        nj_join_kernel<<<1, ARGMIN_THREADS, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, sums, part, nblk, prm, join, dj1, dj2, dd1, dd2);
+        nj_update_kernel<<<(dim + 255) / 256, 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, prm);
+        nj_drop_kernel<<<1, 1024, 0, st>>>(alive, dim, prm);
         e = cudaGetLastError();
     }
+    if (e == cudaSuccess) nj_rest_kernel<<<1, 32, 0, st>>>(Dm[cur], dim, N, alive, rest);
     if (e == cudaSuccess) e = cudaMemcpyAsync(join_i1, dj1, (size_t)n_joins * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(join_i2, dj2, (size_t)n_joins * 4, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(join_d1, dd1, (size_t)n_joins * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(join_d2, dd2, (size_t)n_joins * 8, cudaMemcpyDeviceToHost, st);
-    if (e == cudaSuccess) e = cudaMemcpy2DAsync(D_rest, (size_t)dim * 8, Dm[cur], (size_t)N * 8, (size_t)dim * 8, dim, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(D_rest, rest, (size_t)dim * dim * 8, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     pgm_ctx_give_dev(c, buf);
     if (e != cudaSuccess) { pgm_set_error("CUDA error in BioNJ: %s", cudaGetErrorString(e)); cudaGetLastError(); return PGM_ERR_CUDA; }
