@@ -34,7 +34,7 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 // band, which the band's first row needs on every diagonal, is staged 8 diagonals at a time into shared memory right after
 // the flag check (it is complete by then), so that row runs the chain fast path like any other.
 template <bool STAGE, int RPT, int RING, bool SPF, bool BANDED>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(BANDED ? 512 : 1024)
 graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch, int max_bands) {
     const GraphJobDev& J = jobs[order[BANDED ? blockIdx.x / max_bands : blockIdx.x]];
     // A CTA takes its band index from a per-job atomic ticket, so a band only ever waits on bands whose CTAs have already
@@ -80,6 +80,21 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         return BANDED ? __ldcg(p) : *p;
     };
 
+    // BANDED: the loads of a multi-predecessor cell are issued together (up to 4 x 4 predecessor pairs) instead of one L2 round
+    // trip per loop iteration: the step of an anti-diagonal takes as long as its slowest cell, and on the deep profiles near
+    // the root of a guide tree (a third of the nodes non-chain) some row meets a 3 x 3 cell on every diagonal.  One generic
+    // load per value: the ring (shared) or the {M,X,Y,W} array (L2: other bands write it, so never through L1).
+    auto cell_addr = [&](int yy, int xx, int d) -> const float4* {
+        const int dd = yy + xx;
+        const float4* g = C + (size_t)dd * pitch + (yy - max(0, dd - (N2 - 1)));
+        const float4* q = ring + (dd & (RING - 1)) * ring_pitch + (yy - y0);
+        return (d - dd < RING && yy >= y0) ? q : g;
+    };
+    auto ld_w = [](const float4* p) -> float { float v; asm volatile("ld.relaxed.gpu.f32 %0, [%1+12];" : "=f"(v) : "l"(p)); return v; };
+    auto ld_zw = [](const float4* p) -> float2 { float2 v; asm volatile("ld.relaxed.gpu.v2.f32 {%0,%1}, [%2+8];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v; };
+    auto ld_yw = [](const float4* p) -> float2 { float4 v; asm volatile("ld.relaxed.gpu.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return make_float2(v.y, v.w); };
+    constexpr int GB = 4;                                        // predecessors per side the batched path holds
+
     NodeInfo ny[RPT]; bool ysimple[RPT]; float4 left[RPT];
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
@@ -108,11 +123,13 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     for (int d = dmin; d <= dmax; ++d) {
         if (BANDED && band > 0 && ((d - dmin) & 7) == 0) {      // the earlier bands must be past the next 8 diagonals
             if (tid == 0) {
-                for (int bq = 0; bq < band; ++bq) {
-                    const int last_q = min(N1 - 2, (bq + 1) * band_rows - 1) + (N2 - 2);
-                    const int need = min(d + 8, last_q + 1);
-                    while (*(volatile int*)(J.progress + bq) < need) __nanosleep(64);
-                }
+                // only the previous band's flag: that band published diagonal d' after it had itself seen ITS predecessor past
+                // d' + 8, so by induction every earlier band is past d' too (and the fences make their cells visible in turn);
+                // a job of 78 bands otherwise spends 78 serial L2 reads here every 8 diagonals
+                const int bq = band - 1;
+                const int last_q = min(N1 - 2, (bq + 1) * band_rows - 1) + (N2 - 2);
+                const int need = min(d + 8, last_q + 1);
+                while (*(volatile int*)(J.progress + bq) < need) __nanosleep(64);
                 __threadfence();
             }
             __syncthreads();
@@ -139,8 +156,12 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
 #pragma unroll
         for (int r = 0; r < RPT; ++r) {
             const int y = y0 + tid + r * T, x = d - y;
-            if (y > N1 - 2 || x < 0 || x > N2 - 2) continue;
+            const bool valid = !(y > N1 - 2 || x < 0 || x > N2 - 2);
+            if (!BANDED && !valid) continue;
             float m = NINF, xs = NINF, ys = NINF, w = NINF;
+            bool heavy = false;                                  // BANDED: a cell with more than GB predecessors on a side: the whole warp folds it (below)
+            NodeInfo hx = NodeInfo{0, 0, 0, 0.f}; float hs = 0.f;
+            if (valid) {
             if (x == 0) {
                 if (y == 0) w = start_init;
                 else {
@@ -177,6 +198,41 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                         ys = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
                         m = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
                         xs = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
+                        w = fmaxf(m, fmaxf(xs, ys));
+                    } else if (BANDED && ((ny[r].cnt & 0x7fffffff) > GB || (nx.cnt & 0x7fffffff) > GB || (ny[r].cnt & 0x7fffffff) < 1 || (nx.cnt & 0x7fffffff) < 1)) {
+                        heavy = true; hx = nx; hs = s;
+                    } else if (BANDED) {
+                        // every candidate of the cell at once (same candidates as the loops below; a maximum does not depend on
+                        // the order): absent predecessors get -inf cells, which never win
+                        const int c1 = ny[r].cnt & 0x7fffffff, c2 = nx.cnt & 0x7fffffff;
+                        int ypv[GB], xpv[GB]; float eyv[GB], exv[GB];
+#pragma unroll
+                        for (int j = 0; j < GB; ++j) {
+                            ypv[j] = ny[r].idx0; eyv[j] = ny[r].val0; xpv[j] = nx.idx0; exv[j] = nx.val0;
+                            if (j > 0 && j < c1) { ypv[j] = P1I[ny[r].ptr + j]; eyv[j] = P1V[ny[r].ptr + j]; }
+                            if (j > 0 && j < c2) { xpv[j] = P2I[nx.ptr + j]; exv[j] = P2V[nx.ptr + j]; }
+                        }
+                        float2 cu[GB], cl[GB]; float cdw[GB][GB];
+#pragma unroll
+                        for (int j = 0; j < GB; ++j) {
+                            cu[j] = make_float2(NINF, NINF); cl[j] = make_float2(NINF, NINF);
+                            if (j < c1) cu[j] = ld_zw(cell_addr(ypv[j], x, d));                  // (yp, x): Y, W
+                            if (j < c2) cl[j] = ld_yw(cell_addr(y, xpv[j], d));                  // (y, xp): X, W
+#pragma unroll
+                            for (int k = 0; k < GB; ++k) {
+                                cdw[j][k] = NINF;
+                                if (j < c1 && k < c2) cdw[j][k] = ld_w(cell_addr(ypv[j], xpv[k], d));   // (yp, xp): W
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < GB; ++k)
+                            xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(cl[k].x, gap_extend), __fadd_rn(cl[k].y, gap_init)), exv[k]));
+#pragma unroll
+                        for (int j = 0; j < GB; ++j) {
+                            ys = fmaxf(ys, __fsub_rn(fmaxf(__fadd_rn(cu[j].x, gap_extend), __fadd_rn(cu[j].y, gap_init)), eyv[j]));
+#pragma unroll
+                            for (int k = 0; k < GB; ++k) m = fmaxf(m, __fsub_rn(__fsub_rn(__fadd_rn(cdw[j][k], s), eyv[j]), exv[k]));
+                        }
                         w = fmaxf(m, fmaxf(xs, ys));
                     } else if (nx.cnt == 1 && nx.idx0 == x - 1 && (ny[r].cnt & 0x7fffffff) >= 1) {
                         // row with several (or a non-adjacent) predecessors at a chain column: X through the left neighbour
@@ -219,10 +275,57 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                     }
                 }
             }
-            const float4 out = make_float4(m, xs, ys, w);
-            left[r] = out;
-            rcur[y - y0] = out;
-            C[(size_t)d * pitch + (y - ylo)] = out;
+            }
+            if (BANDED) {
+                // Cells with many predecessors (deep profile columns reach dozens): one thread folding c1 x c2 pairs with an L2 round
+                // trip per pair held the whole band for tens of microseconds per anti-diagonal (ncu: a fifth of the kernel's
+                // instructions ran with 1.6 of 32 lanes active).  The warp folds such a cell together: lane l takes the pairs l, l + 32, ...,
+                // three warp maxima, the owner keeps the result.  A maximum does not depend on the order, so the values are unchanged.
+                unsigned hb = __ballot_sync(0xffffffffu, heavy);
+                const int lane = tid & 31;
+                while (hb) {
+                    const int src = __ffs(hb) - 1;
+                    hb &= hb - 1;
+                    const int by = __shfl_sync(0xffffffffu, y, src), bx = __shfl_sync(0xffffffffu, x, src);
+                    const int c1 = __shfl_sync(0xffffffffu, ny[r].cnt, src) & 0x7fffffff, c2 = __shfl_sync(0xffffffffu, hx.cnt, src) & 0x7fffffff;
+                    const int p1 = __shfl_sync(0xffffffffu, ny[r].ptr, src), p2 = __shfl_sync(0xffffffffu, hx.ptr, src);
+                    const int yi0 = __shfl_sync(0xffffffffu, ny[r].idx0, src), xi0 = __shfl_sync(0xffffffffu, hx.idx0, src);
+                    const float yv0 = __shfl_sync(0xffffffffu, ny[r].val0, src), xv0 = __shfl_sync(0xffffffffu, hx.val0, src);
+                    const float bs = __shfl_sync(0xffffffffu, hs, src);
+                    float pm = NINF, pxs = NINF, pys = NINF;
+                    for (int q = lane; q < c1 * c2; q += 32) {
+                        const int j = q / c2, k = q - j * c2;
+                        const int yp = j ? P1I[p1 + j] : yi0, xp = k ? P2I[p2 + k] : xi0;
+                        const float ey = j ? P1V[p1 + j] : yv0, ex = k ? P2V[p2 + k] : xv0;
+                        pm = fmaxf(pm, __fsub_rn(__fsub_rn(__fadd_rn(ld_w(cell_addr(yp, xp, d)), bs), ey), ex));
+                    }
+                    for (int k = lane; k < c2; k += 32) {
+                        const int xp = k ? P2I[p2 + k] : xi0;
+                        const float ex = k ? P2V[p2 + k] : xv0;
+                        const float2 cl = ld_yw(cell_addr(by, xp, d));
+                        pxs = fmaxf(pxs, __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gap_init)), ex));
+                    }
+                    for (int j = lane; j < c1; j += 32) {
+                        const int yp = j ? P1I[p1 + j] : yi0;
+                        const float ey = j ? P1V[p1 + j] : yv0;
+                        const float2 cu = ld_zw(cell_addr(yp, bx, d));
+                        pys = fmaxf(pys, __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, gap_init)), ey));
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        pm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, o));
+                        pxs = fmaxf(pxs, __shfl_xor_sync(0xffffffffu, pxs, o));
+                        pys = fmaxf(pys, __shfl_xor_sync(0xffffffffu, pys, o));
+                    }
+                    if (lane == src) { m = pm; xs = pxs; ys = pys; w = fmaxf(pm, fmaxf(pxs, pys)); }
+                }
+            }
+            if (valid) {
+                const float4 out = make_float4(m, xs, ys, w);
+                left[r] = out;
+                rcur[y - y0] = out;
+                C[(size_t)d * pitch + (y - ylo)] = out;
+            }
         }
         __syncthreads();
         if (BANDED && tid == 0 && (((d - dmin) & 3) == 3 || d == dmax)) {

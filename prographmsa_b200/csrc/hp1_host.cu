@@ -142,7 +142,7 @@ struct BatchEnv {                 // environment switches, read once per create 
         if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
         if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
         if (const char* e = getenv("PGM_FILL_BAND_MIN_N1")) band_min_n1 = std::max(66, atoi(e));
-        if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 64 && v <= 1024) long_band_rows = v; }
+        if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 64 && v <= 512) long_band_rows = v; }
         if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
         if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
         if (const char* e = getenv("PGM_FILL_SMALL_BATCH")) small_batch = atoi(e);      // fewer jobs than three per SM: latency-bound (measured crossover 300..440 jobs of 400 x 400)
@@ -334,7 +334,9 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
                     for (int e = bb.e_rowptr[x]; e < bb.e_rowptr[x + 1]; ++e) visit(bb.e_col[e]);
                     if (bb.r_rowptr) for (int e = bb.r_rowptr[x]; e < bb.r_rowptr[x + 1]; ++e) visit(bb.r_col[e]);
                 }
-                int rr = 64; while (rr < best_ns + 2) rr *= 2;
+                // source rings: a reader looks back at most rr - 2 - strips (- SG_SLACK: with several warps per job the owner of a
+                // column may be that many steps ahead of the reader); at least the previous row must be there
+                int rr = 64; while (rr < best_ns + 4 + (best_ns > 32 ? SG_SLACK : 0)) rr *= 2;
                 // history ring: (Y,W) of the last hist_rows rows of every column, for the rows with non-adjacent predecessors
                 int hr = 32;                                        // fewer jobs than SMs: the whole shared memory of an SM is the job's
                 size_t hist_budget = (n_jobs < 148 ? 128 : 24) * 1024;

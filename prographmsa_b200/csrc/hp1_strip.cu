@@ -205,7 +205,7 @@ struct SharedF2 {
 };
 #define SG_MAXP 4            // column predecessors of a special column held in registers (more: read from the lists)
 template <int C, int WB>     // WB: most warps per job of the launch (1, 2, 4 or SG_MAX_WARPS); the smaller ones leave room for several jobs per SM
-__global__ void __launch_bounds__(32 * WB, WB >= 8 ? 1 : 12 / WB)
+__global__ void __launch_bounds__(32 * WB, WB >= 8 ? 1 : (C <= 4 ? 16 : 12) / WB)
 graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order) {
     constexpr int B = 7;                                            // the side arrays hold 32-bit index words
     typedef uint32_t DW;
@@ -214,18 +214,23 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
     constexpr uint32_t MF = (dir_mask<B>() << 4) | (dir_mask<B>() << (4 + B)); // the M fields
     constexpr uint32_t XF = DIR_XOPEN | (dir_mask<B>() << (4 + 3 * B));        // the X fields
     extern __shared__ __align__(16) unsigned char sg_smem[];
-    __shared__ float2 hand[SG_MAX_WARPS][2];                        // (X, W) of a warp's last strip, by step parity
+    __shared__ float2 hand[WB][SG_HAND_ROWS];                       // (X, W)(row, last column) of a warp's last strip: the next warp's left neighbour
+    __shared__ int prog[WB];                                        // steps a warp has completed (release / acquire, see the step loop)
     const GraphJobDev& J = jobs[order[blockIdx.x]];
     const int lane = (int)threadIdx.x & 31, warp = (int)threadIdx.x >> 5, L = (int)threadIdx.x;
     const int N1 = J.N1, ns = J.nstrips, ldS = J.ldS, RRm = J.ring_rows - 1, RR = J.ring_rows, HR = J.hist_rows, HRm = J.hist_rows - 1;
     const int NSP = (ns + 31) & ~31;
     const int dbg = J.dbg;
     uint32_t smem_a = (uint32_t)__cvta_generic_to_shared(sg_smem), hand_a = (uint32_t)__cvta_generic_to_shared(&hand[0][0]);
+    uint32_t prog_a = (uint32_t)__cvta_generic_to_shared(&prog[0]);
     asm volatile("mov.u32 %0, %0;" : "+r"(smem_a));                 // opaque: kept in registers instead of being rematerialised at every use
     asm volatile("mov.u32 %0, %0;" : "+r"(hand_a));
+    asm volatile("mov.u32 %0, %0;" : "+r"(prog_a));
+    constexpr int HDm = SG_HAND_ROWS - 1;
+    constexpr int SLACK = WB > 1 ? SG_SLACK : 0;                    // steps a warp may be ahead of the job's last warp
     const SharedF2 ring{smem_a};                                    // [nsrc][RR]: (X, W)(y, source column) of the last RR rows
     const SharedF2 hist{smem_a + (uint32_t)((size_t)J.nsrc * RR * 8)};   // [HR][C + 1][NSP]: (Y, W)(row, slot) per strip; slot C = (X, W) of the strip's last column
-    const SharedF2 handv{hand_a};                                   // hand[w][p] at w * 2 + p
+    const SharedF2 handv{hand_a};                                   // hand[w][row & HDm] at w * SG_HAND_ROWS + (row & HDm)
     const float gap_init = J.sc[0], gap_extend = J.sc[1], start_gap = J.sc[6], start_init = J.sc[7];
     const float NINF = -CUDART_INF_F;
     const float* __restrict__ S = J.S;
@@ -302,25 +307,46 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
     };
     // the rings start at -inf: a dummy predecessor (infinite edge) may read a row nobody has written yet, and -inf stays -inf
     for (int i = L; i < J.nsrc * RR + HR * (C + 1) * NSP; i += (int)blockDim.x) ring.st(i, make_float2(NINF, NINF));
-    if (L < 2 * SG_MAX_WARPS) handv.st(L, make_float2(NINF, NINF));   // a warp's first strip reads the hand-over before the previous warp's last strip has started: row -1 is -inf
+    for (int i = L; i < WB * SG_HAND_ROWS; i += (int)blockDim.x) handv.st(i, make_float2(NINF, NINF));   // a warp's first strip reads the hand-over before the previous warp's last strip has started: row -1 is -inf
+    if (L < WB) prog[L] = 0;
     __syncthreads();
+    const int nwj = (ns + 31) >> 5;                                 // warps of this job that own strips (the launch may have more)
+    int seen_lo = 0, seen_hi = 0;                                   // last progress read of the previous / of the job's last warp
     int y = -L;                                                     // the row of step t is t - L
     RowInfo cur = rzero, n1 = rzero;
     if (lane_on) { if (row_ok(y)) cur = load_row(y); if (row_ok(y + 1)) n1 = load_row(y + 1); }
     float sv[C];
 #pragma unroll
     for (int k = 0; k < C; ++k) sv[k] = 0.f;
-    const int steps = (N1 - 1) + (ns - 1);
+    const int steps = (WB == 1 || warp < nwj) ? (N1 - 1) + (ns - 1) : 0;   // (a warp without strips has nothing to hand over)
     for (int t = 0; t < steps; ++t) {
         float sn[C];
 #pragma unroll
         for (int k = 0; k < C; ++k) sn[k] = 0.f;
-        if (WB > 1) __syncthreads(); else __syncwarp();             // the previous step's rings, hand-over and value-store writes are visible
+        // Warps of a job are coupled point to point, not by a CTA barrier: warp w starts step t once warp w - 1 has completed
+        // step t - 1 (everything a strip reads from other strips -- hand-over, source rings, value store -- was produced by a
+        // strip to its left at an earlier step, and progress is monotone in w), and no warp runs more than SLACK steps ahead of
+        // the job's last warp (the rings are that much deeper than their readers look back).  A warp that is slow for a while
+        // (a row with several predecessors passing through its 32 strips) then delays its neighbours only once the slack is used
+        // up, instead of all warps of the job at every step.
+        __syncwarp();                                               // the warp's own ring / value-store writes of the previous step
+        if (WB > 1 && (dbg & 16)) __syncthreads();                  // (A/B: the CTA barrier instead)
+        else if (WB > 1) {
+            // every lane polls (one broadcast read per warp, a warp-uniform loop): a loop run by lane 0 alone left the warp split in
+            // {lane 0} and {lanes 1..31} for the rest of the step (ncu: 18 of 32 threads per instruction, twice the instructions)
+            const uint32_t mine = prog_a + 4u * (uint32_t)warp;
+            asm volatile("{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %2, 0;\n\t@p st.volatile.shared.b32 [%0], %1;\n\t}" ::"r"(mine), "r"(t), "r"(lane) : "memory");
+            if (warp > 0)
+                while (seen_lo < t) asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(seen_lo) : "r"(mine - 4u) : "memory");
+            if (warp < nwj - 1)
+                while (seen_hi < t - SLACK) asm volatile("ld.volatile.shared.b32 %0, [%1];" : "=r"(seen_hi) : "r"(prog_a + 4u * (uint32_t)(nwj - 1)) : "memory");
+            __syncwarp();
+        }
         if (dbg & 2) __threadfence();
         float gX = __shfl_up_sync(0xffffffffu, outX, 1), gW = __shfl_up_sync(0xffffffffu, outW, 1);   // (y, x0 - 1) from strip L - 1
         if (lane == 0) {
             if (WB == 1 || warp == 0) { gX = NINF; gW = NINF; }
-            else { const float2 h = handv.ld((warp - 1) * 2 + ((t + 1) & 1)); gX = h.x; gW = h.y; }
+            else { const float2 h = handv.ld((warp - 1) * SG_HAND_ROWS + (y & HDm)); gX = h.x; gW = h.y; }   // row y of strip L - 1 (produced at step t - 1)
         }
         RowInfo n2 = rzero;
         if (lane_on) {                                              // two rows ahead: row record; one row ahead: S (consumed next step)
@@ -390,7 +416,10 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                 // W(yp, x0 - 1) of an earlier row: the neighbour strip's history, else the value store
                 auto w_left_of_strip = [&](int yp, int kq) -> float {
                     if (x0 == 0) return NINF;
-                    if (y - yp <= HR - 2) return hist.ld(((size_t)(yp & HRm) * (C + 1) + C) * NSP + (L - 1)).y;
+                    if (y - yp <= HR - 2) {
+                        if (WB > 1 && lane == 0) return handv.ld((warp - 1) * SG_HAND_ROWS + (yp & HDm)).y;   // the neighbour is another warp's strip: its hand-over ring
+                        return hist.ld(((size_t)(yp & HRm) * (C + 1) + C) * NSP + (L - 1)).y;
+                    }
                     return kq < 0 ? CUDART_NAN_F : __ldcg(Vrow + (size_t)kq * ldVr + (x0 - 1)).w;
                 };
                 // ---- phase 1: row predecessors -> ys[k], m[k] (through the chain column edge x-1 -> x), index fields ----
@@ -419,13 +448,17 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                 const bool near0 = c1 < 1 || y - yp0 <= HR - 2, near1 = c1 < 2 || y - yp1 <= HR - 2;
                 const bool slowrow = c1 > 2 || !near0 || !near1;
                 {
-                    const int r0 = (c1 > 0 && near0) ? (yp0 & HRm) : (y & HRm), r1 = (c1 > 1 && near1) ? (yp1 & HRm) : r0;
+                    const int q0 = (c1 > 0 && near0) ? yp0 : y, q1 = (c1 > 1 && near1) ? yp1 : q0;
+                    const int r0 = q0 & HRm, r1 = q1 & HRm;
                     const SharedF2 h0 = hist.at(((size_t)r0 * (C + 1)) * NSP + L);
                     const SharedF2 h1 = hist.at(((size_t)r1 * (C + 1)) * NSP + L);
                     float2 win0[C], win1[C];
 #pragma unroll
                     for (int k = 0; k < C; ++k) { win0[k] = h0.ld((size_t)k * NSP); win1[k] = h1.ld((size_t)k * NSP); }
-                    const float wp0 = (x0 == 0) ? NINF : h0.ld((size_t)C * NSP - 1).y, wp1 = (x0 == 0) ? NINF : h1.ld((size_t)C * NSP - 1).y;
+                    float wp0, wp1;                                 // W(row, x0 - 1): slot C of the strip to the left
+                    if (x0 == 0) { wp0 = NINF; wp1 = NINF; }
+                    else if (WB > 1 && lane == 0) { wp0 = handv.ld((warp - 1) * SG_HAND_ROWS + (q0 & HDm)).y; wp1 = handv.ld((warp - 1) * SG_HAND_ROWS + (q1 & HDm)).y; }
+                    else { wp0 = h0.ld((size_t)C * NSP - 1).y; wp1 = h1.ld((size_t)C * NSP - 1).y; }
                     fold(0u, ey0, true, win0, wp0);
                     fold(1u, ey1, false, win1, wp1);
                 }
@@ -462,7 +495,7 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
                     // W(yp, xp) for the M pairs: the source ring, the neighbour strip's history, the value store
                     auto w_cell = [&](int yp, int kq, int xp, int src) -> float {
                         if (src < 0) return w_left_of_strip(yp, kq);
-                        if (yp == y - 1 || y - yp < RR - 1 - ns) return ring.ld((size_t)src * RR + (yp & RRm)).y;
+                        if (yp == y - 1 || y - yp < RR - 1 - ns - SLACK) return ring.ld((size_t)src * RR + (yp & RRm)).y;   // (the owner may be SLACK steps ahead)
                         return kq < 0 ? CUDART_NAN_F : __ldcg(Vrow + (size_t)kq * ldVr + xp).w;
                     };
                     auto x_cand = [&](uint32_t kx, int src, float exj) {
@@ -543,7 +576,7 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
             }
             if (L == 0) Vcol[(size_t)kc0 * ldVc + y] = make_float4(m0, xs0, ys0, w0);   // column 0 is always kept
             outX = xl; outW = wl;
-            if (WB > 1 && lane == 31) handv.st(warp * 2 + (t & 1), make_float2(xl, wl));
+            if (WB > 1 && lane == 31) handv.st(warp * SG_HAND_ROWS + (y & HDm), make_float2(xl, wl));
             uint32_t* dp = D + ((size_t)t * ns + L) * W32;
             if (W32 == 1) dp[0] = rr[0];
             else if (W32 == 2) *reinterpret_cast<uint2*>(dp) = make_uint2(rr[0], rr[1]);

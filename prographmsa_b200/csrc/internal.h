@@ -262,5 +262,7 @@ size_t wave_smem_bytes(int ring, int max_n1, int max_n2, int max_tr, int max_np1
 int launch_graph_fill_wave(cudaStream_t st, int L, int ring, int threads, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_n1,
                            int max_n2, int max_tr, int max_np1, int max_nx);
 #define SG_MAX_WARPS 8       // warps per job of the general strip kernel (256 strips)
+#define SG_SLACK 48          // steps a warp of a job may run ahead of the job's last warp (point-to-point coupling of the warps)
+#define SG_HAND_ROWS 128     // rows of a warp's hand-over ring: >= SG_SLACK + 2 + the deepest history look-back (30 rows)
 #define SG_MAX_SRC 256       // source columns of non-adjacent column edges per job (shared-memory rings)
 __host__ __device__ __forceinline__ int strip_words(int C) { return C <= 8 ? 1 : (C <= 16 ? 2 : 4); }   // uint32 words of direction nibbles per strip and row
