@@ -90,10 +90,22 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         const float4* q = ring + (dd & (RING - 1)) * ring_pitch + (yy - y0);
         return (d - dd < RING && yy >= y0) ? q : g;
     };
-    auto ld_w = [](const float4* p) -> float { float v; asm volatile("ld.relaxed.gpu.f32 %0, [%1+12];" : "=f"(v) : "l"(p)); return v; };
-    auto ld_zw = [](const float4* p) -> float2 { float2 v; asm volatile("ld.relaxed.gpu.v2.f32 {%0,%1}, [%2+8];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v; };
-    auto ld_yw = [](const float4* p) -> float2 { float4 v; asm volatile("ld.relaxed.gpu.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return make_float2(v.y, v.w); };
+    auto ld_w = [](const float4* p) -> float {
+        if (!BANDED) return reinterpret_cast<const float*>(p)[3];           // one CTA per job: its own cells, through L1 as before
+        float v; asm volatile("ld.relaxed.gpu.f32 %0, [%1+12];" : "=f"(v) : "l"(p)); return v;
+    };
+    auto ld_zw = [](const float4* p) -> float2 {
+        if (!BANDED) return reinterpret_cast<const float2*>(p)[1];
+        float2 v; asm volatile("ld.relaxed.gpu.v2.f32 {%0,%1}, [%2+8];" : "=f"(v.x), "=f"(v.y) : "l"(p)); return v;
+    };
+    auto ld_yw = [](const float4* p) -> float2 {
+        if (!BANDED) { const float* f = reinterpret_cast<const float*>(p); return make_float2(f[1], f[3]); }
+        float4 v; asm volatile("ld.relaxed.gpu.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return make_float2(v.y, v.w);
+    };
     constexpr int GB = 4;                                        // predecessors per side the batched path holds
+    constexpr bool COOP = BANDED;                                // cells with many predecessor pairs are folded by the whole warp.  (In the one-CTA
+                                                                 // flavour the ballot per step cost 10 % on moderately deep jobs, 7.9 -> 8.7 ms at
+                                                                 // 629 x 1743, and gained 3 % on the deepest, 53.1 -> 51.2 ms at 566 x 10982.)
 
     NodeInfo ny[RPT]; bool ysimple[RPT]; float4 left[RPT];
 #pragma unroll
@@ -157,7 +169,7 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         for (int r = 0; r < RPT; ++r) {
             const int y = y0 + tid + r * T, x = d - y;
             const bool valid = !(y > N1 - 2 || x < 0 || x > N2 - 2);
-            if (!BANDED && !valid) continue;
+            if (!COOP && !valid) continue;
             float m = NINF, xs = NINF, ys = NINF, w = NINF;
             bool heavy = false;                                  // BANDED: a cell with more than GB predecessors on a side: the whole warp folds it (below)
             NodeInfo hx = NodeInfo{0, 0, 0, 0.f}; float hs = 0.f;
@@ -261,22 +273,38 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                             const float ey = ky ? P1V[ny[r].ptr + ky] : ny[r].val0;
                             const float4 cu = cell(yp, x, d);                        // (yp, x): Y, W
                             const float Sy = __fsub_rn(fmaxf(__fadd_rn(cu.z, gap_extend), __fadd_rn(cu.w, gap_init)), ey);
-                            for (int kx = 0; kx < c2; ++kx) {
-                                const int xp = kx ? P2I[nx.ptr + kx] : nx.idx0;
-                                const float ex = kx ? P2V[nx.ptr + kx] : nx.val0;
-                                const float4 cd = cell(yp, xp, d);                   // (yp, xp): W
-                                const float4 cl = cell(y, xp, d);                    // (y, xp): X, W
-                                const float Sm = __fsub_rn(__fsub_rn(__fadd_rn(cd.w, s), ey), ex);
-                                const float Sx = __fsub_rn(fmaxf(__fadd_rn(cl.y, gap_extend), __fadd_rn(cl.w, gap_init)), ex);
-                                const float Sw = fmaxf(Sm, fmaxf(Sx, Sy));
-                                m = fmaxf(m, Sm); xs = fmaxf(xs, Sx); ys = fmaxf(ys, Sy); w = fmaxf(w, Sw);
+                            if (c2 > 0) ys = fmaxf(ys, Sy);                      // (a column without predecessors has no candidates at all)
+                            // the column's predecessors four at a time, their cells loaded together: a deep profile column has a dozen
+                            // predecessors, and one L2 round trip per predecessor made the thread that met it the whole diagonal's pace
+                            // (a 632 x 6238 job took 6.8 us per anti-diagonal).  Absent slots repeat the first predecessor: a maximum
+                            // does not mind duplicates.
+                            for (int kx0 = 0; kx0 < c2; kx0 += 4) {
+                                int xpv[4]; float exv[4], cdw[4]; float2 clv[4];
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    const int kx = kx0 + q;
+                                    const bool on = kx > 0 && kx < c2;
+                                    xpv[q] = on ? P2I[nx.ptr + kx] : nx.idx0;
+                                    exv[q] = on ? P2V[nx.ptr + kx] : nx.val0;
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    cdw[q] = ld_w(cell_addr(yp, xpv[q], d));             // (yp, xp): W
+                                    clv[q] = ld_yw(cell_addr(y, xpv[q], d));             // (y, xp): X, W
+                                }
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    m = fmaxf(m, __fsub_rn(__fsub_rn(__fadd_rn(cdw[q], s), ey), exv[q]));
+                                    xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(clv[q].x, gap_extend), __fadd_rn(clv[q].y, gap_init)), exv[q]));
+                                }
                             }
                         }
+                        w = fmaxf(m, fmaxf(xs, ys));
                     }
                 }
             }
             }
-            if (BANDED) {
+            if (COOP) {
                 // Cells with many predecessors (deep profile columns reach dozens): one thread folding c1 x c2 pairs with an L2 round
                 // trip per pair held the whole band for tens of microseconds per anti-diagonal (ncu: a fifth of the kernel's
                 // instructions ran with 1.6 of 32 lanes active).  The warp folds such a cell together: lane l takes the pairs l, l + 32, ...,

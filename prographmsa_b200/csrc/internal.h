@@ -148,9 +148,10 @@ struct WaveCol { int x; int cnt; int xp0; float ex0; int xp1; float ex1; int ptr
 struct WaveCI { float ex_adj; int flags; };                  // flags bit 0: non-chain column (its cells belong to the column threads), bit 1: column x-1 is one
 #define GF_MAX_PREDS 128     // predecessors per node the packed traceback's index fields can hold (graphs beyond it take the dense kernels)
 
-#define GF_BAND_ROWS 512      // rows per band (= threads per CTA) of the banded anti-diagonal kernel
-#define GF_BAND_MIN_N1 1026    // graph 1 from this many nodes on is swept in bands (measured on the 5000-sequence run: 1026 / 512
-                              // gives 2.35 s of fill time against 2.79 s for 3074 / 1024)
+#define GF_BAND_ROWS 128      // rows per band (= threads per CTA) of the banded anti-diagonal kernel (<= 512: its register budget)
+#define GF_BAND_MIN_N1 700     // graph 1 from this many nodes on is swept in bands.  Measured on the upper levels (<= 12 jobs) of a
+                              // 5000-sequence pass (tools/levels_knobs.py), fill time per pass: 1026 / 512 rows 261 ms, 1026 / 128 rows
+                              // 237 ms, 600 / 128 rows 232 ms (graphs of ~600 rows with few non-chain rows lose 5-10 % in bands)
 #define GF_DIAG_REGULAR_ROWS 1024   // anti-diagonal kernel: up to this many rows one row per thread and the 8-diagonal ring
 #define GF_LAYOUT_BLOCK 0
 #define GF_LAYOUT_DIAG 1
