@@ -8,6 +8,7 @@
 #include "internal.h"
 #include <math_constants.h>
 #include <algorithm>
+#include <type_traits>
 #include <cstdlib>
 
 __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
@@ -33,7 +34,7 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 // Cells of other bands are read from HBM/L2 (the {M,X,Y,W} array itself is the exchange buffer); the row just above the
 // band, which the band's first row needs on every diagonal, is staged 8 diagonals at a time into shared memory right after
 // the flag check (it is complete by then), so that row runs the chain fast path like any other.
-template <bool STAGE, int RPT, int RING, bool SPF, bool BANDED>
+template <bool STAGE, int RPT, int RING, bool SPF, bool BANDED, bool DEEP = false>
 __global__ void __launch_bounds__(BANDED ? 512 : 1024)
 graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restrict__ order, int ring_pitch, int max_bands) {
     const GraphJobDev& J = jobs[order[BANDED ? blockIdx.x / max_bands : blockIdx.x]];
@@ -278,26 +279,32 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                             // predecessors, and one L2 round trip per predecessor made the thread that met it the whole diagonal's pace
                             // (a 632 x 6238 job took 6.8 us per anti-diagonal).  Absent slots repeat the first predecessor: a maximum
                             // does not mind duplicates.
-                            for (int kx0 = 0; kx0 < c2; kx0 += 4) {
-                                int xpv[4]; float exv[4], cdw[4]; float2 clv[4];
+                            auto fold_cols = [&](auto nb_tag) {
+                                constexpr int NB = decltype(nb_tag)::value;
+                                for (int kx0 = 0; kx0 < c2; kx0 += NB) {
+                                    int xpv[NB]; float exv[NB], cdw[NB]; float2 clv[NB];
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    const int kx = kx0 + q;
-                                    const bool on = kx > 0 && kx < c2;
-                                    xpv[q] = on ? P2I[nx.ptr + kx] : nx.idx0;
-                                    exv[q] = on ? P2V[nx.ptr + kx] : nx.val0;
-                                }
+                                    for (int q = 0; q < NB; ++q) {
+                                        const int kx = kx0 + q;
+                                        const bool on = kx > 0 && kx < c2;
+                                        xpv[q] = on ? P2I[nx.ptr + kx] : nx.idx0;
+                                        exv[q] = on ? P2V[nx.ptr + kx] : nx.val0;
+                                    }
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    cdw[q] = ld_w(cell_addr(yp, xpv[q], d));             // (yp, xp): W
-                                    clv[q] = ld_yw(cell_addr(y, xpv[q], d));             // (y, xp): X, W
-                                }
+                                    for (int q = 0; q < NB; ++q) {
+                                        cdw[q] = ld_w(cell_addr(yp, xpv[q], d));             // (yp, xp): W
+                                        clv[q] = ld_yw(cell_addr(y, xpv[q], d));             // (y, xp): X, W
+                                    }
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    m = fmaxf(m, __fsub_rn(__fsub_rn(__fadd_rn(cdw[q], s), ey), exv[q]));
-                                    xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(clv[q].x, gap_extend), __fadd_rn(clv[q].y, gap_init)), exv[q]));
+                                    for (int q = 0; q < NB; ++q) {
+                                        m = fmaxf(m, __fsub_rn(__fsub_rn(__fadd_rn(cdw[q], s), ey), exv[q]));
+                                        xs = fmaxf(xs, __fsub_rn(fmaxf(__fadd_rn(clv[q].x, gap_extend), __fadd_rn(clv[q].y, gap_init)), exv[q]));
+                                    }
                                 }
-                            }
+                            };
+                            // (chosen per launch: per cell it would diverge, per job at run time both loops in one kernel ran slower.  Measured: 629 x 1743 with 571 non-chain columns 7.9 ms one at
+                            // a time, 8.8 ms four at a time; 566 x 10982 74 against 53 ms)
+                            fold_cols(std::integral_constant<int, DEEP ? 4 : 1>{});   // DEEP: the launch has a graph 2 of >= 4000 nodes (a profile of ~1000 sequences or more)
                         }
                         w = fmaxf(m, fmaxf(xs, ys));
                     }
@@ -321,21 +328,38 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                     const float yv0 = __shfl_sync(0xffffffffu, ny[r].val0, src), xv0 = __shfl_sync(0xffffffffu, hx.val0, src);
                     const float bs = __shfl_sync(0xffffffffu, hs, src);
                     float pm = NINF, pxs = NINF, pys = NINF;
-                    for (int q = lane; q < c1 * c2; q += 32) {
+                    {   // first round: the lane's pair, X candidate and Y candidate -- index loads together, then the three cell loads
+                        // together (two dependent round trips per cell instead of six)
+                        const int n12 = c1 * c2;
+                        const bool op = lane < n12, ox = lane < c2, oy = lane < c1;
+                        const int j = op ? lane / c2 : 0, k = op ? lane - j * c2 : 0;
+                        const int ypP = j ? P1I[p1 + j] : yi0, xpP = k ? P2I[p2 + k] : xi0;
+                        const float eyP = j ? P1V[p1 + j] : yv0, exP = k ? P2V[p2 + k] : xv0;
+                        const int xpX = (ox && lane) ? P2I[p2 + lane] : xi0; const float exX = (ox && lane) ? P2V[p2 + lane] : xv0;
+                        const int ypY = (oy && lane) ? P1I[p1 + lane] : yi0; const float eyY = (oy && lane) ? P1V[p1 + lane] : yv0;
+                        float cdw = NINF; float2 cl = make_float2(NINF, NINF), cu = make_float2(NINF, NINF);
+                        if (op) cdw = ld_w(cell_addr(ypP, xpP, d));
+                        if (ox) cl = ld_yw(cell_addr(by, xpX, d));
+                        if (oy) cu = ld_zw(cell_addr(ypY, bx, d));
+                        pm = __fsub_rn(__fsub_rn(__fadd_rn(cdw, bs), eyP), exP);
+                        pxs = __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gap_init)), exX);
+                        pys = __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, gap_init)), eyY);
+                    }
+                    for (int q = lane + 32; q < c1 * c2; q += 32) {
                         const int j = q / c2, k = q - j * c2;
                         const int yp = j ? P1I[p1 + j] : yi0, xp = k ? P2I[p2 + k] : xi0;
                         const float ey = j ? P1V[p1 + j] : yv0, ex = k ? P2V[p2 + k] : xv0;
                         pm = fmaxf(pm, __fsub_rn(__fsub_rn(__fadd_rn(ld_w(cell_addr(yp, xp, d)), bs), ey), ex));
                     }
-                    for (int k = lane; k < c2; k += 32) {
-                        const int xp = k ? P2I[p2 + k] : xi0;
-                        const float ex = k ? P2V[p2 + k] : xv0;
+                    for (int k = lane + 32; k < c2; k += 32) {
+                        const int xp = P2I[p2 + k];
+                        const float ex = P2V[p2 + k];
                         const float2 cl = ld_yw(cell_addr(by, xp, d));
                         pxs = fmaxf(pxs, __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gap_init)), ex));
                     }
-                    for (int j = lane; j < c1; j += 32) {
-                        const int yp = j ? P1I[p1 + j] : yi0;
-                        const float ey = j ? P1V[p1 + j] : yv0;
+                    for (int j = lane + 32; j < c1; j += 32) {
+                        const int yp = P1I[p1 + j];
+                        const float ey = P1V[p1 + j];
                         const float2 cu = ld_zw(cell_addr(yp, bx, d));
                         pys = fmaxf(pys, __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, gap_init)), ey));
                     }
@@ -382,10 +406,10 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
     }
 }
 
-template <bool STAGE, int RPT, int RING, bool SPF>
+template <bool STAGE, int RPT, int RING, bool SPF, bool DEEP>
 static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int threads, int ring_pitch, size_t smem) {
-    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, RPT, RING, SPF, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_fill_diag_kernel<STAGE, RPT, RING, SPF, false><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch, 1);
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, RPT, RING, SPF, false, DEEP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_fill_diag_kernel<STAGE, RPT, RING, SPF, false, DEEP><<<n_jobs, threads, smem, st>>>(d_jobs, d_order, ring_pitch, 1);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -436,8 +460,10 @@ int launch_graph_fill_diag(cudaStream_t st, int n_jobs, const GraphJobDev* d_job
     if (ring > 227 * 1024) { pgm_set_error("graph too large for the shared-memory diagonal ring (N1 = %d, limit ~3500)", max_n1); return PGM_ERR_ARG; }
     const bool stage = ring + info <= 200 * 1024;
     const size_t smem = ring + (stage ? info : 0);
-#define GO(S_, R_) do { if (regular) return launch_fill_diag_t<S_, R_, GF_RING, true>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); \
-                        return launch_fill_diag_t<S_, R_, GF_RING_LONG, false>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); } while (0)
+    const bool deep = max_n2 >= 4000 && rpt == 1;
+#define GO(S_, R_) do { if (regular && deep && R_ == 1) return launch_fill_diag_t<S_, 1, GF_RING, true, true>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); \
+                        if (regular) return launch_fill_diag_t<S_, R_, GF_RING, true, false>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); \
+                        return launch_fill_diag_t<S_, R_, GF_RING_LONG, false, false>(st, n_jobs, d_jobs, d_order, threads, ring_pitch, smem); } while (0)
     if (stage) { if (rpt == 1) GO(true, 1); if (rpt == 2) GO(true, 2); GO(true, 4); }
     if (rpt == 1) GO(false, 1); if (rpt == 2) GO(false, 2); GO(false, 4);
 #undef GO
