@@ -36,6 +36,8 @@ import numpy as np
 N_SEQ, SEQ_LEN, SEED = 500, 400, 1
 GRAPH_N_SEQ = 256
 GRAPH_REPLICAS = 4
+LEAF_LEVEL_JOBS = 2500      # bottom level of BASELINE configs[4] (5000 sequences x 500 aa)
+LEAF_LEVEL_LEN = 500
 WORKLOAD = "all-pairs NW+ML distance matrix, %d synthetic protein seqs x %d aa, WAG, -a -m" % (N_SEQ, SEQ_LEN)
 METRIC = "all-pairs NW+ML distance-matrix throughput (graph-DP GCUPS in graph_dp)"
 UNIT = "GCUPS"
@@ -333,6 +335,53 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 score_checksum=float(sum(r["score"] for r in res)))
         finally:
             gb.close()
+    # Second workload: the bottom level of BASELINE configs[4] -- 2500 leaf x leaf jobs of a 5000-sequence x 500-aa family (half of a
+    # progressive pass's cells sit in its two bottom levels).  Enough independent sweeps to fill the GPU, so this is the fill kernels'
+    # THROUGHPUT, where the mixed batch above measures the latency of its few long sweeps.
+    try:
+        from prographmsa_b200.graph import sequence_graph
+        seqs5, _ = synth.simulate_family(LEAF_LEVEL_JOBS * 2, LEAF_LEVEL_LEN, mf, seed=SEED + 2)
+        names5 = sorted(seqs5)
+        mdl = mf.getModel(0.3, 0.3)
+        ljobs = [(sequence_graph(seqs5[names5[2 * k]], 20), sequence_graph(seqs5[names5[2 * k + 1]], 20), mdl) for k in range(LEAF_LEVEL_JOBS)]
+        gb = graphalign.GraphBatch(ljobs, opts, graphalign.EMISSION_EXACT, ctx)
+        try:
+            flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+            ctx.enable_timing(True)
+            os.environ["PGM_GRAPH_PIPELINE"] = "0"
+            for _ in range(warmup):
+                gb.run(); ctx.sync()
+            tl = dict(emission_ms=0.0, graph_fill_ms=0.0, graph_trace_ms=0.0)
+            tot = 0.0
+            for _ in range(steps):
+                flush.fill_(1); torch.cuda.synchronize()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); gb.run(); ctx.sync(); b.record(); torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+                t = ctx.timing()
+                for k in tl: tl[k] += t[k]
+                upd5, cells5 = t["graph_cell_updates"], t["graph_cells"]
+            os.environ.pop("PGM_GRAPH_PIPELINE")
+            fill5 = tl["graph_fill_ms"] / steps
+            lanes_peak = 148 * 128 * pk.get("sm_max_mhz", 1965.0) * 1e6 / 1e12
+            out["leaf_level"] = dict(
+                workload="%d leaf x leaf alignGraphs jobs, %d aa (bottom level of a %d-sequence progressive pass, BASELINE configs[4])" % (LEAF_LEVEL_JOBS, LEAF_LEVEL_LEN, 2 * LEAF_LEVEL_JOBS),
+                value=upd5 / (tot / steps) / 1e6, unit="GCUPS", ms_per_step=tot / steps, jobs=LEAF_LEVEL_JOBS, cell_updates=upd5, cells=cells5,
+                kernels_ms=dict(emission=tl["emission_ms"] / steps, fill=fill5, trace=tl["graph_trace_ms"] / steps),
+                fill_gcups=upd5 / fill5 / 1e6,
+                roofline=dict(bound="hbm", kernel="graph_fill_strip_kernel", achieved=5.0 * cells5 / fill5 / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
+                              frac=5.0 * cells5 / fill5 / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                              note="algorithmic bytes = 5 B/cell (SURVEY 8d: 4 B S read + 1 B packed traceback).  The kernel itself moves ~0.6 B/cell: "
+                                   "leaf graphs are class-coded (S is a 21 x 21 table per job) and the traceback is 4 bits per cell, so this is the "
+                                   "section-8d figure, not DRAM traffic; the binding roof is instruction issue (roofline_issue)"),
+                roofline_issue=dict(bound="sm fp32 issue", kernel="graph_fill_strip_kernel", achieved=17.0 * upd5 / fill5 / 1e9, peak=lanes_peak, unit="Tlane-op/s",
+                                    frac=17.0 * upd5 / fill5 / 1e9 / lanes_peak,
+                                    note="algorithmic work = 17 fp32 add/max per cell update; the kernel executes 1.39 warp instructions per cell "
+                                         "(25 for the recurrences and the 4 direction bits, the rest per-step overhead), profiles/r2_strip_chain.txt"))
+        finally:
+            gb.close()
+    except Exception as e:
+        out["leaf_level"] = dict(unavailable=str(e))
     out["workload"] = ("%d alignGraphs jobs in one batch: the %d internal-node jobs (leaf x leaf up to profile x profile graphs) of a "
                        "progressive pass over %d synthetic seqs x %d aa (WAG), replicated x%d" % (len(jobs), base_jobs, GRAPH_N_SEQ, SEQ_LEN, GRAPH_REPLICAS))
     return out

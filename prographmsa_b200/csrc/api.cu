@@ -35,6 +35,8 @@ struct pgm_ctx {
     std::vector<NwTask> h_tasks, h_ftasks; std::vector<int8_t> h_tab8;
     DevBuf d_off, d_codes, d_descs, d_tasks, d_ftasks, d_tab, d_tb, d_colbuf, d_list, d_list_len, d_gaps, d_dist, d_var,
            d_counts, d_scores, d_misc, d_rows, d_seqlen;
+    DevBuf d_full;                                  // two N x N matrices (Prealigned all-pairs result, scattered on the device)
+    DevBuf d_pre_rows, d_pre_counts, d_pre_gaps;    // Prealigned: pitched rows, one chunk's uint16 counts and gap openings
     DevBuf d_tb2, d_list2;                          // second traceback / list set: chunk k+1's forward overlaps chunk k's walk + ML
     cudaStream_t stream2 = nullptr;                 // walk + ML of the chunk pipeline
     cudaEvent_t ev_fwd[2] = {nullptr, nullptr}, ev_wm[2] = {nullptr, nullptr};
@@ -119,7 +121,7 @@ void pgm_destroy(pgm_ctx* c) {
     resolve_timing(c);
     for (DevBuf* b : {&c->d_model, &c->d_off, &c->d_ftasks, &c->d_codes, &c->d_descs, &c->d_tasks, &c->d_tab, &c->d_tb, &c->d_colbuf, &c->d_list,
                       &c->d_list_len, &c->d_gaps, &c->d_dist, &c->d_var, &c->d_counts, &c->d_scores, &c->d_misc, &c->d_rows,
-                      &c->d_seqlen, &c->d_tb2, &c->d_list2}) b->release();
+                      &c->d_seqlen, &c->d_tb2, &c->d_list2, &c->d_pre_rows, &c->d_pre_counts, &c->d_pre_gaps, &c->d_full}) b->release();
     if (c->stream2) cudaStreamDestroy(c->stream2);
     for (int k = 0; k < 2; ++k) { if (c->ev_fwd[k]) cudaEventDestroy(c->ev_fwd[k]); if (c->ev_wm[k]) cudaEventDestroy(c->ev_wm[k]); }
     c->h_stage.release();
@@ -440,6 +442,18 @@ static int nw_ml_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* 
     return 0;
 }
 
+// full[i][j] = full[j][i] = packed[p(i,j)], zero diagonal: one thread per matrix element (both triangles read the packed arrays)
+__global__ void scatter_pairs_kernel(const double* __restrict__ dp, const double* __restrict__ vp, int N, double* __restrict__ dist, double* __restrict__ var) {
+    const size_t total = (size_t)N * N;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (size_t)gridDim.x * blockDim.x) {
+        const int r = (int)(k / N), q = (int)(k - (size_t)r * N);
+        const int i = r < q ? r : q, j = r < q ? q : r;
+        double d = 0.0, v = 0.0;
+        if (i != j) { const size_t p = (size_t)i * N - (size_t)i * (i + 1) / 2 + (size_t)(j - i - 1); d = dp[p]; v = vp[p]; }
+        dist[k] = d; var[k] = v;
+    }
+}
+
 static void scatter_pairs(const double* dp, const double* vp, int N, double* dist, double* var) {
     for (size_t k = 0; k < (size_t)N * N; ++k) dist[k] = var[k] = 0;
     size_t p = 0;
@@ -515,8 +529,28 @@ static int prealigned_range_dev(pgm_ctx* c, const pgm_ml_params* prm, const uint
     unsigned long long* d_evals = (unsigned long long*)(c->d_misc.as<char>() + 16);
     {
         ScopedKernelTimer t(c, K_ML);
-        rc = launch_ml_from_rows(c->stream, ml, N, L, pb, pe - pb, d_rows, d_dist, d_var, d_counts, d_gaps, d_evals);
-        if (rc) return rc;
+        const char* e = getenv("PGM_PREALIGNED_FUSED");
+        if ((e && e[0] == '1') || L > 65535) {                         // (16-bit counters)  the round-1 flavour: column scan inside the Newton kernel (A-B runs)
+            rc = launch_ml_from_rows(c->stream, ml, N, L, pb, pe - pb, d_rows, d_dist, d_var, d_counts, d_gaps, d_evals);
+            if (rc) return rc;
+        } else {
+            // residue lists per row, then list merge (thread per pair) and Newton kernel per chunk of pairs; the chunk's counts (lim x lim uint16 per pair) live in
+            // scratch: 4 Mi pairs = 3.4 GB for proteins
+            const int lim = ml.n < 20 ? ml.n : 20;
+            const int64_t np = pe - pb, chunk = std::min<int64_t>(np, (int64_t)4 << 20);
+            if ((rc = c->d_pre_rows.reserve((size_t)std::max(N, 1) * prealigned_pitch(L) * 4))) return rc;      // residue lists (uint32 entries)
+            if ((rc = c->d_pre_counts.reserve((size_t)chunk * lim * lim * 2))) return rc;
+            if ((rc = c->d_pre_gaps.reserve((size_t)chunk * 4))) return rc;
+            if ((rc = launch_prealigned_repitch(c->stream, d_rows, N, L, c->d_pre_rows.as<uint8_t>()))) return rc;
+            const size_t nn = (size_t)ml.n * ml.n;
+            for (int64_t q = 0; q < np; q += chunk) {
+                const int64_t m = std::min<int64_t>(chunk, np - q);
+                rc = launch_ml_from_rows_split(c->stream, ml, N, L, pb + q, m, c->d_pre_rows.as<uint8_t>(), c->d_pre_counts.as<uint16_t>(),
+                                               c->d_pre_gaps.as<uint32_t>(), d_dist + q, d_var + q, d_counts ? d_counts + (size_t)q * nn : nullptr,
+                                               d_gaps ? d_gaps + q : nullptr, d_evals);
+                if (rc) return rc;
+            }
+        }
     }
     unsigned long long ev = 0;
     PGM_CUDA(cudaMemcpyAsync(&ev, d_evals, 8, cudaMemcpyDeviceToHost, c->stream));
@@ -559,13 +593,29 @@ int pgm_prealigned_ml_pair_range(pgm_ctx* c, const pgm_ml_params* prm, const uin
 }
 
 int pgm_prealigned_ml_all_pairs(pgm_ctx* c, const pgm_ml_params* prm, const uint8_t* rows, int N, int L, double* dist, double* var) {
-    if (N < 0) { pgm_set_error("N < 0"); return PGM_ERR_ARG; }
+    if (!c || !prm) { pgm_set_error("ctx/prm is NULL"); return PGM_ERR_ARG; }
+    if (N < 0 || L < 0) { pgm_set_error("bad arguments"); return PGM_ERR_ARG; }
+    PGM_CUDA(cudaSetDevice(c->device));
+    reset_timing(c);
     const int64_t np = (int64_t)N * (N - 1) / 2;
-    std::vector<double> dp(std::max<int64_t>(np, 1)), vp(std::max<int64_t>(np, 1));
-    int rc = pgm_prealigned_ml_pair_range(c, prm, rows, N, L, 0, np, dp.data(), vp.data(), nullptr, nullptr);
+    const size_t full = (size_t)N * N;
+    if (np == 0) { for (size_t k = 0; k < full; ++k) dist[k] = var[k] = 0; return 0; }
+    // the packed (dist, var) of the pairs are spread into the two symmetric N x N matrices on the device and come back as two copies:
+    // at N = 5000 the host-side scatter (two 200 MB matrices written with stride N) took longer than all the kernels together
+    int rc;
+    if ((rc = c->d_rows.reserve(std::max<size_t>((size_t)N * L, 1)))) return rc;
+    if ((rc = c->d_dist.reserve(np * 8))) return rc;
+    if ((rc = c->d_var.reserve(np * 8))) return rc;
+    if ((rc = c->d_full.reserve(2 * full * 8))) return rc;
+    PGM_CUDA(cudaMemcpyAsync(c->d_rows.p, rows, (size_t)N * L, cudaMemcpyHostToDevice, c->stream));
+    rc = prealigned_range_dev(c, prm, c->d_rows.as<uint8_t>(), N, L, 0, np, c->d_dist.as<double>(), c->d_var.as<double>(), nullptr, nullptr);
     if (rc) return rc;
-    scatter_pairs(dp.data(), vp.data(), N, dist, var);
-    return 0;
+    double* fd = c->d_full.as<double>(); double* fv = fd + full;
+    scatter_pairs_kernel<<<148 * 8, 256, 0, c->stream>>>(c->d_dist.as<double>(), c->d_var.as<double>(), N, fd, fv);
+    PGM_CUDA(cudaGetLastError());
+    PGM_CUDA(cudaMemcpyAsync(dist, fd, full * 8, cudaMemcpyDeviceToHost, c->stream));
+    PGM_CUDA(cudaMemcpyAsync(var, fv, full * 8, cudaMemcpyDeviceToHost, c->stream));
+    return pgm_sync(c);
 }
 
 int pgm_angle_all_pairs(pgm_ctx* c, int n, int K, const uint8_t* codes, const uint32_t* offsets, int N, int ml_flag,

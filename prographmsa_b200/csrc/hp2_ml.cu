@@ -19,7 +19,7 @@
 #include "internal.h"
 #include <mutex>
 
-enum { FRONT_LIST = 0, FRONT_ROWS = 1, FRONT_COUNTS = 2 };
+enum { FRONT_LIST = 0, FRONT_ROWS = 1, FRONT_COUNTS = 2, FRONT_COUNTS16 = 3 };
 
 struct MlFront {
     // LIST
@@ -28,6 +28,8 @@ struct MlFront {
     const uint8_t* rows; int N; int L; long long pair_begin;
     // COUNTS
     const int32_t* counts_in; const double* seqlen_in;
+    // COUNTS16 (the column-scan kernel's output: lim x lim uint16 per pair, lim = min(n, 20); gaps_in; every pair's length is L)
+    const uint16_t* counts16_in; int lim;
     uint32_t* gaps_out; int32_t* counts_out;
 };
 
@@ -182,6 +184,12 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
                 if (ns) { const int q = 31 - __clz(ns); carry = ((mA >> q) & 1u) ? 1 : (((mB >> q) & 1u) ? 2 : 0); }
               }
             }
+            seqlen = ((double)fr.L + (double)fr.L) / 2.0;
+        } else if (FRONT == FRONT_COUNTS16) {
+            const int lim = fr.lim, ll = lim * lim;
+            const uint16_t* __restrict__ cp = fr.counts16_in + (size_t)p * ll;
+            for (int q = lane; q < ll; q += 32) { const int ci = q / lim, cj = q - ci * lim; hist[ci * n + cj] = (uint32_t)cp[q]; }
+            gaps = fr.gaps_in[p];
             seqlen = ((double)fr.L + (double)fr.L) / 2.0;
         } else {
             const int32_t* cp = fr.counts_in + (size_t)p * nn;
@@ -342,6 +350,137 @@ int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_tasks, const ui
     fr.tasks = d_tasks; fr.off = d_off; fr.list = d_list; fr.list_len = d_list_len; fr.gaps_in = d_gaps;
     fr.counts_out = d_counts; fr.task_pairs = task_pairs;
     return launch_ml<FRONT_LIST>(st, ml, fr, (long long)n_tasks * task_pairs, d_dist, d_var, d_evals);
+}
+
+// ---- K2: the column scan of DistanceFactoryPrealigned<A>::computePwDistances (DistanceFactoryPrealigned.h:57-84) on its own ----
+// The warp-per-pair scan above spends a shared-memory atomic, four ballots and two byte loads per 32 columns and runs at 16 warps per SM next
+// to the 67 KB likelihood table: 69 ns per pair at 11,000 columns.  But a row of a large alignment is mostly gaps (500 residues in 11,000
+// columns for 5000 sequences), and a column where both rows have a gap changes nothing (:68-69).  So:
+//   * prealigned_lists_kernel turns every row into the sorted list of its residues, (column << 8 | state), closed by two sentinels;
+//   * prealigned_count_kernel gives one THREAD a pair and MERGES the two lists by column: equal columns are a match (counted when both
+//     states are < 20, :65), a column in one list only opens or continues a gap run in that row (:70-79) -- len1 + len2 - matches steps
+//     instead of L_aln columns, every step branch-free (what counts nothing increments a dummy bin), the next entry of either list
+//     already in a register;
+//   * the thread's lim x lim histogram of 16-bit counters sits in shared memory as hist[bin][thread], laid out so that the 32 lanes of a
+//     warp hit 32 different banks whatever their bins: no atomics, no conflicts, no ballots;
+//   * the counts go to HBM as lim x lim uint16 per pair and the Newton kernel reads them back (ml_kernel<FRONT_COUNTS16>).
+#define PC_THREADS 128
+#define PC_GAP 254u
+#define PC_SENT 0xffffffu
+__global__ void __launch_bounds__(256)
+prealigned_lists_kernel(const uint8_t* __restrict__ rows, int L, uint32_t* __restrict__ lists, size_t lp) {
+    __shared__ int wsum[8];
+    __shared__ int base_s;
+    const uint8_t* __restrict__ r = rows + (size_t)blockIdx.x * L;
+    uint32_t* __restrict__ out = lists + (size_t)blockIdx.x * lp;
+    const int tid = (int)threadIdx.x, lane = tid & 31, w = tid >> 5;
+    if (tid == 0) base_s = 0;
+    __syncthreads();
+    for (int k0 = 0; k0 < L; k0 += 256) {
+        const int k = k0 + tid;
+        const uint32_t c = k < L ? (uint32_t)r[k] : PC_GAP;
+        const bool res = c != PC_GAP;
+        const uint32_t m = __ballot_sync(0xffffffffu, res);
+        if (lane == 0) wsum[w] = __popc(m);
+        __syncthreads();
+        int off = base_s;
+        for (int q = 0; q < w; ++q) off += wsum[q];
+        if (res) out[off + __popc(m & ((1u << lane) - 1u))] = ((uint32_t)k << 8) | c;
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int q = 0; q < 8; ++q) t += wsum[q]; base_s += t; }
+        __syncthreads();
+    }
+    if (tid < 2) out[base_s + tid] = PC_SENT << 8;
+}
+
+__global__ void __launch_bounds__(PC_THREADS, 2)
+prealigned_count_kernel(const uint32_t* __restrict__ lists, size_t lp, int N, long long pair_begin, long long n_pairs, int lim,
+                        uint16_t* __restrict__ counts16, uint32_t* __restrict__ gaps_out) {
+    extern __shared__ __align__(16) unsigned char pc_smem[];
+    const int tid = (int)threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int ll = lim * lim;
+    // halfword (bin, thread) at byte bin * 2 * PC_THREADS + my: warps 2k and 2k+1 share the words of one 128-byte row
+    const uint32_t my = (uint32_t)__cvta_generic_to_shared(pc_smem) + (uint32_t)((lane + 32 * (w >> 1)) * 4 + (w & 1) * 2);
+    constexpr uint32_t BIN = 2u * PC_THREADS;
+    for (int b = 0; b <= ll; ++b) asm volatile("st.shared.u16 [%0], %1;" ::"r"(my + (uint32_t)b * BIN), "h"((unsigned short)0) : "memory");
+    const long long p = (long long)blockIdx.x * PC_THREADS + tid;
+    const bool on = p < n_pairs;
+    int i = 0, j = 1;
+    if (on) pair_from_index(pair_begin + p, N, i, j);
+    const uint32_t* __restrict__ A = lists + (size_t)i * lp;
+    const uint32_t* __restrict__ B = lists + (size_t)j * lp;
+    uint32_t gaps = 0, carry = 0;                                // carry: 0 = none / match, 1 = run in row 1, 2 = run in row 2
+    const uint32_t dummy = (uint32_t)ll;
+    uint32_t ea = on ? __ldg(A) : (PC_SENT << 8), eb = on ? __ldg(B) : (PC_SENT << 8);
+    uint32_t ean = __ldg(A + 1), ebn = __ldg(B + 1);
+    int ia = 1, ib = 1;                                          // index of ean / ebn
+    for (;;) {
+        const uint32_t ca = ea >> 8, cb = eb >> 8;
+        if ((ca & cb) == PC_SENT) break;                         // both lists are through
+        const bool ta = ca <= cb, tb = cb <= ca;                 // the earlier column comes next; equal columns: both rows have a residue
+        const uint32_t c1 = ea & 0xffu, c2 = eb & 0xffu;
+        const bool cnt = ta && tb && c1 < (uint32_t)lim && c2 < (uint32_t)lim;          // hard-coded 20, DistanceFactoryPrealigned.h:65
+        const uint32_t addr = my + (cnt ? c1 * (uint32_t)lim + c2 : dummy) * BIN;
+        unsigned short v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+        v = (unsigned short)(v + 1);
+        asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+        const uint32_t t = ta ? (tb ? 0u : 1u) : 2u;             // 0 match, 1 residue in row 1 only, 2 in row 2 only
+        gaps += (uint32_t)(t != 0u && t != carry);               // a run opens (DistanceFactoryPrealigned.h:70-79)
+        carry = t;
+        ea = ta ? ean : ea; eb = tb ? ebn : eb;
+        ia += ta ? 1 : 0; ib += tb ? 1 : 0;
+        ean = __ldg(A + ia); ebn = __ldg(B + ib);                // (behind a sentinel sits the second sentinel: never past the list)
+    }
+    if (on) {
+        uint16_t* __restrict__ out = counts16 + (size_t)p * ll;
+        if ((ll & 7) == 0) {
+            for (int b0 = 0; b0 < ll; b0 += 8) {
+                uint32_t h[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(my + (uint32_t)(b0 + u) * BIN) : "memory"); h[u] = v; }
+                *reinterpret_cast<uint4*>(out + b0) = make_uint4(h[0] | (h[1] << 16), h[2] | (h[3] << 16), h[4] | (h[5] << 16), h[6] | (h[7] << 16));
+            }
+        } else {
+            for (int b0 = 0; b0 < ll; ++b0) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(my + (uint32_t)b0 * BIN) : "memory"); out[b0] = v; }
+        }
+        gaps_out[p] = gaps;
+    }
+}
+
+size_t prealigned_pitch(int L) { return (size_t)std::max(L, 0) + 2; }      // entries per row list: every column a residue + two sentinels
+
+// rows (N x L, device) -> residue lists in d_lists (N x prealigned_pitch(L) uint32)
+int launch_prealigned_repitch(cudaStream_t st, const uint8_t* d_rows, int N, int L, uint8_t* d_lists) {
+    if (N <= 0) return 0;
+    prealigned_lists_kernel<<<N, 256, 0, st>>>(d_rows, L, (uint32_t*)d_lists, prealigned_pitch(L));
+    PGM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// one chunk of pairs [pair_begin, pair_begin + n_pairs): list merge into d_counts16 / d_gaps16 (chunk-local indices), then the Newton
+// kernel on those counts; d_dist / d_var / d_counts / d_gaps are the chunk's output positions
+int launch_ml_from_rows_split(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs, const uint8_t* d_lists,
+                              uint16_t* d_counts16, uint32_t* d_gaps16, double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps,
+                              unsigned long long* d_evals) {
+    if (n_pairs <= 0) return 0;
+    const int lim = ml.n < 20 ? ml.n : 20;
+    const size_t smem = (size_t)(lim * lim + 1) * 2 * PC_THREADS;
+    static std::mutex mu; static size_t opted[64] = {0};
+    int dev = 0; PGM_CUDA(cudaGetDevice(&dev));
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (opted[dev & 63] < smem) {
+            PGM_CUDA(cudaFuncSetAttribute(prealigned_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            opted[dev & 63] = smem;
+        }
+    }
+    prealigned_count_kernel<<<(unsigned)((n_pairs + PC_THREADS - 1) / PC_THREADS), PC_THREADS, smem, st>>>(
+        (const uint32_t*)d_lists, prealigned_pitch(L), N, (long long)pair_begin, (long long)n_pairs, lim, d_counts16, d_gaps16);
+    PGM_CUDA(cudaGetLastError());
+    MlFront fr{};
+    fr.counts16_in = d_counts16; fr.lim = lim; fr.gaps_in = d_gaps16; fr.L = L; fr.counts_out = d_counts; fr.gaps_out = d_gaps;
+    return launch_ml<FRONT_COUNTS16>(st, ml, fr, n_pairs, d_dist, d_var, d_evals);
 }
 
 int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,

@@ -120,6 +120,11 @@ int launch_nw_walk(cudaStream_t st, int n_tasks, int n_states, const uint8_t* d_
 int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_tasks, const uint32_t* d_off, const NwTask* d_tasks,
                          const uint16_t* d_list, const uint32_t* d_list_len, const uint32_t* d_gaps, double* d_dist,
                          double* d_var, int32_t* d_counts, unsigned long long* d_evals, int task_pairs);
+size_t prealigned_pitch(int L);
+int launch_prealigned_repitch(cudaStream_t st, const uint8_t* d_rows, int N, int L, uint8_t* d_pitched);
+int launch_ml_from_rows_split(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs, const uint8_t* d_pitched,
+                              uint16_t* d_counts16, uint32_t* d_gaps16, double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps,
+                              unsigned long long* d_evals);
 int launch_ml_from_rows(cudaStream_t st, const MlDev& ml, int N, int L, int64_t pair_begin, int64_t n_pairs,
                         const uint8_t* d_rows, double* d_dist, double* d_var, int32_t* d_counts, uint32_t* d_gaps,
                         unsigned long long* d_evals);
