@@ -364,7 +364,7 @@ int launch_ml_from_lists(cudaStream_t st, const MlDev& ml, int n_tasks, const ui
 //   * the thread's lim x lim histogram of 16-bit counters sits in shared memory as hist[bin][thread], laid out so that the 32 lanes of a
 //     warp hit 32 different banks whatever their bins: no atomics, no conflicts, no ballots;
 //   * the counts go to HBM as lim x lim uint16 per pair and the Newton kernel reads them back (ml_kernel<FRONT_COUNTS16>).
-#define PC_THREADS 128
+#define PC_THREADS 64
 #define PC_GAP 254u
 #define PC_SENT 0xffffffu
 __global__ void __launch_bounds__(256)
@@ -393,7 +393,7 @@ prealigned_lists_kernel(const uint8_t* __restrict__ rows, int L, uint32_t* __res
     if (tid < 2) out[base_s + tid] = PC_SENT << 8;
 }
 
-__global__ void __launch_bounds__(PC_THREADS, 2)
+__global__ void __launch_bounds__(PC_THREADS)
 prealigned_count_kernel(const uint32_t* __restrict__ lists, size_t lp, int N, long long pair_begin, long long n_pairs, int lim,
                         uint16_t* __restrict__ counts16, uint32_t* __restrict__ gaps_out) {
     extern __shared__ __align__(16) unsigned char pc_smem[];
@@ -472,6 +472,12 @@ int launch_ml_from_rows_split(cudaStream_t st, const MlDev& ml, int N, int L, in
         std::lock_guard<std::mutex> lk(mu);
         if (opted[dev & 63] < smem) {
             PGM_CUDA(cudaFuncSetAttribute(prealigned_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            // the lists are read 4 bytes at a time, 64 different rows per CTA: with all 228 KB as shared memory (four CTAs per SM) the
+            // L1 that is left thrashes and every step of the merge is an L2 round trip (430 cycles per step measured); three CTAs
+            // leave ~90 KB of L1
+            int carve = 64;
+            if (const char* e = getenv("PGM_PC_CARVEOUT")) carve = atoi(e);
+            PGM_CUDA(cudaFuncSetAttribute(prealigned_count_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve));
             opted[dev & 63] = smem;
         }
     }

@@ -183,6 +183,41 @@ def test_prealigned_vs_oracle(dist_mod, po, n, L):
         assert v[p] == pytest.approx(v_ref, rel=1e-7, abs=1e-300)
 
 
+def test_prealigned_flavours_and_all_pairs_matrix_agree(dist_mod, po, monkeypatch):
+    """The list-merge column scan (default) against the round-1 scan fused into the Newton kernel (PGM_PREALIGNED_FUSED=1): identical
+    counts, gap openings, distances and variances; and pgm_prealigned_ml_all_pairs (results scattered into the N x N matrices on the
+    device) against the packed pair range.  Rows as a large alignment has them: mostly gaps, a few residues each, some rows empty."""
+    opts = Options(mldist_flag=True)
+    mf = model.getDefault(opts)
+    rng = np.random.default_rng(77)
+    N, L = 40, 2000
+    rows = np.full((N, L), alphabet.GAP, dtype=np.uint8)
+    shared = np.sort(rng.choice(L, 120, replace=False))
+    for i in range(N):
+        cols = np.unique(np.concatenate([shared[rng.random(120) < 0.8], rng.integers(0, L, 25)]))
+        rows[i, cols] = rng.integers(0, 21, len(cols))              # 20 = an unknown state: resets the runs, is not counted
+    rows[3, :] = alphabet.GAP                                        # a row without residues
+    rows[5, :] = alphabet.GAP; rows[5, L - 1] = 4                    # one residue in the last column
+    fac = dist_mod.DistanceFactoryPrealigned(mf, opts)
+    P = N * (N - 1) // 2
+    d, v, counts, gaps = fac.pair_range(rows, 0, P, want_counts=True)
+    for p, (i, j) in list(enumerate(_pairs(N)))[::7]:
+        c_ref, g_ref = po.prealigned_counts(rows[i], rows[j], 20)
+        assert np.array_equal(counts[p], c_ref) and gaps[p] == g_ref, (i, j, gaps[p], g_ref)
+    monkeypatch.setenv("PGM_PREALIGNED_FUSED", "1")
+    d2, v2, counts2, gaps2 = fac.pair_range(rows, 0, P, want_counts=True)
+    monkeypatch.delenv("PGM_PREALIGNED_FUSED")
+    assert np.array_equal(counts, counts2) and np.array_equal(gaps, gaps2)
+    assert np.array_equal(d, d2) and np.array_equal(v, v2)
+    d3, v3 = fac.pair_range(rows, 100, 300)                          # a pair range that starts inside row 2
+    assert np.array_equal(d3, d[100:300]) and np.array_equal(v3, v[100:300])
+    seqs = {"r%03d" % i: rows[i] for i in range(N)}
+    dm = fac.computePwDistances(seqs, sorted(seqs))
+    for p, (i, j) in enumerate(_pairs(N)):
+        assert dm.distances[i, j] == d[p] and dm.distances[j, i] == d[p] and dm.variances[i, j] == v[p] and dm.variances[j, i] == v[p]
+    assert not dm.distances.diagonal().any() and not dm.variances.diagonal().any()
+
+
 def test_prealigned_matches_reference_binary(dist_mod):
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
