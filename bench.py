@@ -370,10 +370,11 @@ def graph_dp_bench(ctx, torch, steps, warmup, pk):
                 kernels_ms=dict(emission=tl["emission_ms"] / steps, fill=fill5, trace=tl["graph_trace_ms"] / steps),
                 fill_gcups=upd5 / fill5 / 1e6,
                 roofline=dict(bound="hbm", kernel="graph_fill_strip_kernel", achieved=5.0 * cells5 / fill5 / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
-                              frac=5.0 * cells5 / fill5 / 1e6 / pk["hbm_gbs"], traffic=None, peak_source=pk["source"],
+                              frac=5.0 * cells5 / fill5 / 1e6 / pk["hbm_gbs"], traffic=379235584.0, peak_source=pk["source"],
                               note="algorithmic bytes = 5 B/cell (SURVEY 8d: 4 B S read + 1 B packed traceback).  The kernel itself moves ~0.6 B/cell: "
                                    "leaf graphs are class-coded (S is a 21 x 21 table per job) and the traceback is 4 bits per cell, so this is the "
-                                   "section-8d figure, not DRAM traffic; the binding roof is instruction issue (roofline_issue)"),
+                                   "section-8d figure, not DRAM traffic (traffic: 55 MB read + 324 MB written per launch, ncu capture profiles/r2b_strip_leaf_level.txt); "
+                                   "the binding roof is instruction issue (roofline_issue: ncu shows 64 % of the issue slots busy)"),
                 roofline_issue=dict(bound="sm fp32 issue", kernel="graph_fill_strip_kernel", achieved=17.0 * upd5 / fill5 / 1e9, peak=lanes_peak, unit="Tlane-op/s",
                                     frac=17.0 * upd5 / fill5 / 1e9 / lanes_peak,
                                     note="algorithmic work = 17 fp32 add/max per cell update; the kernel executes 1.39 warp instructions per cell "
@@ -406,7 +407,8 @@ def other_kernels_bench(ctx, torch, lib, prm, acc, steps, pk, seqs, names):
     # Prealigned: a pseudo-alignment of the bench family (gap columns inserted at random), all pairs, device-resident
     rng = np.random.default_rng(3)
     L_aln = int(max(len(seqs[k]) for k in names) * 1.6) & ~15
-    rows = np.full((len(names), L_aln), 255, dtype=np.uint8)
+    from prographmsa_b200 import alphabet as _alpha
+    rows = np.full((len(names), L_aln), _alpha.GAP, dtype=np.uint8)
     for r, k in enumerate(names):
         pos = np.sort(rng.choice(L_aln, size=len(seqs[k]), replace=False))
         rows[r, pos] = seqs[k]
@@ -427,11 +429,41 @@ def other_kernels_bench(ctx, torch, lib, prm, acc, steps, pk, seqs, names):
     b.record(); torch.cuda.synchronize()
     ms = a.elapsed_time(b) / steps
     alg = 2.0 * L_aln * P                                                # bytes if both rows of every pair are read once
-    out["prealigned"] = dict(bound="hbm", kernel="ml_kernel<FRONT_ROWS> (column scan + Newton)", workload="%d rows x %d columns, %d pairs" % (N, L_aln, P),
+    out["prealigned"] = dict(bound="hbm", kernel="prealigned_lists_kernel + prealigned_count_kernel (list merge) + ml_kernel<FRONT_COUNTS16> (Newton)", workload="%d rows x %d columns, %d pairs" % (N, L_aln, P),
                              ms_per_matrix=ms, pairs_per_s=P / ms * 1e3, achieved=alg / ms / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
                              frac=alg / ms / 1e6 / pk["hbm_gbs"],
                              note="algorithmic bytes = 2 L_aln per pair (section 8d, rows re-read per pair); the rows (%.1f MB) stay in L2, so this "
                                   "is a fraction of HBM peak reached out of L2, and the time includes the Newton iterations" % (rows.nbytes / 1e6))
+    # the same path on rows shaped like BASELINE configs[4]'s alignment: 11,000 columns, 500 residues per row (the rest gaps)
+    try:
+        N5, L5, R5 = 2000, 11008, 500
+        rows5 = np.full((N5, L5), _alpha.GAP, dtype=np.uint8)
+        shared = np.sort(rng.choice(L5, R5, replace=False))
+        for r in range(N5):
+            cols = shared.copy()
+            k = rng.integers(0, R5, 60); cols[k] = rng.integers(0, L5, 60)      # ~10 % of a row's residues sit in columns of its own
+            cols = np.unique(cols)
+            rows5[r, cols] = rng.integers(0, 20, len(cols))
+        P5 = N5 * (N5 - 1) // 2
+        d_rows5 = torch.from_numpy(rows5).cuda()
+        d_out5 = torch.zeros(2, P5, dtype=torch.float64, device="cuda")
+        def step5():
+            _lib.check(lib.pgm_prealigned_ml_pair_range_dev(ctx.handle, C.byref(prm), vp(d_rows5), N5, L5, C.c_int64(0), C.c_int64(P5),
+                                                            vp(d_out5[0]), vp(d_out5[1]), None, None))
+        step5(); torch.cuda.synchronize()
+        a.record()
+        for _ in range(3):
+            step5()
+        b.record(); torch.cuda.synchronize()
+        ms5 = a.elapsed_time(b) / 3
+        alg5 = 2.0 * L5 * P5
+        out["prealigned_config5_shape"] = dict(bound="hbm", kernel=out["prealigned"]["kernel"], workload="%d rows x %d columns (%d residues each), %d pairs" % (N5, L5, R5, P5),
+                                               ms_per_matrix=ms5, pairs_per_s=P5 / ms5 * 1e3, achieved=alg5 / ms5 / 1e6, peak=pk["hbm_gbs"], unit="GB/s",
+                                               frac=alg5 / ms5 / 1e6 / pk["hbm_gbs"],
+                                               note="algorithmic bytes = 2 L_aln per pair (section 8d).  The list merge reads 4 B per residue instead "
+                                                    "(~8 KB per pair at 500 residues per row, from L2), so this is the section-8d figure, not traffic")
+    except Exception as e:
+        out["prealigned_config5_shape"] = dict(unavailable=str(e))
     return out
 
 
