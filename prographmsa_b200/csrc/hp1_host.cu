@@ -136,13 +136,14 @@ int max_preds(const pgm_graph& g) {
 // ---- job analysis (parallel over jobs): everything that decides sizes ------------------------------------------------------
 struct BatchEnv {                 // environment switches, read once per create (tests, A-B runs, profiling)
     int force_layout = -1, diag_min_generic = 8, band_min_n1 = GF_BAND_MIN_N1, long_band_rows = GF_BAND_ROWS;
+    bool band_rows_forced = false;
     int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, strip = 2, coding = 1, strip_c = 0, hist_kb = 0, dbg = 0, strip_max_generic = 16;
     int wave = 1, wave_L = 0, wave_ring = 0;
     BatchEnv() {
         if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
         if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
         if (const char* e = getenv("PGM_FILL_BAND_MIN_N1")) band_min_n1 = std::max(66, atoi(e));
-        if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 64 && v <= 512) long_band_rows = v; }
+        if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 32 && v <= 512) { long_band_rows = v; band_rows_forced = true; } }
         if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
         if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
         if (const char* e = getenv("PGM_FILL_SMALL_BATCH")) small_batch = atoi(e);      // fewer jobs than three per SM: latency-bound (measured crossover 300..440 jobs of 400 x 400)
@@ -359,7 +360,10 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
         // the first row of a band pays an L2 round trip per anti-diagonal
         L.band_rows = 0;
         if (L.layout == GF_LAYOUT_DIAG) {
-            if (a.N >= env.band_min_n1) L.band_rows = env.long_band_rows;
+            // band height: one warp per band (no CTA barrier per diagonal) for a short graph against a long profile -- 700-1100 rows against
+            // 10,000 columns 55.9 -> 47.8 ms; on a tall graph the pipeline of 100+ bands costs more than the barrier saves (3455 x 1982:
+            // 38.7 ms at 128 rows, 42.5 at 32), and squarish graphs lose as well (868 x 1120: 6.8 -> 7.5 ms).  PGM_FILL_BAND_ROWS forces one height.
+            if (a.N >= env.band_min_n1) L.band_rows = env.band_rows_forced ? env.long_band_rows : (a.N <= 1100 && bb.N >= 4 * a.N ? 32 : env.long_band_rows);
             else if (env.split_rows > 0 && generic > env.split_min_generic && a.N - 1 >= 2 * env.split_rows) L.band_rows = env.split_rows;
         }
         L.bands = L.band_rows ? (a.N - 1 + L.band_rows - 1) / L.band_rows : 1;

@@ -228,6 +228,9 @@ FLAVOURS = {
     "block": {"PGM_FILL_LAYOUT": "block"},
     "diag": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_WAVE": "0"},
     "banded": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_BAND_MIN_N1": "66", "PGM_FILL_BAND_ROWS": "64"},
+    "banded_one_warp": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_BAND_MIN_N1": "66", "PGM_FILL_BAND_ROWS": "32"},
+    "banded_auto_height": {"PGM_FILL_LAYOUT": "diag", "PGM_FILL_BAND_MIN_N1": "66"},
+    "strip_cta_barrier": {"PGM_STRIP_DEBUG": "16", "PGM_FILL_STRIP": "3"},
     "nostrip": {"PGM_FILL_STRIP": "0"},
     "strip_chain_only": {"PGM_FILL_STRIP": "1"},
     "strip_c4": {"PGM_STRIP_C": "4"},
