@@ -18,6 +18,7 @@ __device__ __forceinline__ size_t skew(int y, int x, int N2, int pitch) {
 }
 
 #define GF_RING 8            // anti-diagonals of {M,X,Y,W} kept in shared memory (power of two): covers skip edges spanning <= 5 nodes
+#define GF_RING_BAND 8       // banded flavour (16 or 32 diagonals: -5 % where graph 2's node infos still fit in shared memory beside the ring, +10 % where they no longer do)
 #define GF_RING_LONG 4       // ... for graphs too long for 8 (>= 4: rows d, d-1, d-2 are live at once); S is then read directly
 // S is row-major by y; each (thread,row) streams its own row 16 bytes (4 columns) at a time with cp.async,
 // 8 columns (= 8 anti-diagonals) ahead, into a private ring of four float4 slots
@@ -419,8 +420,8 @@ static int launch_fill_diag_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_
 template <bool STAGE>
 static int launch_banded_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows, size_t smem) {
     (void)n_sms;
-    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, 1, GF_RING, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    graph_fill_diag_kernel<STAGE, 1, GF_RING, true, true><<<n_jobs * max_bands, band_rows, smem, st>>>(d_jobs, d_order, band_rows, max_bands);
+    PGM_CUDA(cudaFuncSetAttribute(graph_fill_diag_kernel<STAGE, 1, GF_RING_BAND, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    graph_fill_diag_kernel<STAGE, 1, GF_RING_BAND, true, true><<<n_jobs * max_bands, band_rows, smem, st>>>(d_jobs, d_order, band_rows, max_bands);
     PGM_CUDA(cudaGetLastError());
     return 0;
 }
@@ -431,7 +432,7 @@ static int launch_banded_t(cudaStream_t st, int n_jobs, const GraphJobDev* d_job
 int launch_graph_fill_banded(cudaStream_t st, int n_jobs, const GraphJobDev* d_jobs, const int* d_order, int max_bands, int n_sms, int band_rows,
                              int max_n2, int max_np) {
     if (n_jobs == 0) return 0;
-    const size_t ring = (size_t)GF_RING * band_rows * sizeof(float4) + (size_t)4 * band_rows * sizeof(float4);
+    const size_t ring = (size_t)GF_RING_BAND * band_rows * sizeof(float4) + (size_t)4 * band_rows * sizeof(float4);
     const size_t info = (size_t)max_n2 * sizeof(NodeInfo) + (size_t)max_np * 8 + 64;
     if (ring + info <= 200 * 1024) return launch_banded_t<true>(st, n_jobs, d_jobs, d_order, max_bands, n_sms, band_rows, ring + info);
     return launch_banded_t<false>(st, n_jobs, d_jobs, d_order, max_bands, n_sms, band_rows, ring);
