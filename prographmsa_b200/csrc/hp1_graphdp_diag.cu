@@ -319,49 +319,50 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                 // three warp maxima, the owner keeps the result.  A maximum does not depend on the order, so the values are unchanged.
                 unsigned hb = __ballot_sync(0xffffffffu, heavy);
                 const int lane = tid & 31;
-                while (hb) {
-                    const int src = __ffs(hb) - 1;
-                    hb &= hb - 1;
-                    const int by = __shfl_sync(0xffffffffu, y, src), bx = __shfl_sync(0xffffffffu, x, src);
-                    const int c1 = __shfl_sync(0xffffffffu, ny[r].cnt, src) & 0x7fffffff, c2 = __shfl_sync(0xffffffffu, hx.cnt, src) & 0x7fffffff;
-                    const int p1 = __shfl_sync(0xffffffffu, ny[r].ptr, src), p2 = __shfl_sync(0xffffffffu, hx.ptr, src);
-                    const int yi0 = __shfl_sync(0xffffffffu, ny[r].idx0, src), xi0 = __shfl_sync(0xffffffffu, hx.idx0, src);
-                    const float yv0 = __shfl_sync(0xffffffffu, ny[r].val0, src), xv0 = __shfl_sync(0xffffffffu, hx.val0, src);
-                    const float bs = __shfl_sync(0xffffffffu, hs, src);
-                    float pm = NINF, pxs = NINF, pys = NINF;
-                    {   // first round: the lane's pair, X candidate and Y candidate -- index loads together, then the three cell loads
-                        // together (two dependent round trips per cell instead of six)
-                        const int n12 = c1 * c2;
-                        const bool op = lane < n12, ox = lane < c2, oy = lane < c1;
-                        const int j = op ? lane / c2 : 0, k = op ? lane - j * c2 : 0;
-                        const int ypP = j ? P1I[p1 + j] : yi0, xpP = k ? P2I[p2 + k] : xi0;
-                        const float eyP = j ? P1V[p1 + j] : yv0, exP = k ? P2V[p2 + k] : xv0;
-                        const int xpX = (ox && lane) ? P2I[p2 + lane] : xi0; const float exX = (ox && lane) ? P2V[p2 + lane] : xv0;
-                        const int ypY = (oy && lane) ? P1I[p1 + lane] : yi0; const float eyY = (oy && lane) ? P1V[p1 + lane] : yv0;
-                        float cdw = NINF; float2 cl = make_float2(NINF, NINF), cu = make_float2(NINF, NINF);
-                        if (op) cdw = ld_w(cell_addr(ypP, xpP, d));
-                        if (ox) cl = ld_yw(cell_addr(by, xpX, d));
-                        if (oy) cu = ld_zw(cell_addr(ypY, bx, d));
-                        pm = __fsub_rn(__fsub_rn(__fadd_rn(cdw, bs), eyP), exP);
-                        pxs = __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gap_init)), exX);
-                        pys = __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, gap_init)), eyY);
+                // two cells per round: the second cell's loads are in flight while the first is finished (a warp of a deep profile meets
+                // two or three such cells on most anti-diagonals, and each costs two dependent L2 round trips)
+                struct Fold { int src, by, bx, c1, c2, p1, p2, yi0, xi0; float yv0, xv0, bs, eyP, exP, exX, eyY, cdw; float2 cl, cu; };
+                auto fold_issue = [&](const int src, Fold& F) {
+                    F.src = src;
+                    F.by = __shfl_sync(0xffffffffu, y, src); F.bx = __shfl_sync(0xffffffffu, x, src);
+                    F.c1 = __shfl_sync(0xffffffffu, ny[r].cnt, src) & 0x7fffffff; F.c2 = __shfl_sync(0xffffffffu, hx.cnt, src) & 0x7fffffff;
+                    F.p1 = __shfl_sync(0xffffffffu, ny[r].ptr, src); F.p2 = __shfl_sync(0xffffffffu, hx.ptr, src);
+                    F.yi0 = __shfl_sync(0xffffffffu, ny[r].idx0, src); F.xi0 = __shfl_sync(0xffffffffu, hx.idx0, src);
+                    F.yv0 = __shfl_sync(0xffffffffu, ny[r].val0, src); F.xv0 = __shfl_sync(0xffffffffu, hx.val0, src);
+                    F.bs = __shfl_sync(0xffffffffu, hs, src);
+                    // first round: the lane's pair, X candidate and Y candidate -- index loads together, then the three cell loads together
+                    const int n12 = F.c1 * F.c2;
+                    const bool op = lane < n12, ox = lane < F.c2, oy = lane < F.c1;
+                    const int j = op ? lane / F.c2 : 0, k = op ? lane - j * F.c2 : 0;
+                    const int ypP = j ? P1I[F.p1 + j] : F.yi0, xpP = k ? P2I[F.p2 + k] : F.xi0;
+                    F.eyP = j ? P1V[F.p1 + j] : F.yv0; F.exP = k ? P2V[F.p2 + k] : F.xv0;
+                    const int xpX = (ox && lane) ? P2I[F.p2 + lane] : F.xi0; F.exX = (ox && lane) ? P2V[F.p2 + lane] : F.xv0;
+                    const int ypY = (oy && lane) ? P1I[F.p1 + lane] : F.yi0; F.eyY = (oy && lane) ? P1V[F.p1 + lane] : F.yv0;
+                    F.cdw = NINF; F.cl = make_float2(NINF, NINF); F.cu = make_float2(NINF, NINF);
+                    if (op) F.cdw = ld_w(cell_addr(ypP, xpP, d));
+                    if (ox) F.cl = ld_yw(cell_addr(F.by, xpX, d));
+                    if (oy) F.cu = ld_zw(cell_addr(ypY, F.bx, d));
+                };
+                auto fold_finish = [&](const Fold& F) {
+                    float pm = __fsub_rn(__fsub_rn(__fadd_rn(F.cdw, F.bs), F.eyP), F.exP);
+                    float pxs = __fsub_rn(fmaxf(__fadd_rn(F.cl.x, gap_extend), __fadd_rn(F.cl.y, gap_init)), F.exX);
+                    float pys = __fsub_rn(fmaxf(__fadd_rn(F.cu.x, gap_extend), __fadd_rn(F.cu.y, gap_init)), F.eyY);
+                    for (int q = lane + 32; q < F.c1 * F.c2; q += 32) {
+                        const int j = q / F.c2, k = q - j * F.c2;
+                        const int yp = j ? P1I[F.p1 + j] : F.yi0, xp = k ? P2I[F.p2 + k] : F.xi0;
+                        const float ey = j ? P1V[F.p1 + j] : F.yv0, ex = k ? P2V[F.p2 + k] : F.xv0;
+                        pm = fmaxf(pm, __fsub_rn(__fsub_rn(__fadd_rn(ld_w(cell_addr(yp, xp, d)), F.bs), ey), ex));
                     }
-                    for (int q = lane + 32; q < c1 * c2; q += 32) {
-                        const int j = q / c2, k = q - j * c2;
-                        const int yp = j ? P1I[p1 + j] : yi0, xp = k ? P2I[p2 + k] : xi0;
-                        const float ey = j ? P1V[p1 + j] : yv0, ex = k ? P2V[p2 + k] : xv0;
-                        pm = fmaxf(pm, __fsub_rn(__fsub_rn(__fadd_rn(ld_w(cell_addr(yp, xp, d)), bs), ey), ex));
-                    }
-                    for (int k = lane + 32; k < c2; k += 32) {
-                        const int xp = P2I[p2 + k];
-                        const float ex = P2V[p2 + k];
-                        const float2 cl = ld_yw(cell_addr(by, xp, d));
+                    for (int k = lane + 32; k < F.c2; k += 32) {
+                        const int xp = P2I[F.p2 + k];
+                        const float ex = P2V[F.p2 + k];
+                        const float2 cl = ld_yw(cell_addr(F.by, xp, d));
                         pxs = fmaxf(pxs, __fsub_rn(fmaxf(__fadd_rn(cl.x, gap_extend), __fadd_rn(cl.y, gap_init)), ex));
                     }
-                    for (int j = lane + 32; j < c1; j += 32) {
-                        const int yp = P1I[p1 + j];
-                        const float ey = P1V[p1 + j];
-                        const float2 cu = ld_zw(cell_addr(yp, bx, d));
+                    for (int j = lane + 32; j < F.c1; j += 32) {
+                        const int yp = P1I[F.p1 + j];
+                        const float ey = P1V[F.p1 + j];
+                        const float2 cu = ld_zw(cell_addr(yp, F.bx, d));
                         pys = fmaxf(pys, __fsub_rn(fmaxf(__fadd_rn(cu.x, gap_extend), __fadd_rn(cu.y, gap_init)), ey));
                     }
 #pragma unroll
@@ -370,7 +371,19 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
                         pxs = fmaxf(pxs, __shfl_xor_sync(0xffffffffu, pxs, o));
                         pys = fmaxf(pys, __shfl_xor_sync(0xffffffffu, pys, o));
                     }
-                    if (lane == src) { m = pm; xs = pxs; ys = pys; w = fmaxf(pm, fmaxf(pxs, pys)); }
+                    if (lane == F.src) { m = pm; xs = pxs; ys = pys; w = fmaxf(pm, fmaxf(pxs, pys)); }
+                };
+                while (hb) {
+                    const int src0 = __ffs(hb) - 1;
+                    hb &= hb - 1;
+                    const bool two = hb != 0u;
+                    const int src1 = two ? __ffs(hb) - 1 : src0;
+                    hb &= hb - 1;                                    // (0 stays 0)
+                    Fold A, B;
+                    fold_issue(src0, A);
+                    if (two) fold_issue(src1, B);
+                    fold_finish(A);
+                    if (two) fold_finish(B);
                 }
             }
             if (valid) {
