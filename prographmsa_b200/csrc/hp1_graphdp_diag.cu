@@ -104,7 +104,7 @@ graph_fill_diag_kernel(const GraphJobDev* __restrict__ jobs, const int* __restri
         if (!BANDED) { const float* f = reinterpret_cast<const float*>(p); return make_float2(f[1], f[3]); }
         float4 v; asm volatile("ld.relaxed.gpu.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p)); return make_float2(v.y, v.w);
     };
-    constexpr int GB = 4;                                        // predecessors per side the batched path holds
+    constexpr int GB = 4;                                        // predecessors per side the batched path holds (measured: 2 -> the top levels 178 -> 325 ms, cells with 3-4 predecessors are common; extra 2 x 8 / 8 x 2 shapes -> 195 ms, the variants diverge)
     constexpr bool COOP = BANDED;                                // cells with many predecessor pairs are folded by the whole warp.  (In the one-CTA
                                                                  // flavour the ballot per step cost 10 % on moderately deep jobs, 7.9 -> 8.7 ms at
                                                                  // 629 x 1743, and gained 3 % on the deepest, 53.1 -> 51.2 ms at 566 x 10982.)
