@@ -119,9 +119,11 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
     double* wb = sW + warp * n * 4;
     uint32_t* hist = sHist + warp * nn;
     unsigned long long my_evals = 0;
+    const uint32_t div_n = ((1u << 20) + (uint32_t)n - 1u) / (uint32_t)n;
 
     for (long long p = (long long)blockIdx.x * WARPS + warp; p < n_pairs; p += (long long)gridDim.x * WARPS) {
-        for (int i = lane; i < nn; i += 32) hist[i] = 0;
+        if (!(FRONT == FRONT_COUNTS16 && fr.lim == n))              // (that front-end overwrites every entry)
+            for (int i = lane; i < nn; i += 32) hist[i] = 0;
         __syncwarp();
         uint32_t gaps = 0;
         double seqlen = 0;
@@ -188,7 +190,13 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
         } else if (FRONT == FRONT_COUNTS16) {
             const int lim = fr.lim, ll = lim * lim;
             const uint16_t* __restrict__ cp = fr.counts16_in + (size_t)p * ll;
-            for (int q = lane; q < ll; q += 32) { const int ci = q / lim, cj = q - ci * lim; hist[ci * n + cj] = (uint32_t)cp[q]; }
+            if (lim == n) {                                         // the histogram is the count matrix: two counts per load
+                const uint32_t* __restrict__ cw = reinterpret_cast<const uint32_t*>(cp);      // (lim x lim uint16 per pair, lim even or 1 pair: 4-byte aligned when ll is even)
+                if ((ll & 1) == 0) { for (int q = lane; 2 * q < ll; q += 32) { const uint32_t v = cw[q]; hist[2 * q] = v & 0xffffu; hist[2 * q + 1] = v >> 16; } }
+                else for (int q = lane; q < ll; q += 32) hist[q] = (uint32_t)cp[q];
+            } else {
+                for (int q = lane; q < ll; q += 32) { const int ci = q / lim, cj = q - ci * lim; hist[ci * n + cj] = (uint32_t)cp[q]; }
+            }
             gaps = fr.gaps_in[p];
             seqlen = ((double)fr.L + (double)fr.L) / 2.0;
         } else {
@@ -210,7 +218,7 @@ ml_kernel(MlDev ml, MlFront fr, long long n_pairs, double* __restrict__ dist_out
         for (int base = 0; base < nn; base += 32) {
             const int idx = base + lane;
             uint32_t c = (idx < nn) ? hist[idx] : 0u;
-            const int ci = idx / n, cj = idx - ci * n;
+            const int ci = (int)(((uint32_t)idx * div_n) >> 20), cj = idx - ci * n;     // idx / n for idx < 4096, n <= 63 (div_n = ceil(2^20 / n))
             if (c) { total += c; if (ci == cj) ident += c; }
             // reversible model: P'/P and P''/P are the same for (i,j) and (j,i), so the two counts share one entry
             if (ml.symmetric && idx < nn) { if (ci > cj) c = 0u; else if (ci < cj) c += hist[cj * n + ci]; }
