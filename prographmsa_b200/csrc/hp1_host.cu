@@ -137,12 +137,14 @@ int max_preds(const pgm_graph& g) {
 struct BatchEnv {                 // environment switches, read once per create (tests, A-B runs, profiling)
     int force_layout = -1, diag_min_generic = 8, band_min_n1 = GF_BAND_MIN_N1, long_band_rows = GF_BAND_ROWS;
     bool band_rows_forced = false;
+    int band_min_nowave = 550;
     int split_rows = 0, split_min_generic = 24, small_batch = 3 * 148, strip = 2, coding = 1, strip_c = 0, hist_kb = 0, dbg = 0, strip_max_generic = 16;
     int wave = 1, wave_L = 0, wave_ring = 0;
     BatchEnv() {
         if (const char* e = getenv("PGM_FILL_LAYOUT")) force_layout = !strcmp(e, "diag") ? GF_LAYOUT_DIAG : (!strcmp(e, "block") ? GF_LAYOUT_BLOCK : (!strcmp(e, "strip") ? GF_LAYOUT_STRIP : -1));
         if (const char* e = getenv("PGM_FILL_DIAG_MIN")) diag_min_generic = atoi(e);
-        if (const char* e = getenv("PGM_FILL_BAND_MIN_N1")) band_min_n1 = std::max(66, atoi(e));
+        if (const char* e = getenv("PGM_FILL_BAND_MIN_N1")) { band_min_n1 = std::max(66, atoi(e)); band_min_nowave = band_min_n1; }
+        if (const char* e = getenv("PGM_FILL_BAND_MIN_NOWAVE")) band_min_nowave = std::max(66, atoi(e));
         if (const char* e = getenv("PGM_FILL_BAND_ROWS")) { const int v = atoi(e) & ~31; if (v >= 32 && v <= 512) { long_band_rows = v; band_rows_forced = true; } }
         if (const char* e = getenv("PGM_FILL_SPLIT_ROWS")) split_rows = atoi(e) & ~31;
         if (const char* e = getenv("PGM_FILL_SPLIT_MIN")) split_min_generic = atoi(e);
@@ -409,6 +411,15 @@ int pgm_graph_batch_create(pgm_ctx* c, int n, int n_jobs, const pgm_graph* g1, c
             if (lw && !dup && wave_smem_bytes(8, a.N, bb.N, tr, L.np1, nx) <= 227 * 1024) {
                 L.wave = 1; L.wv_tr = tr; L.wv_chain_pad = ru32(nchain); L.wv_ncols = generic2; L.wv_nx = nx; L.wv_L = lw; L.wv_tcols = tcols;
             }
+        }
+        // Graphs of band_min_nowave .. band_min_n1 rows that the wave kernel does not take (too many non-chain columns in flight): bands too.
+        // The one-CTA thread-per-row kernel folds a cell's predecessor pairs one at a time; the banded one does it with the warp
+        // (629 x 1743 with 118 + 571 non-chain nodes 7.7 -> 6.9 ms, levels of 675-700-row graphs 3.1-3.6 -> 2.9-3.1 ms), while the
+        // wave kernel's jobs lose in bands (levels of ~600-row graphs with ~50 + 50 non-chain nodes 1.5-1.9 -> 2.2-2.4 ms).
+        if (!L.wave && L.layout == GF_LAYOUT_DIAG && L.band_rows == 0 && a.N >= env.band_min_nowave && a.N < env.band_min_n1 && !env.split_rows) {
+            L.band_rows = env.band_rows_forced ? env.long_band_rows : (bb.N >= 4 * a.N ? 32 : env.long_band_rows);
+            L.bands = (a.N - 1 + L.band_rows - 1) / L.band_rows;
+            if (L.bands == 1) L.band_rows = 0;
         }
         {   // keep sets of the strip kernels (see mark_far_sources); the dense kernels keep everything
             L.keep1.assign(a.N, 0); L.keep2.assign(bb.N, 0);
