@@ -197,14 +197,18 @@ nj_join_kernel(const double* __restrict__ D, const double* __restrict__ V, int d
 
 // the join's new taxon takes row and column alive[i1], in place: the BioNJ combination of the two joined rows
 __global__ void __launch_bounds__(256)
-nj_update_kernel(double* __restrict__ D, double* __restrict__ V, int dim, int P, const int* __restrict__ alive, const NjParams* __restrict__ prm) {
+nj_update_kernel(double* __restrict__ D, double* __restrict__ V, int dim, int P, const int* __restrict__ alive, const NjParams* __restrict__ prm, int clamp) {
     const int i1 = prm->i1, i2 = prm->i2;
     const double d1 = prm->d1, d2 = prm->d2, lam = prm->lam, v12 = prm->v12;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;            // the other taxon, logical
     if (k >= dim || k == i1 || k == i2) return;
     const int a1 = alive[i1], a2 = alive[i2], ks = alive[k];
-    const double d = lam * (D[(size_t)a1 * P + ks] - d1) + (1.0 - lam) * (D[(size_t)a2 * P + ks] - d2);
-    const double v = lam * V[(size_t)a1 * P + ks] + (1.0 - lam) * V[(size_t)a2 * P + ks] - lam * (1.0 - lam) * v12;
+    double d = lam * (D[(size_t)a1 * P + ks] - d1) + (1.0 - lam) * (D[(size_t)a2 * P + ks] - d2);
+    double v = lam * V[(size_t)a1 * P + ks] + (1.0 - lam) * V[(size_t)a2 * P + ks] - lam * (1.0 - lam) * v12;
+    // the next iteration's clamp (TreeNJ.cpp: distances >= 1e-4, variances >= 1e-5 at the top of the loop) touches only what this
+    // join writes, so it is applied here instead of by a launch of its own (the diagonal entry stays 0); the last join's values are
+    // what the caller gets back, unclamped
+    if (clamp) { d = fmax(d, NJ_MIN_DIST); v = fmax(v, NJ_MIN_VAR); }
     D[(size_t)a1 * P + ks] = d; D[(size_t)ks * P + a1] = d;
     V[(size_t)a1 * P + ks] = v; V[(size_t)ks * P + a1] = v;
 }
@@ -282,13 +286,12 @@ extern "C" int pgm_bionj_joins(pgm_ctx* c, int N, const double* D, const double*
             nj_iota_kernel<<<(dim + 255) / 256, 256, 0, st>>>(alive, dim);
             cur ^= 1; phys = dim;
         }
-        const size_t n_clamp = join == 0 ? (size_t)dim * dim : 2 * (size_t)dim;
-        nj_clamp_kernel<<<(unsigned)((n_clamp + 255) / 256), 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, prm, join == 0);
+        if (join == 0) nj_clamp_kernel<<<(unsigned)(((size_t)dim * dim + 255) / 256), 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, prm, 1);   // later joins: nj_update_kernel clamps what it writes
         nj_colsum_kernel<<<(dim + 31) / 32, 256, CS_STAGES * CS_ROWS * 32 * sizeof(double), st>>>(Dm[cur], dim, N, alive, sums);
         const int nblk = std::min(ARGMIN_BLOCKS, dim);
         nj_argmin_kernel<<<nblk, ARGMIN_THREADS, 0, st>>>(Dm[cur], dim, N, alive, sums, part);
         nj_join_kernel<<<1, ARGMIN_THREADS, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, sums, part, nblk, prm, join, dj1, dj2, dd1, dd2);
-        nj_update_kernel<<<(dim + 255) / 256, 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, prm);
+        nj_update_kernel<<<(dim + 255) / 256, 256, 0, st>>>(Dm[cur], Vm[cur], dim, N, alive, prm, join + 1 < n_joins);
         nj_drop_kernel<<<1, 1024, 0, st>>>(alive, dim, prm);
         e = cudaGetLastError();
     }
