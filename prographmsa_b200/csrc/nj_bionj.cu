@@ -112,14 +112,33 @@ __global__ void __launch_bounds__(ARGMIN_THREADS)
 nj_argmin_kernel(const double* __restrict__ D, int dim, int P, const int* __restrict__ alive, const double* __restrict__ sums, NjCand* __restrict__ part) {
     const double c = 0.5 / ((double)dim - 2.0);
     double bq = CUDART_INF; unsigned long long bf = ~0ull;
-    for (int i = blockIdx.x; i < dim; i += gridDim.x) {
-        const double si = sums[i];
-        const double* __restrict__ row = D + (size_t)alive[i] * P;
+    // the block's rows i = blockIdx.x, + gridDim.x, ...: their physical row and column sum once in shared memory; a thread keeps its
+    // column's (alive, sum) in registers and reads four rows' entries at a time (eight: no faster) (independent loads).  The minimum is over a total
+    // order (q, flat index), so the order of evaluation does not matter.
+    constexpr int MAXR = 64;                                        // rows per block per pass
+    __shared__ int r_phys[MAXR]; __shared__ double r_sum[MAXR];
+    for (int rbase = blockIdx.x; rbase < dim; rbase += MAXR * gridDim.x) {
+        const int nr = min(MAXR, (dim - rbase + (int)gridDim.x - 1) / (int)gridDim.x);
+        __syncthreads();
+        for (int r = threadIdx.x; r < nr; r += blockDim.x) { const int i = rbase + r * gridDim.x; r_phys[r] = alive[i]; r_sum[r] = sums[i]; }
+        __syncthreads();
         for (int j = threadIdx.x; j < dim; j += blockDim.x) {
-            if (i == j) continue;
-            const double q = 0.5 * row[alive[j]] - c * (sums[j] + si);
-            const unsigned long long f = (unsigned long long)j * dim + i;
-            if (nj_better(q, f, bq, bf)) { bq = q; bf = f; }
+            const int aj = alive[j];
+            const double sj = sums[j];
+            for (int r0 = 0; r0 < nr; r0 += 4) {
+                double dv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dv[u] = r0 + u < nr ? D[(size_t)r_phys[r0 + u] * P + aj] : 0.0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = rbase + (r0 + u) * gridDim.x;
+                    if (r0 + u < nr && i != j) {
+                        const double q = 0.5 * dv[u] - c * (sj + r_sum[r0 + u]);
+                        const unsigned long long f = (unsigned long long)j * dim + i;
+                        if (nj_better(q, f, bq, bf)) { bq = q; bf = f; }
+                    }
+                }
+            }
         }
     }
     __shared__ double sq[ARGMIN_THREADS]; __shared__ unsigned long long sf[ARGMIN_THREADS];
