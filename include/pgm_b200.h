@@ -108,7 +108,12 @@ int pgm_nw_ml_all_pairs(pgm_ctx* ctx, const pgm_ml_params* prm,
                         double* dist, double* var);
 
 /* Prealigned: rows is N*L_aln (row-major), 254 = gap.  The reference's hard-coded `< 20` count
- * filter (DistanceFactoryPrealigned.h:65) is applied as min(20, n).                               */
+ * filter (DistanceFactoryPrealigned.h:65) is applied as min(20, n).  Replaces
+ * DistanceFactoryPrealigned<A>::computePwDistances (DistanceFactoryPrealigned.h:33-90): every row becomes the sorted
+ * list of its residues and one thread merges the two lists of a pair (a column where both rows have a gap changes
+ * nothing, :68-69); alignments of more than 65535 columns take the column scan inside the Newton kernel.
+ * pair_range: packed results of the pairs [pair_begin, pair_end) in the order (0,1), (0,2), ..., (N-2,N-1);
+ * all_pairs: the two symmetric N*N matrices (zero diagonal), scattered on the device.                */
 int pgm_prealigned_ml_pair_range(pgm_ctx* ctx, const pgm_ml_params* prm,
                                  const uint8_t* rows, int N, int L_aln,
                                  int64_t pair_begin, int64_t pair_end,
