@@ -69,7 +69,7 @@ def test_leaf_pair_alignment_identical(ga, po, L, t, seed):
 @pytest.mark.parametrize("L", [1100, 1500, 2300, 3300, 4200])
 def test_long_graphs_identical(ga, po, L):
     """graph 1 beyond 1024 rows (BASELINE config 3 has 1500-nt sequences, the root of a 5000-sequence tree > 6000 nodes): the
-    rows are swept in bands of 512 by co-resident CTAs that hand over through HBM; PGM_FILL_BAND_MIN_N1 raises the threshold,
+    rows are swept in bands (128 rows, or one warp) by CTAs that hand over through HBM; PGM_FILL_BAND_MIN_N1 raises the threshold,
     which brings back the single-CTA flavours with several rows per thread"""
     opts = Options(mldist_flag=True)
     mf = model.getDefault(opts)
