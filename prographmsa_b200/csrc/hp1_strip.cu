@@ -595,8 +595,8 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
 
 template <int C, int WB>
 static int launch_strip_gen_t(cudaStream_t st, int warps, size_t smem, int n_jobs, const GraphJobDev* d_jobs, const int* d_order) {
-    // (static + dynamic shared memory beyond 48 KB needs the opt-in; the static part is small)
-    if (smem > 40 * 1024) PGM_CUDA(cudaFuncSetAttribute(graph_fill_strip_gen_kernel<C, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // (static + dynamic shared memory beyond 48 KB needs the opt-in; the static part -- hand-over rings, progress words -- is up to 8.1 KB)
+    if (smem > 32 * 1024) PGM_CUDA(cudaFuncSetAttribute(graph_fill_strip_gen_kernel<C, WB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     graph_fill_strip_gen_kernel<C, WB><<<n_jobs, 32 * warps, smem, st>>>(d_jobs, d_order);
     PGM_CUDA(cudaGetLastError());
     return 0;
