@@ -582,6 +582,9 @@ graph_fill_strip_gen_kernel(const GraphJobDev* __restrict__ jobs, const int* __r
             else if (W32 == 2) *reinterpret_cast<uint2*>(dp) = make_uint2(rr[0], rr[1]);
             else *reinterpret_cast<uint4*>(dp) = make_uint4(rr[0], rr[1], rr[W32 > 2 ? 2 : 0], rr[W32 > 3 ? 3 : 0]);
         }
+        // kept rows go to the value store in global memory, and a strip of another warp may read them back (far predecessors): the
+        // stores are fenced before this warp's progress word moves on (the shared-memory rings need no fence: one in-order pipe)
+        if (WB > 1 && __any_sync(0xffffffffu, active && NI_KEEP(cur.cnt) >= 0)) __threadfence_block();
         diagW = gW;
         cur = n1; n1 = n2;
 #pragma unroll
