@@ -12,7 +12,10 @@ Workload (BASELINE.json configs[1]): the all-pairs NW + ML distance matrix of a 
           distance/variance entries inside the timed region)
 N > 1 shards the pair range over the ranks (no data-path collective while computing) and gathers the
 (distance, variance) entries with one NCCL all-gather -- strong scaling of a fixed matrix.
-At N = 1 the line also carries `graph_dp`: the graph-DP GCUPS half of BASELINE.json's metric.
+At N = 1 the line also carries `graph_dp`: the graph-DP GCUPS half of BASELINE.json's metric -- `exact` / `tensor`: the 1020 jobs
+of a whole progressive pass in one batch (latency of its few long sweeps included); `leaf_level`: the 2500 leaf x leaf jobs at the
+bottom of BASELINE configs[4] (the fill kernels' throughput) -- and `other_kernels`: the ML kernel against the FP64 rate measured in
+the run, the Prealigned path on the bench family and on rows shaped like configs[4]'s alignment.
 
 --impl reference times the reference's own CPU binary (oracle/_ref/ProGraphMSA_64, single-threaded by
 design; one independent instance per host core) on bounded samples of the same family.
